@@ -1,0 +1,198 @@
+/*
+ * ovdet_b200.h -- C ABI of libovdet_b200.so, the sm_100a CUDA implementation of
+ * the detection-geometry / open-vocabulary matching hot path of
+ * timsu1104/Open-vocabulary-3D-Object-Detection.
+ *
+ * The reference has no plugin registry: its native boundary is the Cython
+ * extension `utils.box_intersection.box_intersection` (utils/box_intersection.pyx:166-171,
+ * imported at utils/box_util.py:13-19) plus the Python call surface of the hot
+ * functions.  Each entry point below replaces one of those and
+ * cites it.  INTEGRATION.md shows the reference-side ctypes binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy types.
+ *   - `*_host` entry points take HOST pointers (the Cython ABI's numpy buffers),
+ *     copy in/out on an internal stream and return after the result is in the
+ *     caller's output buffer.  All other entry points take DEVICE pointers and a
+ *     `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *     they enqueue work and return without synchronising.
+ *   - all arrays are C-contiguous; the caller owns every buffer, nothing is
+ *     retained after return.
+ *   - return value: 0 = ok, <0 = error (OVDET_ERR_*); ovdet_last_error() gives a
+ *     thread-local message.  There is no CPU fallback: without a CUDA device every
+ *     compute entry point returns OVDET_ERR_CUDA.
+ */
+#ifndef OVDET_B200_H
+#define OVDET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVDET_OK 0
+#define OVDET_ERR_INVALID (-1) /* bad shape / null pointer / unsupported size */
+#define OVDET_ERR_CUDA (-2)    /* CUDA runtime error, see ovdet_last_error() */
+#define OVDET_ERR_UNSUPPORTED (-3)
+
+int ovdet_version(void);                /* 100*major + minor */
+const char *ovdet_last_error(void);     /* thread-local, never NULL */
+int ovdet_device_count(void);           /* number of visible CUDA devices (0 if none) */
+
+/* ------------------------------------------------------------------------- */
+/* Rotated / axis-aligned 3D GIoU                                             */
+/* replaces generalized_box3d_iou (utils/box_util.py:717-737) and its two     */
+/* bodies (:517-618 torch path, :624-714 Cython-backed path).                 */
+/* ------------------------------------------------------------------------- */
+#define OVDET_GIOU_ROTATED 0x01u     /* rotated_boxes=True: BEV Sutherland-Hodgman clip */
+#define OVDET_GIOU_PREFILTER 0x02u   /* skip clip when the axis-aligned BEV overlap is 0 (box_util.py:587-588, pyx:189) */
+#define OVDET_GIOU_INTER_ONLY 0x04u  /* return_inter_vols_only=True */
+#define OVDET_GIOU_CLIP_F64 0x08u    /* Cython arithmetic: clip in fp64, polygon->fp32, np.dot-style area (pyx:13-19,196-198) */
+#define OVDET_GIOU_ENCL_HULL 0x10u   /* convex-hull enclosing volume (utils/box_ops3d.py:533-571) instead of the AABB (:466-514) */
+
+/* corners1 [B,K1,8,3], corners2 [B,K2,8,3] fp32; nums_k2 [B] int64 or NULL;
+ * k2_cap > 0 clips only GT columns < k2_cap (4 reproduces the shipped
+ * `K2 = rect2.shape[2]` bug, box_intersection.pyx:180); out [B,K1,K2] fp32. */
+int ovdet_giou3d_f32(const float *corners1, const float *corners2, const int64_t *nums_k2,
+                     int B, int K1, int K2, int k2_cap, unsigned flags, float *out, void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* The Cython extension ABI: box_intersection(rect1, rect2,                   */
+/*   non_rot_inter_areas, nums_k2, inter_areas, approximate)                  */
+/* (utils/box_intersection.pyx:166-198).  rect1 [B,K1,4,2], rect2 [B,K2,4,2], */
+/* non_rot_inter_areas / inter_areas [B,K1,K2] fp32, nums_k2 [B] int32.       */
+/* inter_areas is updated IN PLACE (only where a non-empty clip was computed).*/
+/* k2_loop is the reference's `rect2.shape[2]` (=4 as shipped); pass K2 for    */
+/* the intended all-columns behaviour.                                        */
+/* ------------------------------------------------------------------------- */
+int ovdet_box_intersection_f32(const float *rect1, const float *rect2, const float *non_rot_inter_areas,
+                               const int32_t *nums_k2, float *inter_areas, int approximate,
+                               int B, int K1, int K2, int k2_loop, void *stream);          /* device pointers */
+int ovdet_box_intersection_host_f32(const float *rect1, const float *rect2, const float *non_rot_inter_areas,
+                                    const int32_t *nums_k2, float *inter_areas, int approximate,
+                                    int B, int K1, int K2, int k2_loop);                   /* host pointers */
+
+/* Whole generalized_box3d_iou with HOST buffers (the reference call ends in    */
+/* .cpu() round trips, box_util.py:685-698): H2D, kernel, D2H, synchronise.     */
+int ovdet_giou3d_host_f32(const float *corners1, const float *corners2, const int64_t *nums_k2,
+                          int B, int K1, int K2, int k2_cap, unsigned flags, float *out);
+
+/* ------------------------------------------------------------------------- */
+/* Exact pairwise IoU: box3d_iou (utils/box_util.py:116-141), fp64 arithmetic  */
+/* on fp32 corners (eval_det.py:120,122).  dets [S,D,8,3], gts [S,G,8,3],      */
+/* out [S,D,G] fp64 (iou); out2d may be NULL.  nd/ng [S] int32 counts or NULL. */
+/* ------------------------------------------------------------------------- */
+int ovdet_box3d_iou_f64(const float *dets, const float *gts, const int32_t *nd, const int32_t *ng,
+                        int S, int D, int G, double *out, double *out2d, void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* Hungarian matcher (criterion.py:33-92)                                     */
+/* ------------------------------------------------------------------------- */
+/* cost[b,q,g] = w_class*(-prob[b,q,label[b,g]]) + w_obj*(-obj[b,q])
+ *             + w_center*center_dist[b,q,g] + w_giou*(-giou[b,q,g])   (criterion.py:40-63)
+ * center_dist == NULL: L1 distance of center_q [B,Q,3] / center_g [B,G,3]
+ * (torch.cdist(.., p=1), criterion.py:357-359) is computed in the kernel.
+ * gious == NULL: GIoU is computed in the kernel from corners1/corners2 with
+ * (giou_flags, k2_cap) as in ovdet_giou3d_f32 and optionally written to gious_out. */
+int ovdet_matcher_cost_f32(const float *sem_cls_prob, const float *objectness, const float *center_dist,
+                           const float *center_q, const float *center_g, const float *gious,
+                           const float *corners1, const float *corners2, const int64_t *gt_labels,
+                           const int64_t *nactual_gt, int B, int Q, int G, int C,
+                           float w_class, float w_obj, float w_center, float w_giou,
+                           unsigned giou_flags, int k2_cap, float *gious_out, float *cost, void *stream);
+
+/* Per-sample linear sum assignment on cost[b, :, :nactual_gt[b]] (criterion.py:76-86,
+ * scipy.optimize.linear_sum_assignment semantics, fp64 internally).
+ * per_prop_gt_inds [B,Q] int64, proposal_matched_mask [B,Q] fp32 (both fully
+ * written, zeros where unmatched), col_to_row [B,G] int32 (-1 beyond nactual_gt). */
+int ovdet_lsap_f32(const float *cost, const int64_t *nactual_gt, int B, int Q, int G,
+                   int64_t *per_prop_gt_inds, float *proposal_matched_mask, int32_t *col_to_row, void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* Greedy NMS (utils/nms.py:43-162, 3DOVDet_tools/utils/box_3d_utils.py:60-120) */
+/* ------------------------------------------------------------------------- */
+#define OVDET_NMS_2D 0x01u        /* nms_2d_faster: boxes = x1,y1,x2,y2,score */
+#define OVDET_NMS_SAMECLS 0x02u   /* only suppress same-class boxes (cls column after score) */
+#define OVDET_NMS_OLD_TYPE 0x04u  /* overlap = inter / vol_j */
+/* boxes [S,K,ncols] fp64 (dims*2 coords, score, [cls], ...); counts [S] int32 or
+ * NULL (=K); vol_eps added to each volume (1e-8 for the tools variant, else 0).
+ * keep [S,K] uint8; pick_order [S,K] int32 = indices in the reference's pick
+ * order, -1 padded; npick [S] int32.  Scores must be tie-free for a defined order. */
+int ovdet_nms_f64(const double *boxes, const int32_t *counts, int S, int K, int ncols,
+                  double thr, double vol_eps, unsigned flags,
+                  uint8_t *keep, int32_t *pick_order, int32_t *npick, void *stream);
+
+/* parse_predictions (utils/ap_calculator.py:39-238), default branch family:
+ * AABB from corners (:157-176, fp64), score = objectness, cls = argmax prob,
+ * NMS variant by flags (+ OVDET_PARSE_NO_NMS), then keep = picked & obj > conf_thresh.
+ * corners [S,K,8,3] fp32, probs [S,K,C] fp32, obj [S,K] fp32, nonempty [S,K] uint8 or NULL.
+ * Outputs: pred_mask [S,K] uint8 (NMS pick mask), keep [S,K] uint8,
+ * pred_cls [S,K] int32 (argmax), pred_cls_prob [S,K] fp32 (max). */
+#define OVDET_PARSE_NO_NMS 0x100u
+int ovdet_parse_predictions_f32(const float *corners, const float *probs, const float *obj,
+                                const uint8_t *nonempty, int S, int K, int C,
+                                double nms_iou, float conf_thresh, unsigned flags,
+                                uint8_t *pred_mask, uint8_t *keep, int32_t *pred_cls, float *pred_cls_prob,
+                                void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* AP matching (utils/eval_det.py:66-155) on scene-major device arrays         */
+/* ------------------------------------------------------------------------- */
+/* For every scene s, class c and kept detection d (per_class_proposal layout,
+ * ap_calculator.py:196-210): score[s,c,d] = probs[s,d,c]*obj[s,d]; best GT of
+ * class c by exact IoU (first max, strict >); TP at threshold t iff
+ * ovmax > t and d is the highest-scoring claimant of that GT.
+ * Writes records class-major: rec_score [C, S*K] fp32 (-inf for absent
+ * detections), rec_tp [C, S*K] uint8 bit t = TP at thr[t] (nthr <= 8),
+ * npos [C] int64 += number of GT of class c.  iou_ws: [S,K,G] fp64 workspace.
+ * det_cls != NULL selects the single-class layouts (ap_calculator.py:212-236):
+ * detection d only appears in class det_cls[s,d] with score obj[s,d] (probs unused). */
+int ovdet_ap_match(const float *corners, const float *probs, const float *obj, const uint8_t *keep,
+                   const int32_t *det_cls, const float *gt_corners, const int64_t *gt_labels, const uint8_t *gt_present,
+                   int S, int K, int G, int C, const double *thr, int nthr,
+                   double *iou_ws, float *rec_score, uint8_t *rec_tp, int64_t *npos, void *stream);
+
+/* Per-class AP from records (eval_det.py:108-153 + voc_ap :23-54): sort each
+ * class segment by descending score, cumulative TP/FP, precision/recall, AP.
+ * rec_score/rec_tp [C,N] (entries with score == -inf are absent); npos [C] int64.
+ * ap [nthr,C] fp64, recall [nthr,C] fp64 (last recall, 0 when no detections),
+ * n_det [C] int64 = number of present records (may be NULL).  If rec_out/prec_out
+ * != NULL they get the full curves [nthr,C,N] fp64 (first n_det[c] entries of each
+ * row are valid).  ws: device workspace of ovdet_ap_reduce_ws_bytes(C,N) bytes. */
+size_t ovdet_ap_reduce_ws_bytes(int C, int64_t N);
+int ovdet_ap_reduce(const float *rec_score, const uint8_t *rec_tp, const int64_t *npos,
+                    int C, int64_t N, int nthr, int use_07_metric,
+                    double *ap, double *recall, int64_t *n_det, double *rec_out, double *prec_out,
+                    void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* Open-vocabulary logits (models/model_3detr.py:237-238, :58-62;              */
+/* utils/ulip_losses.py:39-47): logits = scale * norm?(x) @ norm?(T)^T,        */
+/* prob = softmax(logits), sem_cls_prob = prob[:, :-1], objectness = 1-prob[:,-1]. */
+/* x [M,K] bf16, text [N,K] bf16 (row-major, K contiguous).  Outputs (any may  */
+/* be NULL): logits [M,N] fp32, prob [M,N-1] bf16, objectness [M] fp32.        */
+/* tcgen05 + TMA; requires K % 64 == 0, N <= 4096.                             */
+/* ------------------------------------------------------------------------- */
+#define OVDET_LOGITS_L2NORM 0x01u
+int ovdet_clip_logits_bf16(const void *x, const void *text, int M, int K, int N, unsigned flags, float scale,
+                           float *logits, void *prob, float *objectness, void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* Pseudo-label "NMS + IoU filtering" per scene                               */
+/* (3DOVDet_tools/scannet/lift_boxes.py:139-166): class-wise NMS(nms_thr) ->   */
+/* argmax-IoU match to the proposal pool (>= match_thr, box_3d_iou with +1e-5) */
+/* keeping the highest-score label per pool box -> size-scored class-wise NMS.  */
+/* boxes [S,P,8] fp64 = x1..z2,score,label; pool [S,M,6] fp64.                 */
+/* Outputs per pool box: out_label [S,M] fp64 (-100 = unmatched), out_score    */
+/* [S,M] fp64, out_keep [S,M] uint8 (survives the final NMS), nms1_keep [S,P]. */
+/* ------------------------------------------------------------------------- */
+int ovdet_pseudo_filter_f64(const double *boxes, const double *pool, const int32_t *nboxes, const int32_t *npool,
+                            int S, int P, int M, double nms_thr, double match_thr, double size_nms_thr,
+                            uint8_t *nms1_keep, double *out_label, double *out_score, uint8_t *out_keep,
+                            void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVDET_B200_H */

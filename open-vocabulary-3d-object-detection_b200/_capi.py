@@ -1,0 +1,94 @@
+"""ctypes binding of lib/libovdet_b200.so (include/ovdet_b200.h).
+
+There is no CPU fallback: if the library has not been built, or a compute entry
+point is called without a CUDA device, an exception is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libovdet_b200.so")
+
+c_p = ctypes.c_void_p
+c_i = ctypes.c_int
+c_u = ctypes.c_uint
+c_f = ctypes.c_float
+c_d = ctypes.c_double
+c_i64 = ctypes.c_int64
+c_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/ovdet_b200.h one to one
+SIGNATURES = {
+    "ovdet_version": (c_i, []),
+    "ovdet_last_error": (ctypes.c_char_p, []),
+    "ovdet_device_count": (c_i, []),
+    "ovdet_giou3d_f32": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_u, c_p, c_p]),
+    "ovdet_box_intersection_f32": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "ovdet_box_intersection_host_f32": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i]),
+    "ovdet_giou3d_host_f32": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_u, c_p]),
+    "ovdet_box3d_iou_f64": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "ovdet_matcher_cost_f32": (c_i, [c_p] * 10 + [c_i] * 4 + [c_f] * 4 + [c_u, c_i, c_p, c_p, c_p]),
+    "ovdet_lsap_f32": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "ovdet_nms_f64": (c_i, [c_p, c_p, c_i, c_i, c_i, c_d, c_d, c_u, c_p, c_p, c_p, c_p]),
+    "ovdet_parse_predictions_f32": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_d, c_f, c_u, c_p, c_p, c_p, c_p, c_p]),
+    "ovdet_ap_match": (c_i, [c_p] * 8 + [c_i] * 4 + [c_p, c_i] + [c_p] * 5),
+    "ovdet_ap_reduce_ws_bytes": (c_sz, [c_i, c_i64]),
+    "ovdet_ap_reduce": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "ovdet_clip_logits_bf16": (c_i, [c_p, c_p, c_i, c_i, c_i, c_u, c_f, c_p, c_p, c_p, c_p]),
+    "ovdet_pseudo_filter_f64": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p]),
+}
+
+# flag words (include/ovdet_b200.h)
+GIOU_ROTATED, GIOU_PREFILTER, GIOU_INTER_ONLY, GIOU_CLIP_F64, GIOU_ENCL_HULL = 1, 2, 4, 8, 16
+NMS_2D, NMS_SAMECLS, NMS_OLD_TYPE, PARSE_NO_NMS = 1, 2, 4, 0x100
+LOGITS_L2NORM = 1
+
+_LIB = None
+
+
+class OvdetError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise OvdetError(
+                "libovdet_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `python open-vocabulary-3d-object-detection_b200/build.py`. There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().ovdet_last_error().decode("utf-8", "replace")
+        raise OvdetError("libovdet_b200 error %d: %s" % (rc, msg))
+
+
+def ptr(t):
+    """Device (or host) address of a contiguous tensor / numpy array, None -> NULL."""
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        assert t.is_contiguous(), "ovdet_b200 kernels need contiguous tensors"
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def stream(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise OvdetError("expected a CUDA tensor (the product path has no CPU implementation)")

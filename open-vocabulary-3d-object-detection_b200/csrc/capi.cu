@@ -1,0 +1,51 @@
+// capi.cu -- library-level pieces of the C ABI: error reporting, version,
+// device probe and the host-staging scratch used by the *_host entry points.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace ovdet {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return OVDET_ERR_CUDA;
+}
+
+int HostStaging::ensure(size_t bytes)
+{
+    if (!stream) OVDET_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (bytes <= cap) return OVDET_OK;
+    if (dev) { OVDET_CUDA_TRY(cudaStreamSynchronize(stream)); OVDET_CUDA_TRY(cudaFree(dev)); dev = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 2;
+    OVDET_CUDA_TRY(cudaMalloc(&dev, want));
+    cap = want;
+    return OVDET_OK;
+}
+
+HostStaging &host_staging()
+{
+    static thread_local HostStaging hs;
+    return hs;
+}
+
+}  // namespace ovdet
+
+extern "C" int ovdet_version(void) { return 1; }
+extern "C" const char *ovdet_last_error(void) { return ovdet::g_err; }
+extern "C" int ovdet_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}

@@ -1,0 +1,238 @@
+// common.cuh -- shared device/host helpers for libovdet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ovdet_b200.h"
+
+namespace ovdet {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define OVDET_CUDA_TRY(expr)                                  \
+    do {                                                      \
+        cudaError_t _e = (expr);                              \
+        if (_e != cudaSuccess) return ::ovdet::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define OVDET_REQUIRE(cond, msg)                              \
+    do {                                                      \
+        if (!(cond)) {                                        \
+            ::ovdet::set_error("invalid argument: %s (%s)", msg, #cond); \
+            return OVDET_ERR_INVALID;                         \
+        }                                                     \
+    } while (0)
+
+static inline int launch_ok(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    return OVDET_OK;
+}
+
+// Grow-only device scratch owned by the library, one per host thread, used only
+// by the *_host entry points (the device-pointer API never allocates).
+struct HostStaging {
+    void *dev = nullptr;
+    size_t cap = 0;
+    cudaStream_t stream = nullptr;
+    int ensure(size_t bytes);
+};
+HostStaging &host_staging();
+
+// ------------------------------------------------ reference-faithful arithmetic
+// The reference evaluates every arithmetic op separately (Python floats, eager
+// torch, numpy), so the geometry kernels must not contract a*b+c into an FMA:
+// all maths goes through these round-to-nearest intrinsics, which nvcc never fuses.
+template <typename T> struct Ar;
+template <> struct Ar<float> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float rcp(float a) { return __frcp_rn(a); }  // == 1.0f / a, IEEE
+    static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+    static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
+    static __device__ __forceinline__ float max(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ float min(float a, float b) { return fminf(a, b); }
+};
+template <> struct Ar<double> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double rcp(double a) { return __ddiv_rn(1.0, a); }
+    static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+    static __device__ __forceinline__ double abs(double a) { return fabs(a); }
+    static __device__ __forceinline__ double max(double a, double b) { return fmax(a, b); }
+    static __device__ __forceinline__ double min(double a, double b) { return fmin(a, b); }
+};
+
+template <typename T> struct V2 { T x, y; };
+
+// ---------------------------------------------------------------------------
+// Sutherland-Hodgman clip of one convex quad by another, restating
+// utils/box_intersection.pyx:27-70 (== utils/box_util.py:404-440): clip edges in
+// order (c[3]->c[0], c[0]->c[1], ...), strict `>` inside test (pyx:23-24),
+// intersection formula pyx:13-19 with n3 = 1/(..) then multiply, stop when the
+// polygon becomes empty.  Vertex lists live in a per-thread shared-memory
+// scratch (two ping-pong rows of MAXV vertices, element i of thread t at
+// buf[i*STRIDE + t]: conflict-free), the subject quad of pass 0 and the output
+// of pass 3 stay in registers.  A convex quad clipped by 4 half-planes has at
+// most 8 vertices; MAXV=8 saturates beyond that (non-convex input only).
+// The last pass streams its vertices into `Sink` (shoelace accumulator).
+// ---------------------------------------------------------------------------
+constexpr int SH_MAXV = 8;
+
+template <typename T> struct ClipEdge {
+    T c1x, c1y, ex, ey, dcx, dcy, n1;
+    __device__ __forceinline__ ClipEdge(T ax, T ay, T bx, T by)
+    {
+        using A = Ar<T>;
+        c1x = ax; c1y = ay;
+        ex = A::sub(bx, ax); ey = A::sub(by, ay);
+        dcx = A::sub(ax, bx); dcy = A::sub(ay, by);
+        n1 = A::sub(A::mul(ax, by), A::mul(ay, bx));
+    }
+    __device__ __forceinline__ bool inside(T px, T py) const
+    {
+        using A = Ar<T>;
+        return A::mul(ex, A::sub(py, c1y)) > A::mul(ey, A::sub(px, c1x));
+    }
+    __device__ __forceinline__ V2<T> isect(T sx, T sy, T px, T py) const
+    {
+        using A = Ar<T>;
+        const T dpx = A::sub(sx, px), dpy = A::sub(sy, py);
+        const T n2 = A::sub(A::mul(sx, py), A::mul(sy, px));
+        const T n3 = A::rcp(A::sub(A::mul(dcx, dpy), A::mul(dcy, dpx)));
+        V2<T> r;
+        r.x = A::mul(A::sub(A::mul(n1, dpx), A::mul(n2, dcx)), n3);
+        r.y = A::mul(A::sub(A::mul(n1, dpy), A::mul(n2, dcy)), n3);
+        return r;
+    }
+};
+
+// Shoelace sinks.  All receive vertices in emission order v0..v(n-1) and return
+// 0.5*|sum_i x_i*y_(i-1) - sum_i y_i*x_(i-1)| (indices cyclic).
+struct SinkF32 {  // fp32 torch path: utils/box_util.py:591-598
+    bool has = false; float fx, fy, px, py, d1 = 0.f, d2 = 0.f;
+    __device__ __forceinline__ void emit(float x, float y)
+    {
+        if (!has) { fx = x; fy = y; has = true; }
+        else { d1 = __fadd_rn(d1, __fmul_rn(x, py)); d2 = __fadd_rn(d2, __fmul_rn(y, px)); }
+        px = x; py = y;
+    }
+    __device__ __forceinline__ float area()
+    {
+        if (!has) return 0.f;
+        d1 = __fadd_rn(d1, __fmul_rn(fx, py)); d2 = __fadd_rn(d2, __fmul_rn(fy, px));
+        return __fmul_rn(fabsf(__fsub_rn(d1, d2)), 0.5f);
+    }
+};
+struct SinkCython {  // pyx:196-198: polygon cast to fp32, fp32 products, double accumulation (np.dot), fp32 result
+    bool has = false; float fx, fy, px, py; double d1 = 0.0, d2 = 0.0;
+    __device__ __forceinline__ void emit(double xd, double yd)
+    {
+        const float x = (float)xd, y = (float)yd;
+        if (!has) { fx = x; fy = y; has = true; }
+        else { d1 = __dadd_rn(d1, (double)__fmul_rn(x, py)); d2 = __dadd_rn(d2, (double)__fmul_rn(y, px)); }
+        px = x; py = y;
+    }
+    __device__ __forceinline__ float area()
+    {
+        if (!has) return 0.f;
+        d1 = __dadd_rn(d1, (double)__fmul_rn(fx, py)); d2 = __dadd_rn(d2, (double)__fmul_rn(fy, px));
+        return __fmul_rn(0.5f, fabsf(__fsub_rn((float)d1, (float)d2)));
+    }
+};
+struct SinkF64 {  // fp64 shoelace (poly_area, box_util.py:84-86; stands in for Qhull's hull area :96)
+    int n = 0; double fx, fy, px, py, d1 = 0.0, d2 = 0.0;
+    __device__ __forceinline__ void emit(double x, double y)
+    {
+        if (n == 0) { fx = x; fy = y; }
+        else { d1 = __dadd_rn(d1, __dmul_rn(x, py)); d2 = __dadd_rn(d2, __dmul_rn(y, px)); }
+        px = x; py = y; ++n;
+    }
+    __device__ __forceinline__ double area()
+    {
+        if (n < 3) return 0.0;
+        d1 = __dadd_rn(d1, __dmul_rn(fx, py)); d2 = __dadd_rn(d2, __dmul_rn(fy, px));
+        return __dmul_rn(0.5, fabs(__dsub_rn(d1, d2)));
+    }
+};
+
+// One pass over a vertex list held in shared scratch, output to shared scratch.
+template <typename T, int STRIDE>
+__device__ __forceinline__ int sh_pass_mem(const ClipEdge<T> &ce, const V2<T> *in, int n, V2<T> *out)
+{
+    V2<T> s = in[(n - 1) * STRIDE];
+    bool s_in = ce.inside(s.x, s.y);
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        const V2<T> e = in[i * STRIDE];
+        const bool e_in = ce.inside(e.x, e.y);
+        if (e_in != s_in && m < SH_MAXV) out[(m++) * STRIDE] = ce.isect(s.x, s.y, e.x, e.y);
+        if (e_in && m < SH_MAXV) out[(m++) * STRIDE] = e;
+        s = e; s_in = e_in;
+    }
+    return m;
+}
+
+// Full clip: subject quad s[4], clip quad c[4] (x,y interleaved, already of type T).
+// bufA/bufB: this thread's scratch rows.  Returns through `sink`.
+template <typename T, int STRIDE, typename Sink>
+__device__ __forceinline__ void sh_clip_quads(const T *s, const T *c, V2<T> *bufA, V2<T> *bufB, Sink &sink)
+{
+    int n;
+    {   // pass 0: subject in registers -> bufA
+        const ClipEdge<T> ce(c[6], c[7], c[0], c[1]);
+        T sx = s[6], sy = s[7];
+        bool s_in = ce.inside(sx, sy);
+        int m = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const T px = s[2 * i], py = s[2 * i + 1];
+            const bool e_in = ce.inside(px, py);
+            if (e_in != s_in) bufA[(m++) * STRIDE] = ce.isect(sx, sy, px, py);
+            if (e_in) { V2<T> v; v.x = px; v.y = py; bufA[(m++) * STRIDE] = v; }
+            sx = px; sy = py; s_in = e_in;
+        }
+        n = m;
+    }
+    if (n == 0) return;
+    {
+        const ClipEdge<T> ce(c[0], c[1], c[2], c[3]);
+        n = sh_pass_mem<T, STRIDE>(ce, bufA, n, bufB);
+    }
+    if (n == 0) return;
+    {
+        const ClipEdge<T> ce(c[2], c[3], c[4], c[5]);
+        n = sh_pass_mem<T, STRIDE>(ce, bufB, n, bufA);
+    }
+    if (n == 0) return;
+    {   // pass 3: bufA -> sink
+        const ClipEdge<T> ce(c[4], c[5], c[6], c[7]);
+        V2<T> sv = bufA[(n - 1) * STRIDE];
+        bool s_in = ce.inside(sv.x, sv.y);
+        for (int i = 0; i < n; ++i) {
+            const V2<T> e = bufA[i * STRIDE];
+            const bool e_in = ce.inside(e.x, e.y);
+            if (e_in != s_in) { const V2<T> q = ce.isect(sv.x, sv.y, e.x, e.y); sink.emit(q.x, q.y); }
+            if (e_in) sink.emit(e.x, e.y);
+            sv = e; s_in = e_in;
+        }
+    }
+}
+
+// giou_hull.cu: GIoU with the convex-hull enclosing volume (OVDET_GIOU_ENCL_HULL)
+int giou3d_hull_impl(const float *corners1, const float *corners2, const int64_t *nums_k2, int B, int K1, int K2,
+                     int k2_cap, unsigned flags, float *out, void *stream);
+
+// 16-byte read-only load
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+}  // namespace ovdet

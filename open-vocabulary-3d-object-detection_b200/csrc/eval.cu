@@ -1,0 +1,585 @@
+// eval.cu -- AP evaluation path for sm_100a.
+//
+//   ovdet_box3d_iou_f64   exact pairwise IoU, box3d_iou (utils/box_util.py:116-141)
+//   ovdet_ap_match        per-scene det x GT exact IoU, argmax and first-claim TP
+//                         flags (utils/eval_det.py:117-140) for all classes and
+//                         all thresholds at once; emits class-major records
+//   ovdet_ap_reduce       per-class segmented LSD radix sort by descending score
+//                         + scans: cumulative TP/FP, precision/recall, VOC AP
+//                         (utils/eval_det.py:108-111, :143-153, voc_ap :23-54)
+//
+// The greedy loop of eval_det_cls only couples detections of one scene and one
+// class, and a detection's best GT (jmax) does not depend on earlier claims, so
+//   TP(d) <=> ovmax(d) > thr  and  d is the highest-scoring detection among
+//             those with the same jmax and ovmax > thr
+// which is evaluated in parallel with a 64-bit atomicMax per GT -- no sequential
+// pass.  Equality with the reference needs tie-free scores (numpy's argsort of
+// -confidence is not stable: documented).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ovdet {
+
+// ---------------------------------------------------------------- exact IoU
+// box3d_iou on fp32 corners cast to fp64 (eval_det.py:120,122).  The hull area of
+// box_util.py:96 (Qhull) is the shoelace area of the clipped polygon (convex).
+template <int STRIDE>
+__device__ __forceinline__ double exact_iou(const float *c1, const float *c2, V2<double> *bufA, V2<double> *bufB,
+                                            bool want2d, double *iou2d)
+{
+    using A = Ar<double>;
+    const double ymax = A::min((double)c1[1], (double)c2[1]);
+    const double ymin = A::max((double)c1[13], (double)c2[13]);
+    const double h = A::max(0.0, A::sub(ymax, ymin));
+    double vol[2];
+    const float *cc[2] = {c1, c2};
+    const int pa[3] = {0, 1, 0}, pb[3] = {1, 2, 4};
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        double e[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const double dx = A::sub((double)cc[w][3 * pa[t]], (double)cc[w][3 * pb[t]]);
+            const double dy = A::sub((double)cc[w][3 * pa[t] + 1], (double)cc[w][3 * pb[t] + 1]);
+            const double dz = A::sub((double)cc[w][3 * pa[t] + 2], (double)cc[w][3 * pb[t] + 2]);
+            e[t] = A::sqrt(A::add(A::add(A::mul(dx, dx), A::mul(dy, dy)), A::mul(dz, dz)));
+        }
+        vol[w] = A::mul(A::mul(e[0], e[1]), e[2]);
+    }
+    double ia = 0.0;
+    if (h > 0.0 || want2d) {
+        double s[8], c[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s[2 * i] = (double)c1[3 * (3 - i)]; s[2 * i + 1] = (double)c1[3 * (3 - i) + 2];
+            c[2 * i] = (double)c2[3 * (3 - i)]; c[2 * i + 1] = (double)c2[3 * (3 - i) + 2];
+        }
+        SinkF64 sink;
+        sh_clip_quads<double, STRIDE>(s, c, bufA, bufB, sink);
+        ia = sink.area();
+        if (want2d) {
+            double a[2];
+            const double *rr[2] = {s, c};
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int j = (i + 3) & 3;
+                    d1 = A::add(d1, A::mul(rr[w][2 * i], rr[w][2 * j + 1]));
+                    d2 = A::add(d2, A::mul(rr[w][2 * i + 1], rr[w][2 * j]));
+                }
+                a[w] = A::mul(0.5, fabs(A::sub(d1, d2)));
+            }
+            *iou2d = A::div(ia, A::sub(A::add(a[0], a[1]), ia));
+        }
+    }
+    const double iv = A::mul(ia, h);
+    return A::div(iv, A::sub(A::add(vol[0], vol[1]), iv));
+}
+
+constexpr int EV_NT = 256;
+
+struct IouParams {
+    const float *dets, *gts; const int32_t *nd, *ng;
+    int S, D, G; double *out, *out2d; long long total;
+};
+
+__global__ void __launch_bounds__(EV_NT) box3d_iou_kernel(IouParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    V2<double> *scratch = reinterpret_cast<V2<double> *>(sm);
+    V2<double> *bufA = scratch + threadIdx.x, *bufB = scratch + SH_MAXV * EV_NT + threadIdx.x;
+    for (long long idx = (long long)blockIdx.x * EV_NT + threadIdx.x; idx < p.total; idx += (long long)gridDim.x * EV_NT) {
+        const int g = (int)(idx % p.G);
+        const long long sd = idx / p.G;
+        const int d = (int)(sd % p.D);
+        const int s = (int)(sd / p.D);
+        double r = 0.0, r2 = 0.0;
+        const bool live = (!p.nd || d < p.nd[s]) && (!p.ng || g < p.ng[s]);
+        if (live) {
+            float c1[24], c2[24];
+            const float *a = p.dets + sd * 24, *b = p.gts + ((long long)s * p.G + g) * 24;
+#pragma unroll
+            for (int i = 0; i < 24; ++i) { c1[i] = __ldg(a + i); c2[i] = __ldg(b + i); }
+            r = exact_iou<EV_NT>(c1, c2, bufA, bufB, p.out2d != nullptr, &r2);
+        }
+        p.out[idx] = r;
+        if (p.out2d) p.out2d[idx] = r2;
+    }
+}
+
+// ---------------------------------------------------------------- AP matching
+struct MatchParams {
+    const float *corners, *probs, *obj; const uint8_t *keep; const int32_t *det_cls;
+    const float *gt_corners; const int64_t *gt_labels; const uint8_t *gt_present;
+    int S, K, G, C, nthr; double thr[8];
+    double *iou_ws; float *rec_score; uint8_t *rec_tp; unsigned long long *npos;
+};
+
+__global__ void __launch_bounds__(EV_NT) ap_match_kernel(MatchParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    // carve: scratch [2*MAXV*NT] V2<double> | best [G*nthr] u64 | kd [K] int | gl [G] int | glab [G] int | jmax [C*K] i16 | cand [C*K] u8 | counters
+    V2<double> *scratch = reinterpret_cast<V2<double> *>(sm);
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(scratch + 2 * SH_MAXV * EV_NT);
+    int *kd = reinterpret_cast<int *>(best + (size_t)p.G * p.nthr);
+    int *gl = kd + p.K;
+    int *glab = gl + p.G;
+    short *jmax = reinterpret_cast<short *>(glab + p.G);
+    unsigned char *cand = reinterpret_cast<unsigned char *>(jmax + (size_t)p.C * p.K);
+    __shared__ int nk_s, ng_s;
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const size_t N = (size_t)p.S * p.K;
+    const uint8_t *keep = p.keep + (size_t)s * p.K;
+
+    // ordered compaction of kept detections / present GT (single warp, ballot + popc)
+    if (tid < 32) {
+        int n = 0;
+        for (int base = 0; base < p.K; base += 32) {
+            const int k = base + tid;
+            const bool f = k < p.K && keep[k];
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            if (f) kd[n + __popc(m & ((1u << tid) - 1))] = k;
+            n += __popc(m);
+        }
+        if (tid == 0) nk_s = n;
+        n = 0;
+        for (int base = 0; base < p.G; base += 32) {
+            const int g = base + tid;
+            const bool f = g < p.G && p.gt_present[(size_t)s * p.G + g];
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            if (f) {
+                const int pos = n + __popc(m & ((1u << tid) - 1));
+                gl[pos] = g;
+                long long lab = p.gt_labels[(size_t)s * p.G + g];
+                glab[pos] = (int)lab;
+                if (lab >= 0 && lab < p.C) atomicAdd(&p.npos[lab], 1ull);
+            }
+            n += __popc(m);
+        }
+        if (tid == 0) ng_s = n;
+    }
+    for (int i = tid; i < p.G * p.nthr; i += EV_NT) best[i] = 0ull;
+    __syncthreads();
+    const int nk = nk_s, ng = ng_s;
+
+    // exact IoU matrix [nk, ng] -> iou_ws[s, i, j]
+    double *iou = p.iou_ws + (size_t)s * p.K * p.G;
+    V2<double> *bufA = scratch + tid, *bufB = scratch + SH_MAXV * EV_NT + tid;
+    for (int pi = tid; pi < nk * ng; pi += EV_NT) {
+        const int i = pi / ng, j = pi - i * ng;
+        float c1[24], c2[24];
+        const float *a = p.corners + ((size_t)s * p.K + kd[i]) * 24;
+        const float *b = p.gt_corners + ((size_t)s * p.G + gl[j]) * 24;
+#pragma unroll
+        for (int t = 0; t < 24; ++t) { c1[t] = __ldg(a + t); c2[t] = __ldg(b + t); }
+        double dummy;
+        iou[(size_t)i * p.G + j] = exact_iou<EV_NT>(c1, c2, bufA, bufB, false, &dummy);
+    }
+    // default records for every (class, detection slot) of this scene
+    for (int it = tid; it < p.C * p.K; it += EV_NT) {
+        const int c = it / p.K, k = it - c * p.K;
+        p.rec_score[(size_t)c * N + (size_t)s * p.K + k] = -INFINITY;
+        p.rec_tp[(size_t)c * N + (size_t)s * p.K + k] = 0;
+    }
+    __syncthreads();
+
+    // pass 1: per (class, kept det): score, jmax, candidate bits, claim
+    for (int it = tid; it < p.C * nk; it += EV_NT) {
+        const int c = it / nk, i = it - c * nk;
+        const int k = kd[i];
+        if (p.det_cls && p.det_cls[(size_t)s * p.K + k] != c) { jmax[it] = -1; cand[it] = 0; continue; }
+        const float sc = p.det_cls ? __ldg(p.obj + (size_t)s * p.K + k)
+                                   : __fmul_rn(__ldg(p.probs + ((size_t)s * p.K + k) * p.C + c), __ldg(p.obj + (size_t)s * p.K + k));
+        p.rec_score[(size_t)c * N + (size_t)s * p.K + k] = sc;
+        double ovmax = -INFINITY; int jm = -1;
+        for (int j = 0; j < ng; ++j) {
+            if (glab[j] != c) continue;
+            const double v = iou[(size_t)i * p.G + j];
+            if (v > ovmax) { ovmax = v; jm = j; }
+        }
+        unsigned char cb = 0;
+        if (jm >= 0) {
+            // non-negative fp32 scores order like their bit patterns; lower det index wins ties
+            const unsigned long long key = ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+            for (int t = 0; t < p.nthr; ++t)
+                if (ovmax > p.thr[t]) { cb |= (unsigned char)(1u << t); atomicMax(&best[(size_t)jm * p.nthr + t], key); }
+        }
+        jmax[it] = (short)jm;
+        cand[it] = cb;
+    }
+    __syncthreads();
+    // pass 2: TP iff this det holds the claim
+    for (int it = tid; it < p.C * nk; it += EV_NT) {
+        const unsigned char cb = cand[it];
+        if (!cb) continue;
+        const int c = it / nk, i = it - c * nk;
+        const int jm = jmax[it];
+        unsigned char tp = 0;
+        for (int t = 0; t < p.nthr; ++t)
+            if ((cb >> t) & 1) {
+                const unsigned long long w = best[(size_t)jm * p.nthr + t];
+                if ((unsigned)(0xFFFFFFFFu - (unsigned)(w & 0xFFFFFFFFull)) == (unsigned)i) tp |= (unsigned char)(1u << t);
+            }
+        p.rec_tp[(size_t)c * N + (size_t)s * p.K + kd[i]] = tp;
+    }
+}
+
+// ------------------------------------------------- segmented radix sort + AP
+constexpr int RS_NT = 256, RS_IPT = 8, RS_TILE = RS_NT * RS_IPT;
+
+__device__ __forceinline__ uint32_t score_key(float s)
+{   // ascending key order == descending score; -inf (absent) sorts last
+    const uint32_t b = __float_as_uint(s);
+    const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ~ord;
+}
+
+__global__ void __launch_bounds__(RS_NT) rs_prep_kernel(const float *__restrict__ score, const uint8_t *__restrict__ tp,
+                                                        uint32_t *keys, uint8_t *vals, unsigned long long *nvalid, long long N)
+{
+    const int c = blockIdx.y;
+    int local = 0;
+    for (long long i = (long long)blockIdx.x * RS_NT + threadIdx.x; i < N; i += (long long)gridDim.x * RS_NT) {
+        const float s = score[(size_t)c * N + i];
+        keys[(size_t)c * N + i] = score_key(s);
+        vals[(size_t)c * N + i] = tp[(size_t)c * N + i];
+        local += (s > -INFINITY) ? 1 : 0;
+    }
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&nvalid[c], (unsigned long long)local);
+}
+
+__global__ void __launch_bounds__(RS_NT) rs_hist_kernel(const uint32_t *__restrict__ keys, uint32_t *hist, long long N, int tiles, int shift)
+{
+    __shared__ unsigned int h[256];
+    const int c = blockIdx.y, tile = blockIdx.x;
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const long long base = (long long)tile * RS_TILE;
+#pragma unroll
+    for (int j = 0; j < RS_IPT; ++j) {
+        const long long i = base + j * RS_NT + threadIdx.x;
+        if (i < N) atomicAdd(&h[(keys[(size_t)c * N + i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[((size_t)c * 256 + threadIdx.x) * tiles + tile] = h[threadIdx.x];
+}
+
+// exclusive scan of hist[c][0 .. 256*tiles) (digit-major), one CTA per class
+__global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *hist, int tiles)
+{
+    __shared__ unsigned int wsum[32];
+    __shared__ unsigned int carry_s;
+    uint32_t *h = hist + (size_t)blockIdx.x * 256 * tiles;
+    const int L = 256 * tiles;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < L; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned int v = i < L ? h[i] : 0u;
+        unsigned int x = v;
+        for (int off = 1; off < 32; off <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, off); if ((threadIdx.x & 31) >= off) x += y; }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned int w = wsum[threadIdx.x];
+            for (int off = 1; off < 32; off <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, w, off); if (threadIdx.x >= off) w += y; }
+            wsum[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const unsigned int carry = carry_s;
+        const unsigned int incl = x + (threadIdx.x >= 32 ? wsum[(threadIdx.x >> 5) - 1] : 0u);
+        if (i < L) h[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(RS_NT) rs_scatter_kernel(const uint32_t *__restrict__ kin, const uint8_t *__restrict__ vin,
+                                                           uint32_t *kout, uint8_t *vout, const uint32_t *__restrict__ hist,
+                                                           long long N, int tiles, int shift)
+{
+    __shared__ unsigned int whist[RS_NT / 32][256];
+    __shared__ unsigned int base[256];
+    const int c = blockIdx.y, tile = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int w = 0; w < RS_NT / 32; ++w) whist[w][threadIdx.x] = 0;
+    __syncthreads();
+    // warp w owns the contiguous 256 elements [tile*2048 + w*256, +256): order (warp, round, lane) == index order
+    const long long wbase = (long long)tile * RS_TILE + (long long)warp * (32 * RS_IPT);
+    uint32_t key[RS_IPT]; uint8_t val[RS_IPT]; unsigned int rank[RS_IPT];
+#pragma unroll
+    for (int j = 0; j < RS_IPT; ++j) {
+        const long long i = wbase + j * 32 + lane;
+        const bool valid = i < N;
+        key[j] = valid ? kin[(size_t)c * N + i] : 0xFFFFFFFFu;
+        val[j] = valid ? vin[(size_t)c * N + i] : 0;
+        const unsigned int digit = (key[j] >> shift) & 255u;
+        const unsigned int peers = __match_any_sync(0xffffffffu, valid ? digit : 0x1000u + lane);
+        const int lead = __ffs(peers) - 1;
+        unsigned int old = 0;
+        if (valid && lane == lead) { old = whist[warp][digit]; whist[warp][digit] = old + __popc(peers); }
+        __syncwarp();
+        old = __shfl_sync(0xffffffffu, old, lead);
+        rank[j] = old + __popc(peers & ((1u << lane) - 1));
+    }
+    __syncthreads();
+    {   // exclusive scan over warps for digit = threadIdx.x, plus the global base of this (digit, tile)
+        const int d = threadIdx.x;
+        unsigned int run = 0;
+        for (int w = 0; w < RS_NT / 32; ++w) { const unsigned int t = whist[w][d]; whist[w][d] = run; run += t; }
+        base[d] = hist[((size_t)c * 256 + d) * tiles + tile];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RS_IPT; ++j) {
+        const long long i = wbase + j * 32 + lane;
+        if (i < N) {
+            const unsigned int digit = (key[j] >> shift) & 255u;
+            const size_t pos = (size_t)c * N + base[digit] + whist[warp][digit] + rank[j];
+            kout[pos] = key[j];
+            vout[pos] = val[j];
+        }
+    }
+}
+
+// Cumulative TP/FP, precision/recall and VOC AP over one sorted class segment.
+// grid = (C, nthr), 1024 threads.  Phase 1: per-chunk TP totals; phase 2: chunks
+// in reverse with the precision envelope (running max from the right, eval_det.py:45-46)
+// carried across chunks; AP = sum over TP positions of (rec_i - rec_{i-1}) * env_i (:50-54).
+struct ApScanParams {
+    const uint8_t *vals; const unsigned long long *nvalid; const long long *npos;
+    long long N; int C, nthr, use07;
+    double *ap, *recall, *rec_out, *prec_out; long long *ndet_out;
+};
+
+__global__ void __launch_bounds__(1024) ap_scan_kernel(ApScanParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    unsigned int *chunk_tp = reinterpret_cast<unsigned int *>(sm);  // [nchunks + 1] exclusive prefix
+    __shared__ unsigned int wsum[32];
+    __shared__ double wmax[32];
+    __shared__ double red[32];
+    __shared__ double carry_max_s;
+    const int c = blockIdx.x, t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long n = (long long)p.nvalid[c];
+    const double npos = (double)p.npos[c];
+    const uint8_t *v = p.vals + (size_t)c * p.N;
+    const int nchunks = (int)((n + 1023) / 1024);
+    const double eps = 2.220446049250313e-16;
+    // ---- phase 1: chunk totals
+    for (int b = warp; b < nchunks; b += 32) {
+        unsigned int cnt = 0;
+        for (int k = lane; k < 1024; k += 32) {
+            const long long i = (long long)b * 1024 + k;
+            if (i < n) cnt += (v[i] >> t) & 1u;
+        }
+        for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        if (lane == 0) chunk_tp[b + 1] = cnt;
+    }
+    if (tid == 0) { chunk_tp[0] = 0; carry_max_s = 0.0; }
+    __syncthreads();
+    if (tid == 0) for (int b = 0; b < nchunks; ++b) chunk_tp[b + 1] += chunk_tp[b];
+    __syncthreads();
+    const unsigned int total_tp = chunk_tp[nchunks];
+    double ap_local = 0.0;
+    double p11[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) p11[k] = 0.0;
+    // ---- phase 2: reverse over chunks
+    for (int b = nchunks - 1; b >= 0; --b) {
+        const long long i = (long long)b * 1024 + tid;
+        const bool valid = i < n;
+        const unsigned int tp = valid ? ((v[i] >> t) & 1u) : 0u;
+        unsigned int x = tp;
+        for (int off = 1; off < 32; off <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (tid < 32) {
+            unsigned int w = wsum[tid];
+            for (int off = 1; off < 32; off <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, w, off); if (tid >= off) w += y; }
+            wsum[tid] = w;
+        }
+        __syncthreads();
+        const unsigned int ctp_u = chunk_tp[b] + x + (warp ? wsum[warp - 1] : 0u);
+        const double ctp = (double)ctp_u;
+        const double tot = (double)(i + 1);                 // tp + fp
+        const double prec = valid ? __ddiv_rn(ctp, fmax(tot, eps)) : 0.0;
+        const double rec = npos > 0.0 ? __ddiv_rn(ctp, npos) : 0.0;
+        if (valid && p.rec_out) {
+            p.rec_out[((size_t)t * p.C + c) * p.N + i] = rec;
+            p.prec_out[((size_t)t * p.C + c) * p.N + i] = prec;
+        }
+        // reverse inclusive max scan of prec within the chunk, then fold the carry of later chunks
+        double m = prec;
+        for (int off = 1; off < 32; off <<= 1) { const double y = __shfl_down_sync(0xffffffffu, m, off); if (lane + off < 32) m = fmax(m, y); }
+        if (lane == 0) wmax[warp] = m;
+        __syncthreads();
+        if (tid < 32) {
+            double w = wmax[tid];
+            for (int off = 1; off < 32; off <<= 1) { const double y = __shfl_down_sync(0xffffffffu, w, off); if (tid + off < 32) w = fmax(w, y); }
+            wmax[tid] = w;
+        }
+        __syncthreads();
+        const double carry = carry_max_s;
+        double env = fmax(m, carry);
+        if (warp < 31) env = fmax(env, wmax[warp + 1]);
+        if (valid && tp) {
+            const double rec_prev = npos > 0.0 ? __ddiv_rn(ctp - 1.0, npos) : 0.0;
+            ap_local += __dmul_rn(__dsub_rn(rec, rec_prev), env);
+        }
+        if (valid && p.use07) {
+#pragma unroll
+            for (int k = 0; k < 11; ++k) if (rec >= k * 0.1) p11[k] = fmax(p11[k], prec);
+        }
+        __syncthreads();
+        if (tid == 0) carry_max_s = fmax(carry, wmax[0]);
+        __syncthreads();
+    }
+    // ---- deterministic block reductions
+    double res;
+    if (!p.use07) {
+        double a = ap_local;
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+        if (lane == 0) red[warp] = a;
+        __syncthreads();
+        if (tid < 32) {
+            double w = red[tid];
+            for (int off = 16; off > 0; off >>= 1) w += __shfl_down_sync(0xffffffffu, w, off);
+            red[0] = w;
+        }
+        __syncthreads();
+        res = red[0];
+    } else {
+        res = 0.0;
+        for (int k = 0; k < 11; ++k) {
+            double a = p11[k];
+            for (int off = 16; off > 0; off >>= 1) a = fmax(a, __shfl_down_sync(0xffffffffu, a, off));
+            __syncthreads();
+            if (lane == 0) red[warp] = a;
+            __syncthreads();
+            if (tid < 32) {
+                double w = red[tid];
+                for (int off = 16; off > 0; off >>= 1) w = fmax(w, __shfl_down_sync(0xffffffffu, w, off));
+                red[0] = w;
+            }
+            __syncthreads();
+            res = res + red[0] / 11.0;
+        }
+    }
+    if (tid == 0) {
+        p.ap[(size_t)t * p.C + c] = n > 0 ? res : 0.0;
+        p.recall[(size_t)t * p.C + c] = (n > 0 && npos > 0.0) ? __ddiv_rn((double)total_tp, npos) : 0.0;
+        if (p.ndet_out && t == 0) p.ndet_out[c] = n;
+    }
+}
+
+static inline size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace ovdet
+
+using namespace ovdet;
+
+extern "C" int ovdet_box3d_iou_f64(const float *dets, const float *gts, const int32_t *nd, const int32_t *ng,
+                                   int S, int D, int G, double *out, double *out2d, void *stream)
+{
+    OVDET_REQUIRE(S >= 0 && D >= 0 && G >= 0, "negative size");
+    if (S == 0 || D == 0 || G == 0) return OVDET_OK;
+    OVDET_REQUIRE(dets && gts && out, "null pointer");
+    IouParams p{dets, gts, nd, ng, S, D, G, out, out2d, (long long)S * D * G};
+    const size_t smem = sizeof(V2<double>) * 2 * SH_MAXV * EV_NT;
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(box3d_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long blocks = (p.total + EV_NT - 1) / EV_NT;
+    if (blocks > 148 * 12) blocks = 148 * 12;
+    box3d_iou_kernel<<<(unsigned)blocks, EV_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return launch_ok("box3d_iou_kernel");
+}
+
+extern "C" int ovdet_ap_match(const float *corners, const float *probs, const float *obj, const uint8_t *keep,
+                              const int32_t *det_cls, const float *gt_corners, const int64_t *gt_labels, const uint8_t *gt_present,
+                              int S, int K, int G, int C, const double *thr, int nthr,
+                              double *iou_ws, float *rec_score, uint8_t *rec_tp, int64_t *npos, void *stream)
+{
+    OVDET_REQUIRE(S >= 0 && K > 0 && G >= 0 && C > 0, "bad size");
+    if (S == 0) return OVDET_OK;
+    OVDET_REQUIRE(corners && obj && keep && rec_score && rec_tp && npos && thr, "null pointer");
+    OVDET_REQUIRE(probs || det_cls, "need probs (per-class proposals) or det_cls");
+    OVDET_REQUIRE(G == 0 || (gt_corners && gt_labels && gt_present && iou_ws), "null GT pointer");
+    OVDET_REQUIRE(nthr >= 1 && nthr <= 8, "1..8 thresholds");
+    OVDET_REQUIRE(K <= 32767 && G <= 32767, "K, G must fit int16");
+    MatchParams p;
+    p.corners = corners; p.probs = probs; p.obj = obj; p.keep = keep; p.det_cls = det_cls; p.gt_corners = gt_corners;
+    p.gt_labels = gt_labels; p.gt_present = gt_present; p.S = S; p.K = K; p.G = G; p.C = C; p.nthr = nthr;
+    for (int t = 0; t < nthr; ++t) p.thr[t] = thr[t];
+    p.iou_ws = iou_ws; p.rec_score = rec_score; p.rec_tp = rec_tp; p.npos = reinterpret_cast<unsigned long long *>(npos);
+    size_t smem = sizeof(V2<double>) * 2 * SH_MAXV * EV_NT + sizeof(unsigned long long) * (size_t)G * nthr +
+                  sizeof(int) * ((size_t)K + 2 * (size_t)G) + (sizeof(short) + 1) * (size_t)C * K + 16;
+    OVDET_REQUIRE(smem <= 220 * 1024, "C*K too large for the shared-memory match tables");
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ap_match_kernel<<<S, EV_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return launch_ok("ap_match_kernel");
+}
+
+extern "C" size_t ovdet_ap_reduce_ws_bytes(int C, int64_t N)
+{
+    if (C <= 0 || N <= 0) return 256;
+    const size_t cn = (size_t)C * (size_t)N;
+    const size_t tiles = ((size_t)N + RS_TILE - 1) / RS_TILE;
+    return 2 * a256(cn * 4) + 2 * a256(cn) + a256((size_t)C * 256 * tiles * 4) + a256((size_t)C * 8) + 256;
+}
+
+extern "C" int ovdet_ap_reduce(const float *rec_score, const uint8_t *rec_tp, const int64_t *npos,
+                               int C, int64_t N, int nthr, int use_07_metric,
+                               double *ap, double *recall, int64_t *n_det, double *rec_out, double *prec_out,
+                               void *ws, size_t ws_bytes, void *stream)
+{
+    OVDET_REQUIRE(C > 0 && N >= 0 && nthr >= 1 && nthr <= 8, "bad size");
+    OVDET_REQUIRE(ap && recall && npos, "null pointer");
+    OVDET_REQUIRE((rec_out == nullptr) == (prec_out == nullptr), "rec_out and prec_out go together");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (N == 0) {
+        OVDET_CUDA_TRY(cudaMemsetAsync(ap, 0, sizeof(double) * nthr * C, st));
+        OVDET_CUDA_TRY(cudaMemsetAsync(recall, 0, sizeof(double) * nthr * C, st));
+        if (n_det) OVDET_CUDA_TRY(cudaMemsetAsync(n_det, 0, sizeof(int64_t) * C, st));
+        return OVDET_OK;
+    }
+    OVDET_REQUIRE(rec_score && rec_tp && ws, "null pointer");
+    OVDET_REQUIRE(ws_bytes >= ovdet_ap_reduce_ws_bytes(C, N), "workspace too small");
+    OVDET_REQUIRE(N < (1ll << 31), "N must be < 2^31");
+    const size_t cn = (size_t)C * (size_t)N;
+    const int tiles = (int)((N + RS_TILE - 1) / RS_TILE);
+    char *w = static_cast<char *>(ws);
+    uint32_t *kA = reinterpret_cast<uint32_t *>(w); w += a256(cn * 4);
+    uint32_t *kB = reinterpret_cast<uint32_t *>(w); w += a256(cn * 4);
+    uint8_t *vA = reinterpret_cast<uint8_t *>(w); w += a256(cn);
+    uint8_t *vB = reinterpret_cast<uint8_t *>(w); w += a256(cn);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(w); w += a256((size_t)C * 256 * tiles * 4);
+    unsigned long long *nvalid = reinterpret_cast<unsigned long long *>(w);
+    OVDET_CUDA_TRY(cudaMemsetAsync(nvalid, 0, sizeof(unsigned long long) * C, st));
+    {
+        int gx = (int)((N + RS_NT - 1) / RS_NT);
+        if (gx > 148 * 8) gx = 148 * 8;
+        rs_prep_kernel<<<dim3(gx, C), RS_NT, 0, st>>>(rec_score, rec_tp, kA, vA, nvalid, N);
+    }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        rs_hist_kernel<<<dim3(tiles, C), RS_NT, 0, st>>>(kA, hist, N, tiles, shift);
+        rs_scan_kernel<<<C, 1024, 0, st>>>(hist, tiles);
+        rs_scatter_kernel<<<dim3(tiles, C), RS_NT, 0, st>>>(kA, vA, kB, vB, hist, N, tiles, shift);
+        uint32_t *tk = kA; kA = kB; kB = tk;
+        uint8_t *tv = vA; vA = vB; vB = tv;
+    }
+    ApScanParams sp;
+    sp.vals = vA; sp.nvalid = nvalid; sp.npos = reinterpret_cast<const long long *>(npos); sp.N = N; sp.C = C; sp.nthr = nthr;
+    sp.use07 = use_07_metric; sp.ap = ap; sp.recall = recall; sp.rec_out = rec_out; sp.prec_out = prec_out;
+    sp.ndet_out = reinterpret_cast<long long *>(n_det);
+    const size_t smem = sizeof(unsigned int) * ((size_t)(N + 1023) / 1024 + 2);
+    if (smem > 48 * 1024) OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OVDET_REQUIRE(smem <= 200 * 1024, "N too large for the chunk table");
+    ap_scan_kernel<<<dim3(C, nthr), 1024, smem, st>>>(sp);
+    return launch_ok("ap_reduce");
+}

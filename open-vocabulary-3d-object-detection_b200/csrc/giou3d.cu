@@ -1,0 +1,527 @@
+// giou3d.cu -- rotated / axis-aligned 3D GIoU for sm_100a.
+//
+// Replaces generalized_box3d_iou (utils/box_util.py:717-737; bodies :517-618 and
+// :624-714) and the Cython hot loop box_intersection (utils/box_intersection.pyx:166-198).
+//
+// Layout.  One CTA owns a tile of TQ query boxes of one batch element and walks
+// the GT boxes in chunks of TG.  Corners ([.,8,3] fp32 = 96 B per box) are staged
+// through shared memory with coalesced float4 loads, reduced once per box to 17
+// features (BEV quad, y-extent, volume, AABB) kept SoA in shared memory.
+//   phase A  every thread takes pairs (row, col) of the tile: height overlap,
+//            axis-aligned prefilter area, AABB enclosing volume, validity; pairs
+//            that need no polygon clip are finished here; the others are pushed
+//            (warp-aggregated) on a CTA-local queue.
+//   phase B  the queue is drained with all lanes busy: one Sutherland-Hodgman
+//            clip per lane, vertex lists in a conflict-free per-thread shared
+//            scratch, shoelace area streamed out of the last pass.
+// Results go to a shared [TQ][TG] tile and leave with coalesced row stores.
+// The pair work is ~60 (skip) to ~1200 (clip) instructions against 4 B written,
+// i.e. issue-bound, not HBM-bound: see DESIGN.md for the roofline used.
+#include "common.cuh"
+
+namespace ovdet {
+
+constexpr int TQ = 32;    // query rows per CTA
+constexpr int TG = 64;    // GT columns per chunk
+constexpr int NT = 256;   // threads per CTA
+constexpr int NF = 17;    // features per box
+// feature indices
+enum { F_RX = 0, F_RZ = 4, F_YTOP = 8, F_YBOT = 9, F_VOL = 10, F_MN = 11, F_MX = 14 };
+
+// optional fused Hungarian-matcher cost epilogue (criterion.py:40-63)
+struct MatcherEpi {
+    const float *prob = nullptr;         // [B,K1,C]
+    const float *obj = nullptr;          // [B,K1]
+    const float *center_dist = nullptr;  // [B,K1,K2] or null -> L1 of cq/cg
+    const float *cq = nullptr, *cg = nullptr;  // [B,K1,3], [B,K2,3]
+    const int64_t *labels = nullptr;     // [B,K2]
+    float *cost = nullptr;               // [B,K1,K2]
+    int C = 0;
+    float wc = 0, wo = 0, wce = 0, wg = 0;
+};
+
+struct GiouParams {
+    const float *c1, *c2;
+    const int64_t *nums_k2;
+    float *out;   // may be null when only the matcher cost is wanted
+    int B, K1, K2, k2_cap;
+    unsigned flags;
+    int tiles_per_b;
+    MatcherEpi epi;
+};
+
+// features of one box from its 24 staged floats (utils/box_util.py:550-555 rect,
+// :544-546 y extent, :443-463 volume with the 1e-8 clamp of :568-569, AABB for :466-514)
+__device__ __forceinline__ void box_features(const float *c, float *f, int stride)
+{
+    using A = Ar<float>;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[(F_RX + i) * stride] = c[3 * (3 - i)];
+        f[(F_RZ + i) * stride] = c[3 * (3 - i) + 2];
+    }
+    f[F_YTOP * stride] = c[1];
+    f[F_YBOT * stride] = c[13];
+    float e[3];
+    const int pa[3] = {0, 1, 0}, pb[3] = {1, 2, 4};
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const float dx = A::sub(c[3 * pa[t]], c[3 * pb[t]]);
+        const float dy = A::sub(c[3 * pa[t] + 1], c[3 * pb[t] + 1]);
+        const float dz = A::sub(c[3 * pa[t] + 2], c[3 * pb[t] + 2]);
+        const float s = A::add(A::add(A::mul(dx, dx), A::mul(dy, dy)), A::mul(dz, dz));
+        e[t] = A::sqrt(fmaxf(s, 1e-6f));
+    }
+    f[F_VOL * stride] = fmaxf(A::mul(A::mul(e[0], e[1]), e[2]), 1e-8f);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float mn = c[a], mx = c[a];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { mn = fminf(mn, c[3 * i + a]); mx = fmaxf(mx, c[3 * i + a]); }
+        f[(F_MN + a) * stride] = mn;
+        f[(F_MX + a) * stride] = mx;
+    }
+}
+
+// cooperative coalesced stage of `n` boxes (n*24 floats) into shared memory
+__device__ __forceinline__ void stage_boxes(const float *__restrict__ g, int n, float *raw, bool vec)
+{
+    const int nfl = n * 24;
+    if (vec) {
+        for (int i = threadIdx.x; i < nfl / 4; i += NT) reinterpret_cast<float4 *>(raw)[i] = ldg4(g + 4 * i);
+    } else {
+        for (int i = threadIdx.x; i < nfl; i += NT) raw[i] = __ldg(g + i);
+    }
+}
+
+struct PairTerms { float h, nonrot, encl, sumv; };
+
+__device__ __forceinline__ PairTerms pair_terms(const float *f1, int r, const float *f2, int c)
+{
+    using A = Ar<float>;
+    PairTerms t;
+    const float ytop = fminf(f1[F_YTOP * TQ + r], f2[F_YTOP * TG + c]);
+    const float ybot = fmaxf(f1[F_YBOT * TQ + r], f2[F_YBOT * TG + c]);
+    t.h = fmaxf(A::sub(ytop, ybot), 0.f);
+    // prefilter: rect points 1 and 3 as lt / rb (box_util.py:557-560)
+    const float w0 = fmaxf(A::sub(fminf(f1[(F_RX + 3) * TQ + r], f2[(F_RX + 3) * TG + c]),
+                                  fmaxf(f1[(F_RX + 1) * TQ + r], f2[(F_RX + 1) * TG + c])), 0.f);
+    const float w1 = fmaxf(A::sub(fminf(f1[(F_RZ + 3) * TQ + r], f2[(F_RZ + 3) * TG + c]),
+                                  fmaxf(f1[(F_RZ + 1) * TQ + r], f2[(F_RZ + 1) * TG + c])), 0.f);
+    t.nonrot = A::mul(w0, w1);
+    float d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float mn = fminf(f1[(F_MN + a) * TQ + r], f2[(F_MN + a) * TG + c]);
+        const float mx = fmaxf(f1[(F_MX + a) * TQ + r], f2[(F_MX + a) * TG + c]);
+        d[a] = fabsf(A::sub(mx, mn));
+    }
+    t.encl = A::mul(A::mul(d[0], d[1]), d[2]);
+    t.sumv = A::add(f1[F_VOL * TQ + r], f2[F_VOL * TG + c]);
+    return t;
+}
+
+// box_util.py:600-618 / :700-714
+__device__ __forceinline__ float finish_pair(const PairTerms &t, float area, bool valid, bool has_nums, bool inter_only)
+{
+    using A = Ar<float>;
+    const float inter = A::mul(area, t.h);
+    if (inter_only) return inter;
+    const float uni = fmaxf(A::sub(t.sumv, inter), 1e-8f);
+    const float iou = A::div(inter, uni);
+    const float second = -A::sub(1.f, A::div(uni, t.encl));
+    float g = A::add(iou, second);
+    const float good = (t.encl > 2e-8f && t.sumv > 4e-8f) ? 1.f : 0.f;
+    g = A::mul(g, good);
+    if (has_nums) g = A::mul(g, valid ? 1.f : 0.f);
+    return g;
+}
+
+template <typename ClipT>
+__global__ void __launch_bounds__(NT) giou3d_kernel(GiouParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // carve: f1[NF*TQ] f2[NF*TG] tile[TQ*TG] raw[TG*24] queue[TQ*TG u16] scratch[2*SH_MAXV*NT V2<ClipT>]
+    float *f1 = reinterpret_cast<float *>(smem_raw);
+    float *f2 = f1 + NF * TQ;
+    float *tile = f2 + NF * TG;
+    float *raw = tile + TQ * TG;
+    unsigned short *queue = reinterpret_cast<unsigned short *>(raw + TG * 24);
+    V2<ClipT> *scratch = reinterpret_cast<V2<ClipT> *>(queue + TQ * TG);
+    __shared__ int qcount;
+
+    const int b = blockIdx.x / p.tiles_per_b;
+    const int q0 = (blockIdx.x - b * p.tiles_per_b) * TQ;
+    const int nq = min(TQ, p.K1 - q0);
+    const bool rotated = p.flags & OVDET_GIOU_ROTATED;
+    const bool prefilter = p.flags & OVDET_GIOU_PREFILTER;
+    const bool inter_only = p.flags & OVDET_GIOU_INTER_ONLY;
+    const bool has_nums = p.nums_k2 != nullptr;
+    int nk = p.K2;
+    if (has_nums) { const long long v = p.nums_k2[b]; nk = v < 0 ? 0 : (v > p.K2 ? p.K2 : (int)v); }
+    const int clip_lim = p.k2_cap > 0 ? min(nk, p.k2_cap) : nk;
+    const bool vec1 = ((reinterpret_cast<uintptr_t>(p.c1) & 15) == 0);
+    const bool vec2 = ((reinterpret_cast<uintptr_t>(p.c2) & 15) == 0);
+    const bool vec_out = p.out && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (p.K2 % 4 == 0);
+
+    // ---- query tile features
+    stage_boxes(p.c1 + ((size_t)b * p.K1 + q0) * 24, nq, raw, vec1);
+    __syncthreads();
+    if (threadIdx.x < nq) box_features(raw + threadIdx.x * 24, f1 + threadIdx.x, TQ);
+    __syncthreads();
+
+    for (int g0 = 0; g0 < p.K2; g0 += TG) {
+        const int ng = min(TG, p.K2 - g0);
+        stage_boxes(p.c2 + ((size_t)b * p.K2 + g0) * 24, ng, raw, vec2);
+        if (threadIdx.x == 0) qcount = 0;
+        __syncthreads();
+        if (threadIdx.x < ng) box_features(raw + threadIdx.x * 24, f2 + threadIdx.x, TG);
+        __syncthreads();
+
+        // ---- phase A
+        const int npairs = nq * ng;
+        for (int base = 0; base < npairs; base += NT) {
+            const int pidx = base + threadIdx.x;
+            bool need_clip = false;
+            int r = 0, c = 0;
+            if (pidx < npairs) {
+                r = pidx / ng;
+                c = pidx - r * ng;
+                const int k2 = g0 + c;
+                const bool valid = k2 < nk;
+                PairTerms t = pair_terms(f1, r, f2, c);
+                if (!valid) t.nonrot = 0.f;  // box_util.py:562-564
+                float area = 0.f;
+                if (rotated) {
+                    need_clip = (k2 < clip_lim) && !(prefilter && t.nonrot == 0.f);
+                } else {
+                    area = t.nonrot;
+                }
+                if (!need_clip) tile[r * TG + c] = finish_pair(t, area, valid, has_nums, inter_only);
+            }
+            // warp-aggregated push
+            const unsigned m = __ballot_sync(0xffffffffu, need_clip);
+            if (m) {
+                const int lane = threadIdx.x & 31;
+                int basepos = 0;
+                if (lane == 0) basepos = atomicAdd(&qcount, __popc(m));
+                basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                if (need_clip) queue[basepos + __popc(m & ((1u << lane) - 1))] = (unsigned short)(r * TG + c);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase B
+        const int nclip = qcount;
+        V2<ClipT> *bufA = scratch + threadIdx.x;
+        V2<ClipT> *bufB = scratch + SH_MAXV * NT + threadIdx.x;
+        for (int qi = threadIdx.x; qi < nclip; qi += NT) {
+            const int code = queue[qi];
+            const int r = code / TG, c = code - r * TG;
+            ClipT s[8], cl[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                s[2 * i] = (ClipT)f1[(F_RX + i) * TQ + r];
+                s[2 * i + 1] = (ClipT)f1[(F_RZ + i) * TQ + r];
+                cl[2 * i] = (ClipT)f2[(F_RX + i) * TG + c];
+                cl[2 * i + 1] = (ClipT)f2[(F_RZ + i) * TG + c];
+            }
+            float area;
+            if constexpr (sizeof(ClipT) == 8) {
+                SinkCython sink;
+                sh_clip_quads<double, NT>(s, cl, bufA, bufB, sink);
+                area = sink.area();
+            } else {
+                SinkF32 sink;
+                sh_clip_quads<float, NT>(s, cl, bufA, bufB, sink);
+                area = sink.area();
+            }
+            const PairTerms t = pair_terms(f1, r, f2, c);
+            tile[r * TG + c] = finish_pair(t, area, true, has_nums, inter_only);
+        }
+        __syncthreads();
+
+        // ---- fused matcher cost: ((wc*-P[label] + wo*-obj) + wce*center) + wg*-giou
+        if (p.epi.cost) {
+            const MatcherEpi &e = p.epi;
+            using A = Ar<float>;
+            for (int i = threadIdx.x; i < nq * ng; i += NT) {
+                const int r = i / ng, c = i - r * ng;
+                const size_t q = (size_t)b * p.K1 + q0 + r, g = (size_t)b * p.K2 + g0 + c;
+                const size_t oidx = q * p.K2 + g0 + c;
+                long long lab = e.labels[g];
+                lab = lab < 0 ? 0 : (lab >= e.C ? e.C - 1 : lab);
+                const float cm = -__ldg(e.prob + q * e.C + lab);
+                const float om = -__ldg(e.obj + q);
+                float cen;
+                if (e.center_dist) cen = __ldg(e.center_dist + oidx);
+                else {
+                    const float d0 = fabsf(A::sub(__ldg(e.cq + 3 * q), __ldg(e.cg + 3 * g)));
+                    const float d1 = fabsf(A::sub(__ldg(e.cq + 3 * q + 1), __ldg(e.cg + 3 * g + 1)));
+                    const float d2 = fabsf(A::sub(__ldg(e.cq + 3 * q + 2), __ldg(e.cg + 3 * g + 2)));
+                    cen = A::add(A::add(d0, d1), d2);
+                }
+                const float gm = -tile[r * TG + c];
+                e.cost[oidx] = A::add(A::add(A::add(A::mul(e.wc, cm), A::mul(e.wo, om)), A::mul(e.wce, cen)), A::mul(e.wg, gm));
+            }
+        }
+        // ---- coalesced store of the [nq][ng] tile
+        float *o = p.out + ((size_t)b * p.K1 + q0) * p.K2 + g0;
+        if (!p.out) {
+        } else if (vec_out && (ng % 4 == 0)) {
+            const int n4 = ng / 4;
+            for (int i = threadIdx.x; i < nq * n4; i += NT) {
+                const int r = i / n4, c4 = i - r * n4;
+                const float4 v = *reinterpret_cast<const float4 *>(tile + r * TG + 4 * c4);
+                *reinterpret_cast<float4 *>(o + (size_t)r * p.K2 + 4 * c4) = v;
+            }
+        } else {
+            for (int i = threadIdx.x; i < nq * ng; i += NT) {
+                const int r = i / ng, c = i - r * ng;
+                o[(size_t)r * p.K2 + c] = tile[r * TG + c];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename ClipT> static size_t giou_smem_bytes()
+{
+    return sizeof(float) * (NF * TQ + NF * TG + TQ * TG + TG * 24) + sizeof(unsigned short) * TQ * TG +
+           sizeof(V2<ClipT>) * 2 * SH_MAXV * NT;
+}
+
+template <typename ClipT> static int launch_giou(const GiouParams &p, cudaStream_t st)
+{
+    const size_t smem = giou_smem_bytes<ClipT>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(giou3d_kernel<ClipT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const long long grid = (long long)p.B * p.tiles_per_b;
+    giou3d_kernel<ClipT><<<(unsigned)grid, NT, smem, st>>>(p);
+    return launch_ok("giou3d_kernel");
+}
+
+// ---------------------------------------------------------------------------
+// Cython ABI kernel: box_intersection(rect1, rect2, non_rot, nums_k2, inter_areas, approximate)
+// one CTA per 2048 consecutive (b,k1,k2) pairs, same queue + drain structure.
+// ---------------------------------------------------------------------------
+struct BiParams {
+    const float *rect1, *rect2, *nonrot;
+    const int32_t *nums_k2;
+    float *inter;
+    int B, K1, K2, k2_loop, approximate;
+    long long total;
+};
+constexpr int BI_PAIRS = 2048;
+
+__global__ void __launch_bounds__(NT) box_intersection_kernel(BiParams p)
+{
+    __shared__ unsigned short queue[BI_PAIRS];
+    __shared__ int qcount;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    V2<double> *scratch = reinterpret_cast<V2<double> *>(smem_raw);
+    const long long base0 = (long long)blockIdx.x * BI_PAIRS;
+    if (threadIdx.x == 0) qcount = 0;
+    __syncthreads();
+    for (int off = 0; off < BI_PAIRS; off += NT) {
+        const long long idx = base0 + off + threadIdx.x;
+        bool need = false;
+        if (idx < p.total) {
+            const int k2 = (int)(idx % p.K2);
+            const long long bk1 = idx / p.K2;
+            const int b = (int)(bk1 / p.K1);
+            need = k2 < p.k2_loop && k2 < p.nums_k2[b] && !(p.approximate && p.nonrot[idx] == 0.f);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (m) {
+            const int lane = threadIdx.x & 31;
+            int bp = 0;
+            if (lane == 0) bp = atomicAdd(&qcount, __popc(m));
+            bp = __shfl_sync(0xffffffffu, bp, 0);
+            if (need) queue[bp + __popc(m & ((1u << lane) - 1))] = (unsigned short)(off + threadIdx.x);
+        }
+    }
+    __syncthreads();
+    const int n = qcount;
+    V2<double> *bufA = scratch + threadIdx.x, *bufB = scratch + SH_MAXV * NT + threadIdx.x;
+    for (int qi = threadIdx.x; qi < n; qi += NT) {
+        const long long idx = base0 + queue[qi];
+        const int k2 = (int)(idx % p.K2);
+        const long long bk1 = idx / p.K2;
+        const int b = (int)(bk1 / p.K1);
+        const float *r1 = p.rect1 + bk1 * 8;
+        const float *r2 = p.rect2 + ((long long)b * p.K2 + k2) * 8;
+        double s[8], c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] = (double)__ldg(r1 + i); c[i] = (double)__ldg(r2 + i); }
+        SinkCython sink;
+        sh_clip_quads<double, NT>(s, c, bufA, bufB, sink);
+        if (sink.has) p.inter[idx] = sink.area();  // pyx:195-198: untouched when the clip is empty
+    }
+}
+
+__global__ void __launch_bounds__(256) matcher_cost_kernel(MatcherEpi e, const float *__restrict__ gious, int Q, int G, long long total)
+{
+    using A = Ar<float>;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long q = idx / G;           // b*Q + q
+        const int gcol = (int)(idx - q * G);
+        const long long b = q / Q;
+        const long long g = b * G + gcol;
+        long long lab = e.labels[g];
+        lab = lab < 0 ? 0 : (lab >= e.C ? e.C - 1 : lab);
+        const float cm = -__ldg(e.prob + q * e.C + lab);
+        const float om = -__ldg(e.obj + q);
+        float cen;
+        if (e.center_dist) cen = __ldg(e.center_dist + idx);
+        else {
+            const float d0 = fabsf(A::sub(__ldg(e.cq + 3 * q), __ldg(e.cg + 3 * g)));
+            const float d1 = fabsf(A::sub(__ldg(e.cq + 3 * q + 1), __ldg(e.cg + 3 * g + 1)));
+            const float d2 = fabsf(A::sub(__ldg(e.cq + 3 * q + 2), __ldg(e.cg + 3 * g + 2)));
+            cen = A::add(A::add(d0, d1), d2);
+        }
+        const float gm = -__ldg(gious + idx);
+        e.cost[idx] = A::add(A::add(A::add(A::mul(e.wc, cm), A::mul(e.wo, om)), A::mul(e.wce, cen)), A::mul(e.wg, gm));
+    }
+}
+
+static int matcher_cost_elementwise(const MatcherEpi &e, const float *gious, int B, int Q, int G, cudaStream_t st)
+{
+    const long long total = (long long)B * Q * G;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    matcher_cost_kernel<<<(unsigned)blocks, 256, 0, st>>>(e, gious, Q, G, total);
+    return launch_ok("matcher_cost_kernel");
+}
+
+int giou3d_launch(const GiouParams &p, cudaStream_t st)
+{
+    if ((p.flags & OVDET_GIOU_ROTATED) && (p.flags & OVDET_GIOU_CLIP_F64)) return launch_giou<double>(p, st);
+    return launch_giou<float>(p, st);
+}
+
+}  // namespace ovdet
+
+using namespace ovdet;
+
+extern "C" int ovdet_giou3d_f32(const float *corners1, const float *corners2, const int64_t *nums_k2,
+                                int B, int K1, int K2, int k2_cap, unsigned flags, float *out, void *stream)
+{
+    OVDET_REQUIRE(B >= 0 && K1 >= 0 && K2 >= 0, "negative size");
+    if (B == 0 || K1 == 0 || K2 == 0) return OVDET_OK;
+    OVDET_REQUIRE(corners1 && corners2 && out, "null pointer");
+    if (flags & OVDET_GIOU_ENCL_HULL) {
+        return giou3d_hull_impl(corners1, corners2, nums_k2, B, K1, K2, k2_cap, flags, out, stream);
+    }
+    GiouParams p;
+    p.c1 = corners1; p.c2 = corners2; p.nums_k2 = nums_k2; p.out = out;
+    p.B = B; p.K1 = K1; p.K2 = K2; p.k2_cap = k2_cap; p.flags = flags;
+    p.tiles_per_b = (K1 + TQ - 1) / TQ;
+    OVDET_REQUIRE((long long)B * p.tiles_per_b < 2147483647LL, "grid too large");
+    return giou3d_launch(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ovdet_matcher_cost_f32(const float *sem_cls_prob, const float *objectness, const float *center_dist,
+                                      const float *center_q, const float *center_g, const float *gious,
+                                      const float *corners1, const float *corners2, const int64_t *gt_labels,
+                                      const int64_t *nactual_gt, int B, int Q, int G, int C,
+                                      float w_class, float w_obj, float w_center, float w_giou,
+                                      unsigned giou_flags, int k2_cap, float *gious_out, float *cost, void *stream)
+{
+    OVDET_REQUIRE(B >= 0 && Q >= 0 && G >= 0 && C > 0, "bad size");
+    if (B == 0 || Q == 0 || G == 0) return OVDET_OK;
+    OVDET_REQUIRE(sem_cls_prob && objectness && gt_labels && cost, "null pointer");
+    OVDET_REQUIRE(center_dist || (center_q && center_g), "need center_dist or center_q/center_g");
+    OVDET_REQUIRE(gious || (corners1 && corners2), "need gious or corners");
+    OVDET_REQUIRE(!(giou_flags & OVDET_GIOU_ENCL_HULL) || gious, "hull GIoU must be precomputed for the fused matcher");
+    MatcherEpi e;
+    e.prob = sem_cls_prob; e.obj = objectness; e.center_dist = center_dist; e.cq = center_q; e.cg = center_g;
+    e.labels = gt_labels; e.cost = cost; e.C = C; e.wc = w_class; e.wo = w_obj; e.wce = w_center; e.wg = w_giou;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (gious) return matcher_cost_elementwise(e, gious, B, Q, G, st);
+    GiouParams p;
+    p.c1 = corners1; p.c2 = corners2; p.nums_k2 = nactual_gt; p.out = gious_out;
+    p.B = B; p.K1 = Q; p.K2 = G; p.k2_cap = k2_cap; p.flags = giou_flags & ~OVDET_GIOU_INTER_ONLY;
+    p.tiles_per_b = (Q + TQ - 1) / TQ;
+    p.epi = e;
+    return giou3d_launch(p, st);
+}
+
+extern "C" int ovdet_box_intersection_f32(const float *rect1, const float *rect2, const float *non_rot_inter_areas,
+                                          const int32_t *nums_k2, float *inter_areas, int approximate,
+                                          int B, int K1, int K2, int k2_loop, void *stream)
+{
+    OVDET_REQUIRE(B >= 0 && K1 >= 0 && K2 >= 0, "negative size");
+    if (B == 0 || K1 == 0 || K2 == 0) return OVDET_OK;
+    OVDET_REQUIRE(rect1 && rect2 && nums_k2 && inter_areas, "null pointer");
+    OVDET_REQUIRE(!approximate || non_rot_inter_areas, "approximate needs non_rot_inter_areas");
+    BiParams p;
+    p.rect1 = rect1; p.rect2 = rect2; p.nonrot = non_rot_inter_areas; p.nums_k2 = nums_k2; p.inter = inter_areas;
+    p.B = B; p.K1 = K1; p.K2 = K2; p.k2_loop = k2_loop; p.approximate = approximate;
+    p.total = (long long)B * K1 * K2;
+    const size_t smem = sizeof(V2<double>) * 2 * SH_MAXV * NT;
+    static bool attr_set = false;
+    if (!attr_set) {
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(box_intersection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const long long grid = (p.total + BI_PAIRS - 1) / BI_PAIRS;
+    OVDET_REQUIRE(grid < 2147483647LL, "grid too large");
+    box_intersection_kernel<<<(unsigned)grid, NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return launch_ok("box_intersection_kernel");
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int ovdet_box_intersection_host_f32(const float *rect1, const float *rect2, const float *non_rot_inter_areas,
+                                               const int32_t *nums_k2, float *inter_areas, int approximate,
+                                               int B, int K1, int K2, int k2_loop)
+{
+    OVDET_REQUIRE(B >= 0 && K1 >= 0 && K2 >= 0, "negative size");
+    if (B == 0 || K1 == 0 || K2 == 0) return OVDET_OK;
+    OVDET_REQUIRE(rect1 && rect2 && nums_k2 && inter_areas, "null pointer");
+    const size_t n1 = (size_t)B * K1 * 8 * 4, n2 = (size_t)B * K2 * 8 * 4, np = (size_t)B * K1 * K2 * 4, nn = (size_t)B * 4;
+    HostStaging &hs = host_staging();
+    const size_t o1 = 0, o2 = o1 + align256(n1), o3 = o2 + align256(n2), o4 = o3 + align256(np), o5 = o4 + align256(np);
+    int rc = hs.ensure(o5 + align256(nn));
+    if (rc) return rc;
+    char *d = static_cast<char *>(hs.dev);
+    OVDET_CUDA_TRY(cudaMemcpyAsync(d + o1, rect1, n1, cudaMemcpyHostToDevice, hs.stream));
+    OVDET_CUDA_TRY(cudaMemcpyAsync(d + o2, rect2, n2, cudaMemcpyHostToDevice, hs.stream));
+    if (non_rot_inter_areas) OVDET_CUDA_TRY(cudaMemcpyAsync(d + o3, non_rot_inter_areas, np, cudaMemcpyHostToDevice, hs.stream));
+    OVDET_CUDA_TRY(cudaMemcpyAsync(d + o4, inter_areas, np, cudaMemcpyHostToDevice, hs.stream));
+    OVDET_CUDA_TRY(cudaMemcpyAsync(d + o5, nums_k2, nn, cudaMemcpyHostToDevice, hs.stream));
+    rc = ovdet_box_intersection_f32((const float *)(d + o1), (const float *)(d + o2),
+                                    non_rot_inter_areas ? (const float *)(d + o3) : nullptr, (const int32_t *)(d + o5),
+                                    (float *)(d + o4), approximate, B, K1, K2, k2_loop, hs.stream);
+    if (rc) return rc;
+    OVDET_CUDA_TRY(cudaMemcpyAsync(inter_areas, d + o4, np, cudaMemcpyDeviceToHost, hs.stream));
+    OVDET_CUDA_TRY(cudaStreamSynchronize(hs.stream));
+    return OVDET_OK;
+}
+
+extern "C" int ovdet_giou3d_host_f32(const float *corners1, const float *corners2, const int64_t *nums_k2,
+                                     int B, int K1, int K2, int k2_cap, unsigned flags, float *out)
+{
+    OVDET_REQUIRE(B >= 0 && K1 >= 0 && K2 >= 0, "negative size");
+    if (B == 0 || K1 == 0 || K2 == 0) return OVDET_OK;
+    OVDET_REQUIRE(corners1 && corners2 && out, "null pointer");
+    const size_t n1 = (size_t)B * K1 * 96, n2 = (size_t)B * K2 * 96, no = (size_t)B * K1 * K2 * 4, nn = (size_t)B * 8;
+    HostStaging &hs = host_staging();
+    const size_t o1 = 0, o2 = o1 + align256(n1), o3 = o2 + align256(n2), o4 = o3 + align256(no);
+    int rc = hs.ensure(o4 + align256(nn));
+    if (rc) return rc;
+    char *d = static_cast<char *>(hs.dev);
+    OVDET_CUDA_TRY(cudaMemcpyAsync(d + o1, corners1, n1, cudaMemcpyHostToDevice, hs.stream));
+    OVDET_CUDA_TRY(cudaMemcpyAsync(d + o2, corners2, n2, cudaMemcpyHostToDevice, hs.stream));
+    if (nums_k2) OVDET_CUDA_TRY(cudaMemcpyAsync(d + o4, nums_k2, nn, cudaMemcpyHostToDevice, hs.stream));
+    rc = ovdet_giou3d_f32((const float *)(d + o1), (const float *)(d + o2), nums_k2 ? (const int64_t *)(d + o4) : nullptr,
+                          B, K1, K2, k2_cap, flags, (float *)(d + o3), hs.stream);
+    if (rc) return rc;
+    OVDET_CUDA_TRY(cudaMemcpyAsync(out, d + o3, no, cudaMemcpyDeviceToHost, hs.stream));
+    OVDET_CUDA_TRY(cudaStreamSynchronize(hs.stream));
+    return OVDET_OK;
+}

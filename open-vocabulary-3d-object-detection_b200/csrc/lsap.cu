@@ -1,0 +1,148 @@
+// lsap.cu -- on-device linear sum assignment for Matcher.forward (criterion.py:76-86).
+//
+// The reference moves the [B,Q,G] cost matrix to the host and calls
+// scipy.optimize.linear_sum_assignment per sample on the first nactual_gt[b]
+// columns.  scipy (1.18.1; not vendored in the reference) implements the
+// shortest-augmenting-path algorithm of Crouse, "On implementing 2D rectangular
+// assignment algorithms" (2016), in fp64, transposing so that rows <= columns.
+// This kernel restates that published algorithm with one warp per sample: the
+// lanes stride over the columns for the Dijkstra relaxation and an argmin
+// shuffle-reduction replaces the serial scan.  On tie-free costs the optimum is
+// unique, so assignments equal scipy's (north_star: bit-exact except ties).
+// Tie-break used here: lowest reduced cost, then unassigned column, then lowest index.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ovdet {
+
+struct LsapParams {
+    const float *cost;
+    const int64_t *nactual;
+    int64_t *inds;
+    float *mask;
+    int32_t *col_to_row;
+    int B, Q, G, M;  // M = max(Q, G): capacity of the shared arrays
+};
+
+__global__ void __launch_bounds__(32) lsap_kernel(LsapParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    double *u = reinterpret_cast<double *>(sm);      // [M] row duals
+    double *v = u + p.M;                              // [M] column duals
+    double *spc = v + p.M;                            // [M] shortest path costs
+    int *path = reinterpret_cast<int *>(spc + p.M);   // [M]
+    int *row4col = path + p.M;                        // [M]
+    int *col4row = row4col + p.M;                     // [M]
+    unsigned char *SR = reinterpret_cast<unsigned char *>(col4row + p.M);  // [M]
+    unsigned char *SC = SR + p.M;                                         // [M]
+
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x;
+    long long nn = p.nactual ? p.nactual[b] : p.G;
+    const int n = nn < 0 ? 0 : (nn > p.G ? p.G : (int)nn);
+    const float *cb = p.cost + (size_t)b * p.Q * p.G;
+
+    for (int q = lane; q < p.Q; q += 32) { p.inds[(size_t)b * p.Q + q] = 0; p.mask[(size_t)b * p.Q + q] = 0.f; }
+    if (p.col_to_row) for (int g = lane; g < p.G; g += 32) p.col_to_row[(size_t)b * p.G + g] = -1;
+    if (n == 0) return;
+
+    const bool transposed = n < p.Q;           // scipy: transpose when nc < nr
+    const int nr = transposed ? n : p.Q;
+    const int nc = transposed ? p.Q : n;
+    auto C = [&](int i, int j) -> double {
+        return transposed ? (double)__ldg(cb + (size_t)j * p.G + i) : (double)__ldg(cb + (size_t)i * p.G + j);
+    };
+
+    for (int i = lane; i < nr; i += 32) { u[i] = 0.0; col4row[i] = -1; }
+    for (int j = lane; j < nc; j += 32) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
+    __syncwarp();
+
+    for (int cur = 0; cur < nr; ++cur) {
+        for (int i = lane; i < nr; i += 32) SR[i] = 0;
+        for (int j = lane; j < nc; j += 32) { SC[j] = 0; spc[j] = INFINITY; }
+        __syncwarp();
+        double minVal = 0.0;
+        int i = cur, sink = -1;
+        while (sink == -1) {
+            if (lane == 0) SR[i] = 1;
+            const double ui = u[i];
+            double best = INFINITY;
+            int bestj = 0x7fffffff, bestasg = 1;
+            for (int j = lane; j < nc; j += 32) {
+                if (SC[j]) continue;
+                const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, C(i, j)), ui), v[j]);
+                double s = spc[j];
+                if (r < s) { s = r; spc[j] = r; path[j] = i; }
+                const int asg = row4col[j] != -1;
+                if (s < best || (s == best && (asg < bestasg || (asg == bestasg && j < bestj)))) {
+                    best = s; bestj = j; bestasg = asg;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oj = __shfl_xor_sync(0xffffffffu, bestj, off);
+                const int oa = __shfl_xor_sync(0xffffffffu, bestasg, off);
+                if (ob < best || (ob == best && (oa < bestasg || (oa == bestasg && oj < bestj)))) {
+                    best = ob; bestj = oj; bestasg = oa;
+                }
+            }
+            if (bestj == 0x7fffffff || best == INFINITY) { sink = -2; break; }  // infeasible (non-finite costs)
+            minVal = best;
+            const int j = bestj;
+            if (lane == 0) SC[j] = 1;
+            if (row4col[j] == -1) sink = j; else i = row4col[j];
+            __syncwarp();
+        }
+        if (sink < 0) break;
+        // dual updates (Crouse 2016, step 4)
+        if (lane == 0) u[cur] = __dadd_rn(u[cur], minVal);
+        for (int r = lane; r < nr; r += 32)
+            if (SR[r] && r != cur) u[r] = __dadd_rn(u[r], __dsub_rn(minVal, spc[col4row[r]]));
+        for (int j = lane; j < nc; j += 32)
+            if (SC[j]) v[j] = __dsub_rn(v[j], __dsub_rn(minVal, spc[j]));
+        __syncwarp();
+        // augment along the alternating path
+        if (lane == 0) {
+            int j = sink;
+            while (true) {
+                const int r = path[j];
+                row4col[j] = r;
+                const int t = col4row[r]; col4row[r] = j; j = t;
+                if (r == cur) break;
+            }
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    for (int r = lane; r < nr; r += 32) {
+        const int c = col4row[r];
+        if (c < 0) continue;
+        const int q = transposed ? c : r, g = transposed ? r : c;
+        p.inds[(size_t)b * p.Q + q] = g;
+        p.mask[(size_t)b * p.Q + q] = 1.f;
+        if (p.col_to_row) p.col_to_row[(size_t)b * p.G + g] = q;
+    }
+}
+
+}  // namespace ovdet
+
+using namespace ovdet;
+
+extern "C" int ovdet_lsap_f32(const float *cost, const int64_t *nactual_gt, int B, int Q, int G,
+                              int64_t *per_prop_gt_inds, float *proposal_matched_mask, int32_t *col_to_row, void *stream)
+{
+    OVDET_REQUIRE(B >= 0 && Q >= 0 && G >= 0, "negative size");
+    if (B == 0 || Q == 0) return OVDET_OK;
+    OVDET_REQUIRE(cost || G == 0, "null cost");
+    OVDET_REQUIRE(per_prop_gt_inds && proposal_matched_mask, "null output");
+    LsapParams p;
+    p.cost = cost; p.nactual = nactual_gt; p.inds = per_prop_gt_inds; p.mask = proposal_matched_mask;
+    p.col_to_row = col_to_row; p.B = B; p.Q = Q; p.G = G; p.M = Q > G ? Q : G;
+    OVDET_REQUIRE(p.M <= 4096, "Q and G must be <= 4096");
+    const size_t smem = (size_t)p.M * (3 * sizeof(double) + 3 * sizeof(int) + 2);
+    if (smem > 48 * 1024) OVDET_CUDA_TRY(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lsap_kernel<<<B, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return launch_ok("lsap_kernel");
+}

@@ -1,0 +1,430 @@
+// nms.cu -- greedy NMS family for sm_100a: one CTA per scene.
+//
+// Replaces nms_2d_faster / nms_3d_faster / nms_3d_faster_samecls (utils/nms.py:43-162),
+// the tools variant (3DOVDet_tools/utils/box_3d_utils.py:60-120), the NMS branches
+// of parse_predictions (utils/ap_calculator.py:86-189) and the per-scene
+// NMS -> pool match -> size-scored NMS of 3DOVDet_tools/scannet/lift_boxes.py:139-166.
+//
+// Algorithm (same picks as the reference's while-loop on tie-free scores):
+//   1. bitonic sort of (score desc) indices in shared memory;
+//   2. boxes gathered in sorted order (SoA, conflict-free);
+//   3. suppression bitmask: warp w owns rows i = w, w+nw, ...; its lanes test 32
+//      columns j > i at a time in fp64 (no FMA contraction, same op order as
+//      numpy) and one __ballot_sync packs the 32 verdicts into a mask word;
+//   4. one warp scans the rows in score order keeping the `removed` bitset
+//      distributed one 32-bit word per lane (K <= 1024): bit test by shuffle,
+//      OR of the picked row's mask words.
+// All compares are IEEE fp64 like the reference (np.zeros default dtype,
+// ap_calculator.py:157), so keep-indices are bit-exact except on score ties
+// (numpy's default argsort is not stable: documented).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ovdet {
+
+constexpr int NMS_NT = 256;
+constexpr int NMS_MAXK = 1024;
+
+struct NmsSmem {
+    double *lo[3], *hi[3], *vol, *cls, *skey;
+    int *sidx;
+    uint32_t *mask;
+    int *misc;  // [0]=n_alive, [1]=npick
+    unsigned char *picked;  // by sorted position
+};
+
+__host__ __device__ inline int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+__host__ __device__ inline size_t nms_smem_bytes(int K)
+{
+    const int Kp = next_pow2(K < 32 ? 32 : K);
+    const int W = (K + 31) / 32;
+    size_t b = sizeof(double) * (size_t)(8 * K + Kp);  // lo3 hi3 vol cls + skey
+    b += sizeof(int) * (size_t)Kp;                     // sidx
+    b += sizeof(uint32_t) * (size_t)K * W;             // mask
+    b += sizeof(int) * 4 + (size_t)K + 16;
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ inline NmsSmem nms_carve(unsigned char *base, int K)
+{
+    const int Kp = next_pow2(K < 32 ? 32 : K);
+    const int W = (K + 31) / 32;
+    NmsSmem s;
+    double *d = reinterpret_cast<double *>(base);
+    for (int a = 0; a < 3; ++a) { s.lo[a] = d; d += K; s.hi[a] = d; d += K; }
+    s.vol = d; d += K;
+    s.cls = d; d += K;
+    s.skey = d; d += Kp;
+    s.sidx = reinterpret_cast<int *>(d);
+    s.mask = reinterpret_cast<uint32_t *>(s.sidx + Kp);
+    s.misc = reinterpret_cast<int *>(s.mask + (size_t)K * W);
+    s.picked = reinterpret_cast<unsigned char *>(s.misc + 4);
+    return s;
+}
+
+// Src provides: bool alive(k); double score(k); void box(k, lo[3], hi[3], double &cls)
+// On return: s.picked[pos] for sorted position pos < n_alive, s.sidx[pos] = original index,
+// s.misc[0] = n_alive, s.misc[1] = npick.  `order_out` (may be null) gets original indices in pick order.
+template <typename Src>
+__device__ void nms_core(const Src &src, int K, int dims, bool samecls, bool old_type, double thr, double eps,
+                         NmsSmem &s, int32_t *order_out)
+{
+    using A = Ar<double>;
+    const int tid = threadIdx.x;
+    const int Kp = next_pow2(K < 32 ? 32 : K);
+    const int W = (K + 31) / 32;
+    // ---- 1. keys
+    for (int k = tid; k < Kp; k += NMS_NT) {
+        const bool al = k < K && src.alive(k);
+        s.skey[k] = al ? src.score(k) : -INFINITY;
+        s.sidx[k] = al ? k : (k | 0x40000000);  // dead entries sort last
+    }
+    __syncthreads();
+    // bitonic sort: "a before b" = alive first, higher score, then higher index (stable-ascending-from-the-end)
+    auto before = [](double ka, int ia, double kb, int ib) {
+        const bool da = ia & 0x40000000, db = ib & 0x40000000;
+        if (da != db) return !da;
+        if (ka != kb) return ka > kb;
+        return ia > ib;
+    };
+    for (int size = 2; size <= Kp; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < Kp / 2; t += NMS_NT) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const double ka = s.skey[lo], kb = s.skey[hi];
+                const int ia = s.sidx[lo], ib = s.sidx[hi];
+                const bool swap = up ? before(kb, ib, ka, ia) : before(ka, ia, kb, ib);
+                if (swap) { s.skey[lo] = kb; s.skey[hi] = ka; s.sidx[lo] = ib; s.sidx[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- 2. gather boxes in sorted order
+    if (tid == 0) { s.misc[0] = 0; s.misc[1] = 0; }
+    __syncthreads();
+    int local_alive = 0;
+    for (int pos = tid; pos < K; pos += NMS_NT) {
+        const int k = s.sidx[pos];
+        if (k & 0x40000000) continue;
+        ++local_alive;
+        double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, cl = 0;
+        src.box(k, lo, hi, cl);
+        double v = A::sub(hi[0], lo[0]);
+        for (int a = 1; a < dims; ++a) v = A::mul(v, A::sub(hi[a], lo[a]));
+        for (int a = 0; a < 3; ++a) { s.lo[a][pos] = lo[a]; s.hi[a][pos] = hi[a]; }
+        s.vol[pos] = A::add(v, eps);
+        s.cls[pos] = cl;
+        s.picked[pos] = 0;
+    }
+    if (local_alive) atomicAdd(&s.misc[0], local_alive);
+    __syncthreads();
+    const int n = s.misc[0];
+    // ---- 3. suppression bitmask
+    const int warp = tid >> 5, lane = tid & 31, nw = NMS_NT / 32;
+    for (int i = warp; i < n; i += nw) {
+        double li[3], hi_[3];
+        for (int a = 0; a < 3; ++a) { li[a] = s.lo[a][i]; hi_[a] = s.hi[a][i]; }
+        const double vi = s.vol[i], ci = s.cls[i];
+        for (int w = 0; w < W; ++w) {
+            const int j = 32 * w + lane;
+            bool sup = false;
+            if (32 * w + 31 > i) {
+                if (j > i && j < n) {
+                    double inter = A::max(0.0, A::sub(A::min(hi_[0], s.hi[0][j]), A::max(li[0], s.lo[0][j])));
+                    for (int a = 1; a < dims; ++a)
+                        inter = A::mul(inter, A::max(0.0, A::sub(A::min(hi_[a], s.hi[a][j]), A::max(li[a], s.lo[a][j]))));
+                    double o = old_type ? A::div(inter, s.vol[j]) : A::div(inter, A::sub(A::add(vi, s.vol[j]), inter));
+                    if (samecls) o = A::mul(o, ci == s.cls[j] ? 1.0 : 0.0);
+                    sup = o > thr;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, sup);
+            if (lane == 0) s.mask[(size_t)i * W + w] = m;
+        }
+    }
+    __syncthreads();
+    // ---- 4. ordered scan by warp 0
+    if (warp == 0) {
+        uint32_t removed = 0;
+        int np = 0;
+        for (int i = 0; i < n; ++i) {
+            const uint32_t word = __shfl_sync(0xffffffffu, removed, i >> 5);
+            if (!((word >> (i & 31)) & 1u)) {
+                if (lane == 0) {
+                    s.picked[i] = 1;
+                    if (order_out) order_out[np] = s.sidx[i];
+                }
+                ++np;
+                if (lane < W) removed |= s.mask[(size_t)i * W + lane];
+            }
+        }
+        if (lane == 0) s.misc[1] = np;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------ plain NMS
+struct ArraySrc {
+    const double *b; int ncols, dims, n; bool has_cls;
+    __device__ bool alive(int k) const { return k < n; }
+    __device__ double score(int k) const { return b[(size_t)k * ncols + 2 * dims]; }
+    __device__ void box(int k, double *lo, double *hi, double &cl) const
+    {
+        const double *r = b + (size_t)k * ncols;
+        for (int a = 0; a < dims; ++a) { lo[a] = r[a]; hi[a] = r[dims + a]; }
+        cl = has_cls ? r[2 * dims + 1] : 0.0;
+    }
+};
+
+struct NmsParams {
+    const double *boxes; const int32_t *counts;
+    int S, K, ncols; double thr, eps; unsigned flags;
+    uint8_t *keep; int32_t *pick_order; int32_t *npick;
+};
+
+__global__ void __launch_bounds__(NMS_NT) nms_kernel(NmsParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int s = blockIdx.x;
+    NmsSmem sh = nms_carve(sm, p.K);
+    const int dims = (p.flags & OVDET_NMS_2D) ? 2 : 3;
+    const bool samecls = p.flags & OVDET_NMS_SAMECLS;
+    int n = p.counts ? p.counts[s] : p.K;
+    n = n < 0 ? 0 : (n > p.K ? p.K : n);
+    ArraySrc src{p.boxes + (size_t)s * p.K * p.ncols, p.ncols, dims, n, samecls};
+    for (int k = threadIdx.x; k < p.K; k += NMS_NT) {
+        p.keep[(size_t)s * p.K + k] = 0;
+        if (p.pick_order) p.pick_order[(size_t)s * p.K + k] = -1;
+    }
+    __syncthreads();
+    nms_core(src, p.K, dims, samecls, p.flags & OVDET_NMS_OLD_TYPE, p.thr, p.eps, sh,
+             p.pick_order ? p.pick_order + (size_t)s * p.K : nullptr);
+    const int na = sh.misc[0];
+    for (int pos = threadIdx.x; pos < na; pos += NMS_NT)
+        if (sh.picked[pos]) p.keep[(size_t)s * p.K + sh.sidx[pos]] = 1;
+    if (threadIdx.x == 0 && p.npick) p.npick[s] = sh.misc[1];
+}
+
+// ------------------------------------------------------- parse_predictions
+struct CornerSrc {
+    const float *corners; const float *obj; const uint8_t *nonempty; const int *cls; int dims2d;
+    __device__ bool alive(int k) const { return nonempty ? nonempty[k] != 0 : true; }
+    __device__ double score(int k) const { return (double)obj[k]; }
+    __device__ void box(int k, double *lo, double *hi, double &cl) const
+    {
+        const float *c = corners + (size_t)k * 24;
+        float mn[3], mx[3];
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = mx[a] = __ldg(c + a);
+            for (int i = 1; i < 8; ++i) { const float v = __ldg(c + 3 * i + a); mn[a] = fminf(mn[a], v); mx[a] = fmaxf(mx[a], v); }
+        }
+        if (dims2d) {  // ap_calculator.py:92-104: x and z extents
+            lo[0] = mn[0]; lo[1] = mn[2]; hi[0] = mx[0]; hi[1] = mx[2];
+        } else {
+            for (int a = 0; a < 3; ++a) { lo[a] = mn[a]; hi[a] = mx[a]; }
+        }
+        cl = (double)cls[k];
+    }
+};
+
+struct ParseParams {
+    const float *corners, *probs, *obj; const uint8_t *nonempty;
+    int S, K, C; double nms_iou; float conf; unsigned flags;
+    uint8_t *pred_mask, *keep; int32_t *pred_cls; float *pred_cls_prob;
+};
+
+__global__ void __launch_bounds__(NMS_NT) parse_predictions_kernel(ParseParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int s = blockIdx.x;
+    NmsSmem sh = nms_carve(sm, p.K);
+    int *cls_sm = reinterpret_cast<int *>(sm + nms_smem_bytes(p.K));
+    const float *probs = p.probs + (size_t)s * p.K * p.C;
+    const float *obj = p.obj + (size_t)s * p.K;
+    const uint8_t *ne = p.nonempty ? p.nonempty + (size_t)s * p.K : nullptr;
+    // argmax / max class prob (ap_calculator.py:59-61; np.argmax = first maximum)
+    for (int k = threadIdx.x; k < p.K; k += NMS_NT) {
+        float best = __ldg(probs + (size_t)k * p.C);
+        int bi = 0;
+        for (int c = 1; c < p.C; ++c) { const float v = __ldg(probs + (size_t)k * p.C + c); if (v > best) { best = v; bi = c; } }
+        cls_sm[k] = bi;
+        p.pred_cls[(size_t)s * p.K + k] = bi;
+        p.pred_cls_prob[(size_t)s * p.K + k] = best;
+        p.pred_mask[(size_t)s * p.K + k] = 0;
+    }
+    __syncthreads();
+    if (p.flags & OVDET_PARSE_NO_NMS) {
+        for (int k = threadIdx.x; k < p.K; k += NMS_NT) {
+            const uint8_t m = ne ? (ne[k] != 0) : 1;
+            p.pred_mask[(size_t)s * p.K + k] = m;
+            p.keep[(size_t)s * p.K + k] = m && (obj[k] > p.conf);
+        }
+        return;
+    }
+    const bool d2 = p.flags & OVDET_NMS_2D;
+    const bool samecls = p.flags & OVDET_NMS_SAMECLS;
+    CornerSrc src{p.corners + (size_t)s * p.K * 24, obj, ne, cls_sm, d2 ? 1 : 0};
+    nms_core(src, p.K, d2 ? 2 : 3, samecls, p.flags & OVDET_NMS_OLD_TYPE, p.nms_iou, 0.0, sh, nullptr);
+    const int na = sh.misc[0];
+    for (int pos = threadIdx.x; pos < na; pos += NMS_NT)
+        if (sh.picked[pos]) p.pred_mask[(size_t)s * p.K + sh.sidx[pos]] = 1;
+    __syncthreads();
+    for (int k = threadIdx.x; k < p.K; k += NMS_NT)
+        p.keep[(size_t)s * p.K + k] = p.pred_mask[(size_t)s * p.K + k] && (obj[k] > p.conf);
+}
+
+// ------------------------------------------------------- pseudo-label filter
+struct PoolSrc {
+    const double *pool; const double *label; const double *tmp_score; int n;
+    __device__ bool alive(int k) const { return k < n && label[k] != -100.0; }
+    __device__ double score(int k) const
+    {   // use_size_score: score *= size, size = prod(scale) (lift_boxes.py:159-160, box_3d_utils.py:76-79)
+        const double *r = pool + (size_t)k * 6;
+        const double v = __dmul_rn(__dmul_rn(__dsub_rn(r[3], r[0]), __dsub_rn(r[4], r[1])), __dsub_rn(r[5], r[2]));
+        return __dmul_rn(tmp_score[k], v);
+    }
+    __device__ void box(int k, double *lo, double *hi, double &cl) const
+    {
+        const double *r = pool + (size_t)k * 6;
+        for (int a = 0; a < 3; ++a) { lo[a] = r[a]; hi[a] = r[3 + a]; }
+        cl = label[k];
+    }
+};
+
+struct PseudoParams {
+    const double *boxes, *pool; const int32_t *nboxes, *npool;
+    int S, P, M, Kmax; double nms_thr, match_thr, size_thr;
+    uint8_t *nms1_keep; double *out_label, *out_score; uint8_t *out_keep;
+};
+
+__global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    using A = Ar<double>;
+    const int s = blockIdx.x;
+    NmsSmem sh = nms_carve(sm, p.Kmax);
+    unsigned int *best = reinterpret_cast<unsigned int *>(sm + nms_smem_bytes(p.Kmax));  // [M] earliest claiming pick
+    int *order = reinterpret_cast<int *>(best + p.M);  // [P] pick order of NMS #1
+    int nb = p.nboxes ? p.nboxes[s] : p.P;
+    nb = nb < 0 ? 0 : (nb > p.P ? p.P : nb);
+    int np_ = p.npool ? p.npool[s] : p.M;
+    np_ = np_ < 0 ? 0 : (np_ > p.M ? p.M : np_);
+    const double *boxes = p.boxes + (size_t)s * p.P * 8;
+    const double *pool = p.pool + (size_t)s * p.M * 6;
+    double *olab = p.out_label + (size_t)s * p.M, *osc = p.out_score + (size_t)s * p.M;
+    for (int k = threadIdx.x; k < p.P; k += NMS_NT) p.nms1_keep[(size_t)s * p.P + k] = 0;
+    for (int j = threadIdx.x; j < p.M; j += NMS_NT) { best[j] = 0xFFFFFFFFu; olab[j] = -100.0; osc[j] = 0.0; p.out_keep[(size_t)s * p.M + j] = 0; }
+    __syncthreads();
+    // 1. class-wise NMS (lift_boxes.py:140; volume + 1e-8, box_3d_utils.py:74)
+    ArraySrc src{boxes, 8, 3, nb, true};
+    nms_core(src, p.P, 3, true, false, p.nms_thr, 1e-8, sh, order);
+    const int npick = sh.misc[1];
+    {
+        const int na = sh.misc[0];
+        for (int pos = threadIdx.x; pos < na; pos += NMS_NT)
+            if (sh.picked[pos]) p.nms1_keep[(size_t)s * p.P + sh.sidx[pos]] = 1;
+    }
+    __syncthreads();
+    // 2. argmax-IoU match to the pool (lift_boxes.py:151-158): one warp per surviving box
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = warp; t < npick; t += NMS_NT / 32) {
+        const double *bx = boxes + (size_t)order[t] * 8;
+        const double qv = A::mul(A::mul(A::sub(bx[3], bx[0]), A::sub(bx[4], bx[1])), A::sub(bx[5], bx[2]));
+        double bi = -INFINITY; int bj = 0x7fffffff;
+        for (int j = lane; j < np_; j += 32) {
+            const double *r = pool + (size_t)j * 6;
+            const double kv = A::mul(A::mul(A::sub(r[3], r[0]), A::sub(r[4], r[1])), A::sub(r[5], r[2]));
+            double inter = A::max(A::sub(A::min(bx[3], r[3]), A::max(bx[0], r[0])), 0.0);
+            inter = A::mul(inter, A::max(A::sub(A::min(bx[4], r[4]), A::max(bx[1], r[1])), 0.0));
+            inter = A::mul(inter, A::max(A::sub(A::min(bx[5], r[5]), A::max(bx[2], r[2])), 0.0));
+            const double iou = A::div(inter, A::add(A::sub(A::add(qv, kv), inter), 1e-5));
+            if (iou > bi) { bi = iou; bj = j; }  // np.argmax: first maximum
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            const double oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+            if (oi > bi || (oi == bi && oj < bj)) { bi = oi; bj = oj; }
+        }
+        if (lane == 0 && bj != 0x7fffffff && !(bi < p.match_thr)) {
+            const double sc = bx[6];
+            // `box[-2] > tmp_score[index]` with tmp_score starting at 0: boxes arrive in pick order
+            // (= descending score), so the earliest claimant with score > 0 wins and is never replaced.
+            if (sc > 0.0) atomicMin(&best[bj], (unsigned int)t);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < np_; j += NMS_NT) {
+        if (best[j] != 0xFFFFFFFFu) {
+            const int t = (int)best[j];
+            const double *bx = boxes + (size_t)order[t] * 8;
+            olab[j] = bx[7];
+            osc[j] = bx[6];
+        }
+    }
+    __syncthreads();
+    // 3. size-scored class-wise NMS over the labelled pool boxes (lift_boxes.py:165)
+    PoolSrc psrc{pool, olab, osc, np_};
+    nms_core(psrc, p.M, 3, true, false, p.size_thr, 1e-8, sh, nullptr);
+    const int na = sh.misc[0];
+    for (int pos = threadIdx.x; pos < na; pos += NMS_NT)
+        if (sh.picked[pos]) p.out_keep[(size_t)s * p.M + sh.sidx[pos]] = 1;
+}
+
+}  // namespace ovdet
+
+using namespace ovdet;
+
+extern "C" int ovdet_nms_f64(const double *boxes, const int32_t *counts, int S, int K, int ncols,
+                             double thr, double vol_eps, unsigned flags,
+                             uint8_t *keep, int32_t *pick_order, int32_t *npick, void *stream)
+{
+    OVDET_REQUIRE(S >= 0 && K >= 0, "negative size");
+    if (S == 0 || K == 0) return OVDET_OK;
+    OVDET_REQUIRE(boxes && keep, "null pointer");
+    OVDET_REQUIRE(K <= NMS_MAXK, "K must be <= 1024");
+    const int dims = (flags & OVDET_NMS_2D) ? 2 : 3;
+    OVDET_REQUIRE(ncols >= 2 * dims + 1 + ((flags & OVDET_NMS_SAMECLS) ? 1 : 0), "ncols too small");
+    NmsParams p{boxes, counts, S, K, ncols, thr, vol_eps, flags, keep, pick_order, npick};
+    const size_t smem = nms_smem_bytes(K);
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_kernel<<<S, NMS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return launch_ok("nms_kernel");
+}
+
+extern "C" int ovdet_parse_predictions_f32(const float *corners, const float *probs, const float *obj,
+                                           const uint8_t *nonempty, int S, int K, int C,
+                                           double nms_iou, float conf_thresh, unsigned flags,
+                                           uint8_t *pred_mask, uint8_t *keep, int32_t *pred_cls, float *pred_cls_prob,
+                                           void *stream)
+{
+    OVDET_REQUIRE(S >= 0 && K >= 0 && C > 0, "bad size");
+    if (S == 0 || K == 0) return OVDET_OK;
+    OVDET_REQUIRE(corners && probs && obj && pred_mask && keep && pred_cls && pred_cls_prob, "null pointer");
+    OVDET_REQUIRE(K <= NMS_MAXK, "K must be <= 1024");
+    ParseParams p{corners, probs, obj, nonempty, S, K, C, nms_iou, conf_thresh, flags, pred_mask, keep, pred_cls, pred_cls_prob};
+    const size_t smem = nms_smem_bytes(K) + sizeof(int) * (size_t)K;
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(parse_predictions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    parse_predictions_kernel<<<S, NMS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return launch_ok("parse_predictions_kernel");
+}
+
+extern "C" int ovdet_pseudo_filter_f64(const double *boxes, const double *pool, const int32_t *nboxes, const int32_t *npool,
+                                       int S, int P, int M, double nms_thr, double match_thr, double size_nms_thr,
+                                       uint8_t *nms1_keep, double *out_label, double *out_score, uint8_t *out_keep,
+                                       void *stream)
+{
+    OVDET_REQUIRE(S >= 0 && P > 0 && M > 0, "bad size");
+    if (S == 0) return OVDET_OK;
+    OVDET_REQUIRE(boxes && pool && nms1_keep && out_label && out_score && out_keep, "null pointer");
+    OVDET_REQUIRE(P <= NMS_MAXK && M <= NMS_MAXK, "P and M must be <= 1024");
+    PseudoParams p{boxes, pool, nboxes, npool, S, P, M, P > M ? P : M, nms_thr, match_thr, size_nms_thr,
+                   nms1_keep, out_label, out_score, out_keep};
+    const size_t smem = nms_smem_bytes(p.Kmax) + sizeof(unsigned int) * (size_t)M + sizeof(int) * (size_t)P;
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(pseudo_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pseudo_filter_kernel<<<S, NMS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return launch_ok("pseudo_filter_kernel");
+}

@@ -1,0 +1,246 @@
+"""Drop-in for the reference's ``utils/ap_calculator.py``.
+
+``APCalculator`` keeps the reference interface (``step_meter/step/accumulate/
+compute_metrics/metrics_to_str/metrics_to_dict/reset``, :272-450) but its state
+is device-resident: every ``step`` runs the fused parse_predictions kernel (AABB,
+argmax, NMS, confidence gate) and the AP matching kernel on the batch and keeps
+only compact class-major (score, tp-bits) records; ``compute_metrics`` runs the
+segmented sort/scan once for all classes and thresholds.  With
+``torch.distributed`` initialised, ``compute_metrics(distributed=True)``
+all-gathers the per-class record lists (the one exchange step of SURVEY.md 8e)
+so that scenes can be sharded across ranks.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .. import _capi as C
+from . import eval_det as E
+
+
+def flip_axis_to_depth(pc):
+    """utils/ap_calculator.py:22-26."""
+    pc2 = np.copy(pc)
+    pc2[..., [0, 1, 2]] = pc2[..., [0, 2, 1]]
+    pc2[..., 2] *= -1
+    return pc2
+
+
+def get_ap_config_dict(remove_empty_box=True, use_3d_nms=True, nms_iou=0.25, use_old_type_nms=False, cls_nms=True,
+                       per_class_proposal=True, use_cls_confidence_only=False, conf_thresh=0.05, no_nms=False,
+                       dataset_config=None):
+    """utils/ap_calculator.py:241-269."""
+    return {
+        "remove_empty_box": remove_empty_box, "use_3d_nms": use_3d_nms, "nms_iou": nms_iou,
+        "use_old_type_nms": use_old_type_nms, "cls_nms": cls_nms, "per_class_proposal": per_class_proposal,
+        "use_cls_confidence_only": use_cls_confidence_only, "conf_thresh": conf_thresh, "no_nms": no_nms,
+        "dataset_config": dataset_config,
+    }
+
+
+def _nms_flags(cfg):
+    if cfg.get("no_nms", False):
+        return C.PARSE_NO_NMS
+    f = C.NMS_OLD_TYPE if cfg["use_old_type_nms"] else 0
+    if not cfg["use_3d_nms"]:
+        return f | C.NMS_2D
+    if cfg["cls_nms"]:
+        f |= C.NMS_SAMECLS
+    return f
+
+
+def parse_predictions_device(predicted_boxes, sem_cls_probs, objectness_probs, config_dict, nonempty_box_mask=None):
+    """Device form of parse_predictions: returns (pred_mask u8 [B,K], keep u8 [B,K],
+    pred_cls i32 [B,K], pred_cls_prob f32 [B,K]).  ``keep`` = NMS pick & obj > conf_thresh
+    (ap_calculator.py:206-207)."""
+    C.require_cuda(predicted_boxes)
+    dev = predicted_boxes.device
+    corners = predicted_boxes.detach().to(torch.float32).contiguous()
+    probs = sem_cls_probs.detach().to(device=dev, dtype=torch.float32).contiguous()
+    obj = objectness_probs.detach().to(device=dev, dtype=torch.float32).contiguous()
+    B, K = corners.shape[0], corners.shape[1]
+    Cn = probs.shape[-1]
+    ne = None if nonempty_box_mask is None else (nonempty_box_mask.to(dev) != 0).to(torch.uint8).contiguous()
+    pred_mask = torch.empty((B, K), dtype=torch.uint8, device=dev)
+    keep = torch.empty((B, K), dtype=torch.uint8, device=dev)
+    cls = torch.empty((B, K), dtype=torch.int32, device=dev)
+    clsp = torch.empty((B, K), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        C.check(C.lib().ovdet_parse_predictions_f32(C.ptr(corners), C.ptr(probs), C.ptr(obj), C.ptr(ne), B, K, Cn,
+                                                    float(config_dict["nms_iou"]), float(config_dict["conf_thresh"]),
+                                                    _nms_flags(config_dict), C.ptr(pred_mask), C.ptr(keep), C.ptr(cls),
+                                                    C.ptr(clsp), C.stream(dev)))
+    return pred_mask, keep, cls, clsp
+
+
+def _nonempty_mask(predicted_boxes, point_cloud, objectness_probs, config_dict):
+    if not config_dict["remove_empty_box"]:
+        return None
+    from .points_in_box import nonempty_box_mask
+    return nonempty_box_mask(predicted_boxes, point_cloud, objectness_probs)
+
+
+def parse_predictions(predicted_boxes, sem_cls_probs, objectness_probs, point_cloud, config_dict):
+    """utils/ap_calculator.py:39-238, same return value: per sample a list of
+    (pred_cls, corners ndarray [8,3], score) tuples."""
+    ne = _nonempty_mask(predicted_boxes, point_cloud, objectness_probs, config_dict)
+    _, keep, cls, clsp = parse_predictions_device(predicted_boxes, sem_cls_probs, objectness_probs, config_dict, ne)
+    keep = keep.cpu().numpy().astype(bool)
+    cls = cls.cpu().numpy()
+    corners = predicted_boxes.detach().cpu().numpy()
+    probs = sem_cls_probs.detach().cpu().numpy()
+    obj = objectness_probs.detach().cpu().numpy()
+    out = []
+    for i in range(corners.shape[0]):
+        ks = np.where(keep[i])[0]
+        if config_dict["per_class_proposal"]:
+            assert config_dict["use_cls_confidence_only"] is False
+            ncls = config_dict["dataset_config"].num_semcls
+            cur = []
+            for ii in range(ncls):
+                cur += [(ii, corners[i, j], probs[i, j, ii] * obj[i, j]) for j in ks]
+        elif config_dict["use_cls_confidence_only"]:
+            cur = [(int(cls[i, j]), corners[i, j], probs[i, j, cls[i, j]]) for j in ks]
+        else:
+            cur = [(int(cls[i, j]), corners[i, j], obj[i, j]) for j in ks]
+        out.append(cur)
+    return out
+
+
+class APCalculator(object):
+    """Calculating Average Precision (utils/ap_calculator.py:272-450), device-resident."""
+
+    def __init__(self, dataset_config, ap_iou_thresh=[0.25, 0.5], class2type_map=None, exact_eval=True,
+                 ap_config_dict=None):
+        self.ap_iou_thresh = ap_iou_thresh
+        if ap_config_dict is None:
+            ap_config_dict = get_ap_config_dict(dataset_config=dataset_config, remove_empty_box=exact_eval)
+        self.ap_config_dict = ap_config_dict
+        self.class2type_map = class2type_map
+        self.num_semcls = dataset_config.num_semcls if dataset_config is not None else None
+        self.reset()
+
+    def make_gt_list(self, gt_box_corners, gt_box_sem_cls_labels, gt_box_present):
+        """utils/ap_calculator.py:298-309 (host lists, for API compatibility)."""
+        return [[(gt_box_sem_cls_labels[i, j].item(), gt_box_corners[i, j])
+                 for j in range(gt_box_corners.shape[1]) if gt_box_present[i, j] == 1]
+                for i in range(gt_box_corners.shape[0])]
+
+    def step_meter(self, outputs, targets):
+        if "outputs" in outputs:
+            outputs = outputs["outputs"]
+        self.step(predicted_box_corners=outputs["box_corners"], sem_cls_probs=outputs["sem_cls_prob"],
+                  objectness_probs=outputs["objectness_prob"], point_cloud=targets.get("point_clouds"),
+                  gt_box_corners=targets["gt_box_corners"], gt_box_sem_cls_labels=targets["gt_box_sem_cls_label"],
+                  gt_box_present=targets["gt_box_present"])
+
+    def step(self, predicted_box_corners, sem_cls_probs, objectness_probs, point_cloud, gt_box_corners,
+             gt_box_sem_cls_labels, gt_box_present):
+        """NMS + confidence gate + AP matching of one batch; keeps (score, tp) records only."""
+        cfg = self.ap_config_dict
+        Cn = self.num_semcls or sem_cls_probs.shape[-1]
+        ne = _nonempty_mask(predicted_box_corners, point_cloud, objectness_probs, cfg)
+        _, keep, cls, clsp = parse_predictions_device(predicted_box_corners, sem_cls_probs, objectness_probs, cfg, ne)
+        if cfg["per_class_proposal"]:
+            assert cfg["use_cls_confidence_only"] is False
+            rs, rt, npos = E.ap_match(predicted_box_corners, sem_cls_probs, objectness_probs, keep, gt_box_corners,
+                                      gt_box_sem_cls_labels, gt_box_present, Cn, self.ap_iou_thresh)
+        else:
+            score = clsp if cfg["use_cls_confidence_only"] else objectness_probs
+            rs, rt, npos = E.ap_match(predicted_box_corners, None, score, keep, gt_box_corners, gt_box_sem_cls_labels,
+                                      gt_box_present, Cn, self.ap_iou_thresh, det_cls=cls)
+        self._scores.append(rs)
+        self._tps.append(rt)
+        self._npos = npos if self._npos is None else self._npos + npos
+        self.scan_cnt += predicted_box_corners.shape[0]
+
+    def accumulate(self, batch_pred_map_cls, batch_gt_map_cls):
+        """utils/ap_calculator.py:355-368: host lists of (cls, corners[, score]) tuples."""
+        bsize = len(batch_pred_map_cls)
+        assert bsize == len(batch_gt_map_cls)
+        for i in range(bsize):
+            self.gt_map_cls[self.scan_cnt] = batch_gt_map_cls[i]
+            self.pred_map_cls[self.scan_cnt] = batch_pred_map_cls[i]
+            self.scan_cnt += 1
+
+    def records(self):
+        """Concatenated class-major records of everything seen by ``step``."""
+        if not self._scores:
+            return None
+        return torch.cat(self._scores, 1), torch.cat(self._tps, 1), self._npos
+
+    def compute_metrics(self, distributed=False):
+        """utils/ap_calculator.py:370-395.  ``distributed=True`` (scene-sharded ranks)
+        all-gathers the record lists and all-reduces npos first."""
+        nthr = len(self.ap_iou_thresh)
+        overall_ret = OrderedDict()
+        if self.pred_map_cls:  # host-list path fed through accumulate()
+            for ti, thr in enumerate(self.ap_iou_thresh):
+                rec, prec, ap = E.eval_det(self.pred_map_cls, self.gt_map_cls, ovthresh=thr)
+                overall_ret[thr] = self._format(ap, {k: (v[-1] if hasattr(v, "__len__") and len(v) else 0) for k, v in rec.items()})
+            return overall_ret
+        recs = self.records()
+        assert recs is not None, "no predictions accumulated"
+        rs, rt, npos = recs
+        if distributed:
+            from ..dist import gather_records
+            rs, rt, npos = gather_records(rs, rt, npos)
+        ap, recall, ndet = E.ap_reduce(rs, rt, npos, nthr)
+        ap, recall = ap.cpu().numpy(), recall.cpu().numpy()
+        for ti, thr in enumerate(self.ap_iou_thresh):
+            apd = {c: ap[ti, c] for c in range(ap.shape[1])}
+            rcd = {c: recall[ti, c] for c in range(ap.shape[1])}
+            overall_ret[thr] = self._format(apd, rcd)
+        return overall_ret
+
+    def _format(self, ap, last_rec):
+        ret_dict = OrderedDict()
+        for key in sorted(ap.keys()):
+            clsname = self.class2type_map[key] if self.class2type_map else str(key)
+            ret_dict["%s Average Precision" % (clsname)] = ap[key]
+        ap_vals = np.array(list(ap.values()), dtype=np.float32)
+        ap_vals[np.isnan(ap_vals)] = 0
+        ret_dict["mAP"] = ap_vals.mean()
+        rec_list = []
+        for key in sorted(ap.keys()):
+            clsname = self.class2type_map[key] if self.class2type_map else str(key)
+            ret_dict["%s Recall" % (clsname)] = last_rec[key]
+            rec_list.append(last_rec[key])
+        ret_dict["AR"] = np.mean(rec_list)
+        return ret_dict
+
+    def __str__(self):
+        return self.metrics_to_str(self.compute_metrics())
+
+    def metrics_to_str(self, overall_ret, per_class=True):
+        """utils/ap_calculator.py:401-436 (same text layout)."""
+        mAP_strs, AR_strs, per_class_metrics = [], [], []
+        for thr in self.ap_iou_thresh:
+            mAP_strs.append(f"{overall_ret[thr]['mAP'] * 100:.2f}")
+            AR_strs.append(f"{overall_ret[thr]['AR'] * 100:.2f}")
+            if per_class:
+                per_class_metrics.append("-" * 5)
+                per_class_metrics.append(f"IOU Thresh={thr}")
+                for x in list(overall_ret[thr].keys()):
+                    if x not in ("mAP", "AR"):
+                        per_class_metrics.append(f"{x}: {overall_ret[thr][x] * 100:.2f}")
+        ap_str = ", ".join([f"mAP{x:.2f}" for x in self.ap_iou_thresh]) + ": " + ", ".join(mAP_strs) + "\n"
+        ap_str += ", ".join([f"AR{x:.2f}" for x in self.ap_iou_thresh]) + ": " + ", ".join(AR_strs)
+        if per_class:
+            ap_str += "\n" + "\n".join(per_class_metrics)
+        return ap_str
+
+    def metrics_to_dict(self, overall_ret):
+        """utils/ap_calculator.py:438-445."""
+        d = {}
+        for thr in self.ap_iou_thresh:
+            d[f"mAP_{thr}"] = overall_ret[thr]["mAP"] * 100
+            d[f"AR_{thr}"] = overall_ret[thr]["AR"] * 100
+        return d
+
+    def reset(self):
+        self.gt_map_cls = {}
+        self.pred_map_cls = {}
+        self.scan_cnt = 0
+        self._scores, self._tps, self._npos = [], [], None

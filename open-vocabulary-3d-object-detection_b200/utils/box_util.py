@@ -1,0 +1,134 @@
+"""Drop-in for the hot functions of the reference's ``utils/box_util.py``.
+
+``generalized_box3d_iou`` keeps the reference signature (utils/box_util.py:717-724)
+and dispatch semantics, but every variant runs as ONE sm_100a kernel
+(csrc/giou3d.cu) instead of ~30 torch kernels, 2B+1 host syncs, two PCIe round
+trips and a Cython triple loop.
+
+Reference quirks are explicit switches, defaulting to the reference's behaviour:
+
+* ``needs_grad=False`` (the ``no_grad`` Cython path, :731-737) -> fp64 clip,
+  fp32 polygon/area, and the shipped ``K2 = rect2.shape[2]`` bug
+  (utils/box_intersection.pyx:180): only GT columns < 4 are clipped.  Override
+  with ``k2_cap=0`` (no cap) or set ``ovdet_b200.utils.box_util.DEFAULT_K2_CAP``.
+* ``needs_grad=True`` (the TorchScript path, :725-730) -> all-fp32 clip, no cap.
+  Only the forward value is provided; the backward is not built
+  and inputs that require grad raise.
+* ``prefilter`` (default True): skip pairs whose axis-aligned BEV overlap is 0
+  (:587-588), which is wrong for rotated boxes but is what the reference does.
+* ``enclosing``: "aabb" (live reference, :466-514) or "hull" (utils/box_ops3d.py:533-571).
+"""
+import numpy as np
+import torch
+
+from .. import _capi as C
+
+DEFAULT_K2_CAP = 4  # the reference as shipped (utils/box_intersection.pyx:180)
+
+
+def _check_shapes(corners1, corners2):
+    # utils/box_util.py:639-645
+    assert len(corners1.shape) == 4
+    assert len(corners2.shape) == 4
+    assert corners1.shape[2] == 8
+    assert corners1.shape[3] == 3
+    assert corners1.shape[0] == corners2.shape[0]
+    assert corners1.shape[2] == corners2.shape[2]
+    assert corners1.shape[3] == corners2.shape[3]
+
+
+def giou_flags(rotated_boxes, return_inter_vols_only, mode, prefilter, enclosing):
+    flags = 0
+    if rotated_boxes:
+        flags |= C.GIOU_ROTATED
+    if prefilter:
+        flags |= C.GIOU_PREFILTER
+    if return_inter_vols_only:
+        flags |= C.GIOU_INTER_ONLY
+    if mode == "cython":
+        flags |= C.GIOU_CLIP_F64
+    else:
+        assert mode == "tensor", mode
+    if enclosing == "hull":
+        flags |= C.GIOU_ENCL_HULL
+    else:
+        assert enclosing == "aabb", enclosing
+    return flags
+
+
+def generalized_box3d_iou(corners1, corners2, nums_k2, rotated_boxes=True, return_inter_vols_only=False,
+                          needs_grad=False, *, mode=None, prefilter=True, k2_cap=None, enclosing="aabb"):
+    """[B,K1,8,3] x [B,K2,8,3] -> [B,K1,K2] fp32 on ``corners1.device``
+    (utils/box_util.py:717-737).  CUDA tensors run stream-ordered with no host
+    sync; CPU tensors go through the host-buffer C entry point (H2D, kernel, D2H)."""
+    _check_shapes(corners1, corners2)
+    if needs_grad and (corners1.requires_grad or corners2.requires_grad) and torch.is_grad_enabled():
+        raise NotImplementedError("GIoU backward (SURVEY.md 8f-4) is not built; call under no_grad or detach")
+    if mode is None:
+        mode = "tensor" if needs_grad else "cython"
+    if k2_cap is None:
+        k2_cap = DEFAULT_K2_CAP if mode == "cython" else 0
+    flags = giou_flags(rotated_boxes, return_inter_vols_only, mode, prefilter, enclosing)
+    B, K1, K2 = corners1.shape[0], corners1.shape[1], corners2.shape[1]
+    c1 = corners1.detach().to(torch.float32).contiguous()
+    c2 = corners2.detach().to(torch.float32).contiguous()
+    nk = None
+    if nums_k2 is not None:
+        nk = torch.as_tensor(nums_k2).detach().to(device=c1.device, dtype=torch.int64).contiguous()
+        assert nk.numel() == B
+    out = torch.empty((B, K1, K2), dtype=torch.float32, device=c1.device)
+    L = C.lib()
+    if c1.is_cuda:
+        C.require_cuda(c2)
+        with torch.cuda.device(c1.device):
+            C.check(L.ovdet_giou3d_f32(C.ptr(c1), C.ptr(c2), C.ptr(nk), B, K1, K2, int(k2_cap), flags, C.ptr(out),
+                                       C.stream(c1.device)))
+    else:
+        C.check(L.ovdet_giou3d_host_f32(C.ptr(c1), C.ptr(c2.cpu()), C.ptr(nk), B, K1, K2, int(k2_cap), flags, C.ptr(out)))
+    return out
+
+
+def generalized_box3d_iou_tensor(corners1, corners2, nums_k2, rotated_boxes=True, return_inter_vols_only=False):
+    """utils/box_util.py:517-618 (values only)."""
+    return generalized_box3d_iou(corners1, corners2, nums_k2, rotated_boxes, return_inter_vols_only,
+                                 mode="tensor", k2_cap=0)
+
+
+def generalized_box3d_iou_cython(corners1, corners2, nums_k2, rotated_boxes=True, return_inter_vols_only=False):
+    """utils/box_util.py:624-714, as shipped."""
+    return generalized_box3d_iou(corners1, corners2, nums_k2, rotated_boxes, return_inter_vols_only, mode="cython")
+
+
+def box3d_iou_batch(dets, gts, nd=None, ng=None, want_2d=False):
+    """Exact fp64 IoU matrices: dets [S,D,8,3] x gts [S,G,8,3] -> [S,D,G] fp64
+    (box3d_iou, utils/box_util.py:116-141, on fp32 corners cast to fp64)."""
+    C.require_cuda(dets, gts)
+    S, D, G = dets.shape[0], dets.shape[1], gts.shape[1]
+    d = dets.detach().to(torch.float32).contiguous()
+    g = gts.detach().to(torch.float32).contiguous()
+    out = torch.empty((S, D, G), dtype=torch.float64, device=d.device)
+    out2 = torch.empty((S, D, G), dtype=torch.float64, device=d.device) if want_2d else None
+    ndt = None if nd is None else torch.as_tensor(nd).to(device=d.device, dtype=torch.int32).contiguous()
+    ngt = None if ng is None else torch.as_tensor(ng).to(device=d.device, dtype=torch.int32).contiguous()
+    with torch.cuda.device(d.device):
+        C.check(C.lib().ovdet_box3d_iou_f64(C.ptr(d), C.ptr(g), C.ptr(ndt), C.ptr(ngt), S, D, G, C.ptr(out), C.ptr(out2),
+                                            C.stream(d.device)))
+    return (out, out2) if want_2d else out
+
+
+def box3d_iou(corners1, corners2):
+    """utils/box_util.py:116-141: (8,3) x (8,3) -> (iou, iou_2d) python floats.
+    One pair per call is a poor use of a GPU; the AP path uses box3d_iou_batch."""
+    dev = torch.device("cuda")
+    a = torch.as_tensor(np.asarray(corners1), dtype=torch.float32, device=dev).reshape(1, 1, 8, 3)
+    b = torch.as_tensor(np.asarray(corners2), dtype=torch.float32, device=dev).reshape(1, 1, 8, 3)
+    iou, iou2 = box3d_iou_batch(a, b, want_2d=True)
+    return float(iou.item()), float(iou2.item())
+
+
+def get_3d_box_batch_tensor(box_size, angle, center):
+    """utils/box_util.py:313-352: (size [...,3] l,w,h; heading [...]; centre [...,3]
+    already in the upright-camera frame) -> corners [...,8,3]."""
+    from ..synth import params_to_corners  # same corner convention; undo its axis flip
+    c = torch.stack([center[..., 0], center[..., 2], -center[..., 1]], -1)
+    return params_to_corners(c.cpu(), box_size.cpu(), angle.cpu()).to(box_size.device)

@@ -1,0 +1,160 @@
+"""Drop-in for the reference's ``utils/eval_det.py`` (VOC-style AP matching).
+
+The dict-based entry points keep their signatures; internally everything is
+packed into scene-major device arrays and evaluated by two kernels families
+(csrc/eval.cu): ``ovdet_ap_match`` (exact fp64 IoU det x GT, argmax, first-claim
+TP flags for all classes/thresholds at once) and ``ovdet_ap_reduce`` (per-class
+segmented radix sort by descending score + scans -> precision/recall/AP).
+``ap_from_arrays`` is the array-level engine the AP calculator uses directly.
+"""
+import numpy as np
+import torch
+
+from .. import _capi as C
+
+
+def voc_ap(rec, prec, use_07_metric=False):
+    """utils/eval_det.py:23-54 on an already sorted PR curve (host arrays, O(nd));
+    the GPU path computes the same quantity inside ``ovdet_ap_reduce``."""
+    rec = np.asarray(rec, np.float64)
+    prec = np.asarray(prec, np.float64)
+    if use_07_metric:
+        ap = 0.0
+        for t in np.arange(0.0, 1.1, 0.1):
+            p = np.max(prec[rec >= t]) if np.sum(rec >= t) != 0 else 0
+            ap = ap + p / 11.0
+        return ap
+    mrec = np.concatenate(([0.0], rec, [1.0]))
+    mpre = np.concatenate(([0.0], prec, [0.0]))
+    mpre = np.maximum.accumulate(mpre[::-1])[::-1]
+    i = np.where(mrec[1:] != mrec[:-1])[0]
+    return np.sum((mrec[i + 1] - mrec[i]) * mpre[i + 1])
+
+
+def ap_match(corners, probs, obj, keep, gt_corners, gt_labels, gt_present, num_classes, thresholds, det_cls=None):
+    """Device tensors in, class-major records out:
+    rec_score fp32 [C, S*K] (-inf = absent), rec_tp uint8 [C, S*K] (bit t = TP at
+    thresholds[t]), npos int64 [C]."""
+    C.require_cuda(corners)
+    dev = corners.device
+    S, K = corners.shape[0], corners.shape[1]
+    G = gt_corners.shape[1]
+    Cn = int(num_classes)
+    f32 = lambda t: None if t is None else t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    corners, probs, obj, gt_corners = f32(corners), f32(probs), f32(obj), f32(gt_corners)
+    keep = keep.to(device=dev, dtype=torch.uint8).contiguous()
+    gt_labels = gt_labels.to(device=dev, dtype=torch.int64).contiguous()
+    gt_present = (gt_present.to(dev) != 0).to(torch.uint8).contiguous()
+    det_cls = None if det_cls is None else det_cls.to(device=dev, dtype=torch.int32).contiguous()
+    thr = np.ascontiguousarray(np.asarray(thresholds, np.float64))
+    rec_score = torch.empty((Cn, S * K), dtype=torch.float32, device=dev)
+    rec_tp = torch.empty((Cn, S * K), dtype=torch.uint8, device=dev)
+    npos = torch.zeros((Cn,), dtype=torch.int64, device=dev)
+    iou_ws = torch.empty((S, K, max(G, 1)), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        C.check(C.lib().ovdet_ap_match(C.ptr(corners), C.ptr(probs), C.ptr(obj), C.ptr(keep), C.ptr(det_cls),
+                                       C.ptr(gt_corners), C.ptr(gt_labels), C.ptr(gt_present), S, K, G, Cn,
+                                       thr.ctypes.data, len(thr), C.ptr(iou_ws), C.ptr(rec_score), C.ptr(rec_tp),
+                                       C.ptr(npos), C.stream(dev)))
+    return rec_score, rec_tp, npos
+
+
+def ap_reduce(rec_score, rec_tp, npos, nthr, use_07_metric=False, curves=False):
+    """Records [C,N] -> (ap [nthr,C], recall [nthr,C], n_det [C][, rec, prec [nthr,C,N]]) on device."""
+    C.require_cuda(rec_score)
+    dev = rec_score.device
+    Cn, N = rec_score.shape
+    rec_score = rec_score.contiguous()
+    rec_tp = rec_tp.contiguous()
+    npos = npos.to(device=dev, dtype=torch.int64).contiguous()
+    ap = torch.empty((nthr, Cn), dtype=torch.float64, device=dev)
+    recall = torch.empty((nthr, Cn), dtype=torch.float64, device=dev)
+    ndet = torch.empty((Cn,), dtype=torch.int64, device=dev)
+    rec = torch.zeros((nthr, Cn, N), dtype=torch.float64, device=dev) if curves else None
+    prec = torch.zeros((nthr, Cn, N), dtype=torch.float64, device=dev) if curves else None
+    L = C.lib()
+    nbytes = L.ovdet_ap_reduce_ws_bytes(Cn, N)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        C.check(L.ovdet_ap_reduce(C.ptr(rec_score), C.ptr(rec_tp), C.ptr(npos), Cn, N, nthr, int(bool(use_07_metric)),
+                                  C.ptr(ap), C.ptr(recall), C.ptr(ndet), C.ptr(rec), C.ptr(prec), C.ptr(ws), nbytes,
+                                  C.stream(dev)))
+    return (ap, recall, ndet, rec, prec) if curves else (ap, recall, ndet)
+
+
+def _pack(pred_all, gt_all):
+    """{img: [(cls, box, score)]}, {img: [(cls, box)]} -> padded scene-major arrays."""
+    imgs = list(dict.fromkeys(list(pred_all.keys()) + list(gt_all.keys())))
+    classes = []
+    for img in pred_all:
+        for cl, _, _ in pred_all[img]:
+            classes.append(cl)
+    for img in gt_all:
+        for cl, _ in gt_all[img]:
+            classes.append(cl)
+    classes = list(dict.fromkeys(classes))
+    cidx = {c: i for i, c in enumerate(classes)}
+    S = len(imgs)
+    K = max([len(pred_all.get(i, [])) for i in imgs] + [1])
+    G = max([len(gt_all.get(i, [])) for i in imgs] + [1])
+    corners = np.zeros((S, K, 8, 3), np.float32)
+    score = np.zeros((S, K), np.float32)
+    dcls = np.zeros((S, K), np.int32)
+    keep = np.zeros((S, K), np.uint8)
+    gcorn = np.zeros((S, G, 8, 3), np.float32)
+    glab = np.zeros((S, G), np.int64)
+    gpres = np.zeros((S, G), np.uint8)
+    for si, img in enumerate(imgs):
+        for k, (cl, box, sc) in enumerate(pred_all.get(img, [])):
+            corners[si, k] = box; score[si, k] = sc; dcls[si, k] = cidx[cl]; keep[si, k] = 1
+        for g, (cl, box) in enumerate(gt_all.get(img, [])):
+            gcorn[si, g] = box; glab[si, g] = cidx[cl]; gpres[si, g] = 1
+    pred_classes = set(cl for img in pred_all for cl, _, _ in pred_all[img])
+    return classes, pred_classes, corners, score, dcls, keep, gcorn, glab, gpres
+
+
+def _eval_packed(pred_all, gt_all, ovthresh, use_07_metric):
+    classes, pred_classes, corners, score, dcls, keep, gcorn, glab, gpres = _pack(pred_all, gt_all)
+    dev = torch.device("cuda")
+    t = lambda a: torch.as_tensor(a, device=dev)
+    rs, rt, npos = ap_match(t(corners), None, t(score), t(keep), t(gcorn), t(glab), t(gpres), len(classes),
+                            [ovthresh], det_cls=t(dcls))
+    ap, recall, ndet, rec, prec = ap_reduce(rs, rt, npos, 1, use_07_metric, curves=True)
+    ap, ndet, rec, prec = ap.cpu().numpy(), ndet.cpu().numpy(), rec.cpu().numpy(), prec.cpu().numpy()
+    out_rec, out_prec, out_ap = {}, {}, {}
+    for ci, cl in enumerate(classes):
+        if cl in pred_classes:
+            n = int(ndet[ci])
+            out_rec[cl], out_prec[cl], out_ap[cl] = rec[0, ci, :n].copy(), prec[0, ci, :n].copy(), float(ap[0, ci])
+        else:  # utils/eval_det.py:266-269
+            out_rec[cl], out_prec[cl], out_ap[cl] = 0, 0, 0
+    return out_rec, out_prec, out_ap
+
+
+def get_iou_obb(bb1, bb2):
+    """utils/eval_det.py:57-59."""
+    from .box_util import box3d_iou
+    return box3d_iou(bb1, bb2)[0]
+
+
+def eval_det_cls(pred, gt, ovthresh=0.25, use_07_metric=False, get_iou_func=get_iou_obb):
+    """utils/eval_det.py:66-155: pred {img: [(bbox, score)]}, gt {img: [bbox]} ->
+    (rec, prec, ap) with rec/prec sorted by descending score."""
+    if get_iou_func is not get_iou_obb:
+        raise NotImplementedError("only get_iou_obb (exact rotated IoU) is built on the GPU path")
+    pred_all = {img: [(0, b, s) for b, s in lst] for img, lst in pred.items()}
+    gt_all = {img: [(0, b) for b in lst] for img, lst in gt.items()}
+    if not any(len(v) for v in pred_all.values()):
+        return np.zeros(0), np.zeros(0), voc_ap(np.zeros(0), np.zeros(0), use_07_metric)
+    rec, prec, ap = _eval_packed(pred_all, gt_all, ovthresh, use_07_metric)
+    return rec[0], prec[0], ap[0]
+
+
+def eval_det(pred_all, gt_all, ovthresh=0.25, use_07_metric=False, get_iou_func=get_iou_obb):
+    """utils/eval_det.py:164-208 / :214-272 -> ({cls: rec}, {cls: prec}, {cls: ap})."""
+    if get_iou_func is not None and get_iou_func is not get_iou_obb:
+        raise NotImplementedError("only get_iou_obb (exact rotated IoU) is built on the GPU path")
+    return _eval_packed(pred_all, gt_all, ovthresh, use_07_metric)
+
+
+eval_det_multiprocessing = eval_det  # the per-class Pool(10) of :253-261 is one kernel launch here

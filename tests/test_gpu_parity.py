@@ -1,0 +1,384 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the
+reference-generated golden fixtures.  Tolerances are north_star's:
+IoU/GIoU 1e-5 relative in fp32 (+1e-6 absolute floor, see conftest), NMS
+keep-indices and matcher assignments bit-exact on tie-free inputs, AP 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import assert_close_giou
+
+pytestmark = pytest.mark.gpu
+
+import ovdet_b200  # noqa: E402
+from ovdet_b200 import synth  # noqa: E402
+from ovdet_b200.utils import box_util as BU  # noqa: E402
+from ovdet_b200.utils import nms as NMS  # noqa: E402
+from ovdet_b200.utils import eval_det as ED  # noqa: E402
+from ovdet_b200.utils import ap_calculator as APC  # noqa: E402
+from ovdet_b200.utils import box_3d_utils as B3  # noqa: E402
+from ovdet_b200.utils.box_intersection import box_intersection  # noqa: E402
+from ovdet_b200.criterion import Matcher, matcher_cost, lsap  # noqa: E402
+
+DEV = "cuda"
+
+
+def cu(x, dtype=None):
+    t = torch.as_tensor(x)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+# ------------------------------------------------------------------ GIoU
+@pytest.mark.parametrize("tag", ["pi", "half"])
+def test_giou_golden(golden, tag):
+    g = golden(f"giou_{tag}.npz")
+    c1, c2, nk = cu(g["corners1"]), cu(g["corners2"]), cu(g["nums_k2"])
+    got = BU.generalized_box3d_iou(c1, c2, nk).cpu().numpy()  # default == reference dispatcher default
+    assert_close_giou(got, g["dispatch_default"], what="default")
+    assert_close_giou(BU.generalized_box3d_iou_cython(c1, c2, nk, True, True).cpu().numpy(), g["cython_shipped_inter"], what="cy inter")
+    assert_close_giou(BU.generalized_box3d_iou(c1, c2, nk, needs_grad=True).cpu().numpy(), g["tensor"], what="tensor")
+    assert_close_giou(BU.generalized_box3d_iou_tensor(c1, c2, nk, True, True).cpu().numpy(), g["tensor_inter"], what="tensor inter")
+    assert_close_giou(BU.generalized_box3d_iou(c1, c2, nk, rotated_boxes=False).cpu().numpy(), g["nonrot"], what="nonrot")
+    # exact IoU kernel against the reference's box3d_iou
+    for b in range(c1.shape[0]):
+        n = int(g["nums_k2"][b])
+        m = BU.box3d_iou_batch(c1[b:b + 1], c2[b:b + 1, :n]).cpu().numpy()[0]
+        np.testing.assert_allclose(m, g["exact_iou"][b, :, :n], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=8, Q=128, G=64, heading=np.pi, room="sunrgbd"),      # BASELINE config 1
+    dict(B=8, Q=128, G=64, heading=0.5, room="sunrgbd"),        # clip-heavy variant
+    dict(B=8, Q=256, G=64, heading=0.0, room="scannet"),        # BASELINE config 2
+    dict(B=3, Q=77, G=19, heading=1.0, room="sunrgbd"),         # ragged tile sizes
+    dict(B=2, Q=40, G=150, heading=0.7, room="sunrgbd"),        # more than one GT chunk
+])
+def test_giou_vs_oracle(cfg):
+    out, tgt = synth.detection_batch(B=cfg["B"], Q=cfg["Q"], G=cfg["G"], seed=21, heading=cfg["heading"],
+                                     room=cfg["room"], max_gt=cfg["G"])
+    c1, c2, nk = out["box_corners"], tgt["gt_box_corners"], tgt["nactual_gt"]
+    rot = cfg["heading"] > 0
+    d1, d2, dn = c1.to(DEV), c2.to(DEV), nk.to(DEV)
+    for mode, cap, pre, inter in (("tensor", 0, True, False), ("cython", 4, True, False), ("cython", 0, True, False),
+                                  ("tensor", 0, False, False), ("cython", 0, False, True), ("tensor", 0, True, True)):
+        want = oracle.generalized_box3d_iou(c1, c2, nk, rot, inter, mode=mode, prefilter=pre, k2_cap=cap or None)
+        got = BU.generalized_box3d_iou(d1, d2, dn, rot, inter, mode=mode, prefilter=pre, k2_cap=cap).cpu().numpy()
+        assert_close_giou(got, want, what=f"{mode} cap={cap} pre={pre} inter={inter}")
+    # nums_k2 = None
+    want = oracle.generalized_box3d_iou(c1, c2, None, rot, False, mode="tensor")
+    got = BU.generalized_box3d_iou(d1, d2, None, rot, mode="tensor", k2_cap=0).cpu().numpy()
+    assert_close_giou(got, want, what="no nums")
+    # CPU tensors go through the host-buffer entry point
+    got = BU.generalized_box3d_iou(c1, c2, nk, rot, mode="tensor", k2_cap=0)
+    assert got.device.type == "cpu"
+    assert_close_giou(got.numpy(), oracle.generalized_box3d_iou(c1, c2, nk, rot, False, mode="tensor"), what="host")
+
+
+def test_giou_properties_full_size():
+    """Size-independent properties at the bench size: symmetry of the intersection volume,
+    GIoU in [-1, 1], zero beyond nums_k2, identical axis-aligned box -> IoU 1."""
+    out, tgt = synth.detection_batch(B=64, Q=128, G=64, seed=5, heading=np.pi)
+    c1, c2 = out["box_corners"].to(DEV), tgt["gt_box_corners"].to(DEV)
+    nk = tgt["nactual_gt"].to(DEV)
+    g = BU.generalized_box3d_iou(c1, c2, nk, mode="tensor", k2_cap=0, prefilter=False)
+    assert torch.isfinite(g).all() and g.min() >= -1.0 - 1e-5 and g.max() <= 1.0 + 1e-5
+    col = torch.arange(64, device=DEV)[None, None, :]
+    assert (g[col.expand_as(g) >= nk[:, None, None]] == 0).all()
+    a = BU.generalized_box3d_iou(c1, c2, None, True, True, mode="tensor", k2_cap=0, prefilter=False)
+    b = BU.generalized_box3d_iou(c2, c1, None, True, True, mode="tensor", k2_cap=0, prefilter=False)
+    assert_close_giou(a.cpu().numpy(), b.transpose(1, 2).cpu().numpy(), rtol=2e-4, atol=2e-5, what="inter symmetry")
+    o2, t2 = synth.detection_batch(B=2, Q=16, G=16, seed=6, heading=0.0)
+    cc = o2["box_corners"].to(DEV)
+    s = BU.generalized_box3d_iou(cc, cc, None, True, mode="tensor", k2_cap=0)
+    np.testing.assert_allclose(torch.diagonal(s, dim1=1, dim2=2).cpu().numpy(), 1.0, atol=1e-5)
+
+
+def test_giou_empty_and_errors():
+    z = torch.zeros((2, 0, 8, 3), device=DEV)
+    c2 = torch.zeros((2, 4, 8, 3), device=DEV)
+    assert BU.generalized_box3d_iou(z, c2, None).shape == (2, 0, 4)
+    with pytest.raises(AssertionError):
+        BU.generalized_box3d_iou(torch.zeros((2, 4, 7, 3), device=DEV), c2, None)
+    x = torch.zeros((1, 2, 8, 3), device=DEV, requires_grad=True)
+    with pytest.raises(NotImplementedError):
+        BU.generalized_box3d_iou(x, c2[:1], None, needs_grad=True)
+
+
+def test_box_intersection_cython_abi(golden):
+    g = golden("box_intersection.npz")
+    for key, approx in (("approx", True), ("exact", False)):
+        out = np.zeros_like(g[key])
+        box_intersection(g["rect1"], g["rect2"], g["nonrot"], g["nums_k2"], out, approx)
+        assert_close_giou(out, g[key], rtol=1e-6, atol=1e-7, what=key)
+    # in-place contract: entries that are not clipped keep their previous value
+    out = np.full_like(g["approx"], 7.0)
+    box_intersection(g["rect1"], g["rect2"], g["nonrot"], g["nums_k2"], out, True)
+    assert (out[:, :, 4:] == 7.0).all()
+    want = np.full_like(g["approx"], 7.0)
+    oracle.box_intersection(g["rect1"], g["rect2"], g["nonrot"], g["nums_k2"], want, True, k2_loop=4)
+    assert_close_giou(out, want, rtol=1e-6, atol=1e-7, what="in place")
+    with pytest.raises(ValueError):
+        box_intersection(g["rect1"].astype(np.float64), g["rect2"], g["nonrot"], g["nums_k2"], out, True)
+
+
+def test_box3d_iou_golden(golden):
+    g = golden("box3d_iou.npz")
+    a, b = cu(g["a"])[:, None], cu(g["b"])[:, None]
+    iou, iou2 = BU.box3d_iou_batch(a, b, want_2d=True)
+    np.testing.assert_allclose(iou.cpu().numpy().ravel(), g["iou"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(iou2.cpu().numpy().ravel(), g["iou2d"], rtol=1e-9, atol=1e-12)
+    k = golden("kat.npz")
+    assert BU.box3d_iou(k["unit"], k["touch"]) == (0.0, 0.0)
+    assert BU.box3d_iou(k["unit"], k["off"])[0] == pytest.approx(float(k["iou_offset"][0]), rel=1e-12)
+    assert BU.box3d_iou(k["ident"], k["ident"])[0] == pytest.approx(float(k["iou_identical_f32"][0]), rel=1e-12)
+
+
+# ------------------------------------------------------------------ NMS
+def test_nms_golden(golden):
+    g = golden("nms.npz")
+    b = g["boxes"]
+    for i in range(b.shape[0]):
+        assert NMS.nms_3d_faster(b[i][:, :7], 0.25) == g[f"p3_{i}"].tolist()
+        assert NMS.nms_3d_faster(b[i][:, :7], 0.25, True) == g[f"p3old_{i}"].tolist()
+        assert NMS.nms_3d_faster_samecls(b[i], 0.25) == g[f"p3c_{i}"].tolist()
+        assert NMS.nms_3d_faster_samecls(b[i], 0.1, True) == g[f"p3cold_{i}"].tolist()
+        b5 = b[i][:, [0, 2, 3, 5, 6]]
+        assert NMS.nms_2d_faster(b5, 0.25) == g[f"p2_{i}"].tolist()
+        assert NMS.nms_2d_faster(b5, 0.25, True) == g[f"p2old_{i}"].tolist()
+        t = np.concatenate([b[i], np.prod(b[i][:, 3:6] - b[i][:, :3], -1, keepdims=True)], 1)
+        np.testing.assert_array_equal(B3.nms_3d_faster(t.copy(), 0.7, class_wise=True), g[f"tools_cw_{i}"])
+        np.testing.assert_array_equal(B3.nms_3d_faster(t.copy(), 0.0, use_size_score=True, class_wise=True, size_typ="Volume"),
+                                      g[f"tools_size_{i}"])
+    k = golden("kat.npz")
+    assert NMS.nms_3d_faster(k["nms_in"], 0.25) == [0, 2]
+    assert NMS.nms_3d_faster(np.zeros((0, 7)), 0.25) == []
+
+
+@pytest.mark.parametrize("K", [1, 31, 256, 600, 1024])
+def test_nms_vs_oracle_sizes(K):
+    g = torch.Generator().manual_seed(K)
+    S = 4
+    c, s, _ = synth.sample_boxes(g, (S, K), "scannet", 0.0)
+    s = s * 1.5
+    score = torch.rand((S, K), generator=g).double()
+    assert len(set(score.flatten().tolist())) == S * K  # tie-free
+    cls = torch.randint(0, 5, (S, K), generator=g).double()
+    bx = torch.cat([(c - s / 2).double(), (c + s / 2).double(), score[..., None], cls[..., None]], -1)
+    keep, order, npick = NMS.nms_batch(bx.to(DEV), 0.25, samecls=True)
+    for i in range(S):
+        want = oracle.nms_3d_faster_samecls(bx[i].numpy(), 0.25)
+        n = int(npick[i])
+        assert order[i, :n].cpu().tolist() == want
+        assert sorted(torch.nonzero(keep[i]).flatten().cpu().tolist()) == sorted(want)
+        assert (order[i, n:] == -1).all()
+    counts = torch.tensor([K, max(K // 2, 1), 1, 0], dtype=torch.int32)
+    keep, order, npick = NMS.nms_batch(bx.to(DEV), 0.25, counts=counts)
+    for i in range(S):
+        want = oracle.nms_3d_faster(bx[i, :int(counts[i]), :7].numpy(), 0.25)
+        assert order[i, :int(npick[i])].cpu().tolist() == want
+
+
+# ------------------------------------------------------------------ AP
+class _Cfg:
+    def __init__(self, n):
+        self.num_semcls = n
+
+
+def test_parse_predictions_golden(golden):
+    g = golden("ap.npz")
+    C = g["sem_cls_prob"].shape[-1]
+    bc, pr, ob = cu(g["box_corners"]), cu(g["sem_cls_prob"]), cu(g["objectness"])
+    cfg = APC.get_ap_config_dict(dataset_config=_Cfg(C), remove_empty_box=False)
+    _, keep, cls, clsp = APC.parse_predictions_device(bc, pr, ob, cfg)
+    np.testing.assert_array_equal(keep.cpu().numpy(), g["kept"])
+    np.testing.assert_array_equal(cls.cpu().numpy(), g["sem_cls_prob"].argmax(-1))
+    preds = APC.parse_predictions(bc, pr, ob, None, cfg)
+    np.testing.assert_array_equal(np.array([len(p) for p in preds]), g["n_pred"])
+    for name, kw in (("nms3d_nocls", dict(cls_nms=False)), ("nms2d", dict(use_3d_nms=False)),
+                     ("no_pcp", dict(per_class_proposal=False)),
+                     ("clsconf", dict(per_class_proposal=False, use_cls_confidence_only=True)),
+                     ("nonms", dict(no_nms=True)), ("old", dict(use_old_type_nms=True))):
+        cfg2 = APC.get_ap_config_dict(dataset_config=_Cfg(C), remove_empty_box=False, **kw)
+        p2 = APC.parse_predictions(bc, pr, ob, None, cfg2)
+        np.testing.assert_array_equal(np.array([len(p) for p in p2]), g[f"v_{name}_n"])
+        np.testing.assert_array_equal(np.concatenate([np.array([t[0] for t in p], np.int64) for p in p2]), g[f"v_{name}_cls"])
+        np.testing.assert_array_equal(np.concatenate([np.array([t[2] for t in p], np.float32) for p in p2]), g[f"v_{name}_score"])
+
+
+def test_ap_calculator_golden(golden):
+    g = golden("ap.npz")
+    C = g["sem_cls_prob"].shape[-1]
+    calc = APC.APCalculator(_Cfg(C), ap_iou_thresh=[0.25, 0.5], exact_eval=False)
+    S = g["box_corners"].shape[0]
+    for lo in range(0, S, 8):  # three batches of 8 scenes, like engine.evaluate
+        sl = slice(lo, lo + 8)
+        calc.step(cu(g["box_corners"][sl]), cu(g["sem_cls_prob"][sl]), cu(g["objectness"][sl]), None,
+                  cu(g["gt_corners"][sl]), cu(g["gt_labels"][sl]), cu(g["gt_present"][sl]))
+    m = calc.compute_metrics()
+    for thr in (0.25, 0.5):
+        for k, v in m[thr].items():
+            assert float(v) == pytest.approx(float(g[f"m{thr}|{k}"]), abs=1e-4), (thr, k)  # north_star: AP within 1e-4
+            assert float(v) == pytest.approx(float(g[f"m{thr}|{k}"]), abs=1e-9), (thr, k)
+    s = calc.metrics_to_str(m)
+    assert s.startswith("mAP0.25, mAP0.50: ")
+    d = calc.metrics_to_dict(m)
+    assert d["mAP_0.25"] == pytest.approx(float(g["m0.25|mAP"]) * 100, abs=1e-6)
+    # full PR curves through the dict API (eval_det_cls)
+    preds = APC.parse_predictions(cu(g["box_corners"]), cu(g["sem_cls_prob"]), cu(g["objectness"]), None, calc.ap_config_dict)
+    for cl in (0, 3, 7):
+        pred = {i: [(bb, sc) for c_, bb, sc in preds[i] if c_ == cl] for i in range(S)}
+        gt = {i: [g["gt_corners"][i, j] for j in range(g["gt_corners"].shape[1])
+                  if g["gt_present"][i, j] == 1 and g["gt_labels"][i, j] == cl] for i in range(S)}
+        for thr in (0.25, 0.5):
+            rec, prec, ap = ED.eval_det_cls(pred, gt, thr)
+            np.testing.assert_allclose(rec, g[f"rec_c{cl}_t{thr}"], rtol=0, atol=1e-12)
+            np.testing.assert_allclose(prec, g[f"prec_c{cl}_t{thr}"], rtol=0, atol=1e-12)
+            assert ap == pytest.approx(float(g[f"ap_c{cl}_t{thr}"]), abs=1e-12)
+    # single-class layouts against the oracle
+    for kw in (dict(per_class_proposal=False), dict(per_class_proposal=False, use_cls_confidence_only=True)):
+        cfg2 = APC.get_ap_config_dict(dataset_config=_Cfg(C), remove_empty_box=False, **kw)
+        calc2 = APC.APCalculator(_Cfg(C), exact_eval=False, ap_config_dict=cfg2)
+        calc2.step(cu(g["box_corners"]), cu(g["sem_cls_prob"]), cu(g["objectness"]), None, cu(g["gt_corners"]),
+                   cu(g["gt_labels"]), cu(g["gt_present"]))
+        m2 = calc2.compute_metrics()
+        ocfg = oracle.default_ap_config(C, **kw)
+        want, _ = oracle.ap_metrics(g["box_corners"], g["sem_cls_prob"], g["objectness"], g["gt_corners"], g["gt_labels"],
+                                    g["gt_present"], C, config=ocfg)
+        for thr in (0.25, 0.5):
+            for k, v in want[thr].items():
+                assert float(m2[thr][k]) == pytest.approx(float(v), abs=1e-9), (kw, thr, k)
+
+
+def test_ap_large_vs_oracle_and_07():
+    S, Q, G, C = 96, 128, 64, 20
+    out, tgt = synth.detection_batch(B=S, Q=Q, G=G, C=C, seed=31, heading=np.pi, max_gt=12)
+    calc = APC.APCalculator(_Cfg(C), exact_eval=False)
+    calc.step(out["box_corners"].to(DEV), out["sem_cls_prob"].to(DEV), out["objectness_prob"].to(DEV), None,
+              tgt["gt_box_corners"].to(DEV), tgt["gt_box_sem_cls_label"].to(DEV), tgt["gt_box_present"].to(DEV))
+    got = calc.compute_metrics()
+    want, curves = oracle.ap_metrics(out["box_corners"], out["sem_cls_prob"], out["objectness_prob"], tgt["gt_box_corners"],
+                                     tgt["gt_box_sem_cls_label"], tgt["gt_box_present"], C)
+    for thr in (0.25, 0.5):
+        for k, v in want[thr].items():
+            assert float(got[thr][k]) == pytest.approx(float(v), abs=1e-9), (thr, k)
+    rs, rt, npos = calc.records()
+    ap07, _, _ = ED.ap_reduce(rs, rt, npos, 2, use_07_metric=True)
+    rec, prec = curves[0.25]
+    for c in range(C):
+        assert float(ap07[0, c]) == pytest.approx(oracle.voc_ap(rec[c], prec[c], True), abs=1e-12)
+
+
+def test_ap_reduce_properties_full_size():
+    """C3-sized record stream (20 classes x 5050*128 slots): sortedness-free checks --
+    recall == total TP / npos, AP in [0,1], AP invariant under a permutation of the records."""
+    C, N = 20, 5050 * 128
+    g = torch.Generator(device=DEV).manual_seed(0)
+    score = torch.rand((C, N), generator=g, device=DEV)
+    score[torch.rand((C, N), generator=g, device=DEV) < 0.3] = float("-inf")
+    tp = (torch.rand((C, N), generator=g, device=DEV) < 0.01).to(torch.uint8) * 3
+    tp[score == float("-inf")] = 0
+    npos = (tp & 1).sum(1).to(torch.int64) + 5
+    ap, recall, ndet = ED.ap_reduce(score, tp, npos, 2)
+    assert (ndet == (score > float("-inf")).sum(1)).all()
+    np.testing.assert_allclose(recall[0].cpu().numpy(), ((tp & 1).sum(1).double() / npos.double()).cpu().numpy(), rtol=1e-15)
+    assert (ap >= 0).all() and (ap <= 1).all()
+    perm = torch.randperm(N, generator=g, device=DEV)
+    ap2, recall2, _ = ED.ap_reduce(score[:, perm].contiguous(), tp[:, perm].contiguous(), npos, 2)
+    np.testing.assert_allclose(ap2.cpu().numpy(), ap.cpu().numpy(), rtol=0, atol=1e-12)
+    # one class against the oracle's voc_ap on a host sort
+    c = 3
+    s_h, t_h = score[c].cpu().numpy(), (tp[c] & 1).cpu().numpy()
+    v = s_h > -np.inf
+    o = np.argsort(-s_h[v], kind="stable")
+    tpc = np.cumsum(t_h[v][o].astype(np.float64))
+    fpc = np.cumsum(1.0 - t_h[v][o].astype(np.float64))
+    want = oracle.voc_ap(tpc / float(npos[c]), tpc / np.maximum(tpc + fpc, np.finfo(np.float64).eps))
+    assert float(ap[0, c]) == pytest.approx(want, abs=1e-12)
+
+
+# ------------------------------------------------------------------ matcher
+@pytest.mark.parametrize("tag", ["sunrgbd", "scannet"])
+def test_matcher_golden(golden, tag):
+    g = golden(f"matcher_{tag}.npz")
+    w = g["weights"]  # Matcher ctor order: class, objectness, giou, center
+    m = Matcher(float(w[0]), float(w[1]), float(w[2]), float(w[3]))
+    outputs = {"sem_cls_prob": cu(g["sem_cls_prob"]), "objectness_prob": cu(g["objectness"]),
+               "center_dist": cu(g["center_dist"]), "gious": cu(g["gious"]),
+               "center_normalized": cu(g["center_q"]), "box_corners": cu(g["corners1"])}
+    targets = {"gt_box_sem_cls_label": cu(g["labels"]), "nactual_gt": cu(g["nactual"]),
+               "gt_box_centers_normalized": cu(g["center_g"]), "gt_box_corners": cu(g["corners2"])}
+    r = m(outputs, targets)
+    np.testing.assert_allclose(r["final_cost"].cpu().numpy(), g["cost"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_array_equal(r["per_prop_gt_inds"].cpu().numpy(), g["per_prop_gt_inds"])
+    np.testing.assert_array_equal(r["proposal_matched_mask"].cpu().numpy(), g["proposal_matched_mask"])
+    assert r["assignments"][1] == []
+    for b in (0, 2):
+        n = int(g["nactual"][b])
+        np.testing.assert_array_equal(r["assignments"][b][0].cpu().numpy(), g["assign_rows"][b, :n])
+        np.testing.assert_array_equal(r["assignments"][b][1].cpu().numpy(), g["assign_cols"][b, :n])
+    # fused path: GIoU + L1 centre distance + cost in one kernel (torch-path GIoU semantics as in the fixture)
+    r2 = m.match_from_boxes(dict(outputs), targets, rotated_boxes=bool(g["rotated"]), needs_grad=True)
+    np.testing.assert_allclose(r2["final_cost"].cpu().numpy(), g["cost"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_array_equal(r2["per_prop_gt_inds"].cpu().numpy(), g["per_prop_gt_inds"])
+    np.testing.assert_array_equal(r2["proposal_matched_mask"].cpu().numpy(), g["proposal_matched_mask"])
+
+
+@pytest.mark.parametrize("Q,G", [(128, 64), (256, 64), (32, 64), (64, 64)])
+def test_lsap_vs_scipy(Q, G):
+    B = 16
+    g = torch.Generator().manual_seed(Q + G)
+    cost = torch.randn((B, Q, G), generator=g)
+    n = torch.randint(0, G + 1, (B,), generator=g)
+    n[0], n[1] = 0, G
+    inds, mask, c2r = lsap(cost.to(DEV), n.to(DEV))
+    _, winds, wmask = oracle.matcher_assign(cost.numpy(), n.numpy())
+    np.testing.assert_array_equal(inds.cpu().numpy(), winds)
+    np.testing.assert_array_equal(mask.cpu().numpy(), wmask)
+
+
+def test_matcher_full_size_property():
+    """BASELINE config 2 size: the assignment is a partial permutation and optimal
+    (total cost equals scipy's)."""
+    from scipy.optimize import linear_sum_assignment
+    out, tgt = synth.detection_batch(B=8, Q=256, G=64, C=18, seed=9, room="scannet", heading=0.0)
+    m = Matcher(1, 0, 2, 0)
+    o = {k: v.to(DEV) for k, v in out.items()}
+    t = {k: v.to(DEV) for k, v in tgt.items()}
+    r = m.match_from_boxes(o, t, rotated_boxes=False)
+    cost = r["final_cost"].cpu().numpy()
+    inds, mask = r["per_prop_gt_inds"].cpu().numpy(), r["proposal_matched_mask"].cpu().numpy()
+    for b in range(8):
+        n = int(tgt["nactual_gt"][b])
+        q = np.where(mask[b] == 1)[0]
+        assert len(q) == n and len(set(inds[b, q].tolist())) == n
+        rr, cc = linear_sum_assignment(cost[b, :, :n])
+        assert cost[b, q, inds[b, q]].sum() == pytest.approx(cost[b, rr, cc].sum(), rel=1e-6)
+        np.testing.assert_array_equal(np.sort(q), rr)
+
+
+# ------------------------------------------------------------------ pseudo-label filter
+def test_lift_golden(golden):
+    g = golden("lift.npz")
+    bx, pool = g["boxes"], g["pool"]
+    r = B3.lift_filter_batch(cu(bx), cu(pool))
+    for s in range(bx.shape[0]):
+        nms1 = oracle.tools_nms_3d_faster(bx[s].copy(), 0.7, class_wise=True)
+        np.testing.assert_array_equal(nms1, g[f"nms1_{s}"])
+        k1 = r["nms1_keep"][s].cpu().numpy().astype(bool)
+        np.testing.assert_array_equal(np.sort(bx[s][k1][:, 6]), np.sort(nms1[:, 6]))
+        got = B3.lift_filter_scene(bx[s], pool[s])
+        np.testing.assert_allclose(got, g[f"final_{s}"], rtol=0, atol=0)
+    np.testing.assert_allclose(B3.box_3d_iou(bx[0, 0, :6], pool[0]), g["iou_vv"][0], rtol=1e-14)
+
+
+def test_lift_full_width_vs_oracle():
+    bx, pool = synth.pseudo_label_scenes(6, P=256, pool=512, seed=3)  # BASELINE config 5 scene shape
+    r = B3.lift_filter_batch(bx.to(DEV), pool.to(DEV))
+    for s in range(6):
+        want = oracle.lift_filter_scene(bx[s].numpy(), pool[s].numpy())
+        got = B3.lift_filter_scene(bx[s].numpy(), pool[s].numpy())
+        np.testing.assert_allclose(got, want, rtol=0, atol=0)
+        assert int(r["keep"][s].sum()) == want.shape[0]
