@@ -171,12 +171,15 @@ int ovdet_ap_reduce(const float *rec_score, const uint8_t *rec_tp, const int64_t
 /* utils/ulip_losses.py:39-47): logits = scale * norm?(x) @ norm?(T)^T,        */
 /* prob = softmax(logits), sem_cls_prob = prob[:, :-1], objectness = 1-prob[:,-1]. */
 /* x [M,K] bf16, text [N,K] bf16 (row-major, K contiguous).  Outputs (any may  */
-/* be NULL): logits [M,N] fp32, prob [M,N-1] bf16, objectness [M] fp32.        */
-/* tcgen05 + TMA; requires K % 64 == 0, N <= 4096.                             */
+/* be NULL): logits fp32 [M, ld_logits] (N columns written), prob bf16          */
+/* [M, ld_prob] = the FULL softmax row (N columns; ld_prob % 8 == 0 so rows are  */
+/* 16-byte aligned -- the reference's sem_cls_prob is the view prob[:, :N-1],    */
+/* model_3detr.py:62), objectness fp32 [M] = 1 - prob[:, N-1].                  */
+/* tcgen05 + TMEM + TMA; requires K % 64 == 0, N <= 2048.                       */
 /* ------------------------------------------------------------------------- */
 #define OVDET_LOGITS_L2NORM 0x01u
 int ovdet_clip_logits_bf16(const void *x, const void *text, int M, int K, int N, unsigned flags, float scale,
-                           float *logits, void *prob, float *objectness, void *stream);
+                           float *logits, int ld_logits, void *prob, int ld_prob, float *objectness, void *stream);
 
 /* ------------------------------------------------------------------------- */
 /* Pseudo-label "NMS + IoU filtering" per scene                               */

@@ -1,7 +1,453 @@
-// clip_logits.cu -- placeholder; the tcgen05/TMA GEMM lands in a later commit.
+// clip_logits.cu -- open-vocabulary logits for sm_100a: tcgen05 + TMEM + TMA.
+//
+// Replaces  cls_logits = sem_cls_head(visual_embeds)            (models/model_3detr.py:237-238,
+//           the frozen CLIP text matrix as an nn.Linear weight, :151-154)
+//           prob = softmax(cls_logits); sem_cls_prob = prob[..., :-1];
+//           objectness = 1 - prob[..., -1]                       (:58-62)
+// and, with OVDET_LOGITS_L2NORM, the normalise + temperature form of
+// utils/ulip_losses.py:39-47 (logits = scale * x/|x| . t/|t|).
+//
+// One CTA computes a 128 x BLOCK_N tile of logits = X[128,K] * T[BLOCK_N,K]^T:
+//   warp 0   TMA producer: 128B-swizzled [128 x 64] bf16 A boxes and [BLOCK_N x 64]
+//            B boxes through a STAGES-deep mbarrier ring
+//   warp 1   one elected thread issues tcgen05.mma (cta_group::1, kind::f16,
+//            M=128, N=BLOCK_N, K=16) with the fp32 accumulator in TMEM;
+//            tcgen05.commit releases ring slots and finally signals the epilogue
+//   warp 2   TMEM allocate / free
+//   warps 4-7 epilogue: thread r owns accumulator row r (tcgen05.ld 32x32b)
+// A softmax row spans all N columns, i.e. several N-tiles: the NC CTAs of a
+// thread-block CLUSTER hold the N-tiles of the same 128 rows, each computes
+// (row max, sum exp) over its tile while the logits stay in TMEM, the pairs are
+// exchanged through distributed shared memory (st.shared::cluster), and after one
+// cluster barrier every CTA normalises its own tile out of TMEM.  No logits round
+// trip through HBM, no second GEMM.  Probabilities leave through a padded shared
+// tile with 16-byte coalesced row stores.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+
 #include "common.cuh"
-extern "C" int ovdet_clip_logits_bf16(const void *, const void *, int, int, int, unsigned, float, float *, void *, float *, void *)
+
+namespace ovdet {
+
+constexpr int GM_M = 128;        // rows per CTA (UMMA_M)
+constexpr int GM_K = 64;         // bf16 per 128B swizzle row
+constexpr int GM_THREADS = 256;
+constexpr int GM_MAX_NC = 8;     // portable cluster size
+
+struct LogitsParams {
+    int M, N, K, block_n, nc, num_kb, stages, tmem_cols;
+    unsigned flags;
+    float scale;
+    float *logits; int ld_logits;
+    __nv_bfloat16 *prob; int ld_prob;
+    float *objectness;
+    const float *inv_nx, *inv_nt;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-    ovdet::set_error("ovdet_clip_logits_bf16 not implemented yet");
-    return OVDET_ERR_UNSUPPORTED;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int x, int y)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v)
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 16-column variant for the tail chunk (BLOCK_N is a multiple of 16)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v)
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f32x2(const void *local_ptr, uint32_t rank, float a, float b)
+{
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_ptr)), "r"(rank));
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(raddr), "f"(a), "f"(b) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 64 bf16 (128 B), 8-row groups 1024 B apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), SWIZZLE_128B=2 [61,64))
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;             // LBO (unused for swizzled K-major), canonical 1
+    d |= (uint64_t)(1024 >> 4) << 32;   // SBO = 1024 B
+    d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ float fast_exp2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(GM_THREADS, 1)
+clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const LogitsParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) float2 stats[GM_MAX_NC][GM_M];   // (row max, row sum-exp) from every CTA of the cluster
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int m_tile = blockIdx.x / p.nc;
+    const int m0 = m_tile * GM_M;
+    const int n0 = (int)rank * p.block_n;
+    const uint32_t a_bytes = GM_M * GM_K * 2, b_bytes = (uint32_t)p.block_n * GM_K * 2;
+    const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    cluster_sync_all();   // every CTA of the cluster is resident before any DSMEM traffic
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                unsigned char *sa = smem + (size_t)s * stage_bytes;
+                mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
+                tma_load_2d(&tmA, &full_bar[s], sa, kb * GM_K, m0);
+                tma_load_2d(&tmB, &full_bar[s], sa + a_bytes, kb * GM_K, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b BF16 (1<<7, 1<<10), K-major both, N>>3 at 17, M>>4 at 24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(GM_M >> 4) << 24);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+            const int s = kb % p.stages;
+            const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + a_bytes);
+#pragma unroll
+                for (int k = 0; k < GM_K / 16; ++k)   // +32 B (>>4 = 2) per UMMA_K=16 step inside the swizzle atom
+                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                umma_commit(&empty_bar[s]);                       // slot free once these MMAs retire
+                if (kb == p.num_kb - 1) umma_commit(&tmem_full_bar);  // accumulator complete
+            }
+            __syncwarp();
+        }
+    }
+
+    // ===================== epilogue (warps 4..7) =====================
+    const bool epi = warp >= 4;
+    const int row = (warp & 3) * 32 + lane;            // accumulator row == TMEM lane
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const float LOG2E = 1.4426950408889634f;
+    float rmax = -INFINITY, rsum = 0.f;
+    float rs = p.scale;
+    if (epi) {
+        if ((p.flags & OVDET_LOGITS_L2NORM) && (m0 + row) < p.M) rs *= __ldg(p.inv_nx + m0 + row);
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        // ---- pass 1: logits (optional store), running (max, sum-exp) of this tile
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+            float v[32];
+            const int w = min(32, p.block_n - c0);
+            if (w == 32) tmem_ld32(trow + (uint32_t)c0, v); else tmem_ld16(trow + (uint32_t)c0, v);
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int col = n0 + c0 + i;
+                if (i < w && col < p.N) {
+                    float x = v[i] * rs;
+                    if (p.flags & OVDET_LOGITS_L2NORM) x *= __ldg(p.inv_nt + col);
+                    v[i] = x;
+                    cmax = fmaxf(cmax, x);
+                } else v[i] = -INFINITY;
+            }
+            if (p.logits && (m0 + row) < p.M) {
+                float *o = p.logits + (size_t)(m0 + row) * p.ld_logits + n0 + c0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < w && n0 + c0 + i < p.N) o[i] = v[i];
+            }
+            if (cmax > -INFINITY) {
+                const float nm = fmaxf(rmax, cmax);
+                float add = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) add += fast_exp2((v[i] - nm) * LOG2E);
+                rsum = rsum * fast_exp2((rmax - nm) * LOG2E) + add;
+                rmax = nm;
+            }
+        }
+        // ---- publish (max, sum) to every CTA of the cluster
+        for (int r = 0; r < p.nc; ++r) st_cluster_f32x2(&stats[rank][row], (uint32_t)r, rmax, rsum);
+    }
+    cluster_sync_all();   // release/acquire: all stats visible cluster-wide
+
+    if (epi && (p.prob || p.objectness)) {
+        float gmax = -INFINITY;
+        for (int r = 0; r < p.nc; ++r) gmax = fmaxf(gmax, stats[r][row].x);
+        float gsum = 0.f;
+        for (int r = 0; r < p.nc; ++r) {
+            const float2 s = stats[r][row];
+            if (s.x > -INFINITY) gsum += s.y * fast_exp2((s.x - gmax) * LOG2E);
+        }
+        const float inv = 1.f / gsum;
+        // ---- pass 2: normalise out of TMEM into the padded shared tile (pipeline smem is idle now)
+        const int tile_ld = p.block_n + 8;   // bf16 elements; +16 B keeps the 16-byte row writes conflict-free
+        __nv_bfloat16 *tile = reinterpret_cast<__nv_bfloat16 *>(smem);
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+            float v[32];
+            const int w = min(32, p.block_n - c0);
+            if (w == 32) tmem_ld32(trow + (uint32_t)c0, v); else tmem_ld16(trow + (uint32_t)c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int col = n0 + c0 + i;
+                float pr = 0.f;
+                if (i < w && col < p.N) {
+                    float x = v[i] * rs;
+                    if (p.flags & OVDET_LOGITS_L2NORM) x *= __ldg(p.inv_nt + col);
+                    pr = fast_exp2((x - gmax) * LOG2E) * inv;
+                    if (col == p.N - 1 && p.objectness && (m0 + row) < p.M) p.objectness[m0 + row] = 1.f - pr;
+                }
+                v[i] = pr;
+            }
+            if (p.prob) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    if (i < w) {
+                        __nv_bfloat162 h[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[i + 2 * j], v[i + 2 * j + 1]);
+                        *reinterpret_cast<uint4 *>(tile + (size_t)row * tile_ld + c0 + i) = *reinterpret_cast<uint4 *>(h);
+                    }
+                }
+            }
+        }
+        if (p.prob) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+            const int pieces = p.block_n / 8;                // 16-byte pieces per row
+            const int et = threadIdx.x - 128;
+            for (int i = et; i < GM_M * pieces; i += 128) {
+                const int r = i / pieces, c8 = (i - r * pieces) * 8;
+                const int grow = m0 + r, gcol = n0 + c8;
+                if (grow < p.M && gcol < p.ld_prob) {
+                    const uint4 val = *reinterpret_cast<const uint4 *>(tile + (size_t)r * tile_ld + c8);
+                    *reinterpret_cast<uint4 *>(p.prob + (size_t)grow * p.ld_prob + gcol) = val;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// inverse L2 norms of bf16 rows (F.normalize(x, dim=-1, p=2): x / max(|x|, 1e-12)), one warp per row
+__global__ void __launch_bounds__(256) inv_norm_kernel(const __nv_bfloat16 *__restrict__ x, int R, int K, float *__restrict__ out)
+{
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= R) return;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) { const float v = __bfloat162float(x[(size_t)row * K + k]); s += v * v; }
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) out[row] = 1.f / fmaxf(sqrtf(s), 1e-12f);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap *map, const void *base, int rows, int K, int box_rows)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return OVDET_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GM_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return OVDET_ERR_CUDA; }
+    return OVDET_OK;
+}
+
+}  // namespace ovdet
+
+using namespace ovdet;
+
+extern "C" int ovdet_clip_logits_bf16(const void *x, const void *text, int M, int K, int N, unsigned flags, float scale,
+                                      float *logits, int ld_logits, void *prob, int ld_prob, float *objectness, void *stream)
+{
+    OVDET_REQUIRE(M >= 0 && K > 0 && N > 0, "bad size");
+    if (M == 0) return OVDET_OK;
+    OVDET_REQUIRE(x && text, "null pointer");
+    OVDET_REQUIRE(K % GM_K == 0, "K must be a multiple of 64");
+    OVDET_REQUIRE(N <= GM_MAX_NC * 256, "N must be <= 2048");
+    OVDET_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(text) & 15) == 0, "x/text must be 16-byte aligned");
+    OVDET_REQUIRE(!logits || ld_logits >= N, "ld_logits < N");
+    OVDET_REQUIRE(!prob || (ld_prob >= N && ld_prob % 8 == 0 && (reinterpret_cast<uintptr_t>(prob) & 15) == 0),
+                  "prob needs ld_prob >= N, ld_prob % 8 == 0 and 16-byte alignment");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // split N over a cluster of nc CTAs (power of two), BLOCK_N = multiple of 16 <= 256
+    int nc = 1;
+    while (nc < GM_MAX_NC && (N + nc - 1) / nc > 256) nc <<= 1;
+    int bn = (((N + nc - 1) / nc) + 15) / 16 * 16;
+    if (bn < 16) bn = 16;
+    LogitsParams p;
+    p.M = M; p.N = N; p.K = K; p.block_n = bn; p.nc = nc; p.num_kb = K / GM_K;
+    p.stages = bn <= 160 ? 3 : 4;
+    if (p.stages > p.num_kb) p.stages = p.num_kb;
+    p.tmem_cols = 32; while (p.tmem_cols < bn) p.tmem_cols <<= 1;
+    p.flags = flags; p.scale = scale;
+    p.logits = logits; p.ld_logits = ld_logits; p.prob = static_cast<__nv_bfloat16 *>(prob); p.ld_prob = ld_prob;
+    p.objectness = objectness; p.inv_nx = nullptr; p.inv_nt = nullptr;
+    float *norms = nullptr;
+    if (flags & OVDET_LOGITS_L2NORM) {
+        OVDET_CUDA_TRY(cudaMallocAsync(&norms, sizeof(float) * ((size_t)M + N), st));
+        inv_norm_kernel<<<(M + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(x), M, K, norms);
+        inv_norm_kernel<<<(N + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(text), N, K, norms + M);
+        p.inv_nx = norms; p.inv_nt = norms + M;
+    }
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, x, M, K, GM_M);
+    if (rc) return rc;
+    rc = make_map(&tmB, text, N, K, bn);
+    if (rc) return rc;
+    const size_t stage_bytes = (size_t)GM_M * GM_K * 2 + (((size_t)bn * GM_K * 2 + 1023) & ~(size_t)1023);
+    size_t smem = stage_bytes * p.stages;
+    const size_t tile_bytes = (size_t)GM_M * (bn + 8) * 2;
+    if (smem < tile_bytes) smem = tile_bytes;
+    smem += 1024;  // manual 1024-byte alignment for the 128B swizzle
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(clip_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    const int m_tiles = (M + GM_M - 1) / GM_M;
+    cfg.gridDim = dim3((unsigned)(m_tiles * nc));
+    cfg.blockDim = dim3(GM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, clip_logits_kernel, tmA, tmB, p));
+    if (norms) OVDET_CUDA_TRY(cudaFreeAsync(norms, st));
+    return launch_ok("clip_logits_kernel");
 }

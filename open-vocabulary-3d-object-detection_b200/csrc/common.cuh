@@ -116,54 +116,55 @@ template <typename T> struct ClipEdge {
     }
 };
 
-// Shoelace sinks.  All receive vertices in emission order v0..v(n-1) and return
-// 0.5*|sum_i x_i*y_(i-1) - sum_i y_i*x_(i-1)| (indices cyclic).
-struct SinkF32 {  // fp32 torch path: utils/box_util.py:591-598
-    bool has = false; float fx, fy, px, py, d1 = 0.f, d2 = 0.f;
-    __device__ __forceinline__ void emit(float x, float y)
-    {
-        if (!has) { fx = x; fy = y; has = true; }
-        else { d1 = __fadd_rn(d1, __fmul_rn(x, py)); d2 = __fadd_rn(d2, __fmul_rn(y, px)); }
+// Shoelace areas of the clipped polygon left in shared scratch (vertex i of this
+// thread at poly[i*STRIDE]).  All follow the reference expression
+// 0.5*|dot(x, roll(y,1)) - dot(y, roll(x,1))| term by term from i = 0 (roll(.,1)[0]
+// is the LAST vertex), because the fp32 sums are ill-conditioned in absolute
+// coordinates (|x*y| ~ 10 against areas ~ 1e-2..1) and the order is visible at 1e-6.
+template <int STRIDE>
+__device__ __forceinline__ float area_f32(const V2<float> *poly, int n)
+{   // fp32 torch path: utils/box_util.py:591-598
+    if (n <= 0) return 0.f;
+    float d1 = 0.f, d2 = 0.f;
+    V2<float> pv = poly[(n - 1) * STRIDE];
+    for (int i = 0; i < n; ++i) {
+        const V2<float> v = poly[i * STRIDE];
+        d1 = __fadd_rn(d1, __fmul_rn(v.x, pv.y));
+        d2 = __fadd_rn(d2, __fmul_rn(v.y, pv.x));
+        pv = v;
+    }
+    return __fmul_rn(fabsf(__fsub_rn(d1, d2)), 0.5f);
+}
+template <int STRIDE>
+__device__ __forceinline__ float area_cython(const V2<double> *poly, int n)
+{   // pyx:196-198: polygon cast to fp32, fp32 products accumulated in double (np.dot), fp32 result
+    if (n <= 0) return 0.f;
+    double d1 = 0.0, d2 = 0.0;
+    const V2<double> l = poly[(n - 1) * STRIDE];
+    float px = (float)l.x, py = (float)l.y;
+    for (int i = 0; i < n; ++i) {
+        const V2<double> v = poly[i * STRIDE];
+        const float x = (float)v.x, y = (float)v.y;
+        d1 = __dadd_rn(d1, (double)__fmul_rn(x, py));
+        d2 = __dadd_rn(d2, (double)__fmul_rn(y, px));
         px = x; py = y;
     }
-    __device__ __forceinline__ float area()
-    {
-        if (!has) return 0.f;
-        d1 = __fadd_rn(d1, __fmul_rn(fx, py)); d2 = __fadd_rn(d2, __fmul_rn(fy, px));
-        return __fmul_rn(fabsf(__fsub_rn(d1, d2)), 0.5f);
+    return __fmul_rn(0.5f, fabsf(__fsub_rn((float)d1, (float)d2)));
+}
+template <int STRIDE>
+__device__ __forceinline__ double area_f64(const V2<double> *poly, int n)
+{   // poly_area (box_util.py:84-86); stands in for Qhull's hull area (:96); <3 vertices -> 0
+    if (n < 3) return 0.0;
+    double d1 = 0.0, d2 = 0.0;
+    V2<double> pv = poly[(n - 1) * STRIDE];
+    for (int i = 0; i < n; ++i) {
+        const V2<double> v = poly[i * STRIDE];
+        d1 = __dadd_rn(d1, __dmul_rn(v.x, pv.y));
+        d2 = __dadd_rn(d2, __dmul_rn(v.y, pv.x));
+        pv = v;
     }
-};
-struct SinkCython {  // pyx:196-198: polygon cast to fp32, fp32 products, double accumulation (np.dot), fp32 result
-    bool has = false; float fx, fy, px, py; double d1 = 0.0, d2 = 0.0;
-    __device__ __forceinline__ void emit(double xd, double yd)
-    {
-        const float x = (float)xd, y = (float)yd;
-        if (!has) { fx = x; fy = y; has = true; }
-        else { d1 = __dadd_rn(d1, (double)__fmul_rn(x, py)); d2 = __dadd_rn(d2, (double)__fmul_rn(y, px)); }
-        px = x; py = y;
-    }
-    __device__ __forceinline__ float area()
-    {
-        if (!has) return 0.f;
-        d1 = __dadd_rn(d1, (double)__fmul_rn(fx, py)); d2 = __dadd_rn(d2, (double)__fmul_rn(fy, px));
-        return __fmul_rn(0.5f, fabsf(__fsub_rn((float)d1, (float)d2)));
-    }
-};
-struct SinkF64 {  // fp64 shoelace (poly_area, box_util.py:84-86; stands in for Qhull's hull area :96)
-    int n = 0; double fx, fy, px, py, d1 = 0.0, d2 = 0.0;
-    __device__ __forceinline__ void emit(double x, double y)
-    {
-        if (n == 0) { fx = x; fy = y; }
-        else { d1 = __dadd_rn(d1, __dmul_rn(x, py)); d2 = __dadd_rn(d2, __dmul_rn(y, px)); }
-        px = x; py = y; ++n;
-    }
-    __device__ __forceinline__ double area()
-    {
-        if (n < 3) return 0.0;
-        d1 = __dadd_rn(d1, __dmul_rn(fx, py)); d2 = __dadd_rn(d2, __dmul_rn(fy, px));
-        return __dmul_rn(0.5, fabs(__dsub_rn(d1, d2)));
-    }
-};
+    return __dmul_rn(0.5, fabs(__dsub_rn(d1, d2)));
+}
 
 // One pass over a vertex list held in shared scratch, output to shared scratch.
 template <typename T, int STRIDE>
@@ -183,9 +184,9 @@ __device__ __forceinline__ int sh_pass_mem(const ClipEdge<T> &ce, const V2<T> *i
 }
 
 // Full clip: subject quad s[4], clip quad c[4] (x,y interleaved, already of type T).
-// bufA/bufB: this thread's scratch rows.  Returns through `sink`.
-template <typename T, int STRIDE, typename Sink>
-__device__ __forceinline__ void sh_clip_quads(const T *s, const T *c, V2<T> *bufA, V2<T> *bufB, Sink &sink)
+// bufA/bufB: this thread's scratch rows.  Returns the vertex count; the polygon is left in bufB.
+template <typename T, int STRIDE>
+__device__ __forceinline__ int sh_clip_quads(const T *s, const T *c, V2<T> *bufA, V2<T> *bufB)
 {
     int n;
     {   // pass 0: subject in registers -> bufA
@@ -203,29 +204,22 @@ __device__ __forceinline__ void sh_clip_quads(const T *s, const T *c, V2<T> *buf
         }
         n = m;
     }
-    if (n == 0) return;
+    if (n == 0) return 0;
     {
         const ClipEdge<T> ce(c[0], c[1], c[2], c[3]);
         n = sh_pass_mem<T, STRIDE>(ce, bufA, n, bufB);
     }
-    if (n == 0) return;
+    if (n == 0) return 0;
     {
         const ClipEdge<T> ce(c[2], c[3], c[4], c[5]);
         n = sh_pass_mem<T, STRIDE>(ce, bufB, n, bufA);
     }
-    if (n == 0) return;
-    {   // pass 3: bufA -> sink
+    if (n == 0) return 0;
+    {
         const ClipEdge<T> ce(c[4], c[5], c[6], c[7]);
-        V2<T> sv = bufA[(n - 1) * STRIDE];
-        bool s_in = ce.inside(sv.x, sv.y);
-        for (int i = 0; i < n; ++i) {
-            const V2<T> e = bufA[i * STRIDE];
-            const bool e_in = ce.inside(e.x, e.y);
-            if (e_in != s_in) { const V2<T> q = ce.isect(sv.x, sv.y, e.x, e.y); sink.emit(q.x, q.y); }
-            if (e_in) sink.emit(e.x, e.y);
-            sv = e; s_in = e_in;
-        }
+        n = sh_pass_mem<T, STRIDE>(ce, bufA, n, bufB);
     }
+    return n;
 }
 
 // giou_hull.cu: GIoU with the convex-hull enclosing volume (OVDET_GIOU_ENCL_HULL)

@@ -55,9 +55,8 @@ __device__ __forceinline__ double exact_iou(const float *c1, const float *c2, V2
             s[2 * i] = (double)c1[3 * (3 - i)]; s[2 * i + 1] = (double)c1[3 * (3 - i) + 2];
             c[2 * i] = (double)c2[3 * (3 - i)]; c[2 * i + 1] = (double)c2[3 * (3 - i) + 2];
         }
-        SinkF64 sink;
-        sh_clip_quads<double, STRIDE>(s, c, bufA, bufB, sink);
-        ia = sink.area();
+        const int n = sh_clip_quads<double, STRIDE>(s, c, bufA, bufB);
+        ia = area_f64<STRIDE>(bufB, n);
         if (want2d) {
             double a[2];
             const double *rr[2] = {s, c};

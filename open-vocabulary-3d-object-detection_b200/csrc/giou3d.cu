@@ -228,13 +228,11 @@ __global__ void __launch_bounds__(NT) giou3d_kernel(GiouParams p)
             }
             float area;
             if constexpr (sizeof(ClipT) == 8) {
-                SinkCython sink;
-                sh_clip_quads<double, NT>(s, cl, bufA, bufB, sink);
-                area = sink.area();
+                const int n = sh_clip_quads<double, NT>(s, cl, bufA, bufB);
+                area = area_cython<NT>(bufB, n);
             } else {
-                SinkF32 sink;
-                sh_clip_quads<float, NT>(s, cl, bufA, bufB, sink);
-                area = sink.area();
+                const int n = sh_clip_quads<float, NT>(s, cl, bufA, bufB);
+                area = area_f32<NT>(bufB, n);
             }
             const PairTerms t = pair_terms(f1, r, f2, c);
             tile[r * TG + c] = finish_pair(t, area, true, has_nums, inter_only);
@@ -357,9 +355,8 @@ __global__ void __launch_bounds__(NT) box_intersection_kernel(BiParams p)
         double s[8], c[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s[i] = (double)__ldg(r1 + i); c[i] = (double)__ldg(r2 + i); }
-        SinkCython sink;
-        sh_clip_quads<double, NT>(s, c, bufA, bufB, sink);
-        if (sink.has) p.inter[idx] = sink.area();  // pyx:195-198: untouched when the clip is empty
+        const int n = sh_clip_quads<double, NT>(s, c, bufA, bufB);
+        if (n > 0) p.inter[idx] = area_cython<NT>(bufB, n);  // pyx:195-198: untouched when the clip is empty
     }
 }
 

@@ -382,3 +382,29 @@ def test_lift_full_width_vs_oracle():
         got = B3.lift_filter_scene(bx[s].numpy(), pool[s].numpy())
         np.testing.assert_allclose(got, want, rtol=0, atol=0)
         assert int(r["keep"][s].sum()) == want.shape[0]
+
+
+# ------------------------------------------------------------------ open-vocab logits (tcgen05)
+@pytest.mark.parametrize("M,K,N,l2,scale", [
+    (8192, 640, 1203, False, 1.0),     # BASELINE config 4
+    (1024, 640, 21, False, 1.0),       # SUN RGB-D head (20 classes + background)
+    (300, 640, 19, False, 1.0),        # ScanNet head, ragged M
+    (512, 640, 1203, True, 1.0 / 0.07),  # CLIPLoss form: normalise + temperature
+    (256, 128, 257, False, 0.5),       # two N tiles, short K
+])
+def test_clip_logits_vs_oracle(M, K, N, l2, scale):
+    from ovdet_b200.models.model_3detr import clip_logits
+    x, t = synth.clip_logits_inputs(M, K, N, seed=M + N)
+    if not l2:
+        x = x * 0.25  # keep the softmax away from saturation so the probabilities carry signal
+    lg, pr, ob = clip_logits(x.to(DEV), t.to(DEV), l2norm=l2, scale=scale, want_logits=True)
+    wl, wp, wo = oracle.clip_logits(x.float(), t.float(), l2norm=l2, scale=scale)  # fp64 on the bf16-rounded inputs
+    wl, wp, wo = wl.numpy(), wp.numpy(), wo.numpy()
+    # fp32 accumulation of exact bf16 products: logits agree far inside bf16 tolerance
+    np.testing.assert_allclose(lg.cpu().numpy(), wl, rtol=2e-3 if l2 else 1e-4, atol=2e-3 if l2 else 1e-4)
+    # probabilities are stored in bf16: 2^-8 relative (+ tiny absolute floor)
+    np.testing.assert_allclose(pr.float().cpu().numpy(), wp, rtol=1.2e-2, atol=1e-6)
+    np.testing.assert_allclose(ob.cpu().numpy(), wo, rtol=0, atol=2e-3)
+    assert pr.shape == (M, N - 1) and ob.shape == (M,)
+    rowsum = pr.float().sum(-1).cpu().numpy() + (1 - ob.cpu().numpy())
+    np.testing.assert_allclose(rowsum, 1.0, atol=8e-3)
