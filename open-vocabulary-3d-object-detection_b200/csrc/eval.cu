@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(1024) ap_scan_kernel(ApScanParams p)
         if (tid < 32) {
             double w = red[tid];
             for (int off = 16; off > 0; off >>= 1) w += __shfl_down_sync(0xffffffffu, w, off);
-            red[0] = w;
+            if (tid == 0) red[0] = w;
         }
         __syncthreads();
         res = red[0];
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(1024) ap_scan_kernel(ApScanParams p)
             if (tid < 32) {
                 double w = red[tid];
                 for (int off = 16; off > 0; off >>= 1) w = fmax(w, __shfl_down_sync(0xffffffffu, w, off));
-                red[0] = w;
+                if (tid == 0) red[0] = w;
             }
             __syncthreads();
             res = res + red[0] / 11.0;

@@ -276,7 +276,9 @@ def test_ap_reduce_properties_full_size():
     recall == total TP / npos, AP in [0,1], AP invariant under a permutation of the records."""
     C, N = 20, 5050 * 128
     g = torch.Generator(device=DEV).manual_seed(0)
-    score = torch.rand((C, N), generator=g, device=DEV)
+    # tie-free scores: a random permutation of N distinct fp32 values per class
+    score = torch.stack([(torch.randperm(N, generator=g, device=DEV).float() + 0.5) / N for _ in range(C)])
+    assert all(torch.unique(score[c]).numel() == N for c in (0, C - 1))
     score[torch.rand((C, N), generator=g, device=DEV) < 0.3] = float("-inf")
     tp = (torch.rand((C, N), generator=g, device=DEV) < 0.01).to(torch.uint8) * 3
     tp[score == float("-inf")] = 0
