@@ -166,6 +166,24 @@ int ovdet_ap_reduce(const float *rec_score, const uint8_t *rec_tp, const int64_t
                     double *ap, double *recall, int64_t *n_det, double *rec_out, double *prec_out,
                     void *ws, size_t ws_bytes, void *stream);
 
+/* Compact AP reduction without a global sort (csrc/ap_compact.cu): VOC AP only needs, for
+ * every TP record, its position in the score order.  Four stages so that a scene-sharded
+ * multi-GPU caller can exchange between them (all-gather the TP lists after collect,
+ * all-reduce `hist` after hist).  cap = per-class TP-list capacity, a power of two in
+ * [1024, 16384]; the lists are pre-filled with key 0xFFFFFFFF / bits 0 so that lists of several
+ * ranks can simply be concatenated (to another power of two) before ovdet_apc_sort.
+ *   collect: tp_key u32 [C,cap], tp_bits u8 [C,cap], tp_cnt i32 [C] (may exceed cap = overflow),
+ *            nvalid i64 [C] (present records);  sort: descending score per class;
+ *   hist:    u32 [C,cap+1], bucket = number of TP-list scores above the record's score;
+ *   final:   ap/recall fp64 [nthr,C], n_det i64 [C] (nullable), overflow i32 [1] (nullable). */
+int ovdet_apc_collect(const float *rec_score, const uint8_t *rec_tp, int C, int64_t N, int cap,
+                      uint32_t *tp_key, uint8_t *tp_bits, int32_t *tp_cnt, int64_t *nvalid, void *stream);
+int ovdet_apc_sort(uint32_t *tp_key, uint8_t *tp_bits, int C, int cap, void *stream);
+int ovdet_apc_hist(const float *rec_score, int C, int64_t N, const uint32_t *tp_key, int cap, uint32_t *hist, void *stream);
+int ovdet_apc_final(const uint8_t *tp_bits, const int32_t *tp_cnt, const uint32_t *hist, const int64_t *npos,
+                    const int64_t *nvalid, int C, int cap, int nthr, int use_07_metric,
+                    double *ap, double *recall, int64_t *n_det, int32_t *overflow, void *stream);
+
 /* ------------------------------------------------------------------------- */
 /* Open-vocabulary logits (models/model_3detr.py:237-238, :58-62;              */
 /* utils/ulip_losses.py:39-47): logits = scale * norm?(x) @ norm?(T)^T,        */

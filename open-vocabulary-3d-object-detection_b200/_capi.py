@@ -36,6 +36,10 @@ SIGNATURES = {
     "ovdet_ap_match": (c_i, [c_p] * 8 + [c_i] * 4 + [c_p, c_i] + [c_p] * 5),
     "ovdet_ap_reduce_ws_bytes": (c_sz, [c_i, c_i64]),
     "ovdet_ap_reduce": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "ovdet_apc_collect": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "ovdet_apc_sort": (c_i, [c_p, c_p, c_i, c_i, c_p]),
+    "ovdet_apc_hist": (c_i, [c_p, c_i, c_i64, c_p, c_i, c_p, c_p]),
+    "ovdet_apc_final": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "ovdet_clip_logits_bf16": (c_i, [c_p, c_p, c_i, c_i, c_i, c_u, c_f, c_p, c_i, c_p, c_i, c_p, c_p]),
     "ovdet_pseudo_filter_f64": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p]),
 }

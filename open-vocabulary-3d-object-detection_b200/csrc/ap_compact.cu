@@ -1,0 +1,313 @@
+// ap_compact.cu -- AP from (score, tp) records WITHOUT a global sort.
+//
+// VOC AP (utils/eval_det.py:23-54) only looks at the precision at the true-positive
+// records: recall changes exactly there, and the running-max envelope of the
+// precision is attained there.  So instead of sorting every record of a class by
+// score (utils/eval_det.py:108-111; csrc/eval.cu's radix sort), it is enough to know,
+// for each TP record, its 1-based position in the sorted order = the number of
+// present records with a score >= its own:
+//   1. collect   the records with any TP bit set into a small per-class list
+//   2. sort      that list by descending score (bitonic, shared memory, <= 16384 entries)
+//   3. hist      ONE streaming pass over all records: binary-search each score in the
+//                sorted TP list, bump that bucket (shared-memory privatised histogram)
+//   4. final     prefix-sum the buckets -> positions; cumulative TP, precision envelope, AP
+// Traffic: the record stream is read twice (5 B/record) instead of ~10 radix passes.
+// The stages are separate entry points because a scene-sharded multi-GPU caller
+// exchanges between them: all-gather of the TP lists after (1), all-reduce of the
+// bucket histogram after (3) -- KBs instead of the whole record stream.
+// Results equal the sorted formulation on tie-free scores (same caveat as the reference's
+// unstable argsort).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ovdet {
+
+constexpr int APC_NT = 256;
+constexpr int APC_MAXCAP = 16384;
+
+__device__ __forceinline__ uint32_t apc_score_key(float s)
+{   // ascending key order == descending score; -inf (absent) maps to the largest finite-score key + ...
+    const uint32_t b = __float_as_uint(s);
+    const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ~ord;
+}
+
+__global__ void __launch_bounds__(APC_NT) apc_collect_kernel(const float *__restrict__ score, const uint8_t *__restrict__ tp,
+                                                             long long N, int cap, uint32_t *tp_key, uint8_t *tp_bits,
+                                                             int *tp_cnt, unsigned long long *nvalid)
+{
+    const int c = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    int local_valid = 0;
+    const long long stride = (long long)gridDim.x * APC_NT;
+    const long long nround = (N + stride - 1) / stride;
+    for (long long it = 0; it < nround; ++it) {
+        const long long i = it * stride + (long long)blockIdx.x * APC_NT + threadIdx.x;
+        float s = -INFINITY; uint8_t t = 0;
+        if (i < N) { s = score[(size_t)c * N + i]; t = tp[(size_t)c * N + i]; }
+        const bool present = s > -INFINITY;
+        local_valid += present ? 1 : 0;
+        const bool is_tp = present && t != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, is_tp);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&tp_cnt[c], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (is_tp) {
+                const int slot = base + __popc(m & ((1u << lane) - 1));
+                if (slot < cap) { tp_key[(size_t)c * cap + slot] = apc_score_key(s); tp_bits[(size_t)c * cap + slot] = t; }
+            }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) local_valid += __shfl_xor_sync(0xffffffffu, local_valid, off);
+    if (lane == 0 && local_valid) atomicAdd(&nvalid[c], (unsigned long long)local_valid);
+}
+
+// per class: bitonic sort of `cap` (power of two) (key, bits) entries, ascending key; unused slots hold key 0xFFFFFFFF
+__global__ void __launch_bounds__(1024) apc_sort_kernel(uint32_t *tp_key, uint8_t *tp_bits, int cap)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint32_t *k = reinterpret_cast<uint32_t *>(sm);
+    uint8_t *b = reinterpret_cast<uint8_t *>(k + cap);
+    const int c = blockIdx.x;
+    for (int i = threadIdx.x; i < cap; i += 1024) { k[i] = tp_key[(size_t)c * cap + i]; b[i] = tp_bits[(size_t)c * cap + i]; }
+    __syncthreads();
+    for (int size = 2; size <= cap; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < cap / 2; t += 1024) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const uint32_t ka = k[lo], kb = k[hi];
+                if (up ? (ka > kb) : (ka < kb)) {
+                    k[lo] = kb; k[hi] = ka;
+                    const uint8_t ba = b[lo]; b[lo] = b[hi]; b[hi] = ba;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < cap; i += 1024) { tp_key[(size_t)c * cap + i] = k[i]; tp_bits[(size_t)c * cap + i] = b[i]; }
+}
+
+// bucket of a record = number of TP-list keys strictly below its key (lower_bound); privatised per CTA
+__global__ void __launch_bounds__(APC_NT) apc_hist_kernel(const float *__restrict__ score, long long N, const uint32_t *__restrict__ tp_key,
+                                                          int cap, uint32_t *hist)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint32_t *k = reinterpret_cast<uint32_t *>(sm);   // [cap]
+    uint32_t *h = k + cap;                            // [cap + 1]
+    const int c = blockIdx.y;
+    for (int i = threadIdx.x; i < cap; i += APC_NT) k[i] = tp_key[(size_t)c * cap + i];
+    for (int i = threadIdx.x; i <= cap; i += APC_NT) h[i] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * APC_NT + threadIdx.x; i < N; i += (long long)gridDim.x * APC_NT) {
+        const float s = score[(size_t)c * N + i];
+        if (!(s > -INFINITY)) continue;
+        const uint32_t key = apc_score_key(s);
+        int lo = 0, n = cap;               // branch-free lower_bound over a power-of-two table
+        while (n > 1) { const int half = n >> 1; lo += (k[lo + half - 1] < key) ? half : 0; n -= half; }
+        lo += (k[lo] < key) ? 1 : 0;
+        atomicAdd(&h[lo], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= cap; i += APC_NT) { const uint32_t v = h[i]; if (v) atomicAdd(&hist[(size_t)c * (cap + 1) + i], v); }
+}
+
+struct ApcFinalParams {
+    const uint8_t *tp_bits; const int *tp_cnt; const uint32_t *hist; const long long *npos; const unsigned long long *nvalid;
+    int C, cap, nthr, use07;
+    double *ap, *recall; long long *ndet; int *overflow;
+};
+
+__global__ void __launch_bounds__(1024) apc_final_kernel(ApcFinalParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    unsigned int *H = reinterpret_cast<unsigned int *>(sm);   // [cap] inclusive prefix of hist = 1-based sorted position
+    unsigned int *ctp = H + p.cap;                            // [cap] inclusive count of TP(t) entries
+    __shared__ unsigned int wsum[32], carry_u;
+    __shared__ double wmax[32], red[32], carry_max_s;
+    const int c = blockIdx.x, t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cap = p.cap;
+    const double npos = (double)p.npos[c];
+    const double eps = 2.220446049250313e-16;
+    const uint8_t *bits = p.tp_bits + (size_t)c * cap;
+    const uint32_t *hist = p.hist + (size_t)c * (cap + 1);
+    // two forward chunked inclusive scans (hist -> H, tp flag -> ctp)
+    for (int pass = 0; pass < 2; ++pass) {
+        if (tid == 0) carry_u = 0;
+        __syncthreads();
+        for (int base = 0; base < cap; base += 1024) {
+            const int i = base + tid;
+            const unsigned int v = pass == 0 ? hist[i] : (unsigned int)((bits[i] >> t) & 1u);
+            unsigned int x = v;
+            for (int off = 1; off < 32; off <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+            if (lane == 31) wsum[warp] = x;
+            __syncthreads();
+            if (tid < 32) {
+                unsigned int w = wsum[tid];
+                for (int off = 1; off < 32; off <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, w, off); if (tid >= off) w += y; }
+                wsum[tid] = w;
+            }
+            __syncthreads();
+            const unsigned int incl = carry_u + x + (warp ? wsum[warp - 1] : 0u);
+            (pass == 0 ? H : ctp)[i] = incl;
+            __syncthreads();
+            if (tid == 1023) carry_u = incl;
+            __syncthreads();
+        }
+    }
+    const unsigned int total_tp = ctp[cap - 1];
+    if (tid == 0) carry_max_s = 0.0;
+    __syncthreads();
+    double ap_local = 0.0;
+    double p11[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) p11[k] = 0.0;
+    for (int base = cap - 1024; base >= 0; base -= 1024) {
+        const int i = base + tid;
+        const bool tp = (bits[i] >> t) & 1u;
+        const double ct = (double)ctp[i];
+        const double prec = tp ? __ddiv_rn(ct, fmax((double)H[i], eps)) : 0.0;   // precision at this TP record
+        const double rec = npos > 0.0 ? __ddiv_rn(ct, npos) : 0.0;
+        double m = prec;
+        for (int off = 1; off < 32; off <<= 1) { const double y = __shfl_down_sync(0xffffffffu, m, off); if (lane + off < 32) m = fmax(m, y); }
+        if (lane == 0) wmax[warp] = m;
+        __syncthreads();
+        if (tid < 32) {
+            double w = wmax[tid];
+            for (int off = 1; off < 32; off <<= 1) { const double y = __shfl_down_sync(0xffffffffu, w, off); if (tid + off < 32) w = fmax(w, y); }
+            wmax[tid] = w;
+        }
+        __syncthreads();
+        const double carry = carry_max_s;
+        double env = fmax(m, carry);
+        if (warp < 31) env = fmax(env, wmax[warp + 1]);
+        if (tp) {
+            const double rec_prev = npos > 0.0 ? __ddiv_rn(ct - 1.0, npos) : 0.0;
+            ap_local += __dmul_rn(__dsub_rn(rec, rec_prev), env);
+            if (p.use07) {
+#pragma unroll
+                for (int k = 0; k < 11; ++k) if (rec >= k * 0.1) p11[k] = fmax(p11[k], prec);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) carry_max_s = fmax(carry, wmax[0]);
+        __syncthreads();
+    }
+    double res;
+    if (!p.use07) {
+        double a = ap_local;
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+        if (lane == 0) red[warp] = a;
+        __syncthreads();
+        if (tid < 32) {
+            double w = red[tid];
+            for (int off = 16; off > 0; off >>= 1) w += __shfl_down_sync(0xffffffffu, w, off);
+            if (tid == 0) red[0] = w;
+        }
+        __syncthreads();
+        res = red[0];
+    } else {
+        // VOC07: max precision over records with rec >= t; attained at a TP record unless t == 0, where the very
+        // first record counts too -- its precision is 1 if it is a TP (covered) else 0 (covered by the 0 init).
+        res = 0.0;
+        for (int k = 0; k < 11; ++k) {
+            double a = p11[k];
+            for (int off = 16; off > 0; off >>= 1) a = fmax(a, __shfl_down_sync(0xffffffffu, a, off));
+            __syncthreads();
+            if (lane == 0) red[warp] = a;
+            __syncthreads();
+            if (tid < 32) {
+                double w = red[tid];
+                for (int off = 16; off > 0; off >>= 1) w = fmax(w, __shfl_down_sync(0xffffffffu, w, off));
+                if (tid == 0) red[0] = w;
+            }
+            __syncthreads();
+            res = res + red[0] / 11.0;
+        }
+    }
+    if (tid == 0) {
+        const long long n = (long long)p.nvalid[c];
+        p.ap[(size_t)t * p.C + c] = n > 0 ? res : 0.0;
+        p.recall[(size_t)t * p.C + c] = (n > 0 && npos > 0.0) ? __ddiv_rn((double)total_tp, npos) : 0.0;
+        if (p.ndet && t == 0) p.ndet[c] = n;
+        if (p.overflow && p.tp_cnt[c] > cap) atomicExch(p.overflow, 1);
+    }
+}
+
+}  // namespace ovdet
+
+using namespace ovdet;
+
+static bool apc_cap_ok(int cap) { return cap >= 1024 && cap <= APC_MAXCAP && (cap & (cap - 1)) == 0; }
+
+extern "C" int ovdet_apc_collect(const float *rec_score, const uint8_t *rec_tp, int C, int64_t N, int cap,
+                                 uint32_t *tp_key, uint8_t *tp_bits, int32_t *tp_cnt, int64_t *nvalid, void *stream)
+{
+    OVDET_REQUIRE(C > 0 && N >= 0 && apc_cap_ok(cap), "bad size (cap must be a power of two in [1024, 16384])");
+    OVDET_REQUIRE(tp_key && tp_bits && tp_cnt && nvalid, "null pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    OVDET_CUDA_TRY(cudaMemsetAsync(tp_key, 0xFF, sizeof(uint32_t) * (size_t)C * cap, st));
+    OVDET_CUDA_TRY(cudaMemsetAsync(tp_bits, 0, (size_t)C * cap, st));
+    OVDET_CUDA_TRY(cudaMemsetAsync(tp_cnt, 0, sizeof(int32_t) * C, st));
+    OVDET_CUDA_TRY(cudaMemsetAsync(nvalid, 0, sizeof(int64_t) * C, st));
+    if (N == 0) return OVDET_OK;
+    OVDET_REQUIRE(rec_score && rec_tp, "null pointer");
+    int gx = (int)((N + APC_NT * 8 - 1) / (APC_NT * 8));
+    if (gx < 1) gx = 1;
+    apc_collect_kernel<<<dim3(gx, C), APC_NT, 0, st>>>(rec_score, rec_tp, N, cap, tp_key, tp_bits, tp_cnt,
+                                                      reinterpret_cast<unsigned long long *>(nvalid));
+    return launch_ok("apc_collect_kernel");
+}
+
+extern "C" int ovdet_apc_sort(uint32_t *tp_key, uint8_t *tp_bits, int C, int cap, void *stream)
+{
+    OVDET_REQUIRE(C > 0 && apc_cap_ok(cap), "bad size");
+    OVDET_REQUIRE(tp_key && tp_bits, "null pointer");
+    const size_t smem = (size_t)cap * 5;
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(apc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    apc_sort_kernel<<<C, 1024, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tp_key, tp_bits, cap);
+    return launch_ok("apc_sort_kernel");
+}
+
+extern "C" int ovdet_apc_hist(const float *rec_score, int C, int64_t N, const uint32_t *tp_key, int cap, uint32_t *hist, void *stream)
+{
+    OVDET_REQUIRE(C > 0 && N >= 0 && apc_cap_ok(cap), "bad size");
+    OVDET_REQUIRE(tp_key && hist, "null pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    OVDET_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)C * (cap + 1), st));
+    if (N == 0) return OVDET_OK;
+    OVDET_REQUIRE(rec_score, "null pointer");
+    const size_t smem = sizeof(uint32_t) * (2 * (size_t)cap + 1);
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(apc_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // enough CTAs to fill the chip a few times over, few enough that the histogram flush stays small
+    int per_sm = (int)(220 * 1024 / (smem + 1024));
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    int gx = (148 * per_sm + C - 1) / C;
+    const long long maxgx = (N + APC_NT * 4 - 1) / (APC_NT * 4);
+    if (gx > maxgx) gx = (int)maxgx;
+    if (gx < 1) gx = 1;
+    apc_hist_kernel<<<dim3(gx, C), APC_NT, smem, st>>>(rec_score, N, tp_key, cap, hist);
+    return launch_ok("apc_hist_kernel");
+}
+
+extern "C" int ovdet_apc_final(const uint8_t *tp_bits, const int32_t *tp_cnt, const uint32_t *hist, const int64_t *npos,
+                               const int64_t *nvalid, int C, int cap, int nthr, int use_07_metric,
+                               double *ap, double *recall, int64_t *n_det, int32_t *overflow, void *stream)
+{
+    OVDET_REQUIRE(C > 0 && apc_cap_ok(cap) && nthr >= 1 && nthr <= 8, "bad size");
+    OVDET_REQUIRE(tp_bits && tp_cnt && hist && npos && nvalid && ap && recall, "null pointer");
+    ApcFinalParams p;
+    p.tp_bits = tp_bits; p.tp_cnt = tp_cnt; p.hist = hist; p.npos = reinterpret_cast<const long long *>(npos);
+    p.nvalid = reinterpret_cast<const unsigned long long *>(nvalid); p.C = C; p.cap = cap; p.nthr = nthr; p.use07 = use_07_metric;
+    p.ap = ap; p.recall = recall; p.ndet = reinterpret_cast<long long *>(n_det); p.overflow = overflow;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (overflow) OVDET_CUDA_TRY(cudaMemsetAsync(overflow, 0, sizeof(int32_t), st));
+    const size_t smem = sizeof(unsigned int) * 2 * (size_t)cap;
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(apc_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    apc_final_kernel<<<dim3(C, nthr), 1024, smem, st>>>(p);
+    return launch_ok("apc_final_kernel");
+}

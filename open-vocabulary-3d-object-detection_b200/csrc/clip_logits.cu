@@ -122,7 +122,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v)
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-// 16-column variant for the tail chunk (BLOCK_N is a multiple of 16)
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr)
+{
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return __uint_as_float(r);
+}
+// 16-column variant (unused: tail chunks read 32 columns of the power-of-two allocation and mask)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v)
 {
     uint32_t r[16];
@@ -175,13 +182,15 @@ __device__ __forceinline__ float fast_exp2(float x)
     return y;
 }
 
-__global__ void __launch_bounds__(GM_THREADS, 1)
+__global__ void __launch_bounds__(GM_THREADS, 2)
 clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const LogitsParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) float2 stats[GM_MAX_NC][GM_M];   // (row max, row sum-exp) from every CTA of the cluster
+    __shared__ __align__(8) float2 part[2][GM_M];            // per-row partials of the two column groups
+    __shared__ __align__(16) float colscale[256 + 32];       // 1/|t_col| of this tile's columns (L2NORM only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -200,6 +209,7 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+    if (p.inv_nt) for (int c = threadIdx.x; c < 256 + 32; c += GM_THREADS) colscale[c] = __ldg(p.inv_nt + min(n0 + c, p.N - 1));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -241,79 +251,109 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
     }
 
-    // ===================== epilogue (warps 4..7) =====================
-    const bool epi = warp >= 4;
+    // ===================== epilogue: all 8 warps =====================
+    // TMEM lane quarter q = warp % 4 holds accumulator rows 32q..32q+31 (hardware rule: a warp may only
+    // touch lanes 32*(warpid%4)..+31).  Warps 4-7 take the even 32-column chunks of the tile, warps 0-3
+    // (free once their producer / MMA / alloc roles end) the odd ones; per-row partial (max, sum-exp) pairs
+    // are merged through shared memory, published to the whole cluster through DSMEM, and after one cluster
+    // barrier each warp normalises its own chunks straight out of TMEM.  Everything is in the log2 domain:
+    // y = logit * log2(e), p = 2^(y - max) / sum.
+    const int grp = (warp >> 2) ^ 1;                   // warps 4-7 -> group 0 (even chunks), warps 0-3 -> group 1
     const int row = (warp & 3) * 32 + lane;            // accumulator row == TMEM lane
     const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const float LOG2E = 1.4426950408889634f;
-    float rmax = -INFINITY, rsum = 0.f;
+    const bool row_ok = (m0 + row) < p.M;
     float rs = p.scale;
-    if (epi) {
-        if ((p.flags & OVDET_LOGITS_L2NORM) && (m0 + row) < p.M) rs *= __ldg(p.inv_nx + m0 + row);
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
-        // ---- pass 1: logits (optional store), running (max, sum-exp) of this tile
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-            float v[32];
-            const int w = min(32, p.block_n - c0);
-            if (w == 32) tmem_ld32(trow + (uint32_t)c0, v); else tmem_ld16(trow + (uint32_t)c0, v);
-            float cmax = -INFINITY;
+    if (p.inv_nx && row_ok) rs *= __ldg(p.inv_nx + m0 + row);
+    const float a2 = rs * LOG2E;
+    float rmax = -INFINITY, rsum = 0.f;
+
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    // ---- pass 1: running (max, sum-exp) over this warp's chunks (+ optional fp32 logits store)
+    for (int c0 = grp * 32; c0 < p.block_n; c0 += 64) {
+        const int w = min(32, p.block_n - c0);
+        const int nv = min(w, p.N - (n0 + c0));      // valid columns in this chunk (warp-uniform)
+        if (nv <= 0) break;
+        float v[32];
+        tmem_ld32(trow + (uint32_t)c0, v);   // the TMEM allocation is a power of two >= BLOCK_N: a 16-column tail chunk may read (and mask) 32
+        if (p.inv_nt) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int col = n0 + c0 + i;
-                if (i < w && col < p.N) {
-                    float x = v[i] * rs;
-                    if (p.flags & OVDET_LOGITS_L2NORM) x *= __ldg(p.inv_nt + col);
-                    v[i] = x;
-                    cmax = fmaxf(cmax, x);
-                } else v[i] = -INFINITY;
-            }
-            if (p.logits && (m0 + row) < p.M) {
-                float *o = p.logits + (size_t)(m0 + row) * p.ld_logits + n0 + c0;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) if (i < w && n0 + c0 + i < p.N) o[i] = v[i];
-            }
-            if (cmax > -INFINITY) {
-                const float nm = fmaxf(rmax, cmax);
-                float add = 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) add += fast_exp2((v[i] - nm) * LOG2E);
-                rsum = rsum * fast_exp2((rmax - nm) * LOG2E) + add;
-                rmax = nm;
+            for (int i = 0; i < 32; i += 4) {
+                const float4 cs = *reinterpret_cast<const float4 *>(colscale + c0 + i);
+                v[i] *= cs.x; v[i + 1] *= cs.y; v[i + 2] *= cs.z; v[i + 3] *= cs.w;
             }
         }
-        // ---- publish (max, sum) to every CTA of the cluster
-        for (int r = 0; r < p.nc; ++r) st_cluster_f32x2(&stats[rank][row], (uint32_t)r, rmax, rsum);
+        if (p.logits && row_ok) {
+            float *o = p.logits + (size_t)(m0 + row) * p.ld_logits + n0 + c0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < nv) o[i] = v[i] * rs;
+        }
+        float cmax = -INFINITY;
+        if (nv == 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] *= a2; cmax = fmaxf(cmax, v[i]); }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = i < nv ? v[i] * a2 : -INFINITY; cmax = fmaxf(cmax, v[i]); }
+        }
+        const float nm = fmaxf(rmax, cmax);
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) { acc0 += fast_exp2(v[i] - nm); acc1 += fast_exp2(v[i + 1] - nm); }
+        rsum = rsum * fast_exp2(rmax - nm) + (acc0 + acc1);
+        rmax = nm;
+    }
+    part[grp][row] = make_float2(rmax, rsum);
+    __syncthreads();
+    {   // merge the two column groups, publish to every CTA of the cluster (each group serves half of the ranks)
+        const float2 s0 = part[0][row], s1 = part[1][row];
+        const float m = fmaxf(s0.x, s1.x);
+        float sm = 0.f;
+        if (m > -INFINITY) sm = s0.y * fast_exp2(s0.x - m) + s1.y * fast_exp2(s1.x - m);
+        for (int r = grp; r < p.nc; r += 2) st_cluster_f32x2(&stats[rank][row], (uint32_t)r, m, sm);
     }
     cluster_sync_all();   // release/acquire: all stats visible cluster-wide
 
-    if (epi && (p.prob || p.objectness)) {
+    if (p.prob || p.objectness) {
         float gmax = -INFINITY;
         for (int r = 0; r < p.nc; ++r) gmax = fmaxf(gmax, stats[r][row].x);
         float gsum = 0.f;
         for (int r = 0; r < p.nc; ++r) {
             const float2 s = stats[r][row];
-            if (s.x > -INFINITY) gsum += s.y * fast_exp2((s.x - gmax) * LOG2E);
+            if (s.x > -INFINITY) gsum += s.y * fast_exp2(s.x - gmax);
         }
         const float inv = 1.f / gsum;
         // ---- pass 2: normalise out of TMEM into the padded shared tile (pipeline smem is idle now)
         const int tile_ld = p.block_n + 8;   // bf16 elements; +16 B keeps the 16-byte row writes conflict-free
         __nv_bfloat16 *tile = reinterpret_cast<__nv_bfloat16 *>(smem);
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-            float v[32];
+        const int obj_c = p.N - 1 - n0;      // tile column holding the background class, if in this tile
+        if (p.objectness && grp == 0 && obj_c >= 0 && obj_c < p.block_n) {   // warp-uniform: one extra 1-column TMEM read
+            float x = tmem_ld1(trow + (uint32_t)obj_c);
+            if (p.inv_nt) x *= colscale[obj_c];
+            if (row_ok) p.objectness[m0 + row] = 1.f - fast_exp2(x * a2 - gmax) * inv;
+        }
+        for (int c0 = grp * 32; c0 < p.block_n; c0 += 64) {
             const int w = min(32, p.block_n - c0);
-            if (w == 32) tmem_ld32(trow + (uint32_t)c0, v); else tmem_ld16(trow + (uint32_t)c0, v);
+            const int nv = min(w, p.N - (n0 + c0));
+            float v[32];
+            if (nv > 0) {
+                tmem_ld32(trow + (uint32_t)c0, v);
+                if (p.inv_nt) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int col = n0 + c0 + i;
-                float pr = 0.f;
-                if (i < w && col < p.N) {
-                    float x = v[i] * rs;
-                    if (p.flags & OVDET_LOGITS_L2NORM) x *= __ldg(p.inv_nt + col);
-                    pr = fast_exp2((x - gmax) * LOG2E) * inv;
-                    if (col == p.N - 1 && p.objectness && (m0 + row) < p.M) p.objectness[m0 + row] = 1.f - pr;
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 cs = *reinterpret_cast<const float4 *>(colscale + c0 + i);
+                        v[i] *= cs.x; v[i + 1] *= cs.y; v[i + 2] *= cs.z; v[i + 3] *= cs.w;
+                    }
                 }
-                v[i] = pr;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float pr = fast_exp2(v[i] * a2 - gmax) * inv;
+                    v[i] = (nv == 32 || i < nv) ? pr : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
             }
             if (p.prob) {
 #pragma unroll
@@ -328,10 +368,9 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         }
         if (p.prob) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+            __syncthreads();
             const int pieces = p.block_n / 8;                // 16-byte pieces per row
-            const int et = threadIdx.x - 128;
-            for (int i = et; i < GM_M * pieces; i += 128) {
+            for (int i = threadIdx.x; i < GM_M * pieces; i += GM_THREADS) {
                 const int r = i / pieces, c8 = (i - r * pieces) * 8;
                 const int grow = m0 + r, gcol = n0 + c8;
                 if (grow < p.M && gcol < p.ld_prob) {
@@ -413,7 +452,7 @@ extern "C" int ovdet_clip_logits_bf16(const void *x, const void *text, int M, in
     if (bn < 16) bn = 16;
     LogitsParams p;
     p.M = M; p.N = N; p.K = K; p.block_n = bn; p.nc = nc; p.num_kb = K / GM_K;
-    p.stages = bn <= 160 ? 3 : 4;
+    p.stages = 2;   // two CTAs are co-resident per SM (4 stages in flight), one in its mainloop while the other normalises
     if (p.stages > p.num_kb) p.stages = p.num_kb;
     p.tmem_cols = 32; while (p.tmem_cols < bn) p.tmem_cols <<= 1;
     p.flags = flags; p.scale = scale;

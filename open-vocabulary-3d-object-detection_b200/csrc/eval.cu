@@ -48,7 +48,15 @@ __device__ __forceinline__ double exact_iou(const float *c1, const float *c2, V2
         vol[w] = A::mul(A::mul(e[0], e[1]), e[2]);
     }
     double ia = 0.0;
-    if (h > 0.0 || want2d) {
+    // disjoint BEV bounding rectangles -> the clip is empty -> area 0 exactly; skip it
+    bool bev = true;
+#pragma unroll
+    for (int a = 0; a < 3; a += 2) {
+        const float lo1 = fminf(fminf(c1[a], c1[3 + a]), fminf(c1[6 + a], c1[9 + a])), hi1 = fmaxf(fmaxf(c1[a], c1[3 + a]), fmaxf(c1[6 + a], c1[9 + a]));
+        const float lo2 = fminf(fminf(c2[a], c2[3 + a]), fminf(c2[6 + a], c2[9 + a])), hi2 = fmaxf(fmaxf(c2[a], c2[3 + a]), fmaxf(c2[6 + a], c2[9 + a]));
+        if (hi1 < lo2 || hi2 < lo1) bev = false;
+    }
+    if ((h > 0.0 && bev) || want2d) {
         double s[8], c[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {

@@ -17,11 +17,13 @@
 // Results go to a shared [TQ][TG] tile and leave with coalesced row stores.
 // The pair work is ~60 (skip) to ~1200 (clip) instructions against 4 B written,
 // i.e. issue-bound, not HBM-bound: see DESIGN.md for the roofline used.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ovdet {
 
-constexpr int TQ = 32;    // query rows per CTA
+constexpr int TQ_MAX = 32;  // query rows per CTA (template parameter TQ: 32, 16 or 8)
 constexpr int TG = 64;    // GT columns per chunk
 constexpr int NT = 256;   // threads per CTA
 constexpr int NF = 17;    // features per box
@@ -96,28 +98,35 @@ __device__ __forceinline__ void stage_boxes(const float *__restrict__ g, int n, 
 
 struct PairTerms { float h, nonrot, encl, sumv; };
 
-__device__ __forceinline__ PairTerms pair_terms(const float *f1, int r, const float *f2, int c)
+// the 13 per-box features the pair maths needs, as registers
+struct BoxF { float ytop, ybot, x1, x3, z1, z3, vol, mn[3], mx[3]; };
+
+__device__ __forceinline__ BoxF load_boxf(const float *f, int i, int stride)
+{
+    BoxF b;
+    b.ytop = f[F_YTOP * stride + i]; b.ybot = f[F_YBOT * stride + i];
+    b.x1 = f[(F_RX + 1) * stride + i]; b.x3 = f[(F_RX + 3) * stride + i];
+    b.z1 = f[(F_RZ + 1) * stride + i]; b.z3 = f[(F_RZ + 3) * stride + i];
+    b.vol = f[F_VOL * stride + i];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { b.mn[a] = f[(F_MN + a) * stride + i]; b.mx[a] = f[(F_MX + a) * stride + i]; }
+    return b;
+}
+
+__device__ __forceinline__ PairTerms pair_terms(const BoxF &q, const BoxF &g)
 {
     using A = Ar<float>;
     PairTerms t;
-    const float ytop = fminf(f1[F_YTOP * TQ + r], f2[F_YTOP * TG + c]);
-    const float ybot = fmaxf(f1[F_YBOT * TQ + r], f2[F_YBOT * TG + c]);
-    t.h = fmaxf(A::sub(ytop, ybot), 0.f);
+    t.h = fmaxf(A::sub(fminf(q.ytop, g.ytop), fmaxf(q.ybot, g.ybot)), 0.f);
     // prefilter: rect points 1 and 3 as lt / rb (box_util.py:557-560)
-    const float w0 = fmaxf(A::sub(fminf(f1[(F_RX + 3) * TQ + r], f2[(F_RX + 3) * TG + c]),
-                                  fmaxf(f1[(F_RX + 1) * TQ + r], f2[(F_RX + 1) * TG + c])), 0.f);
-    const float w1 = fmaxf(A::sub(fminf(f1[(F_RZ + 3) * TQ + r], f2[(F_RZ + 3) * TG + c]),
-                                  fmaxf(f1[(F_RZ + 1) * TQ + r], f2[(F_RZ + 1) * TG + c])), 0.f);
+    const float w0 = fmaxf(A::sub(fminf(q.x3, g.x3), fmaxf(q.x1, g.x1)), 0.f);
+    const float w1 = fmaxf(A::sub(fminf(q.z3, g.z3), fmaxf(q.z1, g.z1)), 0.f);
     t.nonrot = A::mul(w0, w1);
     float d[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const float mn = fminf(f1[(F_MN + a) * TQ + r], f2[(F_MN + a) * TG + c]);
-        const float mx = fmaxf(f1[(F_MX + a) * TQ + r], f2[(F_MX + a) * TG + c]);
-        d[a] = fabsf(A::sub(mx, mn));
-    }
+    for (int a = 0; a < 3; ++a) d[a] = fabsf(A::sub(fmaxf(q.mx[a], g.mx[a]), fminf(q.mn[a], g.mn[a])));
     t.encl = A::mul(A::mul(d[0], d[1]), d[2]);
-    t.sumv = A::add(f1[F_VOL * TQ + r], f2[F_VOL * TG + c]);
+    t.sumv = A::add(q.vol, g.vol);
     return t;
 }
 
@@ -137,16 +146,19 @@ __device__ __forceinline__ float finish_pair(const PairTerms &t, float area, boo
     return g;
 }
 
-template <typename ClipT>
+// ClipT = float: all-fp32 clip (torch path); double: Cython arithmetic.  PB = threads that drain the clip queue
+// (their Sutherland-Hodgman scratch is the largest shared-memory consumer: 128 B (fp32) / 256 B (fp64) per thread).
+template <typename ClipT, int PB, int TQ>
 __global__ void __launch_bounds__(NT) giou3d_kernel(GiouParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // carve: f1[NF*TQ] f2[NF*TG] tile[TQ*TG] raw[TG*24] queue[TQ*TG u16] scratch[2*SH_MAXV*NT V2<ClipT>]
+    // carve: f1[NF*TQ] f2[NF*TG] tile[TQ*TG] raw[(TQ+TG)*24] queue[TQ*TG u16] scratch[2*SH_MAXV*PB V2<ClipT>]
     float *f1 = reinterpret_cast<float *>(smem_raw);
     float *f2 = f1 + NF * TQ;
     float *tile = f2 + NF * TG;
-    float *raw = tile + TQ * TG;
-    unsigned short *queue = reinterpret_cast<unsigned short *>(raw + TG * 24);
+    float *raw1 = tile + TQ * TG;
+    float *raw2 = raw1 + TQ * 24;
+    unsigned short *queue = reinterpret_cast<unsigned short *>(raw2 + TG * 24);
     V2<ClipT> *scratch = reinterpret_cast<V2<ClipT> *>(queue + TQ * TG);
     __shared__ int qcount;
 
@@ -163,79 +175,84 @@ __global__ void __launch_bounds__(NT) giou3d_kernel(GiouParams p)
     const bool vec1 = ((reinterpret_cast<uintptr_t>(p.c1) & 15) == 0);
     const bool vec2 = ((reinterpret_cast<uintptr_t>(p.c2) & 15) == 0);
     const bool vec_out = p.out && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (p.K2 % 4 == 0);
-
-    // ---- query tile features
-    stage_boxes(p.c1 + ((size_t)b * p.K1 + q0) * 24, nq, raw, vec1);
-    __syncthreads();
-    if (threadIdx.x < nq) box_features(raw + threadIdx.x * 24, f1 + threadIdx.x, TQ);
-    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (int g0 = 0; g0 < p.K2; g0 += TG) {
         const int ng = min(TG, p.K2 - g0);
-        stage_boxes(p.c2 + ((size_t)b * p.K2 + g0) * 24, ng, raw, vec2);
+        // ---- stage the query tile (first chunk only) and this GT chunk with one barrier, features with one more
+        if (g0 == 0) stage_boxes(p.c1 + ((size_t)b * p.K1 + q0) * 24, nq, raw1, vec1);
+        stage_boxes(p.c2 + ((size_t)b * p.K2 + g0) * 24, ng, raw2, vec2);
         if (threadIdx.x == 0) qcount = 0;
         __syncthreads();
-        if (threadIdx.x < ng) box_features(raw + threadIdx.x * 24, f2 + threadIdx.x, TG);
+        if (threadIdx.x < TG) { if (threadIdx.x < ng) box_features(raw2 + threadIdx.x * 24, f2 + threadIdx.x, TG); }
+        else if (g0 == 0 && threadIdx.x - TG < nq) box_features(raw1 + (threadIdx.x - TG) * 24, f1 + (threadIdx.x - TG), TQ);
         __syncthreads();
 
-        // ---- phase A
-        const int npairs = nq * ng;
-        for (int base = 0; base < npairs; base += NT) {
-            const int pidx = base + threadIdx.x;
-            bool need_clip = false;
-            int r = 0, c = 0;
-            if (pidx < npairs) {
-                r = pidx / ng;
-                c = pidx - r * ng;
-                const int k2 = g0 + c;
-                const bool valid = k2 < nk;
-                PairTerms t = pair_terms(f1, r, f2, c);
-                if (!valid) t.nonrot = 0.f;  // box_util.py:562-564
-                float area = 0.f;
-                if (rotated) {
-                    need_clip = (k2 < clip_lim) && !(prefilter && t.nonrot == 0.f);
-                } else {
-                    area = t.nonrot;
+        // ---- phase A: warp w owns rows w*4 .. w*4+3, lane l owns columns l and l+32 (features in registers)
+        BoxF gf[2];
+        bool gvalid[2], gin[2], gclip[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = lane + 32 * h;
+            gin[h] = c < ng;
+            gf[h] = load_boxf(f2, gin[h] ? c : 0, TG);
+            gvalid[h] = (g0 + c) < nk;
+            gclip[h] = (g0 + c) < clip_lim;
+        }
+#pragma unroll
+        for (int rr = 0; rr < TQ / (NT / 32); ++rr) {
+            const int r = warp * (TQ / (NT / 32)) + rr;
+            if (r >= nq) break;   // warp-uniform
+            const BoxF qf = load_boxf(f1, r, TQ);   // broadcast loads
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                bool need_clip = false;
+                if (gin[h]) {
+                    PairTerms t = pair_terms(qf, gf[h]);
+                    if (!gvalid[h]) t.nonrot = 0.f;   // box_util.py:562-564
+                    float area = 0.f;
+                    if (rotated) need_clip = gclip[h] && !(prefilter && t.nonrot == 0.f);
+                    else area = t.nonrot;
+                    if (!need_clip) tile[r * TG + lane + 32 * h] = finish_pair(t, area, gvalid[h], has_nums, inter_only);
                 }
-                if (!need_clip) tile[r * TG + c] = finish_pair(t, area, valid, has_nums, inter_only);
-            }
-            // warp-aggregated push
-            const unsigned m = __ballot_sync(0xffffffffu, need_clip);
-            if (m) {
-                const int lane = threadIdx.x & 31;
-                int basepos = 0;
-                if (lane == 0) basepos = atomicAdd(&qcount, __popc(m));
-                basepos = __shfl_sync(0xffffffffu, basepos, 0);
-                if (need_clip) queue[basepos + __popc(m & ((1u << lane) - 1))] = (unsigned short)(r * TG + c);
+                const unsigned m = __ballot_sync(0xffffffffu, need_clip);   // warp-aggregated push
+                if (m) {
+                    int basepos = 0;
+                    if (lane == 0) basepos = atomicAdd(&qcount, __popc(m));
+                    basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                    if (need_clip) queue[basepos + __popc(m & ((1u << lane) - 1))] = (unsigned short)(r * TG + lane + 32 * h);
+                }
             }
         }
         __syncthreads();
 
-        // ---- phase B
+        // ---- phase B: drain the clip queue, one Sutherland-Hodgman clip per lane
         const int nclip = qcount;
-        V2<ClipT> *bufA = scratch + threadIdx.x;
-        V2<ClipT> *bufB = scratch + SH_MAXV * NT + threadIdx.x;
-        for (int qi = threadIdx.x; qi < nclip; qi += NT) {
-            const int code = queue[qi];
-            const int r = code / TG, c = code - r * TG;
-            ClipT s[8], cl[8];
+        if (threadIdx.x < PB) {
+            V2<ClipT> *bufA = scratch + threadIdx.x;
+            V2<ClipT> *bufB = scratch + SH_MAXV * PB + threadIdx.x;
+            for (int qi = threadIdx.x; qi < nclip; qi += PB) {
+                const int code = queue[qi];
+                const int r = code / TG, c = code - r * TG;
+                ClipT s[8], cl[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                s[2 * i] = (ClipT)f1[(F_RX + i) * TQ + r];
-                s[2 * i + 1] = (ClipT)f1[(F_RZ + i) * TQ + r];
-                cl[2 * i] = (ClipT)f2[(F_RX + i) * TG + c];
-                cl[2 * i + 1] = (ClipT)f2[(F_RZ + i) * TG + c];
+                for (int i = 0; i < 4; ++i) {
+                    s[2 * i] = (ClipT)f1[(F_RX + i) * TQ + r];
+                    s[2 * i + 1] = (ClipT)f1[(F_RZ + i) * TQ + r];
+                    cl[2 * i] = (ClipT)f2[(F_RX + i) * TG + c];
+                    cl[2 * i + 1] = (ClipT)f2[(F_RZ + i) * TG + c];
+                }
+                float area;
+                if constexpr (sizeof(ClipT) == 8) {
+                    const int n = sh_clip_quads<double, PB>(s, cl, bufA, bufB);
+                    area = area_cython<PB>(bufB, n);
+                } else {
+                    const int n = sh_clip_quads<float, PB>(s, cl, bufA, bufB);
+                    area = area_f32<PB>(bufB, n);
+                }
+                const PairTerms t = pair_terms(load_boxf(f1, r, TQ), load_boxf(f2, c, TG));
+                tile[r * TG + c] = finish_pair(t, area, true, has_nums, inter_only);
             }
-            float area;
-            if constexpr (sizeof(ClipT) == 8) {
-                const int n = sh_clip_quads<double, NT>(s, cl, bufA, bufB);
-                area = area_cython<NT>(bufB, n);
-            } else {
-                const int n = sh_clip_quads<float, NT>(s, cl, bufA, bufB);
-                area = area_f32<NT>(bufB, n);
-            }
-            const PairTerms t = pair_terms(f1, r, f2, c);
-            tile[r * TG + c] = finish_pair(t, area, true, has_nums, inter_only);
         }
         __syncthreads();
 
@@ -243,63 +260,84 @@ __global__ void __launch_bounds__(NT) giou3d_kernel(GiouParams p)
         if (p.epi.cost) {
             const MatcherEpi &e = p.epi;
             using A = Ar<float>;
-            for (int i = threadIdx.x; i < nq * ng; i += NT) {
-                const int r = i / ng, c = i - r * ng;
-                const size_t q = (size_t)b * p.K1 + q0 + r, g = (size_t)b * p.K2 + g0 + c;
-                const size_t oidx = q * p.K2 + g0 + c;
-                long long lab = e.labels[g];
-                lab = lab < 0 ? 0 : (lab >= e.C ? e.C - 1 : lab);
-                const float cm = -__ldg(e.prob + q * e.C + lab);
+            for (int r = warp; r < nq; r += NT / 32) {
+                const size_t q = (size_t)b * p.K1 + q0 + r;
                 const float om = -__ldg(e.obj + q);
-                float cen;
-                if (e.center_dist) cen = __ldg(e.center_dist + oidx);
-                else {
-                    const float d0 = fabsf(A::sub(__ldg(e.cq + 3 * q), __ldg(e.cg + 3 * g)));
-                    const float d1 = fabsf(A::sub(__ldg(e.cq + 3 * q + 1), __ldg(e.cg + 3 * g + 1)));
-                    const float d2 = fabsf(A::sub(__ldg(e.cq + 3 * q + 2), __ldg(e.cg + 3 * g + 2)));
-                    cen = A::add(A::add(d0, d1), d2);
+                for (int c = lane; c < ng; c += 32) {
+                    const size_t g = (size_t)b * p.K2 + g0 + c;
+                    const size_t oidx = q * p.K2 + g0 + c;
+                    long long lab = e.labels[g];
+                    lab = lab < 0 ? 0 : (lab >= e.C ? e.C - 1 : lab);
+                    const float cm = -__ldg(e.prob + q * e.C + lab);
+                    float cen;
+                    if (e.center_dist) cen = __ldg(e.center_dist + oidx);
+                    else {
+                        const float d0 = fabsf(A::sub(__ldg(e.cq + 3 * q), __ldg(e.cg + 3 * g)));
+                        const float d1 = fabsf(A::sub(__ldg(e.cq + 3 * q + 1), __ldg(e.cg + 3 * g + 1)));
+                        const float d2 = fabsf(A::sub(__ldg(e.cq + 3 * q + 2), __ldg(e.cg + 3 * g + 2)));
+                        cen = A::add(A::add(d0, d1), d2);
+                    }
+                    const float gm = -tile[r * TG + c];
+                    e.cost[oidx] = A::add(A::add(A::add(A::mul(e.wc, cm), A::mul(e.wo, om)), A::mul(e.wce, cen)), A::mul(e.wg, gm));
                 }
-                const float gm = -tile[r * TG + c];
-                e.cost[oidx] = A::add(A::add(A::add(A::mul(e.wc, cm), A::mul(e.wo, om)), A::mul(e.wce, cen)), A::mul(e.wg, gm));
             }
         }
         // ---- coalesced store of the [nq][ng] tile
-        float *o = p.out + ((size_t)b * p.K1 + q0) * p.K2 + g0;
-        if (!p.out) {
-        } else if (vec_out && (ng % 4 == 0)) {
-            const int n4 = ng / 4;
-            for (int i = threadIdx.x; i < nq * n4; i += NT) {
-                const int r = i / n4, c4 = i - r * n4;
-                const float4 v = *reinterpret_cast<const float4 *>(tile + r * TG + 4 * c4);
-                *reinterpret_cast<float4 *>(o + (size_t)r * p.K2 + 4 * c4) = v;
-            }
-        } else {
-            for (int i = threadIdx.x; i < nq * ng; i += NT) {
-                const int r = i / ng, c = i - r * ng;
-                o[(size_t)r * p.K2 + c] = tile[r * TG + c];
+        if (p.out) {
+            float *o = p.out + ((size_t)b * p.K1 + q0) * p.K2 + g0;
+            if (vec_out && ng == TG) {
+                for (int i = threadIdx.x; i < nq * (TG / 4); i += NT) {
+                    const int r = i / (TG / 4), c4 = i % (TG / 4);
+                    *reinterpret_cast<float4 *>(o + (size_t)r * p.K2 + 4 * c4) = *reinterpret_cast<const float4 *>(tile + r * TG + 4 * c4);
+                }
+            } else {
+                for (int r = warp; r < nq; r += NT / 32)
+                    for (int c = lane; c < ng; c += 32) o[(size_t)r * p.K2 + c] = tile[r * TG + c];
             }
         }
         __syncthreads();
     }
 }
 
-template <typename ClipT> static size_t giou_smem_bytes()
+template <typename ClipT, int PB, int TQ> static size_t giou_smem_bytes()
 {
-    return sizeof(float) * (NF * TQ + NF * TG + TQ * TG + TG * 24) + sizeof(unsigned short) * TQ * TG +
-           sizeof(V2<ClipT>) * 2 * SH_MAXV * NT;
+    return sizeof(float) * (NF * TQ + NF * TG + TQ * TG + (TQ + TG) * 24) + sizeof(unsigned short) * TQ * TG +
+           sizeof(V2<ClipT>) * 2 * SH_MAXV * PB;
 }
 
-template <typename ClipT> static int launch_giou(const GiouParams &p, cudaStream_t st)
+template <typename ClipT, int PB, int TQ> static int launch_giou_tq(GiouParams p, cudaStream_t st)
 {
-    const size_t smem = giou_smem_bytes<ClipT>();
+    p.tiles_per_b = (p.K1 + TQ - 1) / TQ;
+    const size_t smem = giou_smem_bytes<ClipT, PB, TQ>();
     static bool attr_set = false;
     if (!attr_set) {
-        OVDET_CUDA_TRY(cudaFuncSetAttribute(giou3d_kernel<ClipT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(giou3d_kernel<ClipT, PB, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const long long grid = (long long)p.B * p.tiles_per_b;
-    giou3d_kernel<ClipT><<<(unsigned)grid, NT, smem, st>>>(p);
+    giou3d_kernel<ClipT, PB, TQ><<<(unsigned)grid, NT, smem, st>>>(p);
     return launch_ok("giou3d_kernel");
+}
+
+
+// Tile height by grid size: this workload is tiny (config 1 = 64 x 128 x 64 pairs), so latency, not
+// throughput, decides; use the smallest row tile that still leaves every SM several CTAs deep.
+template <typename ClipT, int PB> static int launch_giou(const GiouParams &p, cudaStream_t st)
+{
+    const long long t32 = (long long)p.B * ((p.K1 + 31) / 32);
+    OVDET_REQUIRE((long long)p.B * ((p.K1 + 7) / 8) < 2147483647LL, "grid too large");
+    static int force = -1;   // OVDET_GIOU_TQ=8|16|32 overrides the heuristic (profiling experiments)
+    if (force < 0) { const char *e = getenv("OVDET_GIOU_TQ"); force = e ? atoi(e) : 0; }
+    if (force == 32) return launch_giou_tq<ClipT, PB, 32>(p, st);
+    if (force == 16) return launch_giou_tq<ClipT, PB, 16>(p, st);
+    if (force == 8) return launch_giou_tq<ClipT, PB, 8>(p, st);
+    // measured on B200 (profiles/r1_notes.md): when few pairs reach the clipper (prefilter on) the per-CTA staging of
+    // the GT chunk dominates and 32-row tiles win (10.9 us vs 17.3 us at config 1); when every pair is clipped
+    // (no prefilter) small tiles spread the clip work better (20 vs 15 Gpairs/s).
+    const bool clip_heavy = (p.flags & OVDET_GIOU_ROTATED) && !(p.flags & OVDET_GIOU_PREFILTER);
+    if (clip_heavy && t32 < 148 * 8) return launch_giou_tq<ClipT, PB, 8>(p, st);
+    if (t32 * 2 < 148) return launch_giou_tq<ClipT, PB, 16>(p, st);
+    return launch_giou_tq<ClipT, PB, 32>(p, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -396,8 +434,8 @@ static int matcher_cost_elementwise(const MatcherEpi &e, const float *gious, int
 
 int giou3d_launch(const GiouParams &p, cudaStream_t st)
 {
-    if ((p.flags & OVDET_GIOU_ROTATED) && (p.flags & OVDET_GIOU_CLIP_F64)) return launch_giou<double>(p, st);
-    return launch_giou<float>(p, st);
+    if ((p.flags & OVDET_GIOU_ROTATED) && (p.flags & OVDET_GIOU_CLIP_F64)) return launch_giou<double, 128>(p, st);
+    return launch_giou<float, 256>(p, st);
 }
 
 }  // namespace ovdet
@@ -416,8 +454,7 @@ extern "C" int ovdet_giou3d_f32(const float *corners1, const float *corners2, co
     GiouParams p;
     p.c1 = corners1; p.c2 = corners2; p.nums_k2 = nums_k2; p.out = out;
     p.B = B; p.K1 = K1; p.K2 = K2; p.k2_cap = k2_cap; p.flags = flags;
-    p.tiles_per_b = (K1 + TQ - 1) / TQ;
-    OVDET_REQUIRE((long long)B * p.tiles_per_b < 2147483647LL, "grid too large");
+    p.tiles_per_b = 0;
     return giou3d_launch(p, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -442,7 +479,7 @@ extern "C" int ovdet_matcher_cost_f32(const float *sem_cls_prob, const float *ob
     GiouParams p;
     p.c1 = corners1; p.c2 = corners2; p.nums_k2 = nactual_gt; p.out = gious_out;
     p.B = B; p.K1 = Q; p.K2 = G; p.k2_cap = k2_cap; p.flags = giou_flags & ~OVDET_GIOU_INTER_ONLY;
-    p.tiles_per_b = (Q + TQ - 1) / TQ;
+    p.tiles_per_b = 0;
     p.epi = e;
     return giou3d_launch(p, st);
 }

@@ -22,10 +22,21 @@ struct LsapParams {
     int64_t *inds;
     float *mask;
     int32_t *col_to_row;
-    int B, Q, G, M;  // M = max(Q, G): capacity of the shared arrays
+    int B, Q, G, M;   // M = max(Q, G): capacity of the per-column arrays
+    int stage_cost;   // 1: the [min(Q,n), max(Q,n)] cost slab is staged (transposed if needed) in shared memory
 };
 
-__global__ void __launch_bounds__(32) lsap_kernel(LsapParams p)
+constexpr int LS_NT = 256;
+
+struct Cand { double v; int j; int asg; };
+__device__ __forceinline__ bool cand_less(const Cand &a, const Cand &b)
+{   // lowest reduced cost, then unassigned column, then lowest index
+    return a.v < b.v || (a.v == b.v && (a.asg < b.asg || (a.asg == b.asg && a.j < b.j)));
+}
+
+// One CTA (8 warps) per sample.  Thread t owns columns t, t+256, ...: it relaxes them, the per-warp argmin
+// goes through shuffles, the 8 warp winners through a double-buffered shared array (one barrier per Dijkstra step).
+__global__ void __launch_bounds__(LS_NT) lsap_kernel(LsapParams p)
 {
     extern __shared__ __align__(16) unsigned char sm[];
     double *u = reinterpret_cast<double *>(sm);      // [M] row duals
@@ -36,75 +47,87 @@ __global__ void __launch_bounds__(32) lsap_kernel(LsapParams p)
     int *col4row = row4col + p.M;                     // [M]
     unsigned char *SR = reinterpret_cast<unsigned char *>(col4row + p.M);  // [M]
     unsigned char *SC = SR + p.M;                                         // [M]
+    float *sc = reinterpret_cast<float *>(sm + (((size_t)p.M * (3 * sizeof(double) + 3 * sizeof(int) + 2)) + 15 & ~(size_t)15));
+    __shared__ Cand wbest[2][LS_NT / 32];
 
-    const int b = blockIdx.x;
-    const int lane = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long nn = p.nactual ? p.nactual[b] : p.G;
     const int n = nn < 0 ? 0 : (nn > p.G ? p.G : (int)nn);
     const float *cb = p.cost + (size_t)b * p.Q * p.G;
 
-    for (int q = lane; q < p.Q; q += 32) { p.inds[(size_t)b * p.Q + q] = 0; p.mask[(size_t)b * p.Q + q] = 0.f; }
-    if (p.col_to_row) for (int g = lane; g < p.G; g += 32) p.col_to_row[(size_t)b * p.G + g] = -1;
+    for (int q = tid; q < p.Q; q += LS_NT) { p.inds[(size_t)b * p.Q + q] = 0; p.mask[(size_t)b * p.Q + q] = 0.f; }
+    if (p.col_to_row) for (int g = tid; g < p.G; g += LS_NT) p.col_to_row[(size_t)b * p.G + g] = -1;
     if (n == 0) return;
 
     const bool transposed = n < p.Q;           // scipy: transpose when nc < nr
     const int nr = transposed ? n : p.Q;
     const int nc = transposed ? p.Q : n;
+    const int ldc = nc + 1;
+    if (p.stage_cost) {   // coalesced global read, conflict-free (odd stride) shared write
+        for (int idx = tid; idx < p.Q * n; idx += LS_NT) {
+            const int q = idx / n, g = idx - q * n;
+            const float c = __ldg(cb + (size_t)q * p.G + g);
+            if (transposed) sc[g * ldc + q] = c; else sc[q * ldc + g] = c;
+        }
+    }
     auto C = [&](int i, int j) -> double {
+        if (p.stage_cost) return (double)sc[i * ldc + j];
         return transposed ? (double)__ldg(cb + (size_t)j * p.G + i) : (double)__ldg(cb + (size_t)i * p.G + j);
     };
+    for (int i = tid; i < nr; i += LS_NT) { u[i] = 0.0; col4row[i] = -1; }
+    for (int j = tid; j < nc; j += LS_NT) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
+    __syncthreads();
 
-    for (int i = lane; i < nr; i += 32) { u[i] = 0.0; col4row[i] = -1; }
-    for (int j = lane; j < nc; j += 32) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
-    __syncwarp();
-
+    int buf = 0;
     for (int cur = 0; cur < nr; ++cur) {
-        for (int i = lane; i < nr; i += 32) SR[i] = 0;
-        for (int j = lane; j < nc; j += 32) { SC[j] = 0; spc[j] = INFINITY; }
-        __syncwarp();
+        for (int i = tid; i < nr; i += LS_NT) SR[i] = 0;
+        for (int j = tid; j < nc; j += LS_NT) { SC[j] = 0; spc[j] = INFINITY; }
+        __syncthreads();
         double minVal = 0.0;
         int i = cur, sink = -1;
         while (sink == -1) {
-            if (lane == 0) SR[i] = 1;
+            if (tid == 0) SR[i] = 1;
             const double ui = u[i];
-            double best = INFINITY;
-            int bestj = 0x7fffffff, bestasg = 1;
-            for (int j = lane; j < nc; j += 32) {
+            Cand best{INFINITY, 0x7fffffff, 1};
+            for (int j = tid; j < nc; j += LS_NT) {   // own columns only: spc/path/SC[j] are private to this thread
                 if (SC[j]) continue;
                 const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, C(i, j)), ui), v[j]);
                 double s = spc[j];
                 if (r < s) { s = r; spc[j] = r; path[j] = i; }
-                const int asg = row4col[j] != -1;
-                if (s < best || (s == best && (asg < bestasg || (asg == bestasg && j < bestj)))) {
-                    best = s; bestj = j; bestasg = asg;
-                }
+                const Cand c{s, j, row4col[j] != -1};
+                if (cand_less(c, best)) best = c;
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-                const int oj = __shfl_xor_sync(0xffffffffu, bestj, off);
-                const int oa = __shfl_xor_sync(0xffffffffu, bestasg, off);
-                if (ob < best || (ob == best && (oa < bestasg || (oa == bestasg && oj < bestj)))) {
-                    best = ob; bestj = oj; bestasg = oa;
-                }
+                Cand o;
+                o.v = __shfl_xor_sync(0xffffffffu, best.v, off);
+                o.j = __shfl_xor_sync(0xffffffffu, best.j, off);
+                o.asg = __shfl_xor_sync(0xffffffffu, best.asg, off);
+                if (cand_less(o, best)) best = o;
             }
-            if (bestj == 0x7fffffff || best == INFINITY) { sink = -2; break; }  // infeasible (non-finite costs)
-            minVal = best;
-            const int j = bestj;
-            if (lane == 0) SC[j] = 1;
+            if (lane == 0) wbest[buf][warp] = best;
+            __syncthreads();
+            best = wbest[buf][0];
+#pragma unroll
+            for (int w = 1; w < LS_NT / 32; ++w) { const Cand o = wbest[buf][w]; if (cand_less(o, best)) best = o; }
+            buf ^= 1;
+            if (best.j == 0x7fffffff || best.v == INFINITY) { sink = -2; break; }   // infeasible (non-finite costs)
+            minVal = best.v;
+            const int j = best.j;
+            if ((j % LS_NT) == tid) SC[j] = 1;     // the owner marks its column scanned
             if (row4col[j] == -1) sink = j; else i = row4col[j];
-            __syncwarp();
         }
+        __syncthreads();
         if (sink < 0) break;
         // dual updates (Crouse 2016, step 4)
-        if (lane == 0) u[cur] = __dadd_rn(u[cur], minVal);
-        for (int r = lane; r < nr; r += 32)
+        if (tid == 0) u[cur] = __dadd_rn(u[cur], minVal);
+        for (int r = tid; r < nr; r += LS_NT)
             if (SR[r] && r != cur) u[r] = __dadd_rn(u[r], __dsub_rn(minVal, spc[col4row[r]]));
-        for (int j = lane; j < nc; j += 32)
+        for (int j = tid; j < nc; j += LS_NT)
             if (SC[j]) v[j] = __dsub_rn(v[j], __dsub_rn(minVal, spc[j]));
-        __syncwarp();
+        __syncthreads();
         // augment along the alternating path
-        if (lane == 0) {
+        if (tid == 0) {
             int j = sink;
             while (true) {
                 const int r = path[j];
@@ -113,10 +136,10 @@ __global__ void __launch_bounds__(32) lsap_kernel(LsapParams p)
                 if (r == cur) break;
             }
         }
-        __syncwarp();
+        __syncthreads();
     }
-    __syncwarp();
-    for (int r = lane; r < nr; r += 32) {
+    __syncthreads();
+    for (int r = tid; r < nr; r += LS_NT) {
         const int c = col4row[r];
         if (c < 0) continue;
         const int q = transposed ? c : r, g = transposed ? r : c;
@@ -141,8 +164,11 @@ extern "C" int ovdet_lsap_f32(const float *cost, const int64_t *nactual_gt, int 
     p.cost = cost; p.nactual = nactual_gt; p.inds = per_prop_gt_inds; p.mask = proposal_matched_mask;
     p.col_to_row = col_to_row; p.B = B; p.Q = Q; p.G = G; p.M = Q > G ? Q : G;
     OVDET_REQUIRE(p.M <= 4096, "Q and G must be <= 4096");
-    const size_t smem = (size_t)p.M * (3 * sizeof(double) + 3 * sizeof(int) + 2);
-    if (smem > 48 * 1024) OVDET_CUDA_TRY(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lsap_kernel<<<B, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    size_t smem = (((size_t)p.M * (3 * sizeof(double) + 3 * sizeof(int) + 2)) + 15) & ~(size_t)15;
+    const size_t slab = sizeof(float) * (size_t)(Q < G ? Q : G) * ((size_t)p.M + 1);
+    p.stage_cost = (smem + slab <= 200 * 1024) ? 1 : 0;
+    if (p.stage_cost) smem += slab;
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lsap_kernel<<<B, LS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("lsap_kernel");
 }

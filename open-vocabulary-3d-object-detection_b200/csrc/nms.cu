@@ -125,6 +125,7 @@ __device__ void nms_core(const Src &src, int K, int dims, bool samecls, bool old
     const int n = s.misc[0];
     // ---- 3. suppression bitmask
     const int warp = tid >> 5, lane = tid & 31, nw = NMS_NT / 32;
+    const bool fast = thr >= 0.0;
     for (int i = warp; i < n; i += nw) {
         double li[3], hi_[3];
         for (int a = 0; a < 3; ++a) { li[a] = s.lo[a][i]; hi_[a] = s.hi[a][i]; }
@@ -134,12 +135,21 @@ __device__ void nms_core(const Src &src, int K, int dims, bool samecls, bool old
             bool sup = false;
             if (32 * w + 31 > i) {
                 if (j > i && j < n) {
-                    double inter = A::max(0.0, A::sub(A::min(hi_[0], s.hi[0][j]), A::max(li[0], s.lo[0][j])));
-                    for (int a = 1; a < dims; ++a)
-                        inter = A::mul(inter, A::max(0.0, A::sub(A::min(hi_[a], s.hi[a][j]), A::max(li[a], s.lo[a][j]))));
-                    double o = old_type ? A::div(inter, s.vol[j]) : A::div(inter, A::sub(A::add(vi, s.vol[j]), inter));
-                    if (samecls) o = A::mul(o, ci == s.cls[j] ? 1.0 : 0.0);
-                    sup = o > thr;
+                    // exact shortcuts for thr >= 0: a different class (o*0) or an empty overlap on any axis
+                    // (inter == 0) gives o in {0, NaN}, never > thr -- skips the fp64 divide for most pairs
+                    bool maybe = !(fast && samecls && ci != s.cls[j]);
+                    double e[3] = {1.0, 1.0, 1.0};
+                    if (maybe) {
+                        for (int a = 0; a < dims; ++a) e[a] = A::max(0.0, A::sub(A::min(hi_[a], s.hi[a][j]), A::max(li[a], s.lo[a][j])));
+                        if (fast && (e[0] == 0.0 || e[1] == 0.0 || (dims == 3 && e[2] == 0.0))) maybe = false;
+                    }
+                    if (maybe) {
+                        double inter = e[0];
+                        for (int a = 1; a < dims; ++a) inter = A::mul(inter, e[a]);
+                        double o = old_type ? A::div(inter, s.vol[j]) : A::div(inter, A::sub(A::add(vi, s.vol[j]), inter));
+                        if (samecls) o = A::mul(o, ci == s.cls[j] ? 1.0 : 0.0);
+                        sup = o > thr;
+                    }
                 }
             }
             const unsigned m = __ballot_sync(0xffffffffu, sup);

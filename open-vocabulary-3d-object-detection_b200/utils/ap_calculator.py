@@ -119,6 +119,7 @@ class APCalculator(object):
         self.ap_config_dict = ap_config_dict
         self.class2type_map = class2type_map
         self.num_semcls = dataset_config.num_semcls if dataset_config is not None else None
+        self.reduce_mode = "compact"   # "sort" forces the segmented radix sort + scan (full PR curves)
         self.reset()
 
     def make_gt_list(self, gt_box_corners, gt_box_sem_cls_labels, gt_box_present):
@@ -183,11 +184,25 @@ class APCalculator(object):
         recs = self.records()
         assert recs is not None, "no predictions accumulated"
         rs, rt, npos = recs
-        if distributed:
-            from ..dist import gather_records
-            rs, rt, npos = gather_records(rs, rt, npos)
-        ap, recall, ndet = E.ap_reduce(rs, rt, npos, nthr)
-        ap, recall = ap.cpu().numpy(), recall.cpu().numpy()
+        ap = None
+        if self.reduce_mode == "compact":
+            # no global sort: TP lists + one histogram pass; across ranks only the TP lists and the bucket
+            # histogram travel (KBs) instead of the whole record stream
+            npos_local_max = int(npos.max().item()) if npos.numel() else 0
+            npos_g = npos
+            if distributed:
+                import torch.distributed as dist
+                npos_g = npos.clone()
+                dist.all_reduce(npos_g, op=dist.ReduceOp.SUM)
+            out = E.ap_reduce_compact(rs, rt, npos_g, nthr, nthr * npos_local_max, distributed=distributed)
+            if out is not None and int(out[3].item()) == 0:
+                ap, recall = out[0].cpu().numpy(), out[1].cpu().numpy()
+        if ap is None:   # sort-based path: all-gather the (score, tp) records, segmented radix sort + scan
+            if distributed:
+                from ..dist import gather_records
+                rs, rt, npos = gather_records(rs, rt, npos)
+            ap, recall, ndet = E.ap_reduce(rs, rt, npos, nthr)
+            ap, recall = ap.cpu().numpy(), recall.cpu().numpy()
         for ti, thr in enumerate(self.ap_iou_thresh):
             apd = {c: ap[ti, c] for c in range(ap.shape[1])}
             rcd = {c: recall[ti, c] for c in range(ap.shape[1])}

@@ -57,7 +57,7 @@ def giou_flags(rotated_boxes, return_inter_vols_only, mode, prefilter, enclosing
 
 
 def generalized_box3d_iou(corners1, corners2, nums_k2, rotated_boxes=True, return_inter_vols_only=False,
-                          needs_grad=False, *, mode=None, prefilter=True, k2_cap=None, enclosing="aabb"):
+                          needs_grad=False, *, mode=None, prefilter=True, k2_cap=None, enclosing="aabb", out=None):
     """[B,K1,8,3] x [B,K2,8,3] -> [B,K1,K2] fp32 on ``corners1.device``
     (utils/box_util.py:717-737).  CUDA tensors run stream-ordered with no host
     sync; CPU tensors go through the host-buffer C entry point (H2D, kernel, D2H)."""
@@ -76,7 +76,10 @@ def generalized_box3d_iou(corners1, corners2, nums_k2, rotated_boxes=True, retur
     if nums_k2 is not None:
         nk = torch.as_tensor(nums_k2).detach().to(device=c1.device, dtype=torch.int64).contiguous()
         assert nk.numel() == B
-    out = torch.empty((B, K1, K2), dtype=torch.float32, device=c1.device)
+    if out is None:
+        out = torch.empty((B, K1, K2), dtype=torch.float32, device=c1.device)
+    else:  # caller-owned result buffer (e.g. pinned host memory for the host-buffer path)
+        assert out.shape == (B, K1, K2) and out.dtype == torch.float32 and out.is_contiguous() and out.device == c1.device
     L = C.lib()
     if c1.is_cuda:
         C.require_cuda(c2)

@@ -82,6 +82,77 @@ def ap_reduce(rec_score, rec_tp, npos, nthr, use_07_metric=False, curves=False):
     return (ap, recall, ndet, rec, prec) if curves else (ap, recall, ndet)
 
 
+APC_MAXCAP = 16384
+
+
+def _pow2_at_least(x, lo=1024):
+    c = lo
+    while c < x:
+        c <<= 1
+    return c
+
+
+def ap_reduce_compact(rec_score, rec_tp, npos, nthr, tp_bound, use_07_metric=False, distributed=False):
+    """AP without a global sort (csrc/ap_compact.cu).  ``tp_bound`` = caller's upper bound on the number of
+    TP records of any class on THIS rank (e.g. nthr * max GT count); ``npos`` must already be global when
+    ``distributed``.  Returns (ap, recall, n_det) like ap_reduce, or None when the TP lists do not fit the
+    shared-memory sort (caller falls back to the sort-based ap_reduce)."""
+    import torch.distributed as dist
+    C.require_cuda(rec_score)
+    dev = rec_score.device
+    Cn, N = rec_score.shape
+    world = dist.get_world_size() if distributed else 1
+    cap = _pow2_at_least(int(tp_bound))
+    if distributed:  # every rank must use the same capacity
+        t = torch.tensor([cap], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cap = int(t.item())
+    cap_total = _pow2_at_least(cap * world)
+    if cap_total > APC_MAXCAP:
+        return None
+    L = C.lib()
+    st = C.stream(dev)
+    rec_score, rec_tp = rec_score.contiguous(), rec_tp.contiguous()
+    npos = npos.to(device=dev, dtype=torch.int64).contiguous()
+    key = torch.empty((Cn, cap), dtype=torch.int32, device=dev)
+    bits = torch.empty((Cn, cap), dtype=torch.uint8, device=dev)
+    cnt = torch.empty((Cn,), dtype=torch.int32, device=dev)
+    nvalid = torch.empty((Cn,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        C.check(L.ovdet_apc_collect(C.ptr(rec_score), C.ptr(rec_tp), Cn, N, cap, C.ptr(key), C.ptr(bits), C.ptr(cnt),
+                                    C.ptr(nvalid), st))
+        if world > 1 or cap_total != cap:
+            gk = torch.full((world, Cn, cap), -1, dtype=torch.int32, device=dev)   # 0xFFFFFFFF
+            gb = torch.zeros((world, Cn, cap), dtype=torch.uint8, device=dev)
+            if world > 1:
+                dist.all_gather_into_tensor(gk.view(world * Cn, cap), key)
+                dist.all_gather_into_tensor(gb.view(world * Cn, cap), bits)
+                dist.all_reduce(nvalid, op=dist.ReduceOp.SUM)
+                dist.all_reduce(cnt, op=dist.ReduceOp.MAX)   # overflow is a per-rank condition
+            else:
+                gk[0], gb[0] = key, bits
+            key = torch.full((Cn, cap_total), -1, dtype=torch.int32, device=dev)
+            bits = torch.zeros((Cn, cap_total), dtype=torch.uint8, device=dev)
+            key[:, :world * cap] = gk.permute(1, 0, 2).reshape(Cn, world * cap)
+            bits[:, :world * cap] = gb.permute(1, 0, 2).reshape(Cn, world * cap)
+            cnt_chk = torch.clamp(cnt, max=cap) + (cnt > cap).to(torch.int32) * cap_total  # keep the overflow signal
+        else:
+            cnt_chk = cnt
+        C.check(L.ovdet_apc_sort(C.ptr(key), C.ptr(bits), Cn, cap_total, st))
+        hist = torch.empty((Cn, cap_total + 1), dtype=torch.int32, device=dev)
+        C.check(L.ovdet_apc_hist(C.ptr(rec_score), Cn, N, C.ptr(key), cap_total, C.ptr(hist), st))
+        if world > 1:
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        ap = torch.empty((nthr, Cn), dtype=torch.float64, device=dev)
+        recall = torch.empty((nthr, Cn), dtype=torch.float64, device=dev)
+        ndet = torch.empty((Cn,), dtype=torch.int64, device=dev)
+        ovf = torch.zeros((1,), dtype=torch.int32, device=dev)
+        C.check(L.ovdet_apc_final(C.ptr(bits), C.ptr(cnt_chk.contiguous()), C.ptr(hist), C.ptr(npos), C.ptr(nvalid), Cn,
+                                  cap_total, nthr, int(bool(use_07_metric)), C.ptr(ap), C.ptr(recall), C.ptr(ndet),
+                                  C.ptr(ovf), st))
+    return ap, recall, ndet, ovf
+
+
 def _pack(pred_all, gt_all):
     """{img: [(cls, box, score)]}, {img: [(cls, box)]} -> padded scene-major arrays."""
     imgs = list(dict.fromkeys(list(pred_all.keys()) + list(gt_all.keys())))

@@ -212,6 +212,7 @@ def test_ap_calculator_golden(golden):
     g = golden("ap.npz")
     C = g["sem_cls_prob"].shape[-1]
     calc = APC.APCalculator(_Cfg(C), ap_iou_thresh=[0.25, 0.5], exact_eval=False)
+    assert calc.reduce_mode == "compact"
     S = g["box_corners"].shape[0]
     for lo in range(0, S, 8):  # three batches of 8 scenes, like engine.evaluate
         sl = slice(lo, lo + 8)
@@ -221,6 +222,11 @@ def test_ap_calculator_golden(golden):
     for thr in (0.25, 0.5):
         for k, v in m[thr].items():
             assert float(v) == pytest.approx(float(g[f"m{thr}|{k}"]), abs=1e-4), (thr, k)  # north_star: AP within 1e-4
+            assert float(v) == pytest.approx(float(g[f"m{thr}|{k}"]), abs=1e-9), (thr, k)
+    calc.reduce_mode = "sort"   # the radix sort + scan path must give the same metrics
+    m_sort = calc.compute_metrics()
+    for thr in (0.25, 0.5):
+        for k, v in m_sort[thr].items():
             assert float(v) == pytest.approx(float(g[f"m{thr}|{k}"]), abs=1e-9), (thr, k)
     s = calc.metrics_to_str(m)
     assert s.startswith("mAP0.25, mAP0.50: ")
@@ -299,6 +305,35 @@ def test_ap_reduce_properties_full_size():
     fpc = np.cumsum(1.0 - t_h[v][o].astype(np.float64))
     want = oracle.voc_ap(tpc / float(npos[c]), tpc / np.maximum(tpc + fpc, np.finfo(np.float64).eps))
     assert float(ap[0, c]) == pytest.approx(want, abs=1e-12)
+
+
+def test_ap_compact_equals_sort_path():
+    """The no-sort reduction (TP lists + histogram) against the segmented radix sort + scan, C3-sized stream,
+    both VOC metrics; and the overflow signal when the TP list capacity is too small."""
+    C, N = 20, 5050 * 128
+    g = torch.Generator(device=DEV).manual_seed(1)
+    score = torch.stack([(torch.randperm(N, generator=g, device=DEV).float() + 0.5) / N for _ in range(C)])
+    score[torch.rand((C, N), generator=g, device=DEV) < 0.2] = float("-inf")
+    r = torch.rand((C, N), generator=g, device=DEV)
+    tp = (r < 0.004).to(torch.uint8) * 3 + ((r >= 0.004) & (r < 0.006)).to(torch.uint8) * 1 + ((r >= 0.006) & (r < 0.007)).to(torch.uint8) * 2
+    tp[score == float("-inf")] = 0
+    npos = (tp != 0).sum(1).to(torch.int64) + 11
+    bound = int((tp != 0).sum(1).max())
+    for m07 in (False, True):
+        ap, recall, ndet = ED.ap_reduce(score, tp, npos, 2, use_07_metric=m07)
+        out = ED.ap_reduce_compact(score, tp, npos, 2, bound, use_07_metric=m07)
+        assert out is not None and int(out[3]) == 0
+        np.testing.assert_allclose(out[0].cpu().numpy(), ap.cpu().numpy(), rtol=0, atol=1e-13)
+        np.testing.assert_allclose(out[1].cpu().numpy(), recall.cpu().numpy(), rtol=0, atol=0)
+        np.testing.assert_array_equal(out[2].cpu().numpy(), ndet.cpu().numpy())
+    out = ED.ap_reduce_compact(score, tp, npos, 2, 1024)   # capacity below the real TP count -> overflow flag
+    assert int(out[3]) == 1
+    assert ED.ap_reduce_compact(score, tp, npos, 2, 10 ** 6) is None   # does not fit shared memory -> caller falls back
+    # small, ragged N
+    s2, t2 = score[:3, :777].contiguous(), tp[:3, :777].contiguous()
+    ap, recall, _ = ED.ap_reduce(s2, t2, npos[:3], 2)
+    out = ED.ap_reduce_compact(s2, t2, npos[:3], 2, 64)
+    np.testing.assert_allclose(out[0].cpu().numpy(), ap.cpu().numpy(), rtol=0, atol=1e-13)
 
 
 # ------------------------------------------------------------------ matcher
