@@ -213,6 +213,23 @@ int ovdet_pseudo_filter_f64(const double *boxes, const double *pool, const int32
                             uint8_t *nms1_keep, double *out_label, double *out_score, uint8_t *out_keep,
                             void *stream);
 
+/* ------------------------------------------------------------------------- */
+/* Point-in-box passes                                                        */
+/* ------------------------------------------------------------------------- */
+/* remove_empty_box of parse_predictions (utils/ap_calculator.py:70-84 ->
+ * utils/box_util.py:22-31): counts[s,k] = number of points of scene s inside predicted box k.
+ * point_cloud fp32 [S,N,point_stride>=3] in the DEPTH frame, corners fp32 [S,K,8,3] in the
+ * upright-camera frame (the kernel applies flip_axis_to_depth, ap_calculator.py:22-26). */
+int ovdet_points_in_boxes_count(const float *point_cloud, int S, int N, int point_stride,
+                                const float *corners, int K, int32_t *counts, void *stream);
+
+/* LabelFormatter.gen_pseudo vote (utils/label_formatter.py:150-159, crop_pc :183-188):
+ * for each box (centre xyz, size xyz, ... ; row stride box_stride fp64) the mode of the labels
+ * (integers 0..63 stored as fp64) of the points inside its axis-aligned extent, skipping
+ * ignore_label; mode_out = -1 when no labelled point is inside, count_out = points counted. */
+int ovdet_box_label_mode(const double *points, const double *labels, int N, const double *boxes, int box_stride, int M,
+                         double ignore_label, int32_t *mode_out, int32_t *count_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

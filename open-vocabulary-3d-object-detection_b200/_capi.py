@@ -40,6 +40,8 @@ SIGNATURES = {
     "ovdet_apc_sort": (c_i, [c_p, c_p, c_i, c_i, c_p]),
     "ovdet_apc_hist": (c_i, [c_p, c_i, c_i64, c_p, c_i, c_p, c_p]),
     "ovdet_apc_final": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "ovdet_points_in_boxes_count": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_p]),
+    "ovdet_box_label_mode": (c_i, [c_p, c_p, c_i, c_p, c_i, c_i, c_d, c_p, c_p, c_p]),
     "ovdet_clip_logits_bf16": (c_i, [c_p, c_p, c_i, c_i, c_i, c_u, c_f, c_p, c_i, c_p, c_i, c_p, c_p]),
     "ovdet_pseudo_filter_f64": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p]),
 }

@@ -125,3 +125,24 @@ def pseudo_label_scenes(S, P=256, pool=512, C=18, seed=0):
     ps[:, :n] = s[:, :n] * (torch.randn((S, n, 3), generator=g) * 0.08 + 1.0).clamp(0.6, 1.4)
     poolb = torch.cat([pc - ps / 2, pc + ps / 2], -1)
     return boxes.double().contiguous(), poolb.double().contiguous()
+
+
+def scene_points(corners_cam, n_points=4000, seed=0, frac_inside=0.5):
+    """A synthetic depth-frame point cloud [B,N,3] for remove_empty_box: `frac_inside` of the points are
+    sampled inside randomly chosen predicted boxes (so some boxes hold >= 5 points, many hold none),
+    the rest uniformly in the room."""
+    g = torch.Generator().manual_seed(seed)
+    B, K = corners_cam.shape[0], corners_cam.shape[1]
+    depth = torch.stack([corners_cam[..., 0], corners_cam[..., 2], -corners_cam[..., 1]], -1)   # flip_axis_to_depth
+    n_in = int(n_points * frac_inside)
+    pick = torch.randint(0, max(K // 3, 1), (B, n_in), generator=g)          # only the first third of the boxes get points
+    o = torch.gather(depth[:, :, 0], 1, pick[..., None].expand(B, n_in, 3))
+    ea = torch.gather(depth[:, :, 1] - depth[:, :, 0], 1, pick[..., None].expand(B, n_in, 3))
+    eb = torch.gather(depth[:, :, 3] - depth[:, :, 0], 1, pick[..., None].expand(B, n_in, 3))
+    ec = torch.gather(depth[:, :, 4] - depth[:, :, 0], 1, pick[..., None].expand(B, n_in, 3))
+    t = torch.rand((B, n_in, 3), generator=g) * 0.9 + 0.05
+    inside = o + t[..., 0:1] * ea + t[..., 1:2] * eb + t[..., 2:3] * ec
+    lo = depth.reshape(B, -1, 3).min(1).values[:, None]
+    hi = depth.reshape(B, -1, 3).max(1).values[:, None]
+    noise = lo + torch.rand((B, n_points - n_in, 3), generator=g) * (hi - lo)
+    return torch.cat([inside, noise], 1).float().contiguous()

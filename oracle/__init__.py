@@ -599,3 +599,56 @@ def lift_filter_scene(boxes, box_pool, nms_thresh=0.7, match_thresh=0.3, size_nm
     if kept.shape[0] == 0:
         return kept
     return tools_nms_3d_faster(kept, size_nms_thresh, use_size_score=True, class_wise=True, size_typ="Volume")
+
+
+# --------------------------------------------------------------------------- #
+# point-in-box passes
+# --------------------------------------------------------------------------- #
+def points_in_boxes_count(point_cloud, corners):
+    """Points of each scene inside each predicted box: utils/ap_calculator.py:70-82 with
+    extract_pc_in_box3d (utils/box_util.py:22-31).  The reference's Delaunay hull test of the 8
+    corners is restated as three slab tests in the box frame (the boxes are cuboids), fp64."""
+    pc = _np(point_cloud, np.float64)[:, :, :3]
+    cr = _np(corners, np.float64)
+    B, K = cr.shape[0], cr.shape[1]
+    out = np.zeros((B, K), np.int32)
+    for b in range(B):
+        for k in range(K):
+            c = cr[b, k][:, [0, 2, 1]].copy()   # flip_axis_to_depth (ap_calculator.py:22-26)
+            c[:, 2] *= -1
+            o = c[0]
+            inside = np.ones(pc.shape[1], bool)
+            for e in (c[1] - o, c[3] - o, c[4] - o):
+                t = (pc[b] - o) @ e
+                inside &= (t >= 0) & (t <= e @ e)
+            out[b, k] = inside.sum()
+    return out
+
+
+def nonempty_box_mask(corners, point_cloud, objectness_probs, min_points=5):
+    """utils/ap_calculator.py:66-84."""
+    cnt = points_in_boxes_count(point_cloud, corners)
+    mask = (cnt >= min_points).astype(np.float64)
+    obj = _np(objectness_probs, np.float32)
+    for i in range(mask.shape[0]):
+        if mask[i].sum() == 0:
+            mask[i, obj[i].argmax()] = 1
+    return mask
+
+
+def box_label_mode(points, labels, boxes, ignore_label=-100):
+    """utils/label_formatter.py:150-159: per (centre,size) box, mode of the non-ignored labels of the
+    points inside the axis-aligned extent (crop_pc :183-188); -1 when none."""
+    from scipy.stats import mode as sp_mode
+    points = np.asarray(points, np.float64)
+    labels = np.asarray(labels)
+    out_m, out_c = [], []
+    for box in np.asarray(boxes, np.float64):
+        m1 = np.prod(points >= box[0:3] - box[3:6] / 2, axis=-1)
+        m2 = np.prod(points <= box[0:3] + box[3:6] / 2, axis=-1)
+        mask = (m1 * m2).astype(bool) & (labels != ignore_label)
+        if mask.sum() > 0:
+            out_m.append(int(sp_mode(labels[mask], keepdims=False).mode)); out_c.append(int(mask.sum()))
+        else:
+            out_m.append(-1); out_c.append(0)
+    return np.array(out_m, np.int32), np.array(out_c, np.int32)

@@ -322,6 +322,64 @@ def main():
         lift[f"final_{sidx}"] = b2
     save("lift.npz", boxes=bx, pool=pool, iou_vv=iou_vv, iou_cs=iou_cs, **lift)
 
+    # ---------------- remove_empty_box (Delaunay point-in-hull) ----------------
+    class _Cfg2:
+        num_semcls = 10
+
+    out, tgt = synth.detection_batch(B=3, Q=48, G=8, C=10, seed=23, heading=np.pi, max_gt=8)
+    pc = synth.scene_points(out["box_corners"], n_points=3000, seed=5)
+    cfg = apc.get_ap_config_dict(dataset_config=_Cfg2(), remove_empty_box=True)
+    preds = apc.parse_predictions(out["box_corners"], out["sem_cls_prob"], out["objectness_prob"], pc, cfg)
+    counts = np.zeros((3, 48), np.int32)
+    for i in range(3):
+        for j in range(48):
+            box3d = apc.flip_axis_to_depth(out["box_corners"][i, j].numpy())
+            pin, _ = box_util.extract_pc_in_box3d(pc[i].numpy(), box3d)
+            counts[i, j] = len(pin)
+    kept = np.zeros((3, 48), np.uint8)
+    for i in range(3):
+        for cl, bb, sc in preds[i]:
+            if cl == 0:
+                kept[i, np.where((out["box_corners"][i].numpy() == bb).all((1, 2)))[0][0]] = 1
+    save("empty.npz", box_corners=out["box_corners"].numpy(), sem_cls_prob=out["sem_cls_prob"].numpy(),
+         objectness=out["objectness_prob"].numpy(), point_cloud=pc.numpy(), counts=counts, kept=kept,
+         n_pred=np.array([len(p) for p in preds]))
+
+    # ---------------- LabelFormatter.gen_pseudo (file based) ----------------
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    os.makedirs(os.path.join(tmp, "labels")); os.makedirs(os.path.join(tmp, "out"))
+    g = torch.Generator().manual_seed(29)
+    scenes = ["sceneA", "sceneB"]
+    raw, boxes_all = [], []
+    for si, name in enumerate(scenes):
+        c, s_, _ = synth.sample_boxes(g, (12,), "scannet", 0.0)
+        lab = torch.randint(0, 18, (12,), generator=g).double()
+        pts, pl = [], []
+        for k in range(12):   # points inside box k mostly carry its label (or a wrong one for every third box)
+            t = torch.rand((60, 3), generator=g) - 0.5
+            pts.append(c[k] + t * s_[k])
+            true = lab[k] if k % 3 else (lab[k] + 1) % 18
+            l = torch.where(torch.rand(60, generator=g) < 0.7, true, torch.randint(0, 25, (60,), generator=g).double())
+            pl.append(l)
+        noise = torch.rand((500, 3), generator=g) * 8
+        pts.append(noise); pl.append(torch.randint(0, 25, (500,), generator=g).double())
+        arr = torch.cat([torch.cat(pts).double(), torch.cat(pl)[:, None]], 1).numpy()
+        np.save(os.path.join(tmp, "labels", name + ".npy"), arr)
+        raw.append(arr)
+        rows = torch.cat([c.double(), s_.double(), lab[:, None], torch.rand((12, 2), generator=g).double(),
+                          torch.full((12, 1), float(si)).double()], 1).numpy()
+        boxes_all.append(rows)
+    fmt = lf.LabelFormatter(tmp, os.path.join(tmp, "out"), os.path.join(tmp, "labels"), scenes)
+    fmt.pseudo_boxes = np.concatenate(boxes_all, 0)
+    res = {}
+    for si, name in enumerate(scenes):
+        nb = fmt.gen_pseudo(si)
+        res[f"nbox_{si}"] = np.array(nb)
+        res[f"bbox_{si}"] = np.load(os.path.join(tmp, "out", name + "_bbox.npy"))
+        res[f"raw_{si}"] = raw[si]
+    save("labelfmt.npz", pseudo_boxes=fmt.pseudo_boxes, **res)
+
 
 if __name__ == "__main__":
     main()

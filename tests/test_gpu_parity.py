@@ -445,3 +445,50 @@ def test_clip_logits_vs_oracle(M, K, N, l2, scale):
     assert pr.shape == (M, N - 1) and ob.shape == (M,)
     rowsum = pr.float().sum(-1).cpu().numpy() + (1 - ob.cpu().numpy())
     np.testing.assert_allclose(rowsum, 1.0, atol=8e-3)
+
+
+# ------------------------------------------------------------------ point-in-box passes
+def test_remove_empty_box_golden(golden):
+    from ovdet_b200.utils.points_in_box import points_in_boxes_count, nonempty_box_mask
+    g = golden("empty.npz")
+    cnt = points_in_boxes_count(cu(g["point_cloud"]), cu(g["box_corners"]))
+    np.testing.assert_array_equal(cnt.cpu().numpy(), g["counts"])
+    C = g["sem_cls_prob"].shape[-1]
+    cfg = APC.get_ap_config_dict(dataset_config=_Cfg(C), remove_empty_box=True)   # the reference's exact_eval default
+    preds = APC.parse_predictions(cu(g["box_corners"]), cu(g["sem_cls_prob"]), cu(g["objectness"]), cu(g["point_cloud"]), cfg)
+    np.testing.assert_array_equal(np.array([len(p) for p in preds]), g["n_pred"])
+    m = nonempty_box_mask(cu(g["box_corners"]), cu(g["point_cloud"]), cu(g["objectness"]))
+    np.testing.assert_array_equal(m.cpu().numpy(), oracle.nonempty_box_mask(g["box_corners"], g["point_cloud"], g["objectness"]).astype(np.uint8))
+    # a scene with no points at all keeps exactly its best box (ap_calculator.py:83-84)
+    m0 = nonempty_box_mask(cu(g["box_corners"][:1]), torch.full((1, 10, 3), 1e6, device=DEV), cu(g["objectness"][:1]))
+    assert int(m0.sum()) == 1 and int(m0[0].argmax()) == int(g["objectness"][0].argmax())
+
+
+def test_label_formatter_golden(golden, tmp_path):
+    from ovdet_b200.utils.label_formatter import LabelFormatter, box_label_mode
+    g = golden("labelfmt.npz")
+    (tmp_path / "labels").mkdir(); (tmp_path / "out").mkdir()
+    scenes = ["sceneA", "sceneB"]
+    for si, name in enumerate(scenes):
+        np.save(tmp_path / "labels" / (name + ".npy"), g[f"raw_{si}"])
+    fmt = LabelFormatter(str(tmp_path), str(tmp_path / "out"), str(tmp_path / "labels"), scenes)
+    fmt.pseudo_boxes = g["pseudo_boxes"].copy()
+    for si, name in enumerate(scenes):
+        assert fmt.gen_pseudo(si) == int(g[f"nbox_{si}"])
+        np.testing.assert_array_equal(np.load(tmp_path / "out" / (name + "_bbox.npy")), g[f"bbox_{si}"])
+    raw = g["raw_0"]
+    lab = raw[:, 3].copy(); lab[lab >= 18] = -100
+    boxes = g["pseudo_boxes"][g["pseudo_boxes"][:, -1] == 0]
+    mode, cnt = box_label_mode(raw[:, :3], lab, boxes)
+    wm, wc = oracle.box_label_mode(raw[:, :3], lab, boxes)
+    np.testing.assert_array_equal(mode, wm); np.testing.assert_array_equal(cnt, wc)
+    # step + compute on device tensors
+    out, tgt = synth.detection_batch(B=2, Q=16, G=4, C=18, seed=1, room="scannet", heading=0.0, max_gt=4)
+    fmt2 = LabelFormatter(str(tmp_path), str(tmp_path / "out"), str(tmp_path / "labels"), scenes)
+    o = {k: v.to(DEV) for k, v in out.items()}
+    fmt2.step(o, {"scan_idx": torch.tensor([0, 1], device=DEV)})
+    fmt2.compute(10, 0.1, 0.5)
+    rows = fmt2.boxes
+    assert rows.shape == (32, 10)
+    keep = (rows[:, 7] >= 0.1) & (rows[:, 8] >= 0.5)
+    assert fmt2.pseudo_boxes.shape[0] == keep.sum()
