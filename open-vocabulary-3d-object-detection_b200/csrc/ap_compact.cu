@@ -102,15 +102,28 @@ __global__ void __launch_bounds__(APC_NT) apc_hist_kernel(const float *__restric
     for (int i = threadIdx.x; i < cap; i += APC_NT) k[i] = tp_key[(size_t)c * cap + i];
     for (int i = threadIdx.x; i <= cap; i += APC_NT) h[i] = 0;
     __syncthreads();
+    // number of real TP entries = first empty (0xFFFFFFFF) slot.  Every record scoring below all TPs lands in that
+    // one bucket (the bulk of the false positives): count those in a register instead of hammering one shared word.
+    int ntp;
+    {
+        int lo = 0, n = cap;
+        while (n > 1) { const int half = n >> 1; lo += (k[lo + half - 1] < 0xFFFFFFFFu) ? half : 0; n -= half; }
+        ntp = lo + ((k[lo] < 0xFFFFFFFFu) ? 1 : 0);
+    }
+    const int span = ntp > 0 ? (1 << (32 - __clz(ntp))) : 1;   // power of two > ntp-1: search only the occupied prefix
+    const int sp = span < cap ? span : cap;
+    unsigned int tail = 0;
     for (long long i = (long long)blockIdx.x * APC_NT + threadIdx.x; i < N; i += (long long)gridDim.x * APC_NT) {
         const float s = score[(size_t)c * N + i];
         if (!(s > -INFINITY)) continue;
         const uint32_t key = apc_score_key(s);
-        int lo = 0, n = cap;               // branch-free lower_bound over a power-of-two table
+        int lo = 0, n = sp;                // branch-free lower_bound over a power-of-two table
         while (n > 1) { const int half = n >> 1; lo += (k[lo + half - 1] < key) ? half : 0; n -= half; }
         lo += (k[lo] < key) ? 1 : 0;
-        atomicAdd(&h[lo], 1u);
+        if (lo >= ntp) ++tail; else atomicAdd(&h[lo], 1u);
     }
+    for (int off = 16; off > 0; off >>= 1) tail += __shfl_xor_sync(0xffffffffu, tail, off);
+    if ((threadIdx.x & 31) == 0 && tail) atomicAdd(&h[ntp], tail);
     __syncthreads();
     for (int i = threadIdx.x; i <= cap; i += APC_NT) { const uint32_t v = h[i]; if (v) atomicAdd(&hist[(size_t)c * (cap + 1) + i], v); }
 }

@@ -222,10 +222,6 @@ __device__ __forceinline__ int sh_clip_quads(const T *s, const T *c, V2<T> *bufA
     return n;
 }
 
-// giou_hull.cu: GIoU with the convex-hull enclosing volume (OVDET_GIOU_ENCL_HULL)
-int giou3d_hull_impl(const float *corners1, const float *corners2, const int64_t *nums_k2, int B, int K1, int K2,
-                     int k2_cap, unsigned flags, float *out, void *stream);
-
 // 16-byte read-only load
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 

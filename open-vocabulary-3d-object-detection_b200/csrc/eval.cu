@@ -118,6 +118,15 @@ __global__ void __launch_bounds__(EV_NT) box3d_iou_kernel(IouParams p)
 }
 
 // ---------------------------------------------------------------- AP matching
+constexpr int AM_CLIP = 64;   // threads that run the fp64 clip of the surviving det x GT pairs
+
+__host__ __device__ inline size_t am_queue_offset(int K, int G, int C, int nthr)
+{
+    size_t o = sizeof(V2<double>) * 2 * SH_MAXV * AM_CLIP + sizeof(unsigned long long) * (size_t)G * nthr +
+               sizeof(int) * ((size_t)K + 2 * (size_t)G) + (sizeof(short) + 1) * (size_t)C * K;
+    return (o + 15) & ~(size_t)15;
+}
+
 struct MatchParams {
     const float *corners, *probs, *obj; const uint8_t *keep; const int32_t *det_cls;
     const float *gt_corners; const int64_t *gt_labels; const uint8_t *gt_present;
@@ -128,15 +137,16 @@ struct MatchParams {
 __global__ void __launch_bounds__(EV_NT) ap_match_kernel(MatchParams p)
 {
     extern __shared__ __align__(16) unsigned char sm[];
-    // carve: scratch [2*MAXV*NT] V2<double> | best [G*nthr] u64 | kd [K] int | gl [G] int | glab [G] int | jmax [C*K] i16 | cand [C*K] u8 | counters
+    // carve: scratch [2*MAXV*AM_CLIP] V2<double> | best [G*nthr] u64 | kd [K] int | gl [G] int | glab [G] int | jmax [C*K] i16 | cand [C*K] u8 | queue [K*G] u16
     V2<double> *scratch = reinterpret_cast<V2<double> *>(sm);
-    unsigned long long *best = reinterpret_cast<unsigned long long *>(scratch + 2 * SH_MAXV * EV_NT);
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(scratch + 2 * SH_MAXV * AM_CLIP);
     int *kd = reinterpret_cast<int *>(best + (size_t)p.G * p.nthr);
     int *gl = kd + p.K;
     int *glab = gl + p.G;
     short *jmax = reinterpret_cast<short *>(glab + p.G);
     unsigned char *cand = reinterpret_cast<unsigned char *>(jmax + (size_t)p.C * p.K);
-    __shared__ int nk_s, ng_s;
+    unsigned short *queue = reinterpret_cast<unsigned short *>(sm + am_queue_offset(p.K, p.G, p.C, p.nthr));
+    __shared__ int nk_s, ng_s, qn_s;
     const int s = blockIdx.x, tid = threadIdx.x;
     const size_t N = (size_t)p.S * p.K;
     const uint8_t *keep = p.keep + (size_t)s * p.K;
@@ -169,21 +179,57 @@ __global__ void __launch_bounds__(EV_NT) ap_match_kernel(MatchParams p)
         if (tid == 0) ng_s = n;
     }
     for (int i = tid; i < p.G * p.nthr; i += EV_NT) best[i] = 0ull;
+    if (tid == 0) qn_s = 0;
     __syncthreads();
     const int nk = nk_s, ng = ng_s;
 
-    // exact IoU matrix [nk, ng] -> iou_ws[s, i, j]
+    // exact IoU matrix [nk, ng] -> iou_ws[s, i, j].  Step 1 (all threads): the cheap exact rejects -- no height
+    // overlap or disjoint BEV bounding rectangles give IoU 0 -- and a warp-aggregated queue of the survivors.
     double *iou = p.iou_ws + (size_t)s * p.K * p.G;
-    V2<double> *bufA = scratch + tid, *bufB = scratch + SH_MAXV * EV_NT + tid;
-    for (int pi = tid; pi < nk * ng; pi += EV_NT) {
-        const int i = pi / ng, j = pi - i * ng;
-        float c1[24], c2[24];
-        const float *a = p.corners + ((size_t)s * p.K + kd[i]) * 24;
-        const float *b = p.gt_corners + ((size_t)s * p.G + gl[j]) * 24;
+    const int npair = nk * ng;
+    for (int base = 0; base < npair; base += EV_NT) {
+        const int pi = base + tid;
+        bool need = false;
+        if (pi < npair) {
+            const int i = pi / ng, j = pi - i * ng;
+            const float *a = p.corners + ((size_t)s * p.K + kd[i]) * 24;
+            const float *b = p.gt_corners + ((size_t)s * p.G + gl[j]) * 24;
+            need = fminf(__ldg(a + 1), __ldg(b + 1)) > fmaxf(__ldg(a + 13), __ldg(b + 13));
 #pragma unroll
-        for (int t = 0; t < 24; ++t) { c1[t] = __ldg(a + t); c2[t] = __ldg(b + t); }
-        double dummy;
-        iou[(size_t)i * p.G + j] = exact_iou<EV_NT>(c1, c2, bufA, bufB, false, &dummy);
+            for (int ax = 0; ax < 3; ax += 2) {
+                const float lo1 = fminf(fminf(__ldg(a + ax), __ldg(a + 3 + ax)), fminf(__ldg(a + 6 + ax), __ldg(a + 9 + ax)));
+                const float hi1 = fmaxf(fmaxf(__ldg(a + ax), __ldg(a + 3 + ax)), fmaxf(__ldg(a + 6 + ax), __ldg(a + 9 + ax)));
+                const float lo2 = fminf(fminf(__ldg(b + ax), __ldg(b + 3 + ax)), fminf(__ldg(b + 6 + ax), __ldg(b + 9 + ax)));
+                const float hi2 = fmaxf(fmaxf(__ldg(b + ax), __ldg(b + 3 + ax)), fmaxf(__ldg(b + 6 + ax), __ldg(b + 9 + ax)));
+                if (hi1 < lo2 || hi2 < lo1) need = false;
+            }
+            if (!need) iou[(size_t)i * p.G + j] = 0.0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (m) {
+            const int lane = tid & 31;
+            int bp = 0;
+            if (lane == 0) bp = atomicAdd(&qn_s, __popc(m));
+            bp = __shfl_sync(0xffffffffu, bp, 0);
+            if (need) queue[bp + __popc(m & ((1u << lane) - 1))] = (unsigned short)pi;
+        }
+    }
+    __syncthreads();
+    // Step 2 (AM_CLIP threads, small scratch): the fp64 Sutherland-Hodgman clip of the survivors
+    if (tid < AM_CLIP) {
+        V2<double> *bufA = scratch + tid, *bufB = scratch + SH_MAXV * AM_CLIP + tid;
+        const int qn = qn_s;
+        for (int qi = tid; qi < qn; qi += AM_CLIP) {
+            const int pi = queue[qi];
+            const int i = pi / ng, j = pi - i * ng;
+            float c1[24], c2[24];
+            const float *a = p.corners + ((size_t)s * p.K + kd[i]) * 24;
+            const float *b = p.gt_corners + ((size_t)s * p.G + gl[j]) * 24;
+#pragma unroll
+            for (int t = 0; t < 24; ++t) { c1[t] = __ldg(a + t); c2[t] = __ldg(b + t); }
+            double dummy;
+            iou[(size_t)i * p.G + j] = exact_iou<AM_CLIP>(c1, c2, bufA, bufB, false, &dummy);
+        }
     }
     // default records for every (class, detection slot) of this scene
     for (int it = tid; it < p.C * p.K; it += EV_NT) {
@@ -523,9 +569,9 @@ extern "C" int ovdet_ap_match(const float *corners, const float *probs, const fl
     p.gt_labels = gt_labels; p.gt_present = gt_present; p.S = S; p.K = K; p.G = G; p.C = C; p.nthr = nthr;
     for (int t = 0; t < nthr; ++t) p.thr[t] = thr[t];
     p.iou_ws = iou_ws; p.rec_score = rec_score; p.rec_tp = rec_tp; p.npos = reinterpret_cast<unsigned long long *>(npos);
-    size_t smem = sizeof(V2<double>) * 2 * SH_MAXV * EV_NT + sizeof(unsigned long long) * (size_t)G * nthr +
-                  sizeof(int) * ((size_t)K + 2 * (size_t)G) + (sizeof(short) + 1) * (size_t)C * K + 16;
-    OVDET_REQUIRE(smem <= 220 * 1024, "C*K too large for the shared-memory match tables");
+    OVDET_REQUIRE((long long)K * G <= 65535, "K*G must fit the 16-bit pair queue");
+    size_t smem = am_queue_offset(K, G, C, nthr) + sizeof(unsigned short) * (size_t)K * (G > 0 ? G : 1) + 16;
+    OVDET_REQUIRE(smem <= 220 * 1024, "C*K / K*G too large for the shared-memory match tables");
     OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ap_match_kernel<<<S, EV_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("ap_match_kernel");

@@ -137,7 +137,10 @@ __device__ __forceinline__ float finish_pair(const PairTerms &t, float area, boo
     const float inter = A::mul(area, t.h);
     if (inter_only) return inter;
     const float uni = fmaxf(A::sub(t.sumv, inter), 1e-8f);
-    const float iou = A::div(inter, uni);
+    // inter == 0 (most pairs) -> 0 / uni == +0 exactly; skipping it also skips the IEEE divide's slow path, which a
+    // zero numerator always takes (ncu: the CALL was executed by every warp)
+    float iou = 0.f;
+    if (inter != 0.f) iou = A::div(inter, uni);
     const float second = -A::sub(1.f, A::div(uni, t.encl));
     float g = A::add(iou, second);
     const float good = (t.encl > 2e-8f && t.sumv > 4e-8f) ? 1.f : 0.f;
@@ -146,10 +149,82 @@ __device__ __forceinline__ float finish_pair(const PairTerms &t, float area, boo
     return g;
 }
 
+// ---------------------------------------------------------------------------
+// Convex-hull enclosing volume of two upright boxes (utils/box_ops3d.py:458-473: scipy ConvexHull of the 16
+// corners), in closed form.  Both boxes are vertical prisms A x [a0,a1], B x [b0,b1] over BEV quads A, B.  The hull's
+// horizontal cross-section at height y is the Minkowski combination  alpha*A + beta*B + gamma*H,  H = conv(A u B),
+// with (alpha, beta, gamma) = (1-l2, l1, l2-l1) and [l1,l2] the feasible blend interval at y -- piecewise linear in
+// y between the breakpoints {a0,a1,b0,b1}.  Its area is the quadratic form
+//   alpha^2|A| + beta^2|B| + gamma^2|H| + 2ab V(A,B) + 2ag V(A,H) + 2bg V(B,H)
+// (V = mixed area = 1/2 sum over CCW edges e of Q of max_{v in P} v x e), so Simpson's rule per piece is exact.
+// fp64; ~700 flops, only evaluated for pairs whose intersection volume is > 0 (box_ops3d.py:467,:514-519).
+// ---------------------------------------------------------------------------
+struct P2d { double x, z; };
+
+__device__ __forceinline__ double cross2(const P2d &o, const P2d &a, const P2d &b) { return (a.x - o.x) * (b.z - o.z) - (a.z - o.z) * (b.x - o.x); }
+
+__device__ double poly_area_ccw(P2d *p, int n)
+{   // signed shoelace; reverses p in place when clockwise so that callers always see CCW polygons
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) { const P2d &a = p[i], &b = p[(i + 1) % n]; s += a.x * b.z - a.z * b.x; }
+    if (s < 0.0) { for (int i = 0; i < n / 2; ++i) { const P2d t = p[i]; p[i] = p[n - 1 - i]; p[n - 1 - i] = t; } s = -s; }
+    return 0.5 * s;
+}
+
+__device__ double mixed_area(const P2d *P, int np, const P2d *Q, int nq)
+{
+    double v = 0.0;
+    for (int e = 0; e < nq; ++e) {
+        const double dx = Q[(e + 1) % nq].x - Q[e].x, dz = Q[(e + 1) % nq].z - Q[e].z;
+        double h = -1e300;
+        for (int i = 0; i < np; ++i) h = fmax(h, P[i].x * dz - P[i].z * dx);
+        v += h;
+    }
+    return 0.5 * v;
+}
+
+__device__ __noinline__ double hull_enclosing_volume(const float *ax, const float *az, const float *bx, const float *bz,
+                                                     double ay0, double ay1, double by0, double by1)
+{
+    P2d A[4], Bq[4], pts[8], H[16];
+    for (int i = 0; i < 4; ++i) { A[i].x = ax[i]; A[i].z = az[i]; Bq[i].x = bx[i]; Bq[i].z = bz[i]; pts[i] = A[i]; pts[4 + i] = Bq[i]; }
+    const double a0 = fmin(ay0, ay1), a1 = fmax(ay0, ay1), b0 = fmin(by0, by1), b1 = fmax(by0, by1);
+    // Andrew's monotone chain on the 8 BEV points
+    for (int i = 1; i < 8; ++i) {
+        const P2d t = pts[i]; int j = i - 1;
+        while (j >= 0 && (pts[j].x > t.x || (pts[j].x == t.x && pts[j].z > t.z))) { pts[j + 1] = pts[j]; --j; }
+        pts[j + 1] = t;
+    }
+    int k = 0;
+    for (int i = 0; i < 8; ++i) { while (k >= 2 && cross2(H[k - 2], H[k - 1], pts[i]) <= 0.0) --k; H[k++] = pts[i]; }
+    for (int i = 6, lo = k + 1; i >= 0; --i) { while (k >= lo && cross2(H[k - 2], H[k - 1], pts[i]) <= 0.0) --k; H[k++] = pts[i]; }
+    const int nh = k - 1;
+    if (nh < 3) return 0.0;
+    const double aA = poly_area_ccw(A, 4), aB = poly_area_ccw(Bq, 4), aH = poly_area_ccw(H, nh);
+    const double vAB = mixed_area(A, 4, Bq, 4), vAH = mixed_area(A, 4, H, nh), vBH = mixed_area(Bq, 4, H, nh);
+    auto area_at = [&](double y) {
+        double l1 = 0.0, l2 = 1.0;
+        const double d0 = b0 - a0, d1 = b1 - a1;           // lo(l) = a0 + l*d0 <= y <= a1 + l*d1 = hi(l)
+        if (d0 > 0.0) l2 = fmin(l2, (y - a0) / d0); else if (d0 < 0.0) l1 = fmax(l1, (y - a0) / d0);
+        if (d1 > 0.0) l1 = fmax(l1, (y - a1) / d1); else if (d1 < 0.0) l2 = fmin(l2, (y - a1) / d1);
+        l1 = fmin(fmax(l1, 0.0), 1.0); l2 = fmin(fmax(l2, l1), 1.0);
+        const double al = 1.0 - l2, be = l1, ga = l2 - l1;
+        return al * al * aA + be * be * aB + ga * ga * aH + 2.0 * (al * be * vAB + al * ga * vAH + be * ga * vBH);
+    };
+    double ys[4] = {a0, a1, b0, b1};
+    for (int i = 1; i < 4; ++i) { const double t = ys[i]; int j = i - 1; while (j >= 0 && ys[j] > t) { ys[j + 1] = ys[j]; --j; } ys[j + 1] = t; }
+    double vol = 0.0;
+    for (int i = 0; i < 3; ++i) {
+        const double y0 = ys[i], y1 = ys[i + 1];
+        if (y1 > y0) vol += (y1 - y0) / 6.0 * (area_at(y0) + 4.0 * area_at(0.5 * (y0 + y1)) + area_at(y1));
+    }
+    return vol;
+}
+
 // ClipT = float: all-fp32 clip (torch path); double: Cython arithmetic.  PB = threads that drain the clip queue
 // (their Sutherland-Hodgman scratch is the largest shared-memory consumer: 128 B (fp32) / 256 B (fp64) per thread).
-template <typename ClipT, int PB, int TQ>
-__global__ void __launch_bounds__(NT) giou3d_kernel(GiouParams p)
+template <typename ClipT, int PB, int TQ, bool HULL>
+__global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // carve: f1[NF*TQ] f2[NF*TG] tile[TQ*TG] raw[(TQ+TG)*24] queue[TQ*TG u16] scratch[2*SH_MAXV*PB V2<ClipT>]
@@ -168,6 +243,7 @@ __global__ void __launch_bounds__(NT) giou3d_kernel(GiouParams p)
     const bool rotated = p.flags & OVDET_GIOU_ROTATED;
     const bool prefilter = p.flags & OVDET_GIOU_PREFILTER;
     const bool inter_only = p.flags & OVDET_GIOU_INTER_ONLY;
+    const bool hull = HULL && rotated;   // compile-time: the default instantiation carries no call / stack frame
     const bool has_nums = p.nums_k2 != nullptr;
     int nk = p.K2;
     if (has_nums) { const long long v = p.nums_k2[b]; nk = v < 0 ? 0 : (v > p.K2 ? p.K2 : (int)v); }
@@ -250,7 +326,17 @@ __global__ void __launch_bounds__(NT) giou3d_kernel(GiouParams p)
                     const int n = sh_clip_quads<float, PB>(s, cl, bufA, bufB);
                     area = area_f32<PB>(bufB, n);
                 }
-                const PairTerms t = pair_terms(load_boxf(f1, r, TQ), load_boxf(f2, c, TG));
+                PairTerms t = pair_terms(load_boxf(f1, r, TQ), load_boxf(f2, c, TG));
+                if (hull && __fmul_rn(area, t.h) > 0.f) {   // box_ops3d.py:467: hull only where the intersection volume is > 0
+                    float axv[4], azv[4], bxv[4], bzv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        axv[i] = f1[(F_RX + i) * TQ + r]; azv[i] = f1[(F_RZ + i) * TQ + r];
+                        bxv[i] = f2[(F_RX + i) * TG + c]; bzv[i] = f2[(F_RZ + i) * TG + c];
+                    }
+                    t.encl = (float)hull_enclosing_volume(axv, azv, bxv, bzv, f1[F_YTOP * TQ + r], f1[F_YBOT * TQ + r],
+                                                          f2[F_YTOP * TG + c], f2[F_YBOT * TG + c]);
+                }
                 tile[r * TG + c] = finish_pair(t, area, true, has_nums, inter_only);
             }
         }
@@ -305,20 +391,26 @@ template <typename ClipT, int PB, int TQ> static size_t giou_smem_bytes()
            sizeof(V2<ClipT>) * 2 * SH_MAXV * PB;
 }
 
-template <typename ClipT, int PB, int TQ> static int launch_giou_tq(GiouParams p, cudaStream_t st)
+template <typename ClipT, int PB, int TQ, bool HULL> static int launch_giou_tq2(GiouParams p, cudaStream_t st)
 {
     p.tiles_per_b = (p.K1 + TQ - 1) / TQ;
     const size_t smem = giou_smem_bytes<ClipT, PB, TQ>();
     static bool attr_set = false;
     if (!attr_set) {
-        OVDET_CUDA_TRY(cudaFuncSetAttribute(giou3d_kernel<ClipT, PB, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(giou3d_kernel<ClipT, PB, TQ, HULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const long long grid = (long long)p.B * p.tiles_per_b;
-    giou3d_kernel<ClipT, PB, TQ><<<(unsigned)grid, NT, smem, st>>>(p);
+    giou3d_kernel<ClipT, PB, TQ, HULL><<<(unsigned)grid, NT, smem, st>>>(p);
     return launch_ok("giou3d_kernel");
 }
 
+
+template <typename ClipT, int PB, int TQ> static int launch_giou_tq(const GiouParams &p, cudaStream_t st)
+{
+    if (p.flags & OVDET_GIOU_ENCL_HULL) return launch_giou_tq2<ClipT, PB, TQ, true>(p, st);
+    return launch_giou_tq2<ClipT, PB, TQ, false>(p, st);
+}
 
 // Tile height by grid size: this workload is tiny (config 1 = 64 x 128 x 64 pairs), so latency, not
 // throughput, decides; use the smallest row tile that still leaves every SM several CTAs deep.
@@ -334,9 +426,10 @@ template <typename ClipT, int PB> static int launch_giou(const GiouParams &p, cu
     // measured on B200 (profiles/r1_notes.md): when few pairs reach the clipper (prefilter on) the per-CTA staging of
     // the GT chunk dominates and 32-row tiles win (10.9 us vs 17.3 us at config 1); when every pair is clipped
     // (no prefilter) small tiles spread the clip work better (20 vs 15 Gpairs/s).
-    const bool clip_heavy = (p.flags & OVDET_GIOU_ROTATED) && !(p.flags & OVDET_GIOU_PREFILTER);
-    if (clip_heavy && t32 < 148 * 8) return launch_giou_tq<ClipT, PB, 8>(p, st);
-    if (t32 * 2 < 148) return launch_giou_tq<ClipT, PB, 16>(p, st);
+    // 16-row tiles (<= 64 registers, 4 CTAs/SM, one wave at config 1) match 32-row tiles on the default path
+    // (9.7 vs 9.6 us) and beat them when every pair is clipped (20.3 vs 15.3 Gpairs/s); 32-row tiles amortise the
+    // GT-chunk staging better once the grid is many waves deep.
+    if (t32 < 148 * 8) return launch_giou_tq<ClipT, PB, 16>(p, st);
     return launch_giou_tq<ClipT, PB, 32>(p, st);
 }
 
@@ -448,9 +541,6 @@ extern "C" int ovdet_giou3d_f32(const float *corners1, const float *corners2, co
     OVDET_REQUIRE(B >= 0 && K1 >= 0 && K2 >= 0, "negative size");
     if (B == 0 || K1 == 0 || K2 == 0) return OVDET_OK;
     OVDET_REQUIRE(corners1 && corners2 && out, "null pointer");
-    if (flags & OVDET_GIOU_ENCL_HULL) {
-        return giou3d_hull_impl(corners1, corners2, nums_k2, B, K1, K2, k2_cap, flags, out, stream);
-    }
     GiouParams p;
     p.c1 = corners1; p.c2 = corners2; p.nums_k2 = nums_k2; p.out = out;
     p.B = B; p.K1 = K1; p.K2 = K2; p.k2_cap = k2_cap; p.flags = flags;
@@ -470,7 +560,6 @@ extern "C" int ovdet_matcher_cost_f32(const float *sem_cls_prob, const float *ob
     OVDET_REQUIRE(sem_cls_prob && objectness && gt_labels && cost, "null pointer");
     OVDET_REQUIRE(center_dist || (center_q && center_g), "need center_dist or center_q/center_g");
     OVDET_REQUIRE(gious || (corners1 && corners2), "need gious or corners");
-    OVDET_REQUIRE(!(giou_flags & OVDET_GIOU_ENCL_HULL) || gious, "hull GIoU must be precomputed for the fused matcher");
     MatcherEpi e;
     e.prob = sem_cls_prob; e.obj = objectness; e.center_dist = center_dist; e.cq = center_q; e.cg = center_g;
     e.labels = gt_labels; e.cost = cost; e.C = C; e.wc = w_class; e.wo = w_obj; e.wce = w_center; e.wg = w_giou;

@@ -120,6 +120,7 @@ class APCalculator(object):
         self.class2type_map = class2type_map
         self.num_semcls = dataset_config.num_semcls if dataset_config is not None else None
         self.reduce_mode = "compact"   # "sort" forces the segmented radix sort + scan (full PR curves)
+        self.tp_list_cap = 2048        # per-class, per-rank TP-list capacity of the compact reducer (grows on overflow)
         self.reset()
 
     def make_gt_list(self, gt_box_corners, gt_box_sem_cls_labels, gt_box_present):
@@ -187,16 +188,18 @@ class APCalculator(object):
         ap = None
         if self.reduce_mode == "compact":
             # no global sort: TP lists + one histogram pass; across ranks only the TP lists and the bucket
-            # histogram travel (KBs) instead of the whole record stream
-            npos_local_max = int(npos.max().item()) if npos.numel() else 0
-            npos_g = npos
-            if distributed:
-                import torch.distributed as dist
-                npos_g = npos.clone()
-                dist.all_reduce(npos_g, op=dist.ReduceOp.SUM)
-            out = E.ap_reduce_compact(rs, rt, npos_g, nthr, nthr * npos_local_max, distributed=distributed)
-            if out is not None and int(out[3].item()) == 0:
-                ap, recall = out[0].cpu().numpy(), out[1].cpu().numpy()
+            # histogram travel (KBs) instead of the whole record stream.  Sync-free until the
+            # single D2H of the packed result; an overflowing TP list retries with 4x the capacity.
+            cap = self.tp_list_cap
+            while ap is None:
+                res = E.ap_reduce_compact(rs, rt, npos, nthr, cap=cap, distributed=distributed)
+                if res is None:
+                    break
+                ap_, recall_, ovf, _ = E.unpack_compact(res, nthr, rs.shape[0])
+                if ovf == 0:
+                    ap, recall = ap_, recall_
+                else:
+                    cap *= 4
         if ap is None:   # sort-based path: all-gather the (score, tp) records, segmented radix sort + scan
             if distributed:
                 from ..dist import gather_records

@@ -92,65 +92,78 @@ def _pow2_at_least(x, lo=1024):
     return c
 
 
-def ap_reduce_compact(rec_score, rec_tp, npos, nthr, tp_bound, use_07_metric=False, distributed=False):
-    """AP without a global sort (csrc/ap_compact.cu).  ``tp_bound`` = caller's upper bound on the number of
-    TP records of any class on THIS rank (e.g. nthr * max GT count); ``npos`` must already be global when
-    ``distributed``.  Returns (ap, recall, n_det) like ap_reduce, or None when the TP lists do not fit the
-    shared-memory sort (caller falls back to the sort-based ap_reduce)."""
+def ap_reduce_compact(rec_score, rec_tp, npos, nthr, cap=4096, use_07_metric=False, distributed=False):
+    """AP without a global sort (csrc/ap_compact.cu).  ``cap`` = per-class, per-rank TP-list capacity (power of two
+    >= 1024); ``npos`` is the LOCAL GT count (summed across ranks here when ``distributed``).  No host sync inside:
+    returns one device tensor ``res`` fp64 [2*nthr*C + 1 + C] = ap | recall | overflow flag | n_det, to be read back by
+    the caller in a single D2H copy; overflow != 0 means a TP list did not fit and the caller must retry with a
+    larger ``cap`` or use the sort-based ap_reduce.  Returns None when world*cap exceeds the shared-memory sort."""
     import torch.distributed as dist
     C.require_cuda(rec_score)
     dev = rec_score.device
     Cn, N = rec_score.shape
     world = dist.get_world_size() if distributed else 1
-    cap = _pow2_at_least(int(tp_bound))
-    if distributed:  # every rank must use the same capacity
-        t = torch.tensor([cap], dtype=torch.int64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        cap = int(t.item())
+    cap = _pow2_at_least(int(cap))
     cap_total = _pow2_at_least(cap * world)
     if cap_total > APC_MAXCAP:
         return None
     L = C.lib()
     st = C.stream(dev)
     rec_score, rec_tp = rec_score.contiguous(), rec_tp.contiguous()
-    npos = npos.to(device=dev, dtype=torch.int64).contiguous()
-    key = torch.empty((Cn, cap), dtype=torch.int32, device=dev)
-    bits = torch.empty((Cn, cap), dtype=torch.uint8, device=dev)
+    # one int64 buffer for everything that is summed across ranks: npos | nvalid | overflow count
+    sums = torch.zeros((2 * Cn + 1,), dtype=torch.int64, device=dev)
+    sums[:Cn] = npos.to(device=dev, dtype=torch.int64)
+    nvalid = sums[Cn:2 * Cn]
+    # TP lists: keys (int32 view of u32) and bits share one byte buffer so that one all-gather moves both
+    lists = torch.empty((Cn, cap * 5), dtype=torch.uint8, device=dev)
+    kbuf = torch.empty((Cn, cap), dtype=torch.int32, device=dev)
+    bbuf = torch.empty((Cn, cap), dtype=torch.uint8, device=dev)
     cnt = torch.empty((Cn,), dtype=torch.int32, device=dev)
-    nvalid = torch.empty((Cn,), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        C.check(L.ovdet_apc_collect(C.ptr(rec_score), C.ptr(rec_tp), Cn, N, cap, C.ptr(key), C.ptr(bits), C.ptr(cnt),
-                                    C.ptr(nvalid), st))
-        if world > 1 or cap_total != cap:
-            gk = torch.full((world, Cn, cap), -1, dtype=torch.int32, device=dev)   # 0xFFFFFFFF
-            gb = torch.zeros((world, Cn, cap), dtype=torch.uint8, device=dev)
-            if world > 1:
-                dist.all_gather_into_tensor(gk.view(world * Cn, cap), key)
-                dist.all_gather_into_tensor(gb.view(world * Cn, cap), bits)
-                dist.all_reduce(nvalid, op=dist.ReduceOp.SUM)
-                dist.all_reduce(cnt, op=dist.ReduceOp.MAX)   # overflow is a per-rank condition
-            else:
-                gk[0], gb[0] = key, bits
-            key = torch.full((Cn, cap_total), -1, dtype=torch.int32, device=dev)
-            bits = torch.zeros((Cn, cap_total), dtype=torch.uint8, device=dev)
-            key[:, :world * cap] = gk.permute(1, 0, 2).reshape(Cn, world * cap)
-            bits[:, :world * cap] = gb.permute(1, 0, 2).reshape(Cn, world * cap)
-            cnt_chk = torch.clamp(cnt, max=cap) + (cnt > cap).to(torch.int32) * cap_total  # keep the overflow signal
+        C.check(L.ovdet_apc_collect(C.ptr(rec_score), C.ptr(rec_tp), Cn, N, cap, C.ptr(kbuf), C.ptr(bbuf), C.ptr(cnt),
+                                    nvalid.data_ptr(), st))
+        sums[2 * Cn] = (cnt > cap).sum()
+        if world > 1:
+            lists[:, :cap * 4] = kbuf.view(torch.uint8)
+            lists[:, cap * 4:] = bbuf
+            glists = torch.empty((world * Cn, cap * 5), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(glists, lists)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            g = glists.view(world, Cn, cap * 5).permute(1, 0, 2)                      # [C, W, 5cap]
+            gk = g[:, :, :cap * 4].contiguous().view(torch.int32).reshape(Cn, world * cap)
+            gb = g[:, :, cap * 4:].reshape(Cn, world * cap)
         else:
-            cnt_chk = cnt
-        C.check(L.ovdet_apc_sort(C.ptr(key), C.ptr(bits), Cn, cap_total, st))
+            gk, gb = kbuf, bbuf
+        if cap_total != gk.shape[1]:
+            key2 = torch.full((Cn, cap_total), -1, dtype=torch.int32, device=dev)     # 0xFFFFFFFF = empty slot
+            bits2 = torch.zeros((Cn, cap_total), dtype=torch.uint8, device=dev)
+            key2[:, :gk.shape[1]] = gk
+            bits2[:, :gb.shape[1]] = gb
+        else:
+            key2, bits2 = gk.contiguous(), gb.contiguous()
+        C.check(L.ovdet_apc_sort(C.ptr(key2), C.ptr(bits2), Cn, cap_total, st))
         hist = torch.empty((Cn, cap_total + 1), dtype=torch.int32, device=dev)
-        C.check(L.ovdet_apc_hist(C.ptr(rec_score), Cn, N, C.ptr(key), cap_total, C.ptr(hist), st))
+        C.check(L.ovdet_apc_hist(C.ptr(rec_score), Cn, N, C.ptr(key2), cap_total, C.ptr(hist), st))
         if world > 1:
             dist.all_reduce(hist, op=dist.ReduceOp.SUM)
-        ap = torch.empty((nthr, Cn), dtype=torch.float64, device=dev)
-        recall = torch.empty((nthr, Cn), dtype=torch.float64, device=dev)
+        res = torch.empty((2 * nthr * Cn + 1 + Cn,), dtype=torch.float64, device=dev)
         ndet = torch.empty((Cn,), dtype=torch.int64, device=dev)
-        ovf = torch.zeros((1,), dtype=torch.int32, device=dev)
-        C.check(L.ovdet_apc_final(C.ptr(bits), C.ptr(cnt_chk.contiguous()), C.ptr(hist), C.ptr(npos), C.ptr(nvalid), Cn,
-                                  cap_total, nthr, int(bool(use_07_metric)), C.ptr(ap), C.ptr(recall), C.ptr(ndet),
-                                  C.ptr(ovf), st))
-    return ap, recall, ndet, ovf
+        zero_cnt = torch.zeros((Cn,), dtype=torch.int32, device=dev)   # overflow is carried in `sums`, not here
+        npos_g = sums[:Cn].contiguous()
+        nvalid_g = sums[Cn:2 * Cn].contiguous()
+        C.check(L.ovdet_apc_final(C.ptr(bits2), C.ptr(zero_cnt), C.ptr(hist), C.ptr(npos_g), C.ptr(nvalid_g), Cn,
+                                  cap_total, nthr, int(bool(use_07_metric)), res.data_ptr(),
+                                  res.data_ptr() + 8 * nthr * Cn, C.ptr(ndet), None, st))
+        res[2 * nthr * Cn] = sums[2 * Cn].to(torch.float64)
+        res[2 * nthr * Cn + 1:] = ndet.to(torch.float64)
+    return res
+
+
+def unpack_compact(res, nthr, Cn):
+    """Host view of ap_reduce_compact's packed result -> (ap [nthr,C], recall [nthr,C], overflow, n_det [C])."""
+    r = res.cpu().numpy()
+    k = nthr * Cn
+    return r[:k].reshape(nthr, Cn), r[k:2 * k].reshape(nthr, Cn), int(r[2 * k]), r[2 * k + 1:].astype(np.int64)
 
 
 def _pack(pred_all, gt_all):

@@ -171,6 +171,11 @@ def generalized_box3d_iou(corners1, corners2, nums_k2, rotated_boxes=True, retur
                             1 if mode == "cython" else 0, int(bool(prefilter)), cap, out)
         return out
     assert enclosing == "hull"
+    # utils/box_ops3d.py:475-530 (generalized_box3d_iou_convex_hull_nondiff_tensor; the file itself cannot be
+    # imported): the enclosing volume starts as the AABB one (:505) and, for rotated boxes, is
+    # replaced by scipy's ConvexHull(np.vstack([c1, c2])).volume only where the intersection volume is > 0 and
+    # the column is valid (:467,:514-519); stored as fp32.
+    import ctypes as _ct
     inter = np.zeros((B, K1, K2), np.float32)
     lib().oracle_giou3d(c1, c2, ptr, B, K1, K2, int(bool(rotated_boxes)), 1,
                         1 if mode == "cython" else 0, int(bool(prefilter)), cap, inter)
@@ -181,15 +186,20 @@ def generalized_box3d_iou(corners1, corners2, nums_k2, rotated_boxes=True, retur
         for i in range(K1):
             v1 = max(_vol_f32(c1[b, i]), EPS)
             for j in range(K2):
+                valid = nk is None or j < nk[b]
                 v2 = max(_vol_f32(c2[b, j]), EPS)
                 sv = np.float32(v1 + v2)
-                encl = np.float32(enclosing_hull_vol(c1[b, i], c2[b, j])) if _nondegenerate(c1[b, i], c2[b, j]) else np.float32(0)
+                both = np.vstack([c1[b, i], c2[b, j]])
+                d = np.abs(both.max(0) - both.min(0)).astype(np.float32)
+                encl = np.float32(np.float32(d[0] * d[1]) * d[2])
+                if rotated_boxes and valid and inter[b, i, j] > 0:
+                    encl = np.float32(enclosing_hull_vol(c1[b, i], c2[b, j]))
                 uni = max(np.float32(sv - inter[b, i, j]), EPS)
                 good = np.float32((encl > 2 * EPS) and (sv > 4 * EPS))
                 with np.errstate(all="ignore"):
-                    g = np.float32(inter[b, i, j] / uni) + (-(np.float32(1) - np.float32(uni / encl)))
+                    g = np.float32(np.float32(inter[b, i, j] / uni) + (-(np.float32(1) - np.float32(uni / encl))))
                     g = np.float32(g * good)
-                if nk is not None and j >= nk[b]:
+                if nk is not None and not valid:
                     g = np.float32(g * 0)
                 out[b, i, j] = g
     return out

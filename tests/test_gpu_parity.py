@@ -77,6 +77,25 @@ def test_giou_vs_oracle(cfg):
     assert_close_giou(got.numpy(), oracle.generalized_box3d_iou(c1, c2, nk, rot, False, mode="tensor"), what="host")
 
 
+@pytest.mark.parametrize("heading", [0.5, np.pi])
+def test_giou_hull_enclosing(heading):
+    """enclosing="hull" (utils/box_ops3d.py:475-530): convex-hull enclosing volume where the boxes intersect, AABB
+    elsewhere; oracle = scipy ConvexHull of the 16 corners."""
+    out, tgt = synth.detection_batch(B=2, Q=24, G=12, seed=41, heading=heading, max_gt=12)
+    c1, c2, nk = out["box_corners"], tgt["gt_box_corners"], tgt["nactual_gt"]
+    pre = heading < 1.0   # with headings in +-pi the reference's axis-aligned prefilter zeroes almost every intersection
+    want = oracle.generalized_box3d_iou(c1, c2, nk, True, False, mode="tensor", enclosing="hull", prefilter=pre)
+    got = BU.generalized_box3d_iou(c1.to(DEV), c2.to(DEV), nk.to(DEV), mode="tensor", k2_cap=0, enclosing="hull",
+                                   prefilter=pre).cpu().numpy()
+    assert_close_giou(got, want, what="hull")
+    aabb = BU.generalized_box3d_iou(c1.to(DEV), c2.to(DEV), nk.to(DEV), mode="tensor", k2_cap=0, prefilter=pre).cpu().numpy()
+    inter = oracle.generalized_box3d_iou(c1, c2, nk, True, True, mode="tensor", prefilter=pre)
+    assert (inter > 0).sum() > 10
+    assert (got[inter > 0] >= aabb[inter > 0] - 1e-6).all()          # hull volume <= AABB volume -> GIoU can only grow
+    assert (got[inter > 0] > aabb[inter > 0] + 1e-4).any() or heading == 0.0
+    np.testing.assert_array_equal(got[inter == 0], aabb[inter == 0])  # untouched where the boxes do not intersect
+
+
 def test_giou_properties_full_size():
     """Size-independent properties at the bench size: symmetry of the intersection volume,
     GIoU in [-1, 1], zero beyond nums_k2, identical axis-aligned box -> IoU 1."""
@@ -319,21 +338,24 @@ def test_ap_compact_equals_sort_path():
     tp[score == float("-inf")] = 0
     npos = (tp != 0).sum(1).to(torch.int64) + 11
     bound = int((tp != 0).sum(1).max())
+    k = 2 * C
     for m07 in (False, True):
         ap, recall, ndet = ED.ap_reduce(score, tp, npos, 2, use_07_metric=m07)
-        out = ED.ap_reduce_compact(score, tp, npos, 2, bound, use_07_metric=m07)
-        assert out is not None and int(out[3]) == 0
-        np.testing.assert_allclose(out[0].cpu().numpy(), ap.cpu().numpy(), rtol=0, atol=1e-13)
-        np.testing.assert_allclose(out[1].cpu().numpy(), recall.cpu().numpy(), rtol=0, atol=0)
-        np.testing.assert_array_equal(out[2].cpu().numpy(), ndet.cpu().numpy())
-    out = ED.ap_reduce_compact(score, tp, npos, 2, 1024)   # capacity below the real TP count -> overflow flag
-    assert int(out[3]) == 1
-    assert ED.ap_reduce_compact(score, tp, npos, 2, 10 ** 6) is None   # does not fit shared memory -> caller falls back
+        res = ED.ap_reduce_compact(score, tp, npos, 2, cap=bound, use_07_metric=m07)
+        assert res is not None
+        cap_, rec_, ovf, nd_ = ED.unpack_compact(res, 2, C)
+        assert ovf == 0
+        np.testing.assert_allclose(cap_, ap.cpu().numpy(), rtol=0, atol=1e-13)
+        np.testing.assert_allclose(rec_, recall.cpu().numpy(), rtol=0, atol=0)
+        np.testing.assert_array_equal(nd_, ndet.cpu().numpy())
+    res = ED.ap_reduce_compact(score, tp, npos, 2, cap=1024)   # capacity below the real TP count -> overflow flag
+    assert ED.unpack_compact(res, 2, C)[2] > 0
+    assert ED.ap_reduce_compact(score, tp, npos, 2, cap=10 ** 6) is None   # does not fit shared memory -> caller falls back
     # small, ragged N
     s2, t2 = score[:3, :777].contiguous(), tp[:3, :777].contiguous()
     ap, recall, _ = ED.ap_reduce(s2, t2, npos[:3], 2)
-    out = ED.ap_reduce_compact(s2, t2, npos[:3], 2, 64)
-    np.testing.assert_allclose(out[0].cpu().numpy(), ap.cpu().numpy(), rtol=0, atol=1e-13)
+    res = ED.ap_reduce_compact(s2, t2, npos[:3], 2, cap=64)
+    np.testing.assert_allclose(ED.unpack_compact(res, 2, 3)[0], ap.cpu().numpy(), rtol=0, atol=1e-13)
 
 
 # ------------------------------------------------------------------ matcher
