@@ -57,6 +57,17 @@ int ovdet_device_count(void);           /* number of visible CUDA devices (0 if 
 int ovdet_giou3d_f32(const float *corners1, const float *corners2, const int64_t *nums_k2,
                      int B, int K1, int K2, int k2_cap, unsigned flags, float *out, void *stream);
 
+/* Box decode: box_parametrization_to_corners (datasets/sunrgbd.py:145-148 =
+ * flip_axis_to_camera + get_3d_box_batch_tensor, utils/box_util.py:288-352).  center [n,3] in the
+ * depth frame, size [n,3] = l,w,h, angle [n] -> corners [n,8,3] in the upright-camera frame. */
+int ovdet_box_corners_f32(const float *center, const float *size, const float *angle, int64_t n, float *corners, void *stream);
+
+/* ovdet_giou3d_f32 with the query boxes given as (center1 [B,K1,3], size1 [B,K1,3], angle1 [B,K1]): the decode is
+ * fused into the kernel's load stage (28 B/box read instead of 96 B).  corners1_out [B,K1,8,3] is optional. */
+int ovdet_giou3d_decode_f32(const float *center1, const float *size1, const float *angle1, const float *corners2,
+                            const int64_t *nums_k2, int B, int K1, int K2, int k2_cap, unsigned flags,
+                            float *out, float *corners1_out, void *stream);
+
 /* ------------------------------------------------------------------------- */
 /* The Cython extension ABI: box_intersection(rect1, rect2,                   */
 /*   non_rot_inter_areas, nums_k2, inter_areas, approximate)                  */

@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -43,7 +44,16 @@ struct LogitsParams {
     __nv_bfloat16 *prob; int ld_prob;
     float *objectness;
     const float *inv_nx, *inv_nt;
+    unsigned long long *dbg;   // optional [gridDim.x][8] globaltimer stamps of warp 4 lane 0 (profiling; NULL in production)
 };
+
+__device__ __forceinline__ unsigned long long gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define STAMP(i) do { if (p.dbg && threadIdx.x == 128) p.dbg[(size_t)blockIdx.x * 8 + (i)] = gtimer(); } while (0)
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -75,6 +85,13 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
 }
+// multicast: the box lands at the same shared offset in every CTA of cta_mask and completes tx bytes on each one's mbarrier
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap *map, uint64_t *bar, void *dst, int x, int y, uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(cta_mask) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -103,6 +120,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// commit that arrives on the same mbarrier of every CTA in cta_mask (ring-slot release across the cluster)
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread
@@ -201,10 +225,13 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
 
+    STAMP(0);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        // A is multicast: a ring slot may be refilled only when EVERY CTA of the cluster has consumed it,
+        // so each MMA commit arrives on the empty barrier of all nc CTAs
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)p.nc); }
         mbar_init(&tmem_full_bar, 1);
         fence_barrier_init();
     }
@@ -214,7 +241,9 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     __syncthreads();
     tc_fence_after();
     cluster_sync_all();   // every CTA of the cluster is resident before any DSMEM traffic
+    STAMP(1);
     const uint32_t tmem_base = tmem_base_s;
+    const uint16_t mc_mask = (uint16_t)((1u << p.nc) - 1u);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -224,8 +253,13 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 unsigned char *sa = smem + (size_t)s * stage_bytes;
-                mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
-                tma_load_2d(&tmA, &full_bar[s], sa, kb * GM_K, m0);
+                mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);   // 16 KB of A arrive as nc multicast slices, B is ours
+                if (p.nc > 1) {
+                    const int rows = GM_M / p.nc;                  // this CTA fetches rows [rank*rows, +rows) of the A tile for everyone
+                    tma_load_2d_mc(&tmA, &full_bar[s], sa + (size_t)rank * rows * (GM_K * 2), kb * GM_K, m0 + (int)rank * rows, mc_mask);
+                } else {
+                    tma_load_2d(&tmA, &full_bar[s], sa, kb * GM_K, m0);
+                }
                 tma_load_2d(&tmB, &full_bar[s], sa + a_bytes, kb * GM_K, n0);
             }
         }
@@ -244,7 +278,8 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                 for (int k = 0; k < GM_K / 16; ++k)   // +32 B (>>4 = 2) per UMMA_K=16 step inside the swizzle atom
                     umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-                umma_commit(&empty_bar[s]);                       // slot free once these MMAs retire
+                if (p.nc > 1) umma_commit_mc(&empty_bar[s], mc_mask);   // slot free (cluster-wide) once these MMAs retire
+                else umma_commit(&empty_bar[s]);
                 if (kb == p.num_kb - 1) umma_commit(&tmem_full_bar);  // accumulator complete
             }
             __syncwarp();
@@ -270,6 +305,7 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
+    STAMP(2);
     // ---- pass 1: running (max, sum-exp) over this warp's chunks (+ optional fp32 logits store)
     for (int c0 = grp * 32; c0 < p.block_n; c0 += 64) {
         const int w = min(32, p.block_n - c0);
@@ -305,6 +341,7 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         rmax = nm;
     }
     part[grp][row] = make_float2(rmax, rsum);
+    STAMP(3);
     __syncthreads();
     {   // merge the two column groups, publish to every CTA of the cluster (each group serves half of the ranks)
         const float2 s0 = part[0][row], s1 = part[1][row];
@@ -314,6 +351,7 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int r = grp; r < p.nc; r += 2) st_cluster_f32x2(&stats[rank][row], (uint32_t)r, m, sm);
     }
     cluster_sync_all();   // release/acquire: all stats visible cluster-wide
+    STAMP(4);
 
     if (p.prob || p.objectness) {
         float gmax = -INFINITY;
@@ -367,6 +405,7 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
             }
         }
+        STAMP(5);
         if (p.prob) {
             __syncthreads();
             const int pieces = p.block_n / 8;                // 16-byte pieces per row
@@ -380,9 +419,11 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         }
     }
+    STAMP(6);
     tc_fence_before();
     __syncthreads();
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+    STAMP(7);
 }
 
 // inverse L2 norms of bf16 rows (F.normalize(x, dim=-1, p=2): x / max(|x|, 1e-12)), one warp per row
@@ -453,11 +494,14 @@ extern "C" int ovdet_clip_logits_bf16(const void *x, const void *text, int M, in
     LogitsParams p;
     p.M = M; p.N = N; p.K = K; p.block_n = bn; p.nc = nc; p.num_kb = K / GM_K;
     p.stages = 2;   // two CTAs are co-resident per SM (4 stages in flight), one in its mainloop while the other normalises
+    { const char *e = getenv("OVDET_LOGITS_STAGES"); if (e) p.stages = atoi(e); }   // profiling experiments
     if (p.stages > p.num_kb) p.stages = p.num_kb;
+    if (p.stages > 8) p.stages = 8;
     p.tmem_cols = 32; while (p.tmem_cols < bn) p.tmem_cols <<= 1;
     p.flags = flags; p.scale = scale;
     p.logits = logits; p.ld_logits = ld_logits; p.prob = static_cast<__nv_bfloat16 *>(prob); p.ld_prob = ld_prob;
     p.objectness = objectness; p.inv_nx = nullptr; p.inv_nt = nullptr;
+    { const char *e = getenv("OVDET_LOGITS_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
     float *norms = nullptr;
     if (flags & OVDET_LOGITS_L2NORM) {
         OVDET_CUDA_TRY(cudaMallocAsync(&norms, sizeof(float) * ((size_t)M + N), st));
@@ -466,7 +510,7 @@ extern "C" int ovdet_clip_logits_bf16(const void *x, const void *text, int M, in
         p.inv_nx = norms; p.inv_nt = norms + M;
     }
     CUtensorMap tmA, tmB;
-    int rc = make_map(&tmA, x, M, K, GM_M);
+    int rc = make_map(&tmA, x, M, K, GM_M / nc);   // each CTA of the cluster fetches (and multicasts) 128/nc rows of the A tile
     if (rc) return rc;
     rc = make_map(&tmB, text, N, K, bn);
     if (rc) return rc;

@@ -42,6 +42,27 @@ struct MatcherEpi {
     float wc = 0, wo = 0, wce = 0, wg = 0;
 };
 
+// optional fused box decode: query boxes given as (centre in the depth frame, size l/w/h, heading)
+// instead of 8 corners -- 28 B/box read instead of 96 B, and no separate decode kernels
+struct BoxDecode { const float *center = nullptr, *size = nullptr, *angle = nullptr; float *corners_out = nullptr; };
+
+// box_parametrization_to_corners (datasets/sunrgbd.py:145-148): flip_axis_to_camera (utils/box_util.py:288-295)
+// then get_3d_box_batch_tensor (:313-352): corners = local @ roty(angle)^T + centre
+__device__ __forceinline__ void decode_box(const float *ctr, const float *sz, float ang, float *c)
+{
+    const float cx = ctr[0], cy = -ctr[2], cz = ctr[1];
+    const float l = sz[0] * 0.5f, w = sz[1] * 0.5f, h = sz[2] * 0.5f;
+    const float co = cosf(ang), si = sinf(ang);
+    const float sx[8] = {1, 1, -1, -1, 1, 1, -1, -1}, sy[8] = {1, 1, 1, 1, -1, -1, -1, -1}, szn[8] = {1, -1, -1, 1, 1, -1, -1, 1};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float x = sx[i] * l, y = sy[i] * h, z = szn[i] * w;
+        c[3 * i] = __fadd_rn(__fadd_rn(__fmul_rn(x, co), __fmul_rn(z, si)), cx);
+        c[3 * i + 1] = __fadd_rn(y, cy);
+        c[3 * i + 2] = __fadd_rn(__fadd_rn(__fmul_rn(x, -si), __fmul_rn(z, co)), cz);
+    }
+}
+
 struct GiouParams {
     const float *c1, *c2;
     const int64_t *nums_k2;
@@ -50,6 +71,7 @@ struct GiouParams {
     unsigned flags;
     int tiles_per_b;
     MatcherEpi epi;
+    BoxDecode dec1;
 };
 
 // features of one box from its 24 staged floats (utils/box_util.py:550-555 rect,
@@ -256,7 +278,16 @@ __global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams
     for (int g0 = 0; g0 < p.K2; g0 += TG) {
         const int ng = min(TG, p.K2 - g0);
         // ---- stage the query tile (first chunk only) and this GT chunk with one barrier, features with one more
-        if (g0 == 0) stage_boxes(p.c1 + ((size_t)b * p.K1 + q0) * 24, nq, raw1, vec1);
+        if (g0 == 0) {
+            if (p.dec1.center) {   // fused decode: one thread per query box writes its 8 corners straight into the staging buffer
+                if (threadIdx.x < nq) {
+                    const size_t q = (size_t)b * p.K1 + q0 + threadIdx.x;
+                    decode_box(p.dec1.center + 3 * q, p.dec1.size + 3 * q, __ldg(p.dec1.angle + q), raw1 + threadIdx.x * 24);
+                    if (p.dec1.corners_out)
+                        for (int i = 0; i < 24; ++i) p.dec1.corners_out[q * 24 + i] = raw1[threadIdx.x * 24 + i];
+                }
+            } else stage_boxes(p.c1 + ((size_t)b * p.K1 + q0) * 24, nq, raw1, vec1);
+        }
         stage_boxes(p.c2 + ((size_t)b * p.K2 + g0) * 24, ng, raw2, vec2);
         if (threadIdx.x == 0) qcount = 0;
         __syncthreads();
@@ -491,6 +522,17 @@ __global__ void __launch_bounds__(NT) box_intersection_kernel(BiParams p)
     }
 }
 
+__global__ void __launch_bounds__(256) box_corners_kernel(const float *__restrict__ center, const float *__restrict__ size,
+                                                          const float *__restrict__ angle, long long n, float *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float c[24];
+    decode_box(center + 3 * i, size + 3 * i, __ldg(angle + i), c);
+#pragma unroll
+    for (int k = 0; k < 24; ++k) out[i * 24 + k] = c[k];
+}
+
 __global__ void __launch_bounds__(256) matcher_cost_kernel(MatcherEpi e, const float *__restrict__ gious, int Q, int G, long long total)
 {
     using A = Ar<float>;
@@ -545,6 +587,29 @@ extern "C" int ovdet_giou3d_f32(const float *corners1, const float *corners2, co
     p.c1 = corners1; p.c2 = corners2; p.nums_k2 = nums_k2; p.out = out;
     p.B = B; p.K1 = K1; p.K2 = K2; p.k2_cap = k2_cap; p.flags = flags;
     p.tiles_per_b = 0;
+    return giou3d_launch(p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ovdet_box_corners_f32(const float *center, const float *size, const float *angle, int64_t n, float *corners, void *stream)
+{
+    OVDET_REQUIRE(n >= 0, "negative size");
+    if (n == 0) return OVDET_OK;
+    OVDET_REQUIRE(center && size && angle && corners, "null pointer");
+    box_corners_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(center, size, angle, n, corners);
+    return launch_ok("box_corners_kernel");
+}
+
+extern "C" int ovdet_giou3d_decode_f32(const float *center1, const float *size1, const float *angle1, const float *corners2,
+                                       const int64_t *nums_k2, int B, int K1, int K2, int k2_cap, unsigned flags,
+                                       float *out, float *corners1_out, void *stream)
+{
+    OVDET_REQUIRE(B >= 0 && K1 >= 0 && K2 >= 0, "negative size");
+    if (B == 0 || K1 == 0 || K2 == 0) return OVDET_OK;
+    OVDET_REQUIRE(center1 && size1 && angle1 && corners2 && out, "null pointer");
+    GiouParams p;
+    p.c1 = nullptr; p.c2 = corners2; p.nums_k2 = nums_k2; p.out = out;
+    p.B = B; p.K1 = K1; p.K2 = K2; p.k2_cap = k2_cap; p.flags = flags; p.tiles_per_b = 0;
+    p.dec1.center = center1; p.dec1.size = size1; p.dec1.angle = angle1; p.dec1.corners_out = corners1_out;
     return giou3d_launch(p, reinterpret_cast<cudaStream_t>(stream));
 }
 

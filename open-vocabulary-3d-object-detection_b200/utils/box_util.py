@@ -129,9 +129,48 @@ def box3d_iou(corners1, corners2):
     return float(iou.item()), float(iou2.item())
 
 
+def box_parametrization_to_corners(box_center_unnorm, box_size, box_angle):
+    """datasets/sunrgbd.py:145-148 / scannet.py:138-141: (centre in the depth frame [...,3], size l/w/h [...,3],
+    heading [...]) -> corners [...,8,3] in the upright-camera frame; one kernel instead of ~15 torch ops."""
+    C.require_cuda(box_center_unnorm)
+    dev = box_center_unnorm.device
+    shape = box_angle.shape
+    ctr = box_center_unnorm.detach().to(torch.float32).reshape(-1, 3).contiguous()
+    sz = box_size.detach().to(device=dev, dtype=torch.float32).reshape(-1, 3).contiguous()
+    ang = box_angle.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+    n = ang.numel()
+    out = torch.empty((n, 8, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        C.check(C.lib().ovdet_box_corners_f32(C.ptr(ctr), C.ptr(sz), C.ptr(ang), n, C.ptr(out), C.stream(dev)))
+    return out.reshape(*shape, 8, 3)
+
+
 def get_3d_box_batch_tensor(box_size, angle, center):
-    """utils/box_util.py:313-352: (size [...,3] l,w,h; heading [...]; centre [...,3]
-    already in the upright-camera frame) -> corners [...,8,3]."""
-    from ..synth import params_to_corners  # same corner convention; undo its axis flip
-    c = torch.stack([center[..., 0], center[..., 2], -center[..., 1]], -1)
-    return params_to_corners(c.cpu(), box_size.cpu(), angle.cpu()).to(box_size.device)
+    """utils/box_util.py:313-352: centre already in the upright-camera frame."""
+    depth_center = torch.stack([center[..., 0], center[..., 2], -center[..., 1]], -1)   # undo flip_axis_to_camera
+    return box_parametrization_to_corners(depth_center, box_size, angle)
+
+
+def generalized_box3d_iou_from_params(center1, size1, angle1, corners2, nums_k2, rotated_boxes=True,
+                                      return_inter_vols_only=False, needs_grad=False, *, mode=None, prefilter=True,
+                                      k2_cap=None, enclosing="aabb", return_corners=False):
+    """generalized_box3d_iou with the query boxes still in (centre, size, heading) form -- the decode of
+    models/model_3detr.py:279 is fused into the GIoU kernel's load stage."""
+    C.require_cuda(center1, corners2)
+    if mode is None:
+        mode = "tensor" if needs_grad else "cython"
+    if k2_cap is None:
+        k2_cap = DEFAULT_K2_CAP if mode == "cython" else 0
+    flags = giou_flags(rotated_boxes, return_inter_vols_only, mode, prefilter, enclosing)
+    dev = center1.device
+    B, K1 = center1.shape[0], center1.shape[1]
+    K2 = corners2.shape[1]
+    f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    ctr, sz, ang, c2 = f32(center1), f32(size1), f32(angle1), f32(corners2)
+    nk = None if nums_k2 is None else torch.as_tensor(nums_k2).detach().to(device=dev, dtype=torch.int64).contiguous()
+    out = torch.empty((B, K1, K2), dtype=torch.float32, device=dev)
+    c1o = torch.empty((B, K1, 8, 3), dtype=torch.float32, device=dev) if return_corners else None
+    with torch.cuda.device(dev):
+        C.check(C.lib().ovdet_giou3d_decode_f32(C.ptr(ctr), C.ptr(sz), C.ptr(ang), C.ptr(c2), C.ptr(nk), B, K1, K2,
+                                                int(k2_cap), flags, C.ptr(out), C.ptr(c1o), C.stream(dev)))
+    return (out, c1o) if return_corners else out

@@ -514,3 +514,25 @@ def test_label_formatter_golden(golden, tmp_path):
     assert rows.shape == (32, 10)
     keep = (rows[:, 7] >= 0.1) & (rows[:, 8] >= 0.5)
     assert fmt2.pseudo_boxes.shape[0] == keep.sum()
+
+
+# ------------------------------------------------------------------ box decode (8f-3)
+def test_box_decode_and_fused_giou():
+    out, tgt = synth.detection_batch(B=4, Q=96, G=32, seed=51, heading=np.pi, max_gt=32)
+    ctr, sz, ang = out["center_unnormalized"], out["size_unnormalized"], out["angle_continuous"]
+    want = synth.params_to_corners(ctr, sz, ang)           # the reference convention (goldens were generated through it)
+    got = BU.box_parametrization_to_corners(ctr.to(DEV), sz.to(DEV), ang.to(DEV)).cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=2e-6)
+    assert got.shape == (4, 96, 8, 3)
+    cam = torch.stack([ctr[..., 0], -ctr[..., 2], ctr[..., 1]], -1)
+    got2 = BU.get_3d_box_batch_tensor(sz.to(DEV), ang.to(DEV), cam.to(DEV)).cpu()
+    np.testing.assert_allclose(got2.numpy(), want.numpy(), rtol=0, atol=2e-6)
+    # fused: decode inside the GIoU kernel == decode kernel followed by the GIoU kernel, bit for bit
+    c2, nk = tgt["gt_box_corners"].to(DEV), tgt["nactual_gt"].to(DEV)
+    a, c1o = BU.generalized_box3d_iou_from_params(ctr.to(DEV), sz.to(DEV), ang.to(DEV), c2, nk, mode="tensor", k2_cap=0,
+                                                  return_corners=True)
+    b = BU.generalized_box3d_iou(got.to(DEV), c2, nk, mode="tensor", k2_cap=0)
+    np.testing.assert_array_equal(c1o.cpu().numpy(), got.numpy())
+    np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
+    assert_close_giou(a.cpu().numpy(), oracle.generalized_box3d_iou(want, tgt["gt_box_corners"], tgt["nactual_gt"], True, False, mode="tensor"),
+                      rtol=1e-4, atol=1e-5, what="fused decode vs oracle on torch-decoded corners")
