@@ -146,6 +146,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v)
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// registers -> 32 lanes x 32 fp32 columns of TMEM (the un-normalised exponentials are parked in the accumulator)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float *v)
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr),
+          "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr)
 {
     uint32_t r;
@@ -306,40 +326,52 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     STAMP(2);
-    // ---- pass 1: running (max, sum-exp) over this warp's chunks (+ optional fp32 logits store)
-    for (int c0 = grp * 32; c0 < p.block_n; c0 += 64) {
+    // ---- pass 1: online (max, sum-exp) over this warp's chunks.  Each chunk's exponentials 2^(y - m_c) (m_c = the
+    // running max after that chunk) are written BACK into the accumulator's TMEM columns, so pass 2 only rescales:
+    // one MUFU.EX2 per element in total (the epilogue is MUFU-bound: 16 exp/clk/SM).
+    float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // m_c of this warp's chunks (BLOCK_N <= 256 -> <= 4)
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+        const int c0 = grp * 32 + ci * 64;
         const int w = min(32, p.block_n - c0);
         const int nv = min(w, p.N - (n0 + c0));      // valid columns in this chunk (warp-uniform)
-        if (nv <= 0) break;
-        float v[32];
-        tmem_ld32(trow + (uint32_t)c0, v);   // the TMEM allocation is a power of two >= BLOCK_N: a 16-column tail chunk may read (and mask) 32
-        if (p.inv_nt) {
+        if (c0 < p.block_n && nv > 0) {
+            float v[32];
+            tmem_ld32(trow + (uint32_t)c0, v);   // the TMEM allocation is a power of two >= BLOCK_N: a 16-column tail chunk may read (and mask) 32
+            if (p.inv_nt) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 cs = *reinterpret_cast<const float4 *>(colscale + c0 + i);
-                v[i] *= cs.x; v[i + 1] *= cs.y; v[i + 2] *= cs.z; v[i + 3] *= cs.w;
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 cs = *reinterpret_cast<const float4 *>(colscale + c0 + i);
+                    v[i] *= cs.x; v[i + 1] *= cs.y; v[i + 2] *= cs.z; v[i + 3] *= cs.w;
+                }
             }
+            if (p.logits && row_ok) {
+                float *o = p.logits + (size_t)(m0 + row) * p.ld_logits + n0 + c0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < nv) o[i] = v[i] * rs;
+            }
+            float cmax = -INFINITY;
+            if (nv == 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { v[i] *= a2; cmax = fmaxf(cmax, v[i]); }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { v[i] = i < nv ? v[i] * a2 : -INFINITY; cmax = fmaxf(cmax, v[i]); }
+            }
+            const float nm = fmaxf(rmax, cmax);
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                v[i] = fast_exp2(v[i] - nm); v[i + 1] = fast_exp2(v[i + 1] - nm);
+                acc0 += v[i]; acc1 += v[i + 1];
+            }
+            tmem_st32(trow + (uint32_t)c0, v);
+            rsum = rsum * fast_exp2(rmax - nm) + (acc0 + acc1);
+            rmax = nm;
+            cm[ci] = nm;
         }
-        if (p.logits && row_ok) {
-            float *o = p.logits + (size_t)(m0 + row) * p.ld_logits + n0 + c0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (i < nv) o[i] = v[i] * rs;
-        }
-        float cmax = -INFINITY;
-        if (nv == 32) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] *= a2; cmax = fmaxf(cmax, v[i]); }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] = i < nv ? v[i] * a2 : -INFINITY; cmax = fmaxf(cmax, v[i]); }
-        }
-        const float nm = fmaxf(rmax, cmax);
-        float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) { acc0 += fast_exp2(v[i] - nm); acc1 += fast_exp2(v[i + 1] - nm); }
-        rsum = rsum * fast_exp2(rmax - nm) + (acc0 + acc1);
-        rmax = nm;
     }
+    tmem_wait_st();
     part[grp][row] = make_float2(rmax, rsum);
     STAMP(3);
     __syncthreads();
@@ -366,28 +398,22 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int tile_ld = p.block_n + 8;   // bf16 elements; +16 B keeps the 16-byte row writes conflict-free
         __nv_bfloat16 *tile = reinterpret_cast<__nv_bfloat16 *>(smem);
         const int obj_c = p.N - 1 - n0;      // tile column holding the background class, if in this tile
-        if (p.objectness && grp == 0 && obj_c >= 0 && obj_c < p.block_n) {   // warp-uniform: one extra 1-column TMEM read
-            float x = tmem_ld1(trow + (uint32_t)obj_c);
-            if (p.inv_nt) x *= colscale[obj_c];
-            if (row_ok) p.objectness[m0 + row] = 1.f - fast_exp2(x * a2 - gmax) * inv;
-        }
-        for (int c0 = grp * 32; c0 < p.block_n; c0 += 64) {
+        // ---- pass 2: p = e_c * 2^(m_c - gmax) / gsum -- no transcendental per element
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+            const int c0 = grp * 32 + ci * 64;
+            if (c0 >= p.block_n) continue;
             const int w = min(32, p.block_n - c0);
             const int nv = min(w, p.N - (n0 + c0));
             float v[32];
             if (nv > 0) {
+                const float f = fast_exp2(cm[ci] - gmax) * inv;
                 tmem_ld32(trow + (uint32_t)c0, v);
-                if (p.inv_nt) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 cs = *reinterpret_cast<const float4 *>(colscale + c0 + i);
-                        v[i] *= cs.x; v[i + 1] *= cs.y; v[i + 2] *= cs.z; v[i + 3] *= cs.w;
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float pr = fast_exp2(v[i] * a2 - gmax) * inv;
-                    v[i] = (nv == 32 || i < nv) ? pr : 0.f;
+                for (int i = 0; i < 32; ++i) v[i] = (nv == 32 || i < nv) ? v[i] * f : 0.f;
+                if (p.objectness && obj_c >= c0 && obj_c < c0 + 32) {          // warp-uniform: one extra 1-column TMEM read
+                    const float pb = tmem_ld1(trow + (uint32_t)obj_c) * f;
+                    if (row_ok) p.objectness[m0 + row] = 1.f - pb;
                 }
             } else {
 #pragma unroll
