@@ -28,6 +28,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace ovdet {
 
@@ -54,177 +55,6 @@ __device__ __forceinline__ unsigned long long gtimer()
     return t;
 }
 #define STAMP(i) do { if (p.dbg && threadIdx.x == 128) p.dbg[(size_t)blockIdx.x * 8 + (i)] = gtimer(); } while (0)
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int x, int y)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
-}
-// multicast: the box lands at the same shared offset in every CTA of cta_mask and completes tx bytes on each one's mbarrier
-__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap *map, uint64_t *bar, void *dst, int x, int y, uint16_t cta_mask)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(cta_mask) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
-{
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
-{
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// commit that arrives on the same mbarrier of every CTA in cta_mask (ring-slot release across the cluster)
-__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
-}
-
-// 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v)
-{
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-// registers -> 32 lanes x 32 fp32 columns of TMEM (the un-normalised exponentials are parked in the accumulator)
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float *v)
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr),
-          "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
-          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
-          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
-          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float tmem_ld1(uint32_t taddr)
-{
-    uint32_t r;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    return __uint_as_float(r);
-}
-// 16-column variant (unused: tail chunks read 32 columns of the power-of-two allocation and mask)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v)
-{
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void st_cluster_f32x2(const void *local_ptr, uint32_t rank, float a, float b)
-{
-    uint32_t raddr;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_ptr)), "r"(rank));
-    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(raddr), "f"(a), "f"(b) : "memory");
-}
-
-// K-major, 128B-swizzled operand tile: rows of 64 bf16 (128 B), 8-row groups 1024 B apart.
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), SWIZZLE_128B=2 [61,64))
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;             // LBO (unused for swizzled K-major), canonical 1
-    d |= (uint64_t)(1024 >> 4) << 32;   // SBO = 1024 B
-    d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;             // SWIZZLE_128B
-    return d;
-}
-
-__device__ __forceinline__ float fast_exp2(float x)
-{
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 __global__ void __launch_bounds__(GM_THREADS, 2)
 clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const LogitsParams p)
@@ -480,7 +310,7 @@ static EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-static int make_map(CUtensorMap *map, const void *base, int rows, int K, int box_rows)
+int make_bf16_map(CUtensorMap *map, const void *base, int rows, int K, int box_rows)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return OVDET_ERR_CUDA; }
@@ -494,6 +324,10 @@ static int make_map(CUtensorMap *map, const void *base, int rows, int K, int box
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return OVDET_ERR_CUDA; }
     return OVDET_OK;
 }
+
+int clip_logits_persistent_launch(const void *x, const void *text, int M, int K, int N, int nc, int bn, unsigned flags, float scale,
+                                  float *logits, int ld_logits, void *prob, int ld_prob, float *objectness,
+                                  const float *inv_nx, const float *inv_nt, cudaStream_t st);   // clip_logits_persistent.cu
 
 }  // namespace ovdet
 
@@ -535,10 +369,23 @@ extern "C" int ovdet_clip_logits_bf16(const void *x, const void *text, int M, in
         inv_norm_kernel<<<(N + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(text), N, K, norms + M);
         p.inv_nx = norms; p.inv_nt = norms + M;
     }
+    // OVDET_LOGITS_PERSISTENT=1 selects the persistent kernel (one CTA per SM, double-buffered TMEM, epilogue of tile i
+    // under the mainloop of tile i+1, csrc/clip_logits_persistent.cu).  Measured on B200 at config 4 it is 35.7 us against
+    // 31 us for this one-tile-per-CTA kernel: the mainloop is fully hidden, but only 15 clusters of 8 are co-resident
+    // (120 of 148 SMs) and its 8 epilogue warps/SM drain a tile in ~5.3 us, where two co-resident CTAs here bring 16.
+    // Default off until its epilogue is widened (profiles/r1_notes.md).
+    static int persistent = -1;
+    if (persistent < 0) { const char *e = getenv("OVDET_LOGITS_PERSISTENT"); persistent = e ? atoi(e) : 0; }
+    if (persistent && (M + GM_M - 1) / GM_M > 2 * (148 / nc)) {
+        int prc = clip_logits_persistent_launch(x, text, M, K, N, nc, bn, flags, scale, logits, ld_logits, prob, ld_prob, objectness,
+                                                p.inv_nx, p.inv_nt, st);
+        if (norms) OVDET_CUDA_TRY(cudaFreeAsync(norms, st));
+        return prc;
+    }
     CUtensorMap tmA, tmB;
-    int rc = make_map(&tmA, x, M, K, GM_M / nc);   // each CTA of the cluster fetches (and multicasts) 128/nc rows of the A tile
+    int rc = make_bf16_map(&tmA, x, M, K, GM_M / nc);   // each CTA of the cluster fetches (and multicasts) 128/nc rows of the A tile
     if (rc) return rc;
-    rc = make_map(&tmB, text, N, K, bn);
+    rc = make_bf16_map(&tmB, text, N, K, bn);
     if (rc) return rc;
     const size_t stage_bytes = (size_t)GM_M * GM_K * 2 + (((size_t)bn * GM_K * 2 + 1023) & ~(size_t)1023);
     size_t smem = stage_bytes * p.stages;

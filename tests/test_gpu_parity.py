@@ -450,8 +450,27 @@ def test_lift_full_width_vs_oracle():
     (300, 640, 19, False, 1.0),        # ScanNet head, ragged M
     (512, 640, 1203, True, 1.0 / 0.07),  # CLIPLoss form: normalise + temperature
     (256, 128, 257, False, 0.5),       # two N tiles, short K
+    (5000, 640, 1203, True, 1.0 / 0.07),  # persistent kernel (40 M-tiles on 18 clusters), ragged M, normalised
+    (40000, 640, 21, False, 1.0),      # persistent kernel without a cluster (closed-vocabulary head, large batch)
+    (9000, 128, 300, False, 0.5),      # persistent, cluster of 2, short K
 ])
 def test_clip_logits_vs_oracle(M, K, N, l2, scale):
+    _check_clip_logits(M, K, N, l2, scale)
+
+
+def test_clip_logits_persistent_kernel():
+    """The persistent variant (OVDET_LOGITS_PERSISTENT=1) in a fresh process (the switch is read once)."""
+    import subprocess, sys, os
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_parity as t; "
+            "[t._check_clip_logits(*a) for a in ((8192, 640, 1203, False, 1.0), (5000, 640, 1203, True, 1 / 0.07), "
+            "(40000, 640, 21, False, 1.0), (9000, 128, 300, False, 0.5))]; print('persistent ok')") % (
+        os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OVDET_LOGITS_PERSISTENT="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "persistent ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _check_clip_logits(M, K, N, l2, scale):
     from ovdet_b200.models.model_3detr import clip_logits
     x, t = synth.clip_logits_inputs(M, K, N, seed=M + N)
     if not l2:
