@@ -199,6 +199,20 @@ def bench_giou(args, rank, world, dev, peaks):
           torch.empty((1, 1, 1), device=dev))
     msf = timed_graph(lambda i: generalized_box3d_iou(t1[0], t1[1], t1[2], out=t1[3]), args.steps, world, dev)
     res["variants"]["launch_floor_us"] = msf * 1e3 / args.steps
+    # training path (needs_grad=True): torch-path forward + sparse backward, upstream gradient at one GT per query
+    c1g, c2g, nkg, _ = dsets[0]
+    wg = torch.zeros((L_LAYERS * B, Q, G), device=dev)
+    wg.scatter_(2, torch.randint(0, G, (L_LAYERS * B, Q, 1), device=dev), 1.0)
+    xg = c1g.clone().requires_grad_(True)
+
+    def train_step(i):
+        xg.grad = None
+        (generalized_box3d_iou(xg, c2g, nkg, rotated_boxes=True, needs_grad=True) * wg).sum().backward()
+
+    for i in range(3):
+        train_step(i)
+    msg = timed_region(train_step, max(args.steps // 4, 5), world, dev)
+    res["variants"]["train_fwd_bwd_us"] = msg * 1e3 / max(args.steps // 4, 5)
     # throughput regime: 4096 box sets (33.5 M pairs, 240 MB in+out) in one launch, torch-path semantics
     big = 4096
     rep = big // (L_LAYERS * B)

@@ -68,6 +68,13 @@ int ovdet_giou3d_decode_f32(const float *center1, const float *size1, const floa
                             const int64_t *nums_k2, int B, int K1, int K2, int k2_cap, unsigned flags,
                             float *out, float *corners1_out, void *stream);
 
+/* GIoU backward: d loss / d corners1 for the fp32 torch-path GIoU (autograd of
+ * generalized_box3d_iou_tensor, utils/box_util.py:517-618; flags = ROTATED | PREFILTER as in the forward).
+ * grad_out [B,K1,K2] = d loss / d giou (zero entries are skipped: the loss only touches matched pairs,
+ * criterion.py:274-296); grad_corners1 [B,K1,8,3] is overwritten.  No gradient w.r.t. corners2. */
+int ovdet_giou3d_backward_f32(const float *corners1, const float *corners2, const int64_t *nums_k2, const float *grad_out,
+                              int B, int K1, int K2, unsigned flags, float *grad_corners1, void *stream);
+
 /* ------------------------------------------------------------------------- */
 /* The Cython extension ABI: box_intersection(rect1, rect2,                   */
 /*   non_rot_inter_areas, nums_k2, inter_areas, approximate)                  */

@@ -56,6 +56,37 @@ def giou_flags(rotated_boxes, return_inter_vols_only, mode, prefilter, enclosing
     return flags
 
 
+class _GIoU3D(torch.autograd.Function):
+    """Differentiable fp32 torch-path GIoU (utils/box_util.py:517-618): forward = the GIoU kernel, backward = the sparse
+    per-pair backward kernel (csrc/giou3d_bwd.cu).  Gradient w.r.t. corners1 only (the GT boxes carry none in
+    criterion.py:274-296)."""
+
+    @staticmethod
+    def forward(ctx, corners1, corners2, nums_k2, rotated_boxes, prefilter):
+        c1 = corners1.detach().to(torch.float32).contiguous()
+        c2 = corners2.detach().to(torch.float32).contiguous()
+        nk = None if nums_k2 is None else nums_k2.detach().to(device=c1.device, dtype=torch.int64).contiguous()
+        B, K1, K2 = c1.shape[0], c1.shape[1], c2.shape[1]
+        flags = giou_flags(rotated_boxes, False, "tensor", prefilter, "aabb")
+        out = torch.empty((B, K1, K2), dtype=torch.float32, device=c1.device)
+        with torch.cuda.device(c1.device):
+            C.check(C.lib().ovdet_giou3d_f32(C.ptr(c1), C.ptr(c2), C.ptr(nk), B, K1, K2, 0, flags, C.ptr(out), C.stream(c1.device)))
+        ctx.save_for_backward(c1, c2, nk if nk is not None else torch.empty(0, device=c1.device))
+        ctx.has_nk, ctx.flags = nk is not None, flags
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        c1, c2, nk = ctx.saved_tensors
+        B, K1, K2 = c1.shape[0], c1.shape[1], c2.shape[1]
+        go = grad_out.detach().to(torch.float32).contiguous()
+        g1 = torch.empty_like(c1)
+        with torch.cuda.device(c1.device):
+            C.check(C.lib().ovdet_giou3d_backward_f32(C.ptr(c1), C.ptr(c2), C.ptr(nk) if ctx.has_nk else None, C.ptr(go), B, K1, K2,
+                                                      ctx.flags, C.ptr(g1), C.stream(c1.device)))
+        return g1, None, None, None, None
+
+
 def generalized_box3d_iou(corners1, corners2, nums_k2, rotated_boxes=True, return_inter_vols_only=False,
                           needs_grad=False, *, mode=None, prefilter=True, k2_cap=None, enclosing="aabb", out=None):
     """[B,K1,8,3] x [B,K2,8,3] -> [B,K1,K2] fp32 on ``corners1.device``
@@ -63,7 +94,13 @@ def generalized_box3d_iou(corners1, corners2, nums_k2, rotated_boxes=True, retur
     sync; CPU tensors go through the host-buffer C entry point (H2D, kernel, D2H)."""
     _check_shapes(corners1, corners2)
     if needs_grad and (corners1.requires_grad or corners2.requires_grad) and torch.is_grad_enabled():
-        raise NotImplementedError("GIoU backward (SURVEY.md 8f-4) is not built; call under no_grad or detach")
+        # the reference's TorchScript path under enable_grad (:725-730): differentiable w.r.t. the predicted corners
+        if corners2.requires_grad:
+            raise NotImplementedError("no gradient w.r.t. corners2 (ground truth) is produced")
+        if return_inter_vols_only or enclosing != "aabb" or (mode not in (None, "tensor")) or not corners1.is_cuda or k2_cap:
+            raise NotImplementedError("the backward exists for the fp32 torch-path GIoU on CUDA tensors only")
+        nk_t = None if nums_k2 is None else torch.as_tensor(nums_k2)
+        return _GIoU3D.apply(corners1, corners2, nk_t, bool(rotated_boxes), bool(prefilter))
     if mode is None:
         mode = "tensor" if needs_grad else "cython"
     if k2_cap is None:

@@ -90,10 +90,51 @@ def save(name, **arrs):
     print("wrote", name, {k: getattr(v, "shape", None) for k, v in arrs.items()})
 
 
+def golden_giou_grad(box_util):
+    """Autograd of the reference's TorchScript-path GIoU (utils/box_util.py:517-618, the needs_grad=True branch at
+    :725-730) w.r.t. the predicted box PARAMETERS and corners, with the sparse upstream gradient loss_giou produces
+    (criterion.py:274-296): one matched query per ground-truth box."""
+    out = {}
+    for tag, heading, rotated in (("rot", 0.6, True), ("axis", 0.0, False)):
+        g = torch.Generator().manual_seed(41 if rotated else 42)
+        B, K1, K2 = 2, 24, 6
+        ctr2, size2, ang2 = synth.sample_boxes(g, (B, K2), "sunrgbd", heading)
+        c2 = box_util.get_3d_box_batch_tensor(size2, ang2, ctr2)
+        # predictions = jittered copies of the GT boxes (so matched pairs overlap) + random boxes
+        rep = (K1 + K2 - 1) // K2
+        ctr1 = (ctr2.repeat(1, rep, 1)[:, :K1] + 0.15 * torch.randn(B, K1, 3, generator=g)).clone()
+        size1 = (size2.repeat(1, rep, 1)[:, :K1] * (1 + 0.2 * torch.rand(B, K1, 3, generator=g))).clone()
+        ang1 = (ang2.repeat(1, rep)[:, :K1] + (0.3 * torch.randn(B, K1, generator=g) if rotated else 0)).clone()
+        nk = torch.tensor([K2, K2 - 2], dtype=torch.int64)
+        w = torch.zeros(B, K1, K2)
+        for b in range(B):
+            for j in range(K2):          # query j + r*K2 is a jittered copy of GT j
+                w[b, j, j] = float(torch.rand((), generator=g)) + 0.5
+                w[b, j + K2, j] = float(torch.rand((), generator=g)) + 0.5
+                w[b, j + 2 * K2, (j + 1) % K2] = -float(torch.rand((), generator=g)) - 0.5   # a non-matching pair too
+                w[b, j + 3 * K2, j] = 1.0
+        ctr1.requires_grad_(True); size1.requires_grad_(True); ang1.requires_grad_(True)
+        corners1 = box_util.get_3d_box_batch_tensor(size1, ang1, ctr1)
+        corners1.retain_grad()
+        giou = box_util.generalized_box3d_iou(corners1, c2, nk, rotated_boxes=rotated, needs_grad=True)
+        (giou * w).sum().backward()
+        out.update({f"{tag}_center1": ctr1.detach().numpy(), f"{tag}_size1": size1.detach().numpy(),
+                    f"{tag}_angle1": ang1.detach().numpy(), f"{tag}_corners1": corners1.detach().numpy(),
+                    f"{tag}_corners2": c2.numpy(), f"{tag}_nums_k2": nk.numpy(), f"{tag}_w": w.numpy(),
+                    f"{tag}_giou": giou.detach().numpy(), f"{tag}_grad_corners1": corners1.grad.numpy(),
+                    f"{tag}_grad_center1": ctr1.grad.numpy(), f"{tag}_grad_size1": size1.grad.numpy(),
+                    f"{tag}_grad_angle1": ang1.grad.numpy()})
+    save("giou_grad.npz", **out)
+
+
 def main():
     box_util, nms, eval_det, apc, lf, criterion, tools = import_reference()
     torch.manual_seed(0)
     np.random.seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "grad":      # regenerate only the backward fixture
+        golden_giou_grad(box_util)
+        return
+    golden_giou_grad(box_util)
 
     # ---------------- known-answer vectors (SURVEY.md 4 / 8c) ----------------
     sub_poly = [(0, 0), (300, 0), (300, 300), (0, 300)]
