@@ -24,7 +24,11 @@ int cuda_fail(cudaError_t e, const char *what)
 
 int HostStaging::ensure(size_t bytes)
 {
-    if (!stream) OVDET_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (!stream) {
+        OVDET_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        OVDET_CUDA_TRY(cudaStreamCreateWithFlags(&stream_d2h, cudaStreamNonBlocking));
+        for (auto &e : ev) OVDET_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     if (bytes <= cap) return OVDET_OK;
     if (dev) { OVDET_CUDA_TRY(cudaStreamSynchronize(stream)); OVDET_CUDA_TRY(cudaFree(dev)); dev = nullptr; cap = 0; }
     size_t want = bytes + bytes / 2;

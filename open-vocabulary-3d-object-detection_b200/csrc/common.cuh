@@ -40,6 +40,8 @@ struct HostStaging {
     void *dev = nullptr;
     size_t cap = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_d2h = nullptr;   // second stream: result read-back of chunk i overlaps upload + kernel of chunk i+1
+    cudaEvent_t ev[8] = {};
     int ensure(size_t bytes);
 };
 HostStaging &host_staging();
@@ -65,7 +67,7 @@ template <> struct Ar<double> {
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
-    static __device__ __forceinline__ double rcp(double a) { return __ddiv_rn(1.0, a); }
+    static __device__ __forceinline__ double rcp(double a) { return __drcp_rn(a); }  // correctly rounded == 1.0 / a
     static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
     static __device__ __forceinline__ double abs(double a) { return fabs(a); }
     static __device__ __forceinline__ double max(double a, double b) { return fmax(a, b); }
@@ -164,6 +166,81 @@ __device__ __forceinline__ double area_f64(const V2<double> *poly, int n)
         pv = v;
     }
     return __dmul_rn(0.5, fabs(__dsub_rn(d1, d2)));
+}
+
+// ---------------------------------------------------------------------------
+// Cooperative clip: EIGHT lanes per pair, lane i of the group holds vertex i of the current polygon in registers.
+// One pass = one inside test and at most one intersection per lane, all lanes in parallel, then a compaction through
+// an 8-entry shared row (output order = the serial loop's: for each vertex, [intersection], [vertex]; entries past
+// SH_MAXV dropped exactly like the serial `m < SH_MAXV` guards).  Per-element arithmetic is the serial code's, so the
+// polygon is bit-identical; the dependent chain per pass is one vertex long instead of n, which is what matters when
+// only a handful of pairs per CTA reach the clipper (the fp64 serial clip is a 4-5 us chain, profiles/r1_notes.md).
+// All 32 lanes of the warp must call these together (full-mask shuffles of width 8); n is uniform per group.
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ int coop_pass(const ClipEdge<T> &ce, T &vx, T &vy, int n, int gl, int gshift, V2<T> *gbuf)
+{
+    const unsigned full = 0xffffffffu;
+    const bool live = gl < n;
+    const bool e_in = live && ce.inside(vx, vy);
+    const int src = max((gl == 0 ? n : gl) - 1, 0);   // predecessor in the cyclic order
+    const T sx = __shfl_sync(full, vx, src, 8), sy = __shfl_sync(full, vy, src, 8);
+    const unsigned inmask = (__ballot_sync(full, e_in) >> gshift) & 0xffu;
+    const bool s_in = (inmask >> src) & 1u;
+    const bool cross = live && (e_in != s_in);
+    const unsigned crmask = (__ballot_sync(full, cross) >> gshift) & 0xffu;
+    const unsigned lower = (1u << gl) - 1u;
+    const int pos = __popc(crmask & lower) + __popc(inmask & lower);
+    if (cross && pos < SH_MAXV) gbuf[pos] = ce.isect(sx, sy, vx, vy);
+    const int pe = pos + (cross ? 1 : 0);
+    if (e_in && pe < SH_MAXV) { V2<T> v; v.x = vx; v.y = vy; gbuf[pe] = v; }
+    const int m = min(__popc(crmask) + __popc(inmask), SH_MAXV);
+    __syncwarp();
+    if (gl < m) { const V2<T> v = gbuf[gl]; vx = v.x; vy = v.y; }
+    __syncwarp();
+    return m;
+}
+
+// subject vertex gl (< 4) in (vx, vy); clip quad cl[8]; returns n with the polygon left in the lanes' registers
+template <typename T>
+__device__ __forceinline__ int coop_clip_quads(const T *cl, T &vx, T &vy, int n, int gl, int gshift, V2<T> *gbuf)
+{
+    n = coop_pass(ClipEdge<T>(cl[6], cl[7], cl[0], cl[1]), vx, vy, n, gl, gshift, gbuf);
+    n = coop_pass(ClipEdge<T>(cl[0], cl[1], cl[2], cl[3]), vx, vy, n, gl, gshift, gbuf);
+    n = coop_pass(ClipEdge<T>(cl[2], cl[3], cl[4], cl[5]), vx, vy, n, gl, gshift, gbuf);
+    n = coop_pass(ClipEdge<T>(cl[4], cl[5], cl[6], cl[7]), vx, vy, n, gl, gshift, gbuf);
+    return n;
+}
+
+// the two reference shoelace flavours on a register-resident polygon: products in parallel, sums in the reference's order
+__device__ __forceinline__ float coop_area_f32(float vx, float vy, int n, int gl)
+{
+    const unsigned full = 0xffffffffu;
+    const int src = max((gl == 0 ? n : gl) - 1, 0);
+    const float px = __shfl_sync(full, vx, src, 8), py = __shfl_sync(full, vy, src, 8);
+    const float t1 = __fmul_rn(vx, py), t2 = __fmul_rn(vy, px);
+    float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < SH_MAXV; ++i) {
+        const float a = __shfl_sync(full, t1, i, 8), b = __shfl_sync(full, t2, i, 8);
+        if (i < n) { d1 = __fadd_rn(d1, a); d2 = __fadd_rn(d2, b); }
+    }
+    return n <= 0 ? 0.f : __fmul_rn(fabsf(__fsub_rn(d1, d2)), 0.5f);
+}
+__device__ __forceinline__ float coop_area_cython(double vx, double vy, int n, int gl)
+{
+    const unsigned full = 0xffffffffu;
+    const int src = max((gl == 0 ? n : gl) - 1, 0);
+    const float x = (float)vx, y = (float)vy;
+    const float px = __shfl_sync(full, x, src, 8), py = __shfl_sync(full, y, src, 8);
+    const float t1 = __fmul_rn(x, py), t2 = __fmul_rn(y, px);   // fp32 products, widened exactly
+    double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < SH_MAXV; ++i) {
+        const float a = __shfl_sync(full, t1, i, 8), b = __shfl_sync(full, t2, i, 8);
+        if (i < n) { d1 = __dadd_rn(d1, (double)a); d2 = __dadd_rn(d2, (double)b); }
+    }
+    return n <= 0 ? 0.f : __fmul_rn(0.5f, fabsf(__fsub_rn((float)d1, (float)d2)));
 }
 
 // One pass over a vertex list held in shared scratch, output to shared scratch.

@@ -72,7 +72,16 @@ struct GiouParams {
     int tiles_per_b;
     MatcherEpi epi;
     BoxDecode dec1;
+    unsigned long long *dbg;   // optional [grid][8] globaltimer stamps of thread 0 (OVDET_GIOU_DBG_PTR; null in production)
 };
+
+__device__ __forceinline__ unsigned long long gtimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define GSTAMP(i) do { if (p.dbg && threadIdx.x == 0) p.dbg[(size_t)blockIdx.x * 8 + (i)] = gtimer_ns(); } while (0)
 
 // features of one box from its 24 staged floats (utils/box_util.py:550-555 rect,
 // :544-546 y extent, :443-463 volume with the 1e-8 clamp of :568-569, AABB for :466-514)
@@ -274,6 +283,7 @@ __global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams
     const bool vec2 = ((reinterpret_cast<uintptr_t>(p.c2) & 15) == 0);
     const bool vec_out = p.out && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (p.K2 % 4 == 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    GSTAMP(0);
 
     for (int g0 = 0; g0 < p.K2; g0 += TG) {
         const int ng = min(TG, p.K2 - g0);
@@ -291,9 +301,11 @@ __global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams
         stage_boxes(p.c2 + ((size_t)b * p.K2 + g0) * 24, ng, raw2, vec2);
         if (threadIdx.x == 0) qcount = 0;
         __syncthreads();
+        GSTAMP(1);
         if (threadIdx.x < TG) { if (threadIdx.x < ng) box_features(raw2 + threadIdx.x * 24, f2 + threadIdx.x, TG); }
         else if (g0 == 0 && threadIdx.x - TG < nq) box_features(raw1 + (threadIdx.x - TG) * 24, f1 + (threadIdx.x - TG), TQ);
         __syncthreads();
+        GSTAMP(2);
 
         // ---- phase A: warp w owns rows w*4 .. w*4+3, lane l owns columns l and l+32 (features in registers)
         BoxF gf[2];
@@ -332,10 +344,48 @@ __global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams
             }
         }
         __syncthreads();
+        GSTAMP(3);
 
         // ---- phase B: drain the clip queue, one Sutherland-Hodgman clip per lane
         const int nclip = qcount;
-        if (threadIdx.x < PB) {
+        if (p.dbg && threadIdx.x == 0) p.dbg[(size_t)blockIdx.x * 8 + 6] = nclip;
+        constexpr int NGROUP = NT / 8;
+        if (nclip <= 2 * NGROUP) {   // sparse (the shipped semantics: a few pairs per tile): 8 lanes per pair, short chain
+            const int gl = lane & 7, gshift = lane & 24, group = threadIdx.x >> 3;
+            V2<ClipT> *gbuf = scratch + group * 8;
+            for (int base = 0; base < nclip; base += NGROUP) {
+                if (base + warp * 4 >= nclip) break;   // warp-uniform
+                const int qi = base + group;
+                const bool act = qi < nclip;
+                int r = 0, c = 0;
+                if (act) { const int code = queue[qi]; r = code / TG; c = code - r * TG; }
+                ClipT cl[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    cl[2 * i] = (ClipT)f2[(F_RX + i) * TG + c];
+                    cl[2 * i + 1] = (ClipT)f2[(F_RZ + i) * TG + c];
+                }
+                ClipT vx = (ClipT)f1[(F_RX + (gl & 3)) * TQ + r], vy = (ClipT)f1[(F_RZ + (gl & 3)) * TQ + r];
+                const int n = coop_clip_quads<ClipT>(cl, vx, vy, act ? 4 : 0, gl, gshift, gbuf);
+                float area;
+                if constexpr (sizeof(ClipT) == 8) area = coop_area_cython(vx, vy, n, gl);
+                else area = coop_area_f32(vx, vy, n, gl);
+                if (act && gl == 0) {
+                    PairTerms t = pair_terms(load_boxf(f1, r, TQ), load_boxf(f2, c, TG));
+                    if (hull && __fmul_rn(area, t.h) > 0.f) {
+                        float axv[4], azv[4], bxv[4], bzv[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            axv[i] = f1[(F_RX + i) * TQ + r]; azv[i] = f1[(F_RZ + i) * TQ + r];
+                            bxv[i] = f2[(F_RX + i) * TG + c]; bzv[i] = f2[(F_RZ + i) * TG + c];
+                        }
+                        t.encl = (float)hull_enclosing_volume(axv, azv, bxv, bzv, f1[F_YTOP * TQ + r], f1[F_YBOT * TQ + r],
+                                                              f2[F_YTOP * TG + c], f2[F_YBOT * TG + c]);
+                    }
+                    tile[r * TG + c] = finish_pair(t, area, true, has_nums, inter_only);
+                }
+            }
+        } else if (threadIdx.x < PB) {   // dense: one serial clip per lane, PB lanes
             V2<ClipT> *bufA = scratch + threadIdx.x;
             V2<ClipT> *bufB = scratch + SH_MAXV * PB + threadIdx.x;
             for (int qi = threadIdx.x; qi < nclip; qi += PB) {
@@ -372,6 +422,7 @@ __global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams
             }
         }
         __syncthreads();
+        GSTAMP(4);
 
         // ---- fused matcher cost: ((wc*-P[label] + wo*-obj) + wce*center) + wg*-giou
         if (p.epi.cost) {
@@ -413,6 +464,7 @@ __global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams
             }
         }
         __syncthreads();
+        GSTAMP(5);
     }
 }
 
@@ -425,6 +477,7 @@ template <typename ClipT, int PB, int TQ> static size_t giou_smem_bytes()
 template <typename ClipT, int PB, int TQ, bool HULL> static int launch_giou_tq2(GiouParams p, cudaStream_t st)
 {
     p.tiles_per_b = (p.K1 + TQ - 1) / TQ;
+    { const char *e = getenv("OVDET_GIOU_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
     const size_t smem = giou_smem_bytes<ClipT, PB, TQ>();
     static bool attr_set = false;
     if (!attr_set) {
@@ -703,13 +756,47 @@ extern "C" int ovdet_giou3d_host_f32(const float *corners1, const float *corners
     int rc = hs.ensure(o4 + align256(nn));
     if (rc) return rc;
     char *d = static_cast<char *>(hs.dev);
-    OVDET_CUDA_TRY(cudaMemcpyAsync(d + o1, corners1, n1, cudaMemcpyHostToDevice, hs.stream));
-    OVDET_CUDA_TRY(cudaMemcpyAsync(d + o2, corners2, n2, cudaMemcpyHostToDevice, hs.stream));
-    if (nums_k2) OVDET_CUDA_TRY(cudaMemcpyAsync(d + o4, nums_k2, nn, cudaMemcpyHostToDevice, hs.stream));
-    rc = ovdet_giou3d_f32((const float *)(d + o1), (const float *)(d + o2), nums_k2 ? (const int64_t *)(d + o4) : nullptr,
-                          B, K1, K2, k2_cap, flags, (float *)(d + o3), hs.stream);
-    if (rc) return rc;
-    OVDET_CUDA_TRY(cudaMemcpyAsync(out, d + o3, no, cudaMemcpyDeviceToHost, hs.stream));
+    // The call is bound by the PCIe transfers and their fixed latencies (config 1: 1.2 MB up, 2.1 MB down, ~7 us of
+    // kernel).  Measured on B200 (profiles/r1_notes.md): a pinned `out` is written by the kernel itself through its
+    // mapped address -- the read-back then overlaps the compute and needs no copy call (128 -> 89 us); reading the
+    // inputs the same way is slower than a copy (SM loads over PCIe are latency-bound).  Splitting the batch into chunks
+    // on two streams (upload of chunk i+1 under the write-back of chunk i) is kept behind OVDET_HOST_CHUNKS for
+    // experiments: at this size the extra calls cost more than the overlap wins (98 -> 114 us with 2 chunks).
+    float *dout = reinterpret_cast<float *>(d + o3);
+    bool mapped = false;
+    static int zc_env = -1;   // OVDET_HOST_ZEROCOPY=0 forces the copy-back path (A/B measurements)
+    if (zc_env < 0) { const char *e = getenv("OVDET_HOST_ZEROCOPY"); zc_env = e ? atoi(e) : 1; }
+    if (zc_env) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            dout = static_cast<float *>(at.devicePointer); mapped = true;
+        } else cudaGetLastError();
+    }
+    static int nchunk_env = -1;
+    if (nchunk_env < 0) { const char *e = getenv("OVDET_HOST_CHUNKS"); nchunk_env = e ? atoi(e) : 0; }
+    int nchunk = nchunk_env > 0 ? nchunk_env : 1;   // measured: 2+ chunks lose more to per-call latencies than the overlap wins
+    nchunk = nchunk > 8 ? 8 : (nchunk > B ? B : nchunk);
+    cudaStream_t sts[2] = {hs.stream, nchunk > 1 ? hs.stream_d2h : hs.stream};
+    if (nums_k2) {
+        OVDET_CUDA_TRY(cudaMemcpyAsync(d + o4, nums_k2, nn, cudaMemcpyHostToDevice, hs.stream));
+        if (nchunk > 1) {
+            OVDET_CUDA_TRY(cudaEventRecord(hs.ev[0], hs.stream));
+            OVDET_CUDA_TRY(cudaStreamWaitEvent(sts[1], hs.ev[0], 0));
+        }
+    }
+    for (int c = 0; c < nchunk; ++c) {
+        const int b0 = (int)((long long)B * c / nchunk), b1 = (int)((long long)B * (c + 1) / nchunk), nb = b1 - b0;
+        if (nb == 0) continue;
+        cudaStream_t st = sts[c & 1];
+        const size_t s1 = (size_t)b0 * K1 * 96, s2 = (size_t)b0 * K2 * 96, so = (size_t)b0 * K1 * K2;
+        OVDET_CUDA_TRY(cudaMemcpyAsync(d + o1 + s1, (const char *)corners1 + s1, (size_t)nb * K1 * 96, cudaMemcpyHostToDevice, st));
+        OVDET_CUDA_TRY(cudaMemcpyAsync(d + o2 + s2, (const char *)corners2 + s2, (size_t)nb * K2 * 96, cudaMemcpyHostToDevice, st));
+        rc = ovdet_giou3d_f32((const float *)(d + o1 + s1), (const float *)(d + o2 + s2),
+                              nums_k2 ? (const int64_t *)(d + o4) + b0 : nullptr, nb, K1, K2, k2_cap, flags, dout + so, st);
+        if (rc) return rc;
+        if (!mapped) OVDET_CUDA_TRY(cudaMemcpyAsync(out + so, dout + so, (size_t)nb * K1 * K2 * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (nchunk > 1) OVDET_CUDA_TRY(cudaStreamSynchronize(sts[1]));
     OVDET_CUDA_TRY(cudaStreamSynchronize(hs.stream));
     return OVDET_OK;
 }
