@@ -181,7 +181,7 @@ def bench_giou(args, rank, world, dev, peaks):
     achieved = algo_bytes / per_launch_s / 1e9
     res = {"value": value, "ms_per_step": ms / args.steps, "launches": args.steps, "ms_per_step_python_loop": ms_loop / args.steps,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic("giou3d_kernel"),
+                        "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic("giou3d_kernel<double"),
                         "kernel": "giou3d_kernel<double> (reference-default semantics)", "peak_source": peaks["source"],
                         "note": "pair maths is ALU/issue-bound (SURVEY 8d); see profiles/ for pipe utilisation"}}
     # intended semantics (no K2 cap, fp32 clip = the torch path): every prefilter-passing pair is clipped
@@ -260,7 +260,11 @@ def load_traffic(kernel):
     p = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
+            d = json.load(open(p))
+            for k, v in d.items():           # keys carry the template arguments: first launch whose name starts with `kernel`
+                if k.startswith(kernel):
+                    return v.get("dram_bytes_per_launch")
+            return None
         except Exception:
             return None
     return None

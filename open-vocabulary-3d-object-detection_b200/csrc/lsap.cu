@@ -5,9 +5,10 @@
 // columns.  scipy (1.18.1; not vendored in the reference) implements the
 // shortest-augmenting-path algorithm of Crouse, "On implementing 2D rectangular
 // assignment algorithms" (2016), in fp64, transposing so that rows <= columns.
-// This kernel restates that published algorithm with one warp per sample: the
-// lanes stride over the columns for the Dijkstra relaxation and an argmin
-// shuffle-reduction replaces the serial scan.  On tie-free costs the optimum is
+// This kernel restates that published algorithm with one 256-thread CTA per sample:
+// the cost slab is staged transposed in shared memory, the threads stride over the
+// columns for the Dijkstra relaxation, and a shuffle argmin per warp + 8 warp winners
+// through a double-buffered shared array (one barrier per step) replace the serial scan.  On tie-free costs the optimum is
 // unique, so assignments equal scipy's (north_star: bit-exact except ties).
 // Tie-break used here: lowest reduced cost, then unassigned column, then lowest index.
 #include <math.h>

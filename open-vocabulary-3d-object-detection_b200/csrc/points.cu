@@ -18,14 +18,19 @@ namespace ovdet {
 constexpr int PT_NT = 256;
 constexpr int PT_BOXES = 32;   // boxes per CTA
 
-struct ObbFrame { float o[3], a[3], b[3], c[3], la, lb, lc; };
+constexpr int PT_PER_THREAD = 4;                       // points held in registers per thread
+constexpr int PT_CHUNK = PT_NT * PT_PER_THREAD * 2;    // points per CTA (two register rounds)
 
+struct ObbFrame { float o[3], a[3], b[3], c[3], la, lb, lc, pad; };   // 16 floats: four LDS.128 per box
+
+// grid (box chunks, point chunks, scenes): each CTA tests PT_CHUNK points against PT_BOXES boxes; per box the warp's
+// hits are counted with one ballot per point register, one shared atomic per warp, one global atomic per CTA.
 __global__ void __launch_bounds__(PT_NT) points_in_boxes_kernel(const float *__restrict__ pc, int N, int pstride,
                                                                 const float *__restrict__ corners, int K, int32_t *counts)
 {
-    __shared__ ObbFrame fr[PT_BOXES];
+    __shared__ __align__(16) ObbFrame fr[PT_BOXES];
     __shared__ int cnt[PT_BOXES];
-    const int s = blockIdx.y, k0 = blockIdx.x * PT_BOXES;
+    const int s = blockIdx.z, k0 = blockIdx.x * PT_BOXES;
     const int nb = min(PT_BOXES, K - k0);
     if (threadIdx.x < nb) {
         // corners are in the upright-camera frame; the point cloud is in the depth frame:
@@ -35,7 +40,7 @@ __global__ void __launch_bounds__(PT_NT) points_in_boxes_kernel(const float *__r
         auto to_depth = [&](int i, float *o) { o[0] = c[3 * i]; o[1] = c[3 * i + 2]; o[2] = -c[3 * i + 1]; };
         to_depth(0, p0); to_depth(1, p1); to_depth(3, p3); to_depth(4, p4);
         ObbFrame f;
-        f.la = f.lb = f.lc = 0.f;
+        f.la = f.lb = f.lc = 0.f; f.pad = 0.f;
         for (int a = 0; a < 3; ++a) {
             f.o[a] = p0[a];
             f.a[a] = p1[a] - p0[a]; f.b[a] = p3[a] - p0[a]; f.c[a] = p4[a] - p0[a];
@@ -46,19 +51,37 @@ __global__ void __launch_bounds__(PT_NT) points_in_boxes_kernel(const float *__r
     }
     __syncthreads();
     const float *pts = pc + (size_t)s * N * pstride;
-    for (int i = threadIdx.x; i < N; i += PT_NT) {
-        const float x = __ldg(pts + (size_t)i * pstride), y = __ldg(pts + (size_t)i * pstride + 1), z = __ldg(pts + (size_t)i * pstride + 2);
+    const int lane = threadIdx.x & 31;
+    const int base = blockIdx.y * PT_CHUNK;
+    for (int i0 = base; i0 < min(base + PT_CHUNK, N); i0 += PT_NT * PT_PER_THREAD) {
+        float x[PT_PER_THREAD], y[PT_PER_THREAD], z[PT_PER_THREAD];
+        bool ok[PT_PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < PT_PER_THREAD; ++j) {
+            const int i = i0 + j * PT_NT + threadIdx.x;
+            ok[j] = i < N;
+            const size_t o = (size_t)(ok[j] ? i : 0) * pstride;
+            x[j] = __ldg(pts + o); y[j] = __ldg(pts + o + 1); z[j] = __ldg(pts + o + 2);
+        }
         for (int k = 0; k < nb; ++k) {
-            const ObbFrame &f = fr[k];
-            const float dx = x - f.o[0], dy = y - f.o[1], dz = z - f.o[2];
-            const float ta = dx * f.a[0] + dy * f.a[1] + dz * f.a[2];
-            const float tb = dx * f.b[0] + dy * f.b[1] + dz * f.b[2];
-            const float tc = dx * f.c[0] + dy * f.c[1] + dz * f.c[2];
-            if (ta >= 0.f && ta <= f.la && tb >= 0.f && tb <= f.lb && tc >= 0.f && tc <= f.lc) atomicAdd(&cnt[k], 1);
+            const float4 f0 = reinterpret_cast<const float4 *>(&fr[k])[0], f1 = reinterpret_cast<const float4 *>(&fr[k])[1],
+                         f2 = reinterpret_cast<const float4 *>(&fr[k])[2], f3 = reinterpret_cast<const float4 *>(&fr[k])[3];
+            // o = f0.xyz, a = (f0.w, f1.x, f1.y), b = (f1.z, f1.w, f2.x), c = (f2.y, f2.z, f2.w), la/lb/lc = f3.xyz
+            int hits = 0;
+#pragma unroll
+            for (int j = 0; j < PT_PER_THREAD; ++j) {
+                const float dx = x[j] - f0.x, dy = y[j] - f0.y, dz = z[j] - f0.z;
+                const float ta = dx * f0.w + dy * f1.x + dz * f1.y;
+                const float tb = dx * f1.z + dy * f1.w + dz * f2.x;
+                const float tc = dx * f2.y + dy * f2.z + dz * f2.w;
+                const bool in = ok[j] && ta >= 0.f && ta <= f3.x && tb >= 0.f && tb <= f3.y && tc >= 0.f && tc <= f3.z;
+                hits += __popc(__ballot_sync(0xffffffffu, in));
+            }
+            if (hits && lane == 0) atomicAdd(&cnt[k], hits);
         }
     }
     __syncthreads();
-    if (threadIdx.x < nb) counts[(size_t)s * K + k0 + threadIdx.x] = cnt[threadIdx.x];
+    if (threadIdx.x < nb && cnt[threadIdx.x]) atomicAdd(counts + (size_t)s * K + k0 + threadIdx.x, cnt[threadIdx.x]);
 }
 
 constexpr int LM_MAXL = 64;   // label values 0..63
@@ -109,7 +132,11 @@ extern "C" int ovdet_points_in_boxes_count(const float *point_cloud, int S, int 
     OVDET_REQUIRE(S >= 0 && N >= 0 && K >= 0 && point_stride >= 3, "bad size");
     if (S == 0 || K == 0) return OVDET_OK;
     OVDET_REQUIRE(corners && counts && (point_cloud || N == 0), "null pointer");
-    points_in_boxes_kernel<<<dim3((K + PT_BOXES - 1) / PT_BOXES, S), PT_NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    OVDET_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)S * K, st));
+    if (N == 0) return OVDET_OK;
+    OVDET_REQUIRE(S <= 65535 && (N + PT_CHUNK - 1) / PT_CHUNK <= 65535, "grid too large");
+    points_in_boxes_kernel<<<dim3((K + PT_BOXES - 1) / PT_BOXES, (N + PT_CHUNK - 1) / PT_CHUNK, S), PT_NT, 0, st>>>(
         point_cloud, N, point_stride, corners, K, counts);
     return launch_ok("points_in_boxes_kernel");
 }
