@@ -328,6 +328,7 @@ int make_bf16_map(CUtensorMap *map, const void *base, int rows, int K, int box_r
 int clip_logits_persistent_launch(const void *x, const void *text, int M, int K, int N, int nc, int bn, unsigned flags, float scale,
                                   float *logits, int ld_logits, void *prob, int ld_prob, float *objectness,
                                   const float *inv_nx, const float *inv_nt, cudaStream_t st);   // clip_logits_persistent.cu
+int clip_logits_persistent_choose(int M, int K, int N, int *nc_out, int *bn_out);
 
 }  // namespace ovdet
 
@@ -369,15 +370,15 @@ extern "C" int ovdet_clip_logits_bf16(const void *x, const void *text, int M, in
         inv_norm_kernel<<<(N + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(text), N, K, norms + M);
         p.inv_nx = norms; p.inv_nt = norms + M;
     }
-    // OVDET_LOGITS_PERSISTENT=1 selects the persistent kernel (one CTA per SM, double-buffered TMEM, epilogue of tile i
-    // under the mainloop of tile i+1, csrc/clip_logits_persistent.cu).  Measured on B200 at config 4 it is 35.7 us against
-    // 31 us for this one-tile-per-CTA kernel: the mainloop is fully hidden, but only 15 clusters of 8 are co-resident
-    // (120 of 148 SMs) and its 8 epilogue warps/SM drain a tile in ~5.3 us, where two co-resident CTAs here bring 16.
-    // Default off until its epilogue is widened (profiles/r1_notes.md).
+    // Two kernels.  Persistent (csrc/clip_logits_persistent.cu: one CTA per SM, double-buffered TMEM, 16 epilogue warps
+    // working on tile i under the mainloop of tile i+1, cluster size chosen for co-residency) when there are at least two
+    // rounds of M-tiles: 25.8 us at config 4 (cluster of 6 x 208 columns, 22 clusters resident) against 30.6 us for the
+    // one-tile-per-CTA kernel below, which remains the choice for small M.  OVDET_LOGITS_PERSISTENT=0/1 forces either.
     static int persistent = -1;
-    if (persistent < 0) { const char *e = getenv("OVDET_LOGITS_PERSISTENT"); persistent = e ? atoi(e) : 0; }
-    if (persistent && (M + GM_M - 1) / GM_M > 2 * (148 / nc)) {
-        int prc = clip_logits_persistent_launch(x, text, M, K, N, nc, bn, flags, scale, logits, ld_logits, prob, ld_prob, objectness,
+    if (persistent < 0) { const char *e = getenv("OVDET_LOGITS_PERSISTENT"); persistent = e ? atoi(e) : 2; }
+    int pnc = nc, pbn = bn;
+    if (persistent && clip_logits_persistent_choose(M, K, N, &pnc, &pbn)) {
+        int prc = clip_logits_persistent_launch(x, text, M, K, N, pnc, pbn, flags, scale, logits, ld_logits, prob, ld_prob, objectness,
                                                 p.inv_nx, p.inv_nt, st);
         if (norms) OVDET_CUDA_TRY(cudaFreeAsync(norms, st));
         return prc;

@@ -524,7 +524,7 @@ def test_lift_full_width_vs_oracle():
     (300, 640, 19, False, 1.0),        # ScanNet head, ragged M
     (512, 640, 1203, True, 1.0 / 0.07),  # CLIPLoss form: normalise + temperature
     (256, 128, 257, False, 0.5),       # two N tiles, short K
-    (5000, 640, 1203, True, 1.0 / 0.07),  # persistent kernel (40 M-tiles on 18 clusters), ragged M, normalised
+    (5000, 640, 1203, True, 1.0 / 0.07),  # persistent kernel (40 M-tiles, cluster size chosen by co-residency), ragged M, normalised
     (40000, 640, 21, False, 1.0),      # persistent kernel without a cluster (closed-vocabulary head, large batch)
     (9000, 128, 300, False, 0.5),      # persistent, cluster of 2, short K
 ])
@@ -532,16 +532,20 @@ def test_clip_logits_vs_oracle(M, K, N, l2, scale):
     _check_clip_logits(M, K, N, l2, scale)
 
 
-def test_clip_logits_persistent_kernel():
-    """The persistent variant (OVDET_LOGITS_PERSISTENT=1) in a fresh process (the switch is read once)."""
+@pytest.mark.parametrize("env", [
+    {"OVDET_LOGITS_PERSISTENT": "0"},                                # one-tile-per-CTA kernel at sizes the default gives to the persistent one
+    {"OVDET_LOGITS_PERSISTENT": "1", "OVDET_LOGITS_NC": "8"},        # persistent, cluster of 8 (power-of-two A slices)
+    {"OVDET_LOGITS_PERSISTENT": "1", "OVDET_LOGITS_NC": "5"},        # persistent, cluster of 5 (4 multicast slices, one CTA loads no A)
+])
+def test_clip_logits_kernel_variants(env):
+    """Both logits kernels and the non-default cluster sizes, each in a fresh process (the switches are read once)."""
     import subprocess, sys, os
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_parity as t; "
             "[t._check_clip_logits(*a) for a in ((8192, 640, 1203, False, 1.0), (5000, 640, 1203, True, 1 / 0.07), "
-            "(40000, 640, 21, False, 1.0), (9000, 128, 300, False, 0.5))]; print('persistent ok')") % (
+            "(40000, 640, 21, False, 1.0), (9000, 128, 300, False, 0.5))]; print('variant ok')") % (
         os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, OVDET_LOGITS_PERSISTENT="1")
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "persistent ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def _check_clip_logits(M, K, N, l2, scale):
