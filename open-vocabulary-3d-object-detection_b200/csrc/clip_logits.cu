@@ -264,11 +264,14 @@ clip_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         STAMP(5);
         if (p.prob) {
             __syncthreads();
-            const int pieces = p.block_n / 8;                // 16-byte pieces per row
-            for (int i = threadIdx.x; i < GM_M * pieces; i += GM_THREADS) {
-                const int r = i / pieces, c8 = (i - r * pieces) * 8;
-                const int grow = m0 + r, gcol = n0 + c8;
-                if (grow < p.M && gcol < p.ld_prob) {
+            // one row per warp and step, one 16-byte piece per lane (no index division)
+            for (int c8 = lane * 8; c8 < p.block_n; c8 += 256) {
+                const int gcol = n0 + c8;
+                if (gcol >= p.ld_prob) continue;
+#pragma unroll 4
+                for (int r = warp; r < GM_M; r += GM_THREADS / 32) {
+                    const int grow = m0 + r;
+                    if (grow >= p.M) break;
                     const uint4 val = *reinterpret_cast<const uint4 *>(tile + (size_t)r * tile_ld + c8);
                     *reinterpret_cast<uint4 *>(p.prob + (size_t)grow * p.ld_prob + gcol) = val;
                 }

@@ -294,11 +294,15 @@ clip_logits_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             }
             epi_barrier();   // tile + factor table complete
             PSTAMP(5);
-            if (p.prob) {    // coalesced copy-out, rescaling 8 bf16 at a time
-                for (int i = et; i < PK_M * pieces; i += PK_EPI) {
-                    const int r = i / pieces, c8 = (i - r * pieces) * 8;
-                    const int grow = m0 + r, gcol = n0 + c8;
-                    if (grow < p.M && gcol < p.ld_prob) {
+            if (p.prob) {    // coalesced copy-out, rescaling 8 bf16 at a time: one row per warp and step, one 16-byte piece per lane
+                const int ew = warp - 4;
+                for (int c8 = lane * 8; c8 < p.block_n; c8 += 256) {     // block_n <= 256: a single trip
+                    const int gcol = n0 + c8;
+                    if (gcol >= p.ld_prob) continue;
+#pragma unroll 4
+                    for (int r = ew; r < PK_M; r += PK_EPI / 32) {
+                        const int grow = m0 + r;
+                        if (grow >= p.M) break;
                         const float f = ftab[r][c8 >> 4];
                         uint4 val = *reinterpret_cast<const uint4 *>(tile + (size_t)r * tile_ld + c8);
                         __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&val);
