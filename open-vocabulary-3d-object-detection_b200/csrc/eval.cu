@@ -16,6 +16,7 @@
 // pass.  Equality with the reference needs tie-free scores (numpy's argsort of
 // -confidence is not stable: documented).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -118,13 +119,82 @@ __global__ void __launch_bounds__(EV_NT) box3d_iou_kernel(IouParams p)
 }
 
 // ---------------------------------------------------------------- AP matching
-constexpr int AM_CLIP = 64;   // threads that run the fp64 clip of the surviving det x GT pairs
+// One 128-thread CTA per scene (small CTAs: the per-scene work is a chain of short latency-bound phases, so the SM
+// is kept busy by having ~6 scenes in flight, not by wide CTAs):
+//   stage   kept detections (ordered compaction) and present GT -> 64-byte feature records in shared memory
+//           (BEV quad, y extent, BEV bounding rectangle, fp64 volume)
+//   step 1  every det x GT pair: the cheap exact rejects (no height overlap / disjoint BEV rectangles => IoU 0),
+//           survivors on a warp-aggregated queue (processed in slabs of AM_QCAP pairs)
+//   step 2  fp64 Sutherland-Hodgman clip of the survivors: 8 lanes per pair when few (short chain), else one per lane
+//   records score of every (class, slot), tp = 0
+//   pass 1  thread per det: for each GT that is the det's first-max IoU within its class and beats a threshold:
+//           claim = atomicMax((score_bits << 32) | ~det) per (GT, threshold)
+//   pass 2  same walk: TP iff this det holds the claim
+// Candidate pairs and their IoUs live in shared memory; the caller's workspace is only touched in the dense fallback.
+constexpr int AM_NT = 128;
+constexpr int AM_CLIP = 32;        // lanes of the dense (serial) clip path
+constexpr int AM_QCAP = 1024;      // candidate pairs held in shared memory (pair index + IoU)
 
-__host__ __device__ inline size_t am_queue_offset(int K, int G, int C, int nthr)
+struct __align__(16) AmBox { float qx[4], qz[4]; float ytop, ybot, lox, hix, loz, hiz; double vol; };   // 64 B
+
+__device__ __forceinline__ void am_features(const float *c, AmBox &f)
 {
-    size_t o = sizeof(V2<double>) * 2 * SH_MAXV * AM_CLIP + sizeof(unsigned long long) * (size_t)G * nthr +
-               sizeof(int) * ((size_t)K + 2 * (size_t)G) + (sizeof(short) + 1) * (size_t)C * K;
-    return (o + 15) & ~(size_t)15;
+    using A = Ar<double>;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f.qx[i] = c[3 * (3 - i)]; f.qz[i] = c[3 * (3 - i) + 2]; }   // rect order of box3d_iou (box_util.py:127-128)
+    f.ytop = c[1]; f.ybot = c[13];
+    f.lox = fminf(fminf(c[0], c[3]), fminf(c[6], c[9])); f.hix = fmaxf(fmaxf(c[0], c[3]), fmaxf(c[6], c[9]));
+    f.loz = fminf(fminf(c[2], c[5]), fminf(c[8], c[11])); f.hiz = fmaxf(fmaxf(c[2], c[5]), fmaxf(c[8], c[11]));
+    const int pa[3] = {0, 1, 0}, pb[3] = {1, 2, 4};
+    double e[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const double dx = A::sub((double)c[3 * pa[t]], (double)c[3 * pb[t]]);
+        const double dy = A::sub((double)c[3 * pa[t] + 1], (double)c[3 * pb[t] + 1]);
+        const double dz = A::sub((double)c[3 * pa[t] + 2], (double)c[3 * pb[t] + 2]);
+        e[t] = A::sqrt(A::add(A::add(A::mul(dx, dx), A::mul(dy, dy)), A::mul(dz, dz)));
+    }
+    f.vol = A::mul(A::mul(e[0], e[1]), e[2]);
+}
+
+__device__ __forceinline__ void am_load_box(const float *g, float *c)
+{
+    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { const float4 v = __ldg(reinterpret_cast<const float4 *>(g) + i); c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 24; ++i) c[i] = __ldg(g + i);
+    }
+}
+
+__device__ __forceinline__ double am_finish_iou(double ia, const AmBox &a, const AmBox &b)
+{
+    using A = Ar<double>;
+    const double h = A::max(0.0, A::sub(A::min((double)a.ytop, (double)b.ytop), A::max((double)a.ybot, (double)b.ybot)));
+    const double iv = A::mul(ia, h);
+    return A::div(iv, A::sub(A::add(a.vol, b.vol), iv));
+}
+
+__device__ __forceinline__ double coop_area_f64(double vx, double vy, int n, int gl)
+{   // area_f64 on a register-resident polygon: products in parallel, sums in the reference order
+    const unsigned full = 0xffffffffu;
+    const int src = max((gl == 0 ? n : gl) - 1, 0);
+    const double px = __shfl_sync(full, vx, src, 8), py = __shfl_sync(full, vy, src, 8);
+    const double t1 = __dmul_rn(vx, py), t2 = __dmul_rn(vy, px);
+    double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < SH_MAXV; ++i) {
+        const double u = __shfl_sync(full, t1, i, 8), w = __shfl_sync(full, t2, i, 8);
+        if (i < n) { d1 = __dadd_rn(d1, u); d2 = __dadd_rn(d2, w); }
+    }
+    return n < 3 ? 0.0 : __dmul_rn(0.5, fabs(__dsub_rn(d1, d2)));
+}
+
+__host__ __device__ inline size_t am_smem_bytes(int K, int G, int nthr)
+{
+    return sizeof(AmBox) * ((size_t)K + G) + sizeof(V2<double>) * 2 * SH_MAXV * AM_CLIP + sizeof(double) * AM_QCAP +
+           sizeof(unsigned long long) * (size_t)G * nthr + sizeof(int) * ((size_t)K + 2 * (size_t)G) + sizeof(unsigned) * AM_QCAP + 64;
 }
 
 struct MatchParams {
@@ -132,152 +202,306 @@ struct MatchParams {
     const float *gt_corners; const int64_t *gt_labels; const uint8_t *gt_present;
     int S, K, G, C, nthr; double thr[8];
     double *iou_ws; float *rec_score; uint8_t *rec_tp; unsigned long long *npos;
+    unsigned long long *dbg;   // optional [S][8] globaltimer stamps of thread 0 (OVDET_APMATCH_DBG_PTR; null in production)
 };
+#define AMSTAMP(i) do { if (p.dbg && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[(size_t)blockIdx.x * 8 + (i)] = t_; } } while (0)
 
-__global__ void __launch_bounds__(EV_NT) ap_match_kernel(MatchParams p)
+__global__ void __launch_bounds__(AM_NT) ap_match_kernel(MatchParams p)
 {
     extern __shared__ __align__(16) unsigned char sm[];
-    // carve: scratch [2*MAXV*AM_CLIP] V2<double> | best [G*nthr] u64 | kd [K] int | gl [G] int | glab [G] int | jmax [C*K] i16 | cand [C*K] u8 | queue [K*G] u16
-    V2<double> *scratch = reinterpret_cast<V2<double> *>(sm);
-    unsigned long long *best = reinterpret_cast<unsigned long long *>(scratch + 2 * SH_MAXV * AM_CLIP);
+    AmBox *dbox = reinterpret_cast<AmBox *>(sm);
+    AmBox *gbox = dbox + p.K;
+    V2<double> *scratch = reinterpret_cast<V2<double> *>(gbox + p.G);
+    double *qiou = reinterpret_cast<double *>(scratch + 2 * SH_MAXV * AM_CLIP);   // IoU of the queued (surviving) pairs
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(qiou + AM_QCAP);
     int *kd = reinterpret_cast<int *>(best + (size_t)p.G * p.nthr);
     int *gl = kd + p.K;
     int *glab = gl + p.G;
-    short *jmax = reinterpret_cast<short *>(glab + p.G);
-    unsigned char *cand = reinterpret_cast<unsigned char *>(jmax + (size_t)p.C * p.K);
-    unsigned short *queue = reinterpret_cast<unsigned short *>(sm + am_queue_offset(p.K, p.G, p.C, p.nthr));
+    unsigned *queue = reinterpret_cast<unsigned *>(glab + p.G);
     __shared__ int nk_s, ng_s, qn_s;
-    const int s = blockIdx.x, tid = threadIdx.x;
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t N = (size_t)p.S * p.K;
     const uint8_t *keep = p.keep + (size_t)s * p.K;
+    AMSTAMP(0);
 
-    // ordered compaction of kept detections / present GT (single warp, ballot + popc)
-    if (tid < 32) {
+    // ordered compaction of kept detections (warp 0) / present GT (warp 1), ballot + popc
+    if (warp == 0) {
         int n = 0;
         for (int base = 0; base < p.K; base += 32) {
-            const int k = base + tid;
+            const int k = base + lane;
             const bool f = k < p.K && keep[k];
             const unsigned m = __ballot_sync(0xffffffffu, f);
-            if (f) kd[n + __popc(m & ((1u << tid) - 1))] = k;
+            if (f) kd[n + __popc(m & ((1u << lane) - 1))] = k;
             n += __popc(m);
         }
-        if (tid == 0) nk_s = n;
-        n = 0;
+        if (lane == 0) nk_s = n;
+    } else if (warp == 1) {
+        int n = 0;
         for (int base = 0; base < p.G; base += 32) {
-            const int g = base + tid;
+            const int g = base + lane;
             const bool f = g < p.G && p.gt_present[(size_t)s * p.G + g];
             const unsigned m = __ballot_sync(0xffffffffu, f);
             if (f) {
-                const int pos = n + __popc(m & ((1u << tid) - 1));
+                const int pos = n + __popc(m & ((1u << lane) - 1));
                 gl[pos] = g;
-                long long lab = p.gt_labels[(size_t)s * p.G + g];
+                const long long lab = p.gt_labels[(size_t)s * p.G + g];
                 glab[pos] = (int)lab;
                 if (lab >= 0 && lab < p.C) atomicAdd(&p.npos[lab], 1ull);
             }
             n += __popc(m);
         }
-        if (tid == 0) ng_s = n;
+        if (lane == 0) ng_s = n;
     }
-    for (int i = tid; i < p.G * p.nthr; i += EV_NT) best[i] = 0ull;
-    if (tid == 0) qn_s = 0;
+    for (int i = tid; i < p.G * p.nthr; i += AM_NT) best[i] = 0ull;
     __syncthreads();
     const int nk = nk_s, ng = ng_s;
+    AMSTAMP(1);
 
-    // exact IoU matrix [nk, ng] -> iou_ws[s, i, j].  Step 1 (all threads): the cheap exact rejects -- no height
-    // overlap or disjoint BEV bounding rectangles give IoU 0 -- and a warp-aggregated queue of the survivors.
-    double *iou = p.iou_ws + (size_t)s * p.K * p.G;
+    // records: score of every (class, slot), tp = 0.  The scene's [K, C] probability tile is staged through shared
+    // memory (aliasing the clip scratch, idle until step 2) with independent 16-byte loads, so that no thread walks 20
+    // dependent global loads; the stores are coalesced in k for each class.
+    {
+        float *ptile = reinterpret_cast<float *>(scratch);
+        const size_t tile_cap = (sizeof(V2<double>) * 2 * SH_MAXV * AM_CLIP + sizeof(double) * AM_QCAP) / sizeof(float);
+        const size_t kc = (size_t)p.K * p.C;
+        const float *pg = p.probs ? p.probs + (size_t)s * kc : nullptr;
+        const bool staged = pg && kc <= tile_cap;
+        if (staged) {
+            if ((reinterpret_cast<uintptr_t>(pg) & 15) == 0 && (kc & 3) == 0) {
+                for (int i = tid; i < (int)(kc >> 2); i += AM_NT) reinterpret_cast<float4 *>(ptile)[i] = __ldg(reinterpret_cast<const float4 *>(pg) + i);
+            } else {
+                for (int i = tid; i < (int)kc; i += AM_NT) ptile[i] = __ldg(pg + i);
+            }
+            __syncthreads();
+        }
+        for (int k = tid; k < p.K; k += AM_NT) {
+            const size_t slot = (size_t)s * p.K + k;
+            const bool kept = keep[k];
+            const float ob = kept ? __ldg(p.obj + slot) : 0.f;
+            const int dc = (kept && p.det_cls) ? p.det_cls[slot] : -1;
+            for (int c = 0; c < p.C; ++c) {
+                float sc = -INFINITY;
+                if (kept) {
+                    if (p.det_cls) { if (dc == c) sc = ob; }
+                    else sc = __fmul_rn(staged ? ptile[(size_t)k * p.C + c] : __ldg(pg + (size_t)k * p.C + c), ob);
+                }
+                p.rec_score[(size_t)c * N + slot] = sc;
+                p.rec_tp[(size_t)c * N + slot] = 0;
+            }
+        }
+    }
+    AMSTAMP(2);
+    if (ng == 0 || nk == 0) return;   // no claims possible (uniform)
+
+    // stage features
+    for (int i = tid; i < nk + ng; i += AM_NT) {
+        float c[24];
+        if (i < nk) { am_load_box(p.corners + ((size_t)s * p.K + kd[i]) * 24, c); am_features(c, dbox[i]); }
+        else { am_load_box(p.gt_corners + ((size_t)s * p.G + gl[i - nk]) * 24, c); am_features(c, gbox[i - nk]); }
+    }
+    double thr_min = p.thr[0];
+    for (int t = 1; t < p.nthr; ++t) thr_min = fmin(thr_min, p.thr[t]);
     const int npair = nk * ng;
-    for (int base = 0; base < npair; base += EV_NT) {
-        const int pi = base + tid;
-        bool need = false;
-        if (pi < npair) {
-            const int i = pi / ng, j = pi - i * ng;
-            const float *a = p.corners + ((size_t)s * p.K + kd[i]) * 24;
-            const float *b = p.gt_corners + ((size_t)s * p.G + gl[j]) * 24;
-            need = fminf(__ldg(a + 1), __ldg(b + 1)) > fmaxf(__ldg(a + 13), __ldg(b + 13));
-#pragma unroll
-            for (int ax = 0; ax < 3; ax += 2) {
-                const float lo1 = fminf(fminf(__ldg(a + ax), __ldg(a + 3 + ax)), fminf(__ldg(a + 6 + ax), __ldg(a + 9 + ax)));
-                const float hi1 = fmaxf(fmaxf(__ldg(a + ax), __ldg(a + 3 + ax)), fmaxf(__ldg(a + 6 + ax), __ldg(a + 9 + ax)));
-                const float lo2 = fminf(fminf(__ldg(b + ax), __ldg(b + 3 + ax)), fminf(__ldg(b + 6 + ax), __ldg(b + 9 + ax)));
-                const float hi2 = fmaxf(fmaxf(__ldg(b + ax), __ldg(b + 3 + ax)), fmaxf(__ldg(b + 6 + ax), __ldg(b + 9 + ax)));
-                if (hi1 < lo2 || hi2 < lo1) need = false;
-            }
-            if (!need) iou[(size_t)i * p.G + j] = 0.0;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, need);
-        if (m) {
-            const int lane = tid & 31;
-            int bp = 0;
-            if (lane == 0) bp = atomicAdd(&qn_s, __popc(m));
-            bp = __shfl_sync(0xffffffffu, bp, 0);
-            if (need) queue[bp + __popc(m & ((1u << lane) - 1))] = (unsigned short)pi;
-        }
-    }
+    if (tid == 0) { qn_s = 0; }
     __syncthreads();
-    // Step 2 (AM_CLIP threads, small scratch): the fp64 Sutherland-Hodgman clip of the survivors
-    if (tid < AM_CLIP) {
-        V2<double> *bufA = scratch + tid, *bufB = scratch + SH_MAXV * AM_CLIP + tid;
-        const int qn = qn_s;
-        for (int qi = tid; qi < qn; qi += AM_CLIP) {
-            const int pi = queue[qi];
-            const int i = pi / ng, j = pi - i * ng;
-            float c1[24], c2[24];
-            const float *a = p.corners + ((size_t)s * p.K + kd[i]) * 24;
-            const float *b = p.gt_corners + ((size_t)s * p.G + gl[j]) * 24;
-#pragma unroll
-            for (int t = 0; t < 24; ++t) { c1[t] = __ldg(a + t); c2[t] = __ldg(b + t); }
-            double dummy;
-            iou[(size_t)i * p.G + j] = exact_iou<AM_CLIP>(c1, c2, bufA, bufB, false, &dummy);
-        }
-    }
-    // default records for every (class, detection slot) of this scene
-    for (int it = tid; it < p.C * p.K; it += EV_NT) {
-        const int c = it / p.K, k = it - c * p.K;
-        p.rec_score[(size_t)c * N + (size_t)s * p.K + k] = -INFINITY;
-        p.rec_tp[(size_t)c * N + (size_t)s * p.K + k] = 0;
-    }
-    __syncthreads();
+    AMSTAMP(3);
 
-    // pass 1: per (class, kept det): score, jmax, candidate bits, claim
-    for (int it = tid; it < p.C * nk; it += EV_NT) {
-        const int c = it / nk, i = it - c * nk;
-        const int k = kd[i];
-        if (p.det_cls && p.det_cls[(size_t)s * p.K + k] != c) { jmax[it] = -1; cand[it] = 0; continue; }
-        const float sc = p.det_cls ? __ldg(p.obj + (size_t)s * p.K + k)
-                                   : __fmul_rn(__ldg(p.probs + ((size_t)s * p.K + k) * p.C + c), __ldg(p.obj + (size_t)s * p.K + k));
-        p.rec_score[(size_t)c * N + (size_t)s * p.K + k] = sc;
-        double ovmax = -INFINITY; int jm = -1;
-        for (int j = 0; j < ng; ++j) {
-            if (glab[j] != c) continue;
-            const double v = iou[(size_t)i * p.G + j];
-            if (v > ovmax) { ovmax = v; jm = j; }
-        }
-        unsigned char cb = 0;
-        if (jm >= 0) {
-            // non-negative fp32 scores order like their bit patterns; lower det index wins ties
-            const unsigned long long key = ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
-            for (int t = 0; t < p.nthr; ++t)
-                if (ovmax > p.thr[t]) { cb |= (unsigned char)(1u << t); atomicMax(&best[(size_t)jm * p.nthr + t], key); }
-        }
-        jmax[it] = (short)jm;
-        cand[it] = cb;
-    }
-    __syncthreads();
-    // pass 2: TP iff this det holds the claim
-    for (int it = tid; it < p.C * nk; it += EV_NT) {
-        const unsigned char cb = cand[it];
-        if (!cb) continue;
-        const int c = it / nk, i = it - c * nk;
-        const int jm = jmax[it];
-        unsigned char tp = 0;
-        for (int t = 0; t < p.nthr; ++t)
-            if ((cb >> t) & 1) {
-                const unsigned long long w = best[(size_t)jm * p.nthr + t];
-                if ((unsigned)(0xFFFFFFFFu - (unsigned)(w & 0xFFFFFFFFull)) == (unsigned)i) tp |= (unsigned char)(1u << t);
+    // ---- sparse mode (thr_min >= 0): only pairs whose IoU could exceed the smallest threshold are clipped.
+    // Exact rejects: no height overlap or disjoint BEV rectangles (IoU = 0); conservative reject: the IoU is at most
+    // ub = I/(V1+V2-I) with I = (overlap of the BEV bounding rectangles) x (height overlap) >= the true intersection;
+    // a pair with ub(1+1e-6) < thr_min can neither be a TP nor change which GT is a detection's arg-max among those
+    // above the threshold, so its IoU is never needed.  Survivors (with their IoU) form a short list in shared memory.
+    bool dense = !(thr_min >= 0.0);
+    if (!dense) {
+        for (int base = 0; base < npair; base += AM_NT) {
+            const int pi = base + tid;
+            bool need = false;
+            if (pi < npair) {
+                const int i = pi / ng, j = pi - i * ng;
+                const AmBox &a = dbox[i], &b = gbox[j];
+                const float hh = fminf(a.ytop, b.ytop) - fmaxf(a.ybot, b.ybot);
+                const float ox = fminf(a.hix, b.hix) - fmaxf(a.lox, b.lox), oz = fminf(a.hiz, b.hiz) - fmaxf(a.loz, b.loz);
+                if (hh > 0.f && ox >= 0.f && oz >= 0.f) {
+                    const double I = (double)ox * (double)oz * (double)hh * (1.0 + 1e-6);   // fp32 differences: widen
+                    const double den = a.vol + b.vol - I;
+                    need = !(den > 0.0) || I * (1.0 + 1e-6) >= thr_min * den;
+                }
             }
-        p.rec_tp[(size_t)c * N + (size_t)s * p.K + kd[i]] = tp;
+            const unsigned m = __ballot_sync(0xffffffffu, need);
+            if (m) {
+                int bp = 0;
+                if (lane == 0) bp = atomicAdd(&qn_s, __popc(m));
+                bp = __shfl_sync(0xffffffffu, bp, 0);
+                const int q = bp + __popc(m & ((1u << lane) - 1));
+                if (need && q < AM_QCAP) { const int i = pi / ng; queue[q] = ((unsigned)i << 16) | (unsigned)(pi - i * ng); }   // K, G <= 32767
+            }
+        }
+        __syncthreads();
+        if (qn_s > AM_QCAP) dense = true;   // uniform: fall back to the dense matrix in the caller's workspace
     }
+    if (!dense) {
+        const int qn = qn_s;
+        constexpr int NGROUP = AM_NT / 8;
+        if (qn <= 4 * NGROUP) {
+            const int gli = lane & 7, gshift = lane & 24, group = tid >> 3;
+            V2<double> *gbuf = scratch + group * 8;
+            for (int base = 0; base < qn; base += NGROUP) {
+                if (base + warp * 4 >= qn) break;   // warp-uniform
+                const int qi = base + group;
+                const bool act = qi < qn;
+                int i = 0, j = 0;
+                if (act) { const unsigned e = queue[qi]; i = (int)(e >> 16); j = (int)(e & 0xffffu); }
+                const AmBox &a = dbox[i], &b = gbox[j];
+                double cl[8];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { cl[2 * t] = (double)b.qx[t]; cl[2 * t + 1] = (double)b.qz[t]; }
+                double vx = (double)a.qx[gli & 3], vy = (double)a.qz[gli & 3];
+                const int n = coop_clip_quads<double>(cl, vx, vy, act ? 4 : 0, gli, gshift, gbuf);
+                const double ia = coop_area_f64(vx, vy, n, gli);
+                if (act && gli == 0) qiou[qi] = am_finish_iou(ia, a, b);
+            }
+        } else if (tid < AM_CLIP) {
+            V2<double> *bufA = scratch + tid, *bufB = scratch + SH_MAXV * AM_CLIP + tid;
+            for (int qi = tid; qi < qn; qi += AM_CLIP) {
+                const unsigned e = queue[qi];
+                const int i = (int)(e >> 16), j = (int)(e & 0xffffu);
+                const AmBox &a = dbox[i], &b = gbox[j];
+                double sq[8], cq[8];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    sq[2 * t] = (double)a.qx[t]; sq[2 * t + 1] = (double)a.qz[t];
+                    cq[2 * t] = (double)b.qx[t]; cq[2 * t + 1] = (double)b.qz[t];
+                }
+                const int n = sh_clip_quads<double, AM_CLIP>(sq, cq, bufA, bufB);
+                qiou[qi] = am_finish_iou(area_f64<AM_CLIP>(bufB, n), a, b);
+            }
+        }
+        __syncthreads();
+        AMSTAMP(4);
+        if (p.dbg && threadIdx.x == 0) p.dbg[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)qn | ((unsigned long long)nk << 16) | ((unsigned long long)ng << 32);
+        // pass 1 (claims) / pass 2 (TP iff the claim is held): thread per survivor
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int q = tid; q < qn; q += AM_NT) {
+                const double v = qiou[q];
+                if (!(v > thr_min)) continue;
+                const unsigned e = queue[q];
+                const int i = (int)(e >> 16), j = (int)(e & 0xffffu);
+                const int c = glab[j];
+                const size_t slot = (size_t)s * p.K + kd[i];
+                if (c < 0 || c >= p.C || (p.det_cls && p.det_cls[slot] != c)) continue;
+                bool first_max = true;   // jmax of (det, class c): first GT of the class attaining the maximum (eval_det.py:121-126)
+                for (int q2 = 0; q2 < qn; ++q2) {
+                    const unsigned e2 = queue[q2];
+                    if ((int)(e2 >> 16) != i) continue;
+                    const int j2 = (int)(e2 & 0xffffu);
+                    if (glab[j2] != c) continue;
+                    const double v2 = qiou[q2];
+                    if (v2 > v || (v2 == v && j2 < j)) { first_max = false; break; }
+                }
+                if (!first_max) continue;
+                if (pass == 0) {
+                    const float sc = p.det_cls ? __ldg(p.obj + slot) : __fmul_rn(__ldg(p.probs + slot * p.C + c), __ldg(p.obj + slot));
+                    // non-negative fp32 scores order like their bit patterns; lower det index wins ties
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+                    for (int t = 0; t < p.nthr; ++t)
+                        if (v > p.thr[t]) atomicMax(&best[(size_t)j * p.nthr + t], key);
+                } else {
+                    unsigned char tp = 0;
+                    for (int t = 0; t < p.nthr; ++t)
+                        if (v > p.thr[t]) {
+                            const unsigned long long w = best[(size_t)j * p.nthr + t];
+                            if ((unsigned)(0xFFFFFFFFu - (unsigned)(w & 0xFFFFFFFFull)) == (unsigned)i) tp |= (unsigned char)(1u << t);
+                        }
+                    if (tp) p.rec_tp[(size_t)c * N + slot] = tp;
+                }
+            }
+            __syncthreads();
+        }
+        AMSTAMP(5);
+        return;
+    }
+
+    // ---- dense mode (a negative threshold, or more than AM_QCAP candidate pairs): the full IoU matrix in the caller's
+    // workspace, exact rejects only, pairs processed in slabs of AM_QCAP
+    double *iou = p.iou_ws + (size_t)s * p.K * p.G;
+    const int ldi = p.G;
+    for (int slab = 0; slab < npair; slab += AM_QCAP) {
+        __syncthreads();
+        if (tid == 0) qn_s = 0;
+        __syncthreads();
+        const int slab_end = min(npair, slab + AM_QCAP);
+        for (int base = slab; base < slab_end; base += AM_NT) {
+            const int pi = base + tid;
+            bool need = false;
+            if (pi < slab_end) {
+                const int i = pi / ng, j = pi - i * ng;
+                const AmBox &a = dbox[i], &b = gbox[j];
+                need = fminf(a.ytop, b.ytop) > fmaxf(a.ybot, b.ybot) &&
+                       !(a.hix < b.lox || b.hix < a.lox) && !(a.hiz < b.loz || b.hiz < a.loz);
+                if (!need) iou[(size_t)i * ldi + j] = 0.0;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, need);
+            if (m) {
+                int bp = 0;
+                if (lane == 0) bp = atomicAdd(&qn_s, __popc(m));
+                bp = __shfl_sync(0xffffffffu, bp, 0);
+                if (need) queue[bp + __popc(m & ((1u << lane) - 1))] = (unsigned)pi;
+            }
+        }
+        __syncthreads();
+        const int qn = qn_s;
+        if (tid < AM_CLIP) {
+            V2<double> *bufA = scratch + tid, *bufB = scratch + SH_MAXV * AM_CLIP + tid;
+            for (int qi = tid; qi < qn; qi += AM_CLIP) {
+                const int pi = (int)queue[qi];
+                const int i = pi / ng, j = pi - i * ng;
+                const AmBox &a = dbox[i], &b = gbox[j];
+                double sq[8], cq[8];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    sq[2 * t] = (double)a.qx[t]; sq[2 * t + 1] = (double)a.qz[t];
+                    cq[2 * t] = (double)b.qx[t]; cq[2 * t + 1] = (double)b.qz[t];
+                }
+                const int n = sh_clip_quads<double, AM_CLIP>(sq, cq, bufA, bufB);
+                iou[(size_t)i * ldi + j] = am_finish_iou(area_f64<AM_CLIP>(bufB, n), a, b);
+            }
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = tid; i < nk; i += AM_NT) {
+            const size_t slot = (size_t)s * p.K + kd[i];
+            const int dc = p.det_cls ? p.det_cls[slot] : -1;
+            const double *row = iou + (size_t)i * ldi;
+            for (int j = 0; j < ng; ++j) {
+                const double v = row[j];
+                if (!(v > thr_min)) continue;
+                const int c = glab[j];
+                if (c < 0 || c >= p.C || (p.det_cls && dc != c)) continue;
+                bool first_max = true;
+                for (int j2 = 0; j2 < ng; ++j2)
+                    if (glab[j2] == c) { const double v2 = row[j2]; if (v2 > v || (v2 == v && j2 < j)) { first_max = false; break; } }
+                if (!first_max) continue;
+                if (pass == 0) {
+                    const float sc = p.det_cls ? __ldg(p.obj + slot) : __fmul_rn(__ldg(p.probs + slot * p.C + c), __ldg(p.obj + slot));
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+                    for (int t = 0; t < p.nthr; ++t)
+                        if (v > p.thr[t]) atomicMax(&best[(size_t)j * p.nthr + t], key);
+                } else {
+                    unsigned char tp = 0;
+                    for (int t = 0; t < p.nthr; ++t)
+                        if (v > p.thr[t]) {
+                            const unsigned long long w = best[(size_t)j * p.nthr + t];
+                            if ((unsigned)(0xFFFFFFFFu - (unsigned)(w & 0xFFFFFFFFull)) == (unsigned)i) tp |= (unsigned char)(1u << t);
+                        }
+                    if (tp) p.rec_tp[(size_t)c * N + slot] = tp;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    AMSTAMP(5);
 }
 
 // ------------------------------------------------- segmented radix sort + AP
@@ -569,11 +793,12 @@ extern "C" int ovdet_ap_match(const float *corners, const float *probs, const fl
     p.gt_labels = gt_labels; p.gt_present = gt_present; p.S = S; p.K = K; p.G = G; p.C = C; p.nthr = nthr;
     for (int t = 0; t < nthr; ++t) p.thr[t] = thr[t];
     p.iou_ws = iou_ws; p.rec_score = rec_score; p.rec_tp = rec_tp; p.npos = reinterpret_cast<unsigned long long *>(npos);
-    OVDET_REQUIRE((long long)K * G <= 65535, "K*G must fit the 16-bit pair queue");
-    size_t smem = am_queue_offset(K, G, C, nthr) + sizeof(unsigned short) * (size_t)K * (G > 0 ? G : 1) + 16;
-    OVDET_REQUIRE(smem <= 220 * 1024, "C*K / K*G too large for the shared-memory match tables");
+    { const char *e = getenv("OVDET_APMATCH_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
+    OVDET_REQUIRE((long long)K * G < 2147483647LL, "K*G too large");
+    const size_t smem = am_smem_bytes(K, G, nthr);
+    OVDET_REQUIRE(smem <= 220 * 1024, "K + G too large for the shared-memory feature records");
     OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ap_match_kernel<<<S, EV_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    ap_match_kernel<<<S, AM_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("ap_match_kernel");
 }
 

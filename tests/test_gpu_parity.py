@@ -370,6 +370,23 @@ def test_ap_large_vs_oracle_and_07():
         assert float(ap07[0, c]) == pytest.approx(oracle.voc_ap(rec[c], prec[c], True), abs=1e-12)
 
 
+@pytest.mark.parametrize("thrs,max_gt", [((-0.5, 0.25), 12), ((0.0, 0.1), 64), ((0.25, 0.5), 64)])
+def test_ap_match_dense_fallback_and_crowded(thrs, max_gt):
+    """ap_match's two modes against the oracle: a negative threshold forces the dense IoU matrix (zero-IoU pairs count),
+    thresholds 0 / 0.1 and crowded scenes (up to 64 GT) stress the conservative IoU upper-bound reject of the sparse mode."""
+    S, Q, G, C = 24, 128, 64, 20
+    out, tgt = synth.detection_batch(B=S, Q=Q, G=G, C=C, seed=77, heading=np.pi, max_gt=max_gt)
+    calc = APC.APCalculator(_Cfg(C), ap_iou_thresh=list(thrs), exact_eval=False)
+    calc.step(out["box_corners"].to(DEV), out["sem_cls_prob"].to(DEV), out["objectness_prob"].to(DEV), None,
+              tgt["gt_box_corners"].to(DEV), tgt["gt_box_sem_cls_label"].to(DEV), tgt["gt_box_present"].to(DEV))
+    got = calc.compute_metrics()
+    want, _ = oracle.ap_metrics(out["box_corners"], out["sem_cls_prob"], out["objectness_prob"], tgt["gt_box_corners"],
+                                tgt["gt_box_sem_cls_label"], tgt["gt_box_present"], C, ap_iou_thresh=thrs)
+    for thr in thrs:
+        for k, v in want[thr].items():
+            assert float(got[thr][k]) == pytest.approx(float(v), abs=1e-9), (thr, k)
+
+
 def test_ap_reduce_properties_full_size():
     """C3-sized record stream (20 classes x 5050*128 slots): sortedness-free checks --
     recall == total TP / npos, AP in [0,1], AP invariant under a permutation of the records."""
