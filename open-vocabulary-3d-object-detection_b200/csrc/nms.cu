@@ -23,10 +23,13 @@
 // ap_calculator.py:157), so keep-indices are bit-exact except on score ties
 // (numpy's default argsort is not stable: documented).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace ovdet {
+
+#define NSTAMP(ptr, i) do { if ((ptr) && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); (ptr)[(size_t)blockIdx.x * 16 + (i)] = t_; } } while (0)
 
 constexpr int NMS_NT = 256;
 constexpr int NMS_MAXK = 1024;
@@ -77,51 +80,76 @@ __device__ inline NmsSmem nms_carve(unsigned char *base, int K)
     return s;
 }
 
-// Src provides: bool alive(k); double score(k); void box(k, lo[3], hi[3], double &cls)
-// On return: s.picked[pos] for sorted position pos < n_alive, s.sidx[pos] = original index,
-// s.misc[0] = n_alive, s.misc[1] = npick.  `order_out` (may be null) gets original indices in pick order.
+// Src provides: bool alive(k); double score(k); double cls_of(k); void box(k, lo[3], hi[3], double &cls)
+// On return: s.picked[pos] for positions pos < s.misc[0], s.sidx[pos] & 0x3fffffff = original index (bit 30 = dead),
+// s.misc[1] = npick.  `order_out` (may be null) gets original indices in pick order.
 template <typename Src>
 __device__ void nms_core(const Src &src, int K, int dims, bool samecls, bool old_type, double thr, double eps,
-                         NmsSmem &s, int32_t *order_out)
+                         NmsSmem &s, int32_t *order_out, unsigned long long *dbg = nullptr)
 {
     using A = Ar<double>;
     const int tid = threadIdx.x;
+    const int NT = blockDim.x;   // 128 for K <= 128 (more scenes in flight per SM), else 256
     const int Kp = next_pow2(K < 32 ? 32 : K);
     const int W = (K + 31) / 32;
-    // ---- 1. keys
-    for (int k = tid; k < Kp; k += NMS_NT) {
-        const bool al = k < K && src.alive(k);
-        s.skey[k] = al ? src.score(k) : -INFINITY;
-        s.sidx[k] = al ? k : (k | 0x40000000);  // dead entries sort last
-    }
-    __syncthreads();
-    // bitonic sort: "a before b" = alive first, higher score, then higher index (stable-ascending-from-the-end)
+    const int warp = tid >> 5, lane = tid & 31, nw = NT / 32;
+    const bool fast = thr >= 0.0;
+    // "a before b" = alive first, higher score, then higher index (stable-ascending-from-the-end)
     auto before = [](double ka, int ia, double kb, int ib) {
         const bool da = ia & 0x40000000, db = ib & 0x40000000;
         if (da != db) return !da;
         if (ka != kb) return ka > kb;
         return ia > ib;
     };
-    for (int size = 2; size <= Kp; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < Kp / 2; t += NMS_NT) {
-                const int lo = 2 * t - (t & (stride - 1));
-                const int hi = lo + stride;
-                const bool up = ((lo & size) == 0);
-                const double ka = s.skey[lo], kb = s.skey[hi];
-                const int ia = s.sidx[lo], ib = s.sidx[hi];
-                const bool swap = up ? before(kb, ib, ka, ia) : before(ka, ia, kb, ib);
-                if (swap) { s.skey[lo] = kb; s.skey[hi] = ka; s.sidx[lo] = ib; s.sidx[hi] = ia; }
+    // ---- 0. mode.  Class-wise NMS with thr >= 0 and dense class ids (0..255) splits into independent per-class
+    // problems (steps 3'/4'); if the caller does not need the global pick order either, no global sort is needed at all:
+    // boxes stay at their original positions and are ordered inside their class only (`identity`).
+    bool classwise = fast && samecls;
+    if (classwise) {
+        bool bad = false;
+        for (int k = tid; k < K; k += NT)
+            if (src.alive(k)) { const double cd = src.cls_of(k); if (!(cd >= 0.0 && cd < (double)NMS_MAXCLS && (double)(int)cd == cd)) bad = true; }
+        classwise = !__syncthreads_or(bad);
+    }
+    const bool identity = classwise && order_out == nullptr;
+    if (identity) {
+        for (int k = tid; k < K; k += NT) {
+            const bool al = src.alive(k);
+            s.skey[k] = al ? src.score(k) : -INFINITY;
+            s.sidx[k] = al ? k : (k | 0x40000000);
+        }
+        __syncthreads();
+    } else {
+        // ---- 1. bitonic sort of (score, index) in shared memory
+        for (int k = tid; k < Kp; k += NT) {
+            const bool al = k < K && src.alive(k);
+            s.skey[k] = al ? src.score(k) : -INFINITY;
+            s.sidx[k] = al ? k : (k | 0x40000000);  // dead entries sort last
+        }
+        __syncthreads();
+        for (int size = 2; size <= Kp; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = tid; t < Kp / 2; t += NT) {
+                    const int lo = 2 * t - (t & (stride - 1));
+                    const int hi = lo + stride;
+                    const bool up = ((lo & size) == 0);
+                    const double ka = s.skey[lo], kb = s.skey[hi];
+                    const int ia = s.sidx[lo], ib = s.sidx[hi];
+                    const bool swap = up ? before(kb, ib, ka, ia) : before(ka, ia, kb, ib);
+                    if (swap) { s.skey[lo] = kb; s.skey[hi] = ka; s.sidx[lo] = ib; s.sidx[hi] = ia; }
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
-    // ---- 2. gather boxes in sorted order
+    NSTAMP(dbg, 2);
+    // ---- 2. gather box extents at their (sorted or original) positions
     if (tid == 0) { s.misc[0] = 0; s.misc[1] = 0; }
     __syncthreads();
     int local_alive = 0;
-    for (int pos = tid; pos < K; pos += NMS_NT) {
+    for (int pos = tid; pos < K; pos += NT) {
         const int k = s.sidx[pos];
+        s.picked[pos] = 0;
         if (k & 0x40000000) continue;
         ++local_alive;
         double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, cl = 0;
@@ -131,96 +159,138 @@ __device__ void nms_core(const Src &src, int K, int dims, bool samecls, bool old
         for (int a = 0; a < 3; ++a) { s.lo[a][pos] = lo[a]; s.hi[a][pos] = hi[a]; }
         s.vol[pos] = A::add(v, eps);
         s.cls[pos] = cl;
-        s.picked[pos] = 0;
     }
-    if (local_alive) atomicAdd(&s.misc[0], local_alive);
+    if (local_alive && !identity) atomicAdd(&s.misc[0], local_alive);
+    if (identity && tid == 0) s.misc[0] = K;
     __syncthreads();
-    const int n = s.misc[0];
-    const int warp = tid >> 5, lane = tid & 31, nw = NMS_NT / 32;
-    const bool fast = thr >= 0.0;
+    const int n = s.misc[0];   // positions to consider: the alive prefix (sorted) or all K with holes (identity)
+    NSTAMP(dbg, 3);
     // ---- 3'/4'. class-wise NMS with a non-negative threshold: independent per-class greedy loops
-    if (fast && samecls) {
-        for (int c = tid; c < NMS_MAXCLS; c += NMS_NT) s.ccnt[c] = 0;
+    if (classwise) {
+        for (int c = tid; c < NMS_MAXCLS; c += NT) s.ccnt[c] = 0;
         if (tid == 0) s.misc[2] = 0;
         __syncthreads();
-        if (warp == 0) {   // stable rank of every position inside its class
-            bool bad = false;
+        if (warp == 0) {   // rank of every alive position inside its class, in position order
             for (int base = 0; base < n; base += 32) {
                 const int pos = base + lane;
-                int c = -1 - lane;   // lanes past the end: unique dummies
-                if (pos < n) {
-                    const double cd = s.cls[pos];
-                    const int ci = (int)cd;
-                    if (cd >= 0.0 && cd < (double)NMS_MAXCLS && (double)ci == cd) c = ci; else bad = true;
-                }
+                int c = -1 - lane;   // dead / past the end: unique dummies
+                if (pos < n && !(s.sidx[pos] & 0x40000000)) c = (int)s.cls[pos];
                 const unsigned m = __match_any_sync(0xffffffffu, c);
                 if (c >= 0) s.crank[pos] = (unsigned short)(s.ccnt[c] + __popc(m & ((1u << lane) - 1)));
                 __syncwarp();
                 if (c >= 0 && (m & ((1u << lane) - 1)) == 0) s.ccnt[c] += __popc(m);   // lowest lane of each class group
                 __syncwarp();
             }
-            if (__any_sync(0xffffffffu, bad)) { if (lane == 0) s.misc[2] = 1; }
-            else {   // exclusive scan of the class counts (NMS_MAXCLS / 32 per lane)
-                constexpr int PER = NMS_MAXCLS / 32;
-                int loc[PER], sum = 0;
+            // exclusive scan of the class counts (NMS_MAXCLS / 32 per lane)
+            constexpr int PER = NMS_MAXCLS / 32;
+            int loc[PER], sum = 0;
 #pragma unroll
-                for (int q = 0; q < PER; ++q) { loc[q] = s.ccnt[lane * PER + q]; sum += loc[q]; }
-                int incl = sum;
-                for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
-                int run = incl - sum;
+            for (int q = 0; q < PER; ++q) { loc[q] = s.ccnt[lane * PER + q]; sum += loc[q]; }
+            int incl = sum;
+            for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+            int run = incl - sum;
+            int hi_c = -1; bool big = false;
 #pragma unroll
-                for (int q = 0; q < PER; ++q) { s.cstart[lane * PER + q] = run; run += loc[q]; }
+            for (int q = 0; q < PER; ++q) { s.cstart[lane * PER + q] = run; run += loc[q]; if (loc[q] > 0) hi_c = lane * PER + q; if (loc[q] > 32) big = true; }
+            for (int off = 16; off > 0; off >>= 1) hi_c = max(hi_c, __shfl_xor_sync(0xffffffffu, hi_c, off));
+            big = __any_sync(0xffffffffu, big);
+            if (lane == 0) { s.misc[3] = hi_c + 1; s.misc[2] = big ? 2 : 0; }   // class-loop bound; some class needs the warp scan
+        }
+        __syncthreads();
+        const int ncls = s.misc[3];
+        const bool any_big = s.misc[2] & 2;
+        for (int pos = tid; pos < n; pos += NT)
+            if (!(s.sidx[pos] & 0x40000000)) s.grouped[s.cstart[(int)s.cls[pos]] + s.crank[pos]] = (unsigned short)pos;
+        __syncthreads();
+        if (identity) {   // order the members of each class by score: rank = number of classmates that come before
+            for (int pos = tid; pos < n; pos += NT) {
+                const int k = s.sidx[pos];
+                if (k & 0x40000000) continue;
+                const int c = (int)s.cls[pos];
+                const int q0 = s.cstart[c], nc = s.ccnt[c];
+                const double key = s.skey[pos];
+                int r = 0;
+                for (int m = 0; m < nc; ++m) { const int p2 = s.grouped[q0 + m]; r += before(s.skey[p2], s.sidx[p2], key, k) ? 1 : 0; }
+                s.crank[pos] = (unsigned short)r;
+            }
+            __syncthreads();
+            for (int pos = tid; pos < n; pos += NT)
+                if (!(s.sidx[pos] & 0x40000000)) s.grouped[s.cstart[(int)s.cls[pos]] + s.crank[pos]] = (unsigned short)pos;
+            __syncthreads();
+        }
+        NSTAMP(dbg, 4);
+        // (a) thread per box: its suppression words over the LATER boxes of its own class (class-local bit index);
+        //     sum_c n_c^2/2 pair tests in total, rows independent of each other.
+        // (b) the greedy pick per class is then an integer scan over those words: one thread per class when the
+        //     class fits one word (the common case), else one warp with the removed bitset one word per lane.
+        for (int pos = tid; pos < n; pos += NT) {
+            if (s.sidx[pos] & 0x40000000) continue;
+            const int i = pos;
+            const int c = (int)s.cls[i];
+            const int q0 = s.cstart[c], nc = s.ccnt[c];
+            const unsigned short *g = s.grouped + q0;
+            const int ii = s.crank[pos];
+            const int q = q0 + ii;
+            double li[3], hi_[3];
+            for (int a = 0; a < 3; ++a) { li[a] = s.lo[a][i]; hi_[a] = s.hi[a][i]; }
+            const double vi = s.vol[i];
+            uint32_t word = 0;
+            for (int w = 0; w < (ii >> 5); ++w) s.mask[(size_t)q * W + w] = 0u;
+            for (int jj = ii + 1; jj < nc; ++jj) {
+                if ((jj & 31) == 0) { s.mask[(size_t)q * W + ((jj - 1) >> 5)] = word; word = 0; }
+                const int j = g[jj];
+                double e[3] = {1.0, 1.0, 1.0};
+                for (int a = 0; a < dims; ++a) e[a] = A::max(0.0, A::sub(A::min(hi_[a], s.hi[a][j]), A::max(li[a], s.lo[a][j])));
+                if (e[0] == 0.0 || e[1] == 0.0 || (dims == 3 && e[2] == 0.0)) continue;   // inter == 0: o is 0 or NaN, never > thr
+                double inter = e[0];
+                for (int a = 1; a < dims; ++a) inter = A::mul(inter, e[a]);
+                const double o = old_type ? A::div(inter, s.vol[j]) : A::div(inter, A::sub(A::add(vi, s.vol[j]), inter));
+                if (o > thr) word |= 1u << (jj & 31);
+            }
+            s.mask[(size_t)q * W + ((nc - 1) >> 5)] = word;
+        }
+        __syncthreads();
+        NSTAMP(dbg, 8);
+        for (int c = tid; c < ncls; c += NT) {   // classes of <= 32 boxes: one thread each
+            const int nc = s.ccnt[c];
+            if (nc == 0 || nc > 32) continue;
+            const int q0 = s.cstart[c];
+            uint32_t removed = 0;
+            for (int ii = 0; ii < nc; ++ii)
+                if (!((removed >> ii) & 1u)) { s.picked[s.grouped[q0 + ii]] = 1; removed |= s.mask[(size_t)(q0 + ii) * W]; }
+        }
+        NSTAMP(dbg, 9);
+        if (any_big) for (int c = warp; c < ncls; c += nw) {   // larger classes: one warp each
+            const int nc = s.ccnt[c];
+            if (nc <= 32) continue;
+            const int q0 = s.cstart[c];
+            const int Wc = (nc + 31) >> 5;
+            uint32_t removed = 0;
+            for (int ii = 0; ii < nc; ++ii) {
+                const uint32_t word = __shfl_sync(0xffffffffu, removed, ii >> 5);
+                if (!((word >> (ii & 31)) & 1u)) {
+                    if (lane == 0) s.picked[s.grouped[q0 + ii]] = 1;
+                    if (lane < Wc && lane >= (ii >> 5)) removed |= s.mask[(size_t)(q0 + ii) * W + lane];
+                }
             }
         }
         __syncthreads();
-        if (s.misc[2] == 0) {
-            for (int pos = tid; pos < n; pos += NMS_NT) s.grouped[s.cstart[(int)s.cls[pos]] + s.crank[pos]] = (unsigned short)pos;
-            __syncthreads();
-            // one warp per class: state 0 undecided / 1 picked / 2 removed, in s.picked
-            for (int c = warp; c < NMS_MAXCLS; c += nw) {
-                const int nc = s.ccnt[c];
-                if (nc == 0) continue;
-                const unsigned short *g = s.grouped + s.cstart[c];
-                for (int ii = 0; ii < nc; ++ii) {
-                    const int i = g[ii];
-                    if (s.picked[i] == 2) continue;   // warp-uniform (shared read after the previous __syncwarp)
-                    double li[3], hi_[3];
-                    for (int a = 0; a < 3; ++a) { li[a] = s.lo[a][i]; hi_[a] = s.hi[a][i]; }
-                    const double vi = s.vol[i];
-                    for (int jj = ii + 1 + lane; jj < nc; jj += 32) {
-                        const int j = g[jj];
-                        if (s.picked[j] == 2) continue;
-                        double e[3] = {1.0, 1.0, 1.0};
-                        for (int a = 0; a < dims; ++a) e[a] = A::max(0.0, A::sub(A::min(hi_[a], s.hi[a][j]), A::max(li[a], s.lo[a][j])));
-                        if (e[0] == 0.0 || e[1] == 0.0 || (dims == 3 && e[2] == 0.0)) continue;
-                        double inter = e[0];
-                        for (int a = 1; a < dims; ++a) inter = A::mul(inter, e[a]);
-                        const double o = old_type ? A::div(inter, s.vol[j]) : A::div(inter, A::sub(A::add(vi, s.vol[j]), inter));
-                        if (o > thr) s.picked[j] = 2;
-                    }
-                    if (lane == 0) s.picked[i] = 1;
-                    __syncwarp();
-                }
+        NSTAMP(dbg, 5);
+        if (warp == 0) {   // number of picks; their original indices in score order (sorted mode only)
+            int np = 0;
+            for (int base = 0; base < n; base += 32) {
+                const int pos = base + lane;
+                const bool pk = pos < n && s.picked[pos];
+                const unsigned m = __ballot_sync(0xffffffffu, pk);
+                if (pk && order_out) order_out[np + __popc(m & ((1u << lane) - 1))] = s.sidx[pos];
+                np += __popc(m);
             }
-            __syncthreads();
-            for (int pos = tid; pos < n; pos += NMS_NT) s.picked[pos] = s.picked[pos] == 1;
-            __syncthreads();
-            if (warp == 0) {   // picks in score order
-                int np = 0;
-                for (int base = 0; base < n; base += 32) {
-                    const int pos = base + lane;
-                    const bool pk = pos < n && s.picked[pos];
-                    const unsigned m = __ballot_sync(0xffffffffu, pk);
-                    if (pk && order_out) order_out[np + __popc(m & ((1u << lane) - 1))] = s.sidx[pos];
-                    np += __popc(m);
-                }
-                if (lane == 0) s.misc[1] = np;
-            }
-            __syncthreads();
-            return;
+            if (lane == 0) s.misc[1] = np;
         }
+        __syncthreads();
+        return;
     }
-    // ---- 3. suppression bitmask
+    // ---- 3. suppression bitmask (generic path: positions < n are the alive boxes in score order)
     for (int i = warp; i < n; i += nw) {
         double li[3], hi_[3];
         for (int a = 0; a < 3; ++a) { li[a] = s.lo[a][i]; hi_[a] = s.hi[a][i]; }
@@ -277,6 +347,7 @@ struct ArraySrc {
     const double *b; int ncols, dims, n; bool has_cls;
     __device__ bool alive(int k) const { return k < n; }
     __device__ double score(int k) const { return b[(size_t)k * ncols + 2 * dims]; }
+    __device__ double cls_of(int k) const { return has_cls ? b[(size_t)k * ncols + 2 * dims + 1] : 0.0; }
     __device__ void box(int k, double *lo, double *hi, double &cl) const
     {
         const double *r = b + (size_t)k * ncols;
@@ -301,7 +372,7 @@ __global__ void __launch_bounds__(NMS_NT) nms_kernel(NmsParams p)
     int n = p.counts ? p.counts[s] : p.K;
     n = n < 0 ? 0 : (n > p.K ? p.K : n);
     ArraySrc src{p.boxes + (size_t)s * p.K * p.ncols, p.ncols, dims, n, samecls};
-    for (int k = threadIdx.x; k < p.K; k += NMS_NT) {
+    for (int k = threadIdx.x; k < p.K; k += blockDim.x) {
         p.keep[(size_t)s * p.K + k] = 0;
         if (p.pick_order) p.pick_order[(size_t)s * p.K + k] = -1;
     }
@@ -309,7 +380,7 @@ __global__ void __launch_bounds__(NMS_NT) nms_kernel(NmsParams p)
     nms_core(src, p.K, dims, samecls, p.flags & OVDET_NMS_OLD_TYPE, p.thr, p.eps, sh,
              p.pick_order ? p.pick_order + (size_t)s * p.K : nullptr);
     const int na = sh.misc[0];
-    for (int pos = threadIdx.x; pos < na; pos += NMS_NT)
+    for (int pos = threadIdx.x; pos < na; pos += blockDim.x)
         if (sh.picked[pos]) p.keep[(size_t)s * p.K + sh.sidx[pos]] = 1;
     if (threadIdx.x == 0 && p.npick) p.npick[s] = sh.misc[1];
 }
@@ -319,6 +390,7 @@ struct CornerSrc {
     const float *corners; const float *obj; const uint8_t *nonempty; const int *cls; int dims2d;
     __device__ bool alive(int k) const { return nonempty ? nonempty[k] != 0 : true; }
     __device__ double score(int k) const { return (double)obj[k]; }
+    __device__ double cls_of(int k) const { return (double)cls[k]; }
     __device__ void box(int k, double *lo, double *hi, double &cl) const
     {
         const float *c = corners + (size_t)k * 24;
@@ -340,6 +412,7 @@ struct ParseParams {
     const float *corners, *probs, *obj; const uint8_t *nonempty;
     int S, K, C; double nms_iou; float conf; unsigned flags;
     uint8_t *pred_mask, *keep; int32_t *pred_cls; float *pred_cls_prob;
+    unsigned long long *dbg;   // optional [S][16] globaltimer stamps of thread 0 (OVDET_PARSE_DBG_PTR; null in production)
 };
 
 __global__ void __launch_bounds__(NMS_NT) parse_predictions_kernel(ParseParams p)
@@ -351,19 +424,54 @@ __global__ void __launch_bounds__(NMS_NT) parse_predictions_kernel(ParseParams p
     const float *probs = p.probs + (size_t)s * p.K * p.C;
     const float *obj = p.obj + (size_t)s * p.K;
     const uint8_t *ne = p.nonempty ? p.nonempty + (size_t)s * p.K : nullptr;
-    // argmax / max class prob (ap_calculator.py:59-61; np.argmax = first maximum)
-    for (int k = threadIdx.x; k < p.K; k += NMS_NT) {
-        float best = __ldg(probs + (size_t)k * p.C);
-        int bi = 0;
-        for (int c = 1; c < p.C; ++c) { const float v = __ldg(probs + (size_t)k * p.C + c); if (v > best) { best = v; bi = c; } }
-        cls_sm[k] = bi;
-        p.pred_cls[(size_t)s * p.K + k] = bi;
-        p.pred_cls_prob[(size_t)s * p.K + k] = best;
-        p.pred_mask[(size_t)s * p.K + k] = 0;
+    NSTAMP(p.dbg, 0);
+    // argmax / max class prob (ap_calculator.py:59-61; np.argmax = first maximum).  The scene's [K, C] tile is staged
+    // through shared memory (aliasing the NMS tables, not yet in use) with independent 16-byte loads, so that no thread
+    // walks C dependent global loads; row pitch C+1 keeps the per-thread row walks conflict-free.
+    {
+        float *ptile = reinterpret_cast<float *>(sm);
+        const size_t kc = (size_t)p.K * p.C;
+        const bool staged = (size_t)p.K * (p.C + 1) * sizeof(float) <= nms_smem_bytes(p.K);
+        if (staged) {
+            const float inv_c = 1.f / (float)p.C;
+            auto rowcol = [&](int e, int &r, int &c) {   // e / C without an integer divide (e < 2^21: the float estimate is off by at most one)
+                r = (int)(((float)e + 0.5f) * inv_c);
+                c = e - r * p.C;
+                if (c < 0) { --r; c += p.C; } else if (c >= p.C) { ++r; c -= p.C; }
+            };
+            if ((reinterpret_cast<uintptr_t>(probs) & 15) == 0 && (kc & 3) == 0) {
+                for (int i = threadIdx.x; i < (int)(kc >> 2); i += blockDim.x) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(probs) + i);
+                    const float vv[4] = {v.x, v.y, v.z, v.w};
+                    int r, c;
+                    rowcol(4 * i, r, c);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { ptile[r * (p.C + 1) + c] = vv[q]; if (++c == p.C) { c = 0; ++r; } }
+                }
+            } else {
+                for (int e = threadIdx.x; e < (int)kc; e += blockDim.x) { int r, c; rowcol(e, r, c); ptile[r * (p.C + 1) + c] = __ldg(probs + e); }
+            }
+            __syncthreads();
+        }
+        int my_cls[NMS_MAXK / 128];   // a thread owns at most K / blockDim.x <= 8 boxes
+        int cnt = 0;
+        for (int k = threadIdx.x; k < p.K; k += blockDim.x, ++cnt) {
+            const float *row = staged ? ptile + (size_t)k * (p.C + 1) : nullptr;
+            float best = staged ? row[0] : __ldg(probs + (size_t)k * p.C);
+            int bi = 0;
+            for (int c = 1; c < p.C; ++c) { const float v = staged ? row[c] : __ldg(probs + (size_t)k * p.C + c); if (v > best) { best = v; bi = c; } }
+            my_cls[cnt] = bi;
+            p.pred_cls[(size_t)s * p.K + k] = bi;
+            p.pred_cls_prob[(size_t)s * p.K + k] = best;
+            p.pred_mask[(size_t)s * p.K + k] = 0;
+        }
+        __syncthreads();   // the tile aliases the NMS tables and cls_sm's neighbours: everyone is done reading it
+        cnt = 0;
+        for (int k = threadIdx.x; k < p.K; k += blockDim.x, ++cnt) cls_sm[k] = my_cls[cnt];
     }
     __syncthreads();
     if (p.flags & OVDET_PARSE_NO_NMS) {
-        for (int k = threadIdx.x; k < p.K; k += NMS_NT) {
+        for (int k = threadIdx.x; k < p.K; k += blockDim.x) {
             const uint8_t m = ne ? (ne[k] != 0) : 1;
             p.pred_mask[(size_t)s * p.K + k] = m;
             p.keep[(size_t)s * p.K + k] = m && (obj[k] > p.conf);
@@ -373,19 +481,23 @@ __global__ void __launch_bounds__(NMS_NT) parse_predictions_kernel(ParseParams p
     const bool d2 = p.flags & OVDET_NMS_2D;
     const bool samecls = p.flags & OVDET_NMS_SAMECLS;
     CornerSrc src{p.corners + (size_t)s * p.K * 24, obj, ne, cls_sm, d2 ? 1 : 0};
-    nms_core(src, p.K, d2 ? 2 : 3, samecls, p.flags & OVDET_NMS_OLD_TYPE, p.nms_iou, 0.0, sh, nullptr);
+    NSTAMP(p.dbg, 1);
+    nms_core(src, p.K, d2 ? 2 : 3, samecls, p.flags & OVDET_NMS_OLD_TYPE, p.nms_iou, 0.0, sh, nullptr, p.dbg);
+    NSTAMP(p.dbg, 6);
     const int na = sh.misc[0];
-    for (int pos = threadIdx.x; pos < na; pos += NMS_NT)
+    for (int pos = threadIdx.x; pos < na; pos += blockDim.x)
         if (sh.picked[pos]) p.pred_mask[(size_t)s * p.K + sh.sidx[pos]] = 1;
     __syncthreads();
-    for (int k = threadIdx.x; k < p.K; k += NMS_NT)
+    for (int k = threadIdx.x; k < p.K; k += blockDim.x)
         p.keep[(size_t)s * p.K + k] = p.pred_mask[(size_t)s * p.K + k] && (obj[k] > p.conf);
+    NSTAMP(p.dbg, 7);
 }
 
 // ------------------------------------------------------- pseudo-label filter
 struct PoolSrc {
     const double *pool; const double *label; const double *tmp_score; int n;
     __device__ bool alive(int k) const { return k < n && label[k] != -100.0; }
+    __device__ double cls_of(int k) const { return label[k]; }
     __device__ double score(int k) const
     {   // use_size_score: score *= size, size = prod(scale) (lift_boxes.py:159-160, box_3d_utils.py:76-79)
         const double *r = pool + (size_t)k * 6;
@@ -421,8 +533,8 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
     const double *boxes = p.boxes + (size_t)s * p.P * 8;
     const double *pool = p.pool + (size_t)s * p.M * 6;
     double *olab = p.out_label + (size_t)s * p.M, *osc = p.out_score + (size_t)s * p.M;
-    for (int k = threadIdx.x; k < p.P; k += NMS_NT) p.nms1_keep[(size_t)s * p.P + k] = 0;
-    for (int j = threadIdx.x; j < p.M; j += NMS_NT) { best[j] = 0xFFFFFFFFu; olab[j] = -100.0; osc[j] = 0.0; p.out_keep[(size_t)s * p.M + j] = 0; }
+    for (int k = threadIdx.x; k < p.P; k += blockDim.x) p.nms1_keep[(size_t)s * p.P + k] = 0;
+    for (int j = threadIdx.x; j < p.M; j += blockDim.x) { best[j] = 0xFFFFFFFFu; olab[j] = -100.0; osc[j] = 0.0; p.out_keep[(size_t)s * p.M + j] = 0; }
     __syncthreads();
     // 1. class-wise NMS (lift_boxes.py:140; volume + 1e-8, box_3d_utils.py:74)
     ArraySrc src{boxes, 8, 3, nb, true};
@@ -430,13 +542,13 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
     const int npick = sh.misc[1];
     {
         const int na = sh.misc[0];
-        for (int pos = threadIdx.x; pos < na; pos += NMS_NT)
+        for (int pos = threadIdx.x; pos < na; pos += blockDim.x)
             if (sh.picked[pos]) p.nms1_keep[(size_t)s * p.P + sh.sidx[pos]] = 1;
     }
     __syncthreads();
     // 2. argmax-IoU match to the pool (lift_boxes.py:151-158): one warp per surviving box
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int t = warp; t < npick; t += NMS_NT / 32) {
+    for (int t = warp; t < npick; t += blockDim.x / 32) {
         const double *bx = boxes + (size_t)order[t] * 8;
         const double qv = A::mul(A::mul(A::sub(bx[3], bx[0]), A::sub(bx[4], bx[1])), A::sub(bx[5], bx[2]));
         double bi = -INFINITY; int bj = 0x7fffffff;
@@ -462,7 +574,7 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
         }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < np_; j += NMS_NT) {
+    for (int j = threadIdx.x; j < np_; j += blockDim.x) {
         if (best[j] != 0xFFFFFFFFu) {
             const int t = (int)best[j];
             const double *bx = boxes + (size_t)order[t] * 8;
@@ -475,7 +587,7 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
     PoolSrc psrc{pool, olab, osc, np_};
     nms_core(psrc, p.M, 3, true, false, p.size_thr, 1e-8, sh, nullptr);
     const int na = sh.misc[0];
-    for (int pos = threadIdx.x; pos < na; pos += NMS_NT)
+    for (int pos = threadIdx.x; pos < na; pos += blockDim.x)
         if (sh.picked[pos]) p.out_keep[(size_t)s * p.M + sh.sidx[pos]] = 1;
 }
 
@@ -496,7 +608,7 @@ extern "C" int ovdet_nms_f64(const double *boxes, const int32_t *counts, int S, 
     NmsParams p{boxes, counts, S, K, ncols, thr, vol_eps, flags, keep, pick_order, npick};
     const size_t smem = nms_smem_bytes(K);
     OVDET_CUDA_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_kernel<<<S, NMS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    nms_kernel<<<S, K <= 128 ? 128 : NMS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("nms_kernel");
 }
 
@@ -510,10 +622,11 @@ extern "C" int ovdet_parse_predictions_f32(const float *corners, const float *pr
     if (S == 0 || K == 0) return OVDET_OK;
     OVDET_REQUIRE(corners && probs && obj && pred_mask && keep && pred_cls && pred_cls_prob, "null pointer");
     OVDET_REQUIRE(K <= NMS_MAXK, "K must be <= 1024");
-    ParseParams p{corners, probs, obj, nonempty, S, K, C, nms_iou, conf_thresh, flags, pred_mask, keep, pred_cls, pred_cls_prob};
+    ParseParams p{corners, probs, obj, nonempty, S, K, C, nms_iou, conf_thresh, flags, pred_mask, keep, pred_cls, pred_cls_prob, nullptr};
+    { const char *e = getenv("OVDET_PARSE_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
     const size_t smem = nms_smem_bytes(K) + sizeof(int) * (size_t)K;
     OVDET_CUDA_TRY(cudaFuncSetAttribute(parse_predictions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    parse_predictions_kernel<<<S, NMS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    parse_predictions_kernel<<<S, K <= 128 ? 128 : NMS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("parse_predictions_kernel");
 }
 
