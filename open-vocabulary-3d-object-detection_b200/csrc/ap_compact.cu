@@ -91,35 +91,65 @@ __global__ void __launch_bounds__(1024) apc_sort_kernel(uint32_t *tp_key, uint8_
     for (int i = threadIdx.x; i < cap; i += 1024) { tp_key[(size_t)c * cap + i] = k[i]; tp_bits[(size_t)c * cap + i] = b[i]; }
 }
 
-// bucket of a record = number of TP-list keys strictly below its key (lower_bound); privatised per CTA
+// ---- bucket of a record = number of TP-list keys strictly below its key (lower_bound over the sorted TP list).
+// A binary search costs log2(cap) dependent shared loads per record (ncu: 33 short-scoreboard stalls per issue).
+// Instead the score axis is cut into APC_BINS uniform bins; edge[b] = lower_bound(key(b / APC_BINS)) is computed
+// once per class (apc_edges_kernel), and a record of bin b only has to look at entries edge[b+1] .. edge[b] of the
+// list -- on average less than one.  bin() is monotone over all floats (scores <= 0 share bin 0, >= 1 the last).
+constexpr int APC_BINS = 4096;
+
+__device__ __forceinline__ int apc_bin(float s)
+{
+    if (!(s > 0.f)) return 0;
+    if (s >= 1.f) return APC_BINS - 1;
+    return (int)(s * (float)APC_BINS);   // exact: power-of-two scale
+}
+
+// edge[c][b], b = 0..APC_BINS: entries of the sorted list with key < key(b / APC_BINS), i.e. score > b / APC_BINS;
+// edge[0] = number of real entries (everything scores above -inf), edge[APC_BINS] = 0 (nothing scores above +inf)
+__global__ void __launch_bounds__(1024) apc_edges_kernel(const uint32_t *__restrict__ tp_key, int cap, uint16_t *edge)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint32_t *k = reinterpret_cast<uint32_t *>(sm);
+    const int c = blockIdx.x;
+    for (int i = threadIdx.x; i < cap; i += 1024) k[i] = tp_key[(size_t)c * cap + i];
+    __syncthreads();
+    for (int b = threadIdx.x; b <= APC_BINS; b += 1024) {
+        uint32_t key;
+        if (b == 0) key = 0xFFFFFFFFu;                  // above every real key (empty slots hold 0xFFFFFFFF themselves)
+        else if (b == APC_BINS) key = 0u;
+        else key = apc_score_key((float)b / (float)APC_BINS);
+        int lo = 0, n = cap;
+        while (n > 1) { const int half = n >> 1; lo += (k[lo + half - 1] < key) ? half : 0; n -= half; }
+        lo += (k[lo] < key) ? 1 : 0;
+        edge[(size_t)c * (APC_BINS + 1) + b] = (uint16_t)lo;
+    }
+}
+
 __global__ void __launch_bounds__(APC_NT) apc_hist_kernel(const float *__restrict__ score, long long N, const uint32_t *__restrict__ tp_key,
-                                                          int cap, uint32_t *hist)
+                                                          const uint16_t *__restrict__ edge, int cap, uint32_t *hist)
 {
     extern __shared__ __align__(16) unsigned char sm[];
     uint32_t *k = reinterpret_cast<uint32_t *>(sm);   // [cap]
     uint32_t *h = k + cap;                            // [cap + 1]
+    uint16_t *e = reinterpret_cast<uint16_t *>(h + cap + 1);   // [APC_BINS + 1]
     const int c = blockIdx.y;
     for (int i = threadIdx.x; i < cap; i += APC_NT) k[i] = tp_key[(size_t)c * cap + i];
     for (int i = threadIdx.x; i <= cap; i += APC_NT) h[i] = 0;
+    for (int i = threadIdx.x; i <= APC_BINS; i += APC_NT) e[i] = edge[(size_t)c * (APC_BINS + 1) + i];
     __syncthreads();
-    // number of real TP entries = first empty (0xFFFFFFFF) slot.  Every record scoring below all TPs lands in that
-    // one bucket (the bulk of the false positives): count those in a register instead of hammering one shared word.
-    int ntp;
-    {
-        int lo = 0, n = cap;
-        while (n > 1) { const int half = n >> 1; lo += (k[lo + half - 1] < 0xFFFFFFFFu) ? half : 0; n -= half; }
-        ntp = lo + ((k[lo] < 0xFFFFFFFFu) ? 1 : 0);
-    }
-    const int span = ntp > 0 ? (1 << (32 - __clz(ntp))) : 1;   // power of two > ntp-1: search only the occupied prefix
-    const int sp = span < cap ? span : cap;
+    // Every record scoring below all TPs lands in the one bucket after the last real entry (the bulk of the false
+    // positives): count those in a register instead of hammering one shared word.
+    const int ntp = e[0];
     unsigned int tail = 0;
     for (long long i = (long long)blockIdx.x * APC_NT + threadIdx.x; i < N; i += (long long)gridDim.x * APC_NT) {
         const float s = score[(size_t)c * N + i];
         if (!(s > -INFINITY)) continue;
         const uint32_t key = apc_score_key(s);
-        int lo = 0, n = sp;                // branch-free lower_bound over a power-of-two table
-        while (n > 1) { const int half = n >> 1; lo += (k[lo + half - 1] < key) ? half : 0; n -= half; }
-        lo += (k[lo] < key) ? 1 : 0;
+        const int b = apc_bin(s);
+        int lo = e[b + 1];
+        const int hi = e[b];
+        while (lo < hi && k[lo] < key) ++lo;
         if (lo >= ntp) ++tail; else atomicAdd(&h[lo], 1u);
     }
     for (int off = 16; off > 0; off >>= 1) tail += __shfl_xor_sync(0xffffffffu, tail, off);
@@ -293,7 +323,12 @@ extern "C" int ovdet_apc_hist(const float *rec_score, int C, int64_t N, const ui
     OVDET_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)C * (cap + 1), st));
     if (N == 0) return OVDET_OK;
     OVDET_REQUIRE(rec_score, "null pointer");
-    const size_t smem = sizeof(uint32_t) * (2 * (size_t)cap + 1);
+    // per-class bin edges of the sorted list, in the library's grow-only device scratch
+    uint16_t *edge = nullptr;
+    { void *ws = nullptr; int rc = device_scratch().acquire(sizeof(uint16_t) * (size_t)C * (APC_BINS + 1), st, &ws); if (rc) return rc; edge = static_cast<uint16_t *>(ws); }
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(apc_edges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * cap)));
+    apc_edges_kernel<<<C, 1024, sizeof(uint32_t) * cap, st>>>(tp_key, cap, edge);
+    const size_t smem = sizeof(uint32_t) * (2 * (size_t)cap + 1) + sizeof(uint16_t) * (APC_BINS + 2);
     OVDET_CUDA_TRY(cudaFuncSetAttribute(apc_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // enough CTAs to fill the chip a few times over, few enough that the histogram flush stays small
     int per_sm = (int)(220 * 1024 / (smem + 1024));
@@ -303,7 +338,8 @@ extern "C" int ovdet_apc_hist(const float *rec_score, int C, int64_t N, const ui
     const long long maxgx = (N + APC_NT * 4 - 1) / (APC_NT * 4);
     if (gx > maxgx) gx = (int)maxgx;
     if (gx < 1) gx = 1;
-    apc_hist_kernel<<<dim3(gx, C), APC_NT, smem, st>>>(rec_score, N, tp_key, cap, hist);
+    apc_hist_kernel<<<dim3(gx, C), APC_NT, smem, st>>>(rec_score, N, tp_key, edge, cap, hist);
+    { int rc = device_scratch().release(st); if (rc) return rc; }
     return launch_ok("apc_hist_kernel");
 }
 

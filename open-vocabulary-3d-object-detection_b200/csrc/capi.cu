@@ -37,6 +37,38 @@ int HostStaging::ensure(size_t bytes)
     return OVDET_OK;
 }
 
+int DeviceScratch::acquire(size_t bytes, cudaStream_t stream, void **out)
+{
+    if (!last_use) OVDET_CUDA_TRY(cudaEventCreateWithFlags(&last_use, cudaEventDisableTiming));
+    if (bytes > cap) {
+        if (dev) { OVDET_CUDA_TRY(cudaEventSynchronize(last_use)); OVDET_CUDA_TRY(cudaFree(dev)); dev = nullptr; cap = 0; }
+        const size_t want = bytes + bytes / 2 + 4096;
+        OVDET_CUDA_TRY(cudaMalloc(&dev, want));
+        cap = want;
+    } else {
+        // inside a stream capture the captured stream's own order is all there is (an outside event cannot be waited on)
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        OVDET_CUDA_TRY(cudaStreamIsCapturing(stream, &cs));
+        if (cs == cudaStreamCaptureStatusNone) OVDET_CUDA_TRY(cudaStreamWaitEvent(stream, last_use, 0));
+    }
+    *out = dev;
+    return OVDET_OK;
+}
+
+int DeviceScratch::release(cudaStream_t stream)
+{
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    OVDET_CUDA_TRY(cudaStreamIsCapturing(stream, &cs));
+    if (cs == cudaStreamCaptureStatusNone) OVDET_CUDA_TRY(cudaEventRecord(last_use, stream));
+    return OVDET_OK;
+}
+
+DeviceScratch &device_scratch()
+{
+    static thread_local DeviceScratch ds;
+    return ds;
+}
+
 HostStaging &host_staging()
 {
     static thread_local HostStaging hs;

@@ -368,7 +368,7 @@ extern "C" int ovdet_clip_logits_bf16(const void *x, const void *text, int M, in
     { const char *e = getenv("OVDET_LOGITS_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
     float *norms = nullptr;
     if (flags & OVDET_LOGITS_L2NORM) {
-        OVDET_CUDA_TRY(cudaMallocAsync(&norms, sizeof(float) * ((size_t)M + N), st));
+        { void *ws = nullptr; int rc0 = device_scratch().acquire(sizeof(float) * ((size_t)M + N), st, &ws); if (rc0) return rc0; norms = static_cast<float *>(ws); }
         inv_norm_kernel<<<(M + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(x), M, K, norms);
         inv_norm_kernel<<<(N + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(text), N, K, norms + M);
         p.inv_nx = norms; p.inv_nt = norms + M;
@@ -383,7 +383,7 @@ extern "C" int ovdet_clip_logits_bf16(const void *x, const void *text, int M, in
     if (persistent && clip_logits_persistent_choose(M, K, N, &pnc, &pbn)) {
         int prc = clip_logits_persistent_launch(x, text, M, K, N, pnc, pbn, flags, scale, logits, ld_logits, prob, ld_prob, objectness,
                                                 p.inv_nx, p.inv_nt, st);
-        if (norms) OVDET_CUDA_TRY(cudaFreeAsync(norms, st));
+        if (norms) { int rc0 = device_scratch().release(st); if (rc0) return rc0; }
         return prc;
     }
     CUtensorMap tmA, tmB;
@@ -408,6 +408,6 @@ extern "C" int ovdet_clip_logits_bf16(const void *x, const void *text, int M, in
     attr[0].val.clusterDim.x = (unsigned)nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, clip_logits_kernel, tmA, tmB, p));
-    if (norms) OVDET_CUDA_TRY(cudaFreeAsync(norms, st));
+    if (norms) { int rc0 = device_scratch().release(st); if (rc0) return rc0; }
     return launch_ok("clip_logits_kernel");
 }

@@ -46,6 +46,20 @@ struct HostStaging {
 };
 HostStaging &host_staging();
 
+// Grow-only device scratch for kernels that need a small internal table (logits row norms, AP bin edges): one per
+// host thread, reused across calls.  cudaMallocAsync is not used for this: with the default pool's release threshold of
+// zero every synchronisation returns the memory to the OS and the next call pays a multi-millisecond re-map.
+// Stream order across calls is kept with an event: acquire() makes `stream` wait for the previous user, release()
+// records the new last use.
+struct DeviceScratch {
+    void *dev = nullptr;
+    size_t cap = 0;
+    cudaEvent_t last_use = nullptr;
+    int acquire(size_t bytes, cudaStream_t stream, void **out);
+    int release(cudaStream_t stream);
+};
+DeviceScratch &device_scratch();
+
 // ------------------------------------------------ reference-faithful arithmetic
 // The reference evaluates every arithmetic op separately (Python floats, eager
 // torch, numpy), so the geometry kernels must not contract a*b+c into an FMA:
