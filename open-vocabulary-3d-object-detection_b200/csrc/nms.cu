@@ -546,19 +546,42 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
             if (sh.picked[pos]) p.nms1_keep[(size_t)s * p.P + sh.sidx[pos]] = 1;
     }
     __syncthreads();
-    // 2. argmax-IoU match to the pool (lift_boxes.py:151-158): one warp per surviving box
+    // 2. argmax-IoU match to the pool (lift_boxes.py:151-158): one warp per surviving box.  The pool boxes and their
+    // volumes are staged once in shared memory (the suppression-word region, idle between the two NMS passes); a pair
+    // with an empty overlap on some axis has IoU = +0 / positive = 0 exactly, so its fp64 divide is skipped.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int t = warp; t < npick; t += blockDim.x / 32) {
+    const int Wm = (p.Kmax + 31) / 32;
+    const bool pool_staged = (size_t)np_ * 7 * sizeof(double) <= sizeof(uint32_t) * (size_t)p.Kmax * Wm;
+    double *pl = reinterpret_cast<double *>(sh.mask);   // [np_][6] then kv[np_]
+    double *pkv = pl + (size_t)np_ * 6;
+    if (pool_staged) {
+        for (int i = threadIdx.x; i < np_ * 6; i += blockDim.x) pl[i] = pool[i];
+        __syncthreads();
+        for (int j = threadIdx.x; j < np_; j += blockDim.x) {
+            const double *r = pl + (size_t)j * 6;
+            pkv[j] = A::mul(A::mul(A::sub(r[3], r[0]), A::sub(r[4], r[1])), A::sub(r[5], r[2]));
+        }
+        __syncthreads();
+    }
+    for (int t = warp; t < npick; t += (blockDim.x >> 5)) {
         const double *bx = boxes + (size_t)order[t] * 8;
-        const double qv = A::mul(A::mul(A::sub(bx[3], bx[0]), A::sub(bx[4], bx[1])), A::sub(bx[5], bx[2]));
+        const double b0 = bx[0], b1 = bx[1], b2 = bx[2], b3 = bx[3], b4 = bx[4], b5 = bx[5];
+        const double qv = A::mul(A::mul(A::sub(b3, b0), A::sub(b4, b1)), A::sub(b5, b2));
         double bi = -INFINITY; int bj = 0x7fffffff;
         for (int j = lane; j < np_; j += 32) {
-            const double *r = pool + (size_t)j * 6;
-            const double kv = A::mul(A::mul(A::sub(r[3], r[0]), A::sub(r[4], r[1])), A::sub(r[5], r[2]));
-            double inter = A::max(A::sub(A::min(bx[3], r[3]), A::max(bx[0], r[0])), 0.0);
-            inter = A::mul(inter, A::max(A::sub(A::min(bx[4], r[4]), A::max(bx[1], r[1])), 0.0));
-            inter = A::mul(inter, A::max(A::sub(A::min(bx[5], r[5]), A::max(bx[2], r[2])), 0.0));
-            const double iou = A::div(inter, A::add(A::sub(A::add(qv, kv), inter), 1e-5));
+            const double *r = (pool_staged ? pl : pool) + (size_t)j * 6;
+            const double kv = pool_staged ? pkv[j] : A::mul(A::mul(A::sub(r[3], r[0]), A::sub(r[4], r[1])), A::sub(r[5], r[2]));
+            const double e0 = A::max(A::sub(A::min(b3, r[3]), A::max(b0, r[0])), 0.0);
+            const double e1 = A::max(A::sub(A::min(b4, r[4]), A::max(b1, r[1])), 0.0);
+            const double e2 = A::max(A::sub(A::min(b5, r[5]), A::max(b2, r[2])), 0.0);
+            double iou;
+            if (e0 == 0.0 || e1 == 0.0 || e2 == 0.0) {
+                const double den = A::add(A::add(qv, kv), 1e-5);   // inter = +0: (qv + kv - 0) + 1e-5
+                iou = den > 0.0 ? 0.0 : A::div(0.0, den);
+            } else {
+                const double inter = A::mul(A::mul(e0, e1), e2);
+                iou = A::div(inter, A::add(A::sub(A::add(qv, kv), inter), 1e-5));
+            }
             if (iou > bi) { bi = iou; bj = j; }  // np.argmax: first maximum
         }
         for (int off = 16; off > 0; off >>= 1) {
