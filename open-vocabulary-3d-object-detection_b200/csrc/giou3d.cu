@@ -267,6 +267,11 @@ __global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams
     unsigned short *queue = reinterpret_cast<unsigned short *>(raw2 + TG * 24);
     V2<ClipT> *scratch = reinterpret_cast<V2<ClipT> *>(queue + TQ * TG);
     __shared__ int qcount;
+    // Programmatic dependent launch: the grid may be scheduled while the previous kernel of the stream drains; nothing
+    // in global memory is touched before this wait (full completion + visibility of the prerequisite grids), and the
+    // next launch is allowed to start its own scheduling right away.  Plain stream order when the neighbours are not PDL.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int b = blockIdx.x / p.tiles_per_b;
     const int q0 = (blockIdx.x - b * p.tiles_per_b) * TQ;
@@ -485,7 +490,15 @@ template <typename ClipT, int PB, int TQ, bool HULL> static int launch_giou_tq2(
         attr_set = true;
     }
     const long long grid = (long long)p.B * p.tiles_per_b;
-    giou3d_kernel<ClipT, PB, TQ, HULL><<<(unsigned)grid, NT, smem, st>>>(p);
+    static int pdl = -1;   // OVDET_GIOU_PDL=0 switches programmatic dependent launch off (A/B measurements)
+    if (pdl < 0) { const char *e = getenv("OVDET_GIOU_PDL"); pdl = e ? atoi(e) : 1; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    OVDET_CUDA_TRY(cudaLaunchKernelEx(&cfg, giou3d_kernel<ClipT, PB, TQ, HULL>, p));
     return launch_ok("giou3d_kernel");
 }
 
