@@ -323,10 +323,42 @@ __global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams
             gvalid[h] = (g0 + c) < nk;
             gclip[h] = (g0 + c) < clip_lim;
         }
+        // one pair of the clip queue, 8 lanes per pair (shared by phase B and by the clip warps of the split mode)
+        auto clip_pair_coop = [&](int r, int c, bool act, int gl, int gshift, V2<ClipT> *gbuf) {
+            ClipT cl[8];
 #pragma unroll
-        for (int rr = 0; rr < TQ / (NT / 32); ++rr) {
-            const int r = warp * (TQ / (NT / 32)) + rr;
-            if (r >= nq) break;   // warp-uniform
+            for (int i = 0; i < 4; ++i) {
+                cl[2 * i] = (ClipT)f2[(F_RX + i) * TG + c];
+                cl[2 * i + 1] = (ClipT)f2[(F_RZ + i) * TG + c];
+            }
+            ClipT vx = (ClipT)f1[(F_RX + (gl & 3)) * TQ + r], vy = (ClipT)f1[(F_RZ + (gl & 3)) * TQ + r];
+            const int n = coop_clip_quads<ClipT>(cl, vx, vy, act ? 4 : 0, gl, gshift, gbuf);
+            float area;
+            if constexpr (sizeof(ClipT) == 8) area = coop_area_cython(vx, vy, n, gl);
+            else area = coop_area_f32(vx, vy, n, gl);
+            if (act && gl == 0) {
+                PairTerms t = pair_terms(load_boxf(f1, r, TQ), load_boxf(f2, c, TG));
+                if (hull && __fmul_rn(area, t.h) > 0.f) {   // box_ops3d.py:467: hull only where the intersection volume is > 0
+                    float axv[4], azv[4], bxv[4], bzv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        axv[i] = f1[(F_RX + i) * TQ + r]; azv[i] = f1[(F_RZ + i) * TQ + r];
+                        bxv[i] = f2[(F_RX + i) * TG + c]; bzv[i] = f2[(F_RZ + i) * TG + c];
+                    }
+                    t.encl = (float)hull_enclosing_volume(axv, azv, bxv, bzv, f1[F_YTOP * TQ + r], f1[F_YBOT * TQ + r],
+                                                          f2[F_YTOP * TG + c], f2[F_YBOT * TG + c]);
+                }
+                tile[r * TG + c] = finish_pair(t, area, true, has_nums, inter_only);
+            }
+        };
+        // Split mode (the shipped semantics: only GT columns < k2_cap are ever clipped, <= 64 eligible pairs per tile):
+        // the last two warps find and clip those pairs WHILE the other six run phase A, instead of after it -- the fp64
+        // clip chain (~2.3 us) and phase A (~2 us) overlap; every CTA of the one-wave grid finishes together.
+        constexpr int NCW = 2, NWARP = NT / 32;
+        const int clw = min(clip_lim - g0, ng);
+        const int ncand = (rotated && clw > 0) ? nq * clw : 0;
+        const bool split = ncand > 0 && ncand <= 32 * NCW;
+        auto phase_a_row = [&](int r) {
             const BoxF qf = load_boxf(f1, r, TQ);   // broadcast loads
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -339,6 +371,7 @@ __global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams
                     else area = t.nonrot;
                     if (!need_clip) tile[r * TG + lane + 32 * h] = finish_pair(t, area, gvalid[h], has_nums, inter_only);
                 }
+                if (split) continue;   // the clip warps find these pairs themselves
                 const unsigned m = __ballot_sync(0xffffffffu, need_clip);   // warp-aggregated push
                 if (m) {
                     int basepos = 0;
@@ -346,6 +379,37 @@ __global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams
                     basepos = __shfl_sync(0xffffffffu, basepos, 0);
                     if (need_clip) queue[basepos + __popc(m & ((1u << lane) - 1))] = (unsigned short)(r * TG + lane + 32 * h);
                 }
+            }
+        };
+        if (split) {
+            if (warp >= NWARP - NCW) {
+                const int cw = warp - (NWARP - NCW);
+                const int idx = cw + NCW * lane;   // candidates interleaved over the clip warps
+                bool need = false;
+                if (idx < ncand) {
+                    const int r = idx / clw, c = idx - r * clw;
+                    const PairTerms t = pair_terms(load_boxf(f1, r, TQ), load_boxf(f2, c, TG));
+                    need = !(prefilter && t.nonrot == 0.f);   // columns < clip_lim <= nk are valid
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, need);
+                const int n = __popc(m);
+                for (int base = 0; base < n; base += 4) {
+                    const int k = base + (lane >> 3);
+                    const bool act = k < n;
+                    const int src = act ? (int)__fns(m, 0, k + 1) : 0;
+                    const int sidx = cw + NCW * src;
+                    const int r = sidx / clw, c = sidx - r * clw;
+                    clip_pair_coop(r, c, act, lane & 7, lane & 24, scratch + (warp * 4 + (lane >> 3)) * 8);
+                }
+            } else {
+                for (int r = warp; r < nq; r += NWARP - NCW) phase_a_row(r);
+            }
+        } else {
+#pragma unroll
+            for (int rr = 0; rr < TQ / NWARP; ++rr) {
+                const int r = warp * (TQ / NWARP) + rr;
+                if (r >= nq) break;   // warp-uniform
+                phase_a_row(r);
             }
         }
         __syncthreads();
@@ -364,31 +428,7 @@ __global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams
                 const bool act = qi < nclip;
                 int r = 0, c = 0;
                 if (act) { const int code = queue[qi]; r = code / TG; c = code - r * TG; }
-                ClipT cl[8];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    cl[2 * i] = (ClipT)f2[(F_RX + i) * TG + c];
-                    cl[2 * i + 1] = (ClipT)f2[(F_RZ + i) * TG + c];
-                }
-                ClipT vx = (ClipT)f1[(F_RX + (gl & 3)) * TQ + r], vy = (ClipT)f1[(F_RZ + (gl & 3)) * TQ + r];
-                const int n = coop_clip_quads<ClipT>(cl, vx, vy, act ? 4 : 0, gl, gshift, gbuf);
-                float area;
-                if constexpr (sizeof(ClipT) == 8) area = coop_area_cython(vx, vy, n, gl);
-                else area = coop_area_f32(vx, vy, n, gl);
-                if (act && gl == 0) {
-                    PairTerms t = pair_terms(load_boxf(f1, r, TQ), load_boxf(f2, c, TG));
-                    if (hull && __fmul_rn(area, t.h) > 0.f) {
-                        float axv[4], azv[4], bxv[4], bzv[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            axv[i] = f1[(F_RX + i) * TQ + r]; azv[i] = f1[(F_RZ + i) * TQ + r];
-                            bxv[i] = f2[(F_RX + i) * TG + c]; bzv[i] = f2[(F_RZ + i) * TG + c];
-                        }
-                        t.encl = (float)hull_enclosing_volume(axv, azv, bxv, bzv, f1[F_YTOP * TQ + r], f1[F_YBOT * TQ + r],
-                                                              f2[F_YTOP * TG + c], f2[F_YBOT * TG + c]);
-                    }
-                    tile[r * TG + c] = finish_pair(t, area, true, has_nums, inter_only);
-                }
+                clip_pair_coop(r, c, act, gl, gshift, gbuf);
             }
         } else if (threadIdx.x < PB) {   // dense: one serial clip per lane, PB lanes
             V2<ClipT> *bufA = scratch + threadIdx.x;
