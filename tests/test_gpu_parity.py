@@ -274,6 +274,32 @@ def test_nms_vs_oracle_sizes(K):
         assert order[i, :int(npick[i])].cpu().tolist() == want
 
 
+@pytest.mark.parametrize("K,ncls,cls_kind", [(128, 20, "dense"), (300, 3, "dense"), (1024, 1, "dense"), (200, 6, "fractional"),
+                                              (200, 6, "huge"), (64, 6, "negative")])
+def test_nms_classwise_modes(K, ncls, cls_kind):
+    """The class-wise kernel paths against the oracle: no-order (sort-free) and ordered mode, classes larger than one
+    suppression word (warp scan), and class ids that are not small non-negative integers (generic mask path)."""
+    g = torch.Generator().manual_seed(1000 + K)
+    S = 3
+    c, s, _ = synth.sample_boxes(g, (S, K), "scannet", 0.0)
+    s = s * 1.6
+    score = torch.rand((S, K), generator=g).double()
+    cls = torch.randint(0, ncls, (S, K), generator=g).double()
+    if cls_kind == "fractional": cls = cls + 0.5
+    elif cls_kind == "huge": cls = cls * 1000.0 + 300.0
+    elif cls_kind == "negative": cls = cls - 3.0
+    bx = torch.cat([(c - s / 2).double(), (c + s / 2).double(), score[..., None], cls[..., None]], -1)
+    keep_o, order, npick = NMS.nms_batch(bx.to(DEV), 0.25, samecls=True)
+    keep_n, none, npick_n = NMS.nms_batch(bx.to(DEV), 0.25, samecls=True, want_order=False)
+    assert none is None
+    for i in range(S):
+        want = oracle.nms_3d_faster_samecls(bx[i].numpy(), 0.25)
+        assert order[i, :int(npick[i])].cpu().tolist() == want
+        assert sorted(torch.nonzero(keep_n[i]).flatten().cpu().tolist()) == sorted(want)
+        assert int(npick_n[i]) == len(want)
+    assert torch.equal(keep_o, keep_n)
+
+
 # ------------------------------------------------------------------ AP
 class _Cfg:
     def __init__(self, n):
