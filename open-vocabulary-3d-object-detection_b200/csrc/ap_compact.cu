@@ -33,30 +33,49 @@ __device__ __forceinline__ uint32_t apc_score_key(float s)
     return ~ord;
 }
 
+// 16 records per thread: four 16-byte score loads and one 16-byte tp load in flight at once (the pass is a pure stream:
+// 5 B per record), valid records counted in registers, the rare TP records appended with one atomic each.
+constexpr int APC_RPT = 16;
+
 __global__ void __launch_bounds__(APC_NT) apc_collect_kernel(const float *__restrict__ score, const uint8_t *__restrict__ tp,
                                                              long long N, int cap, uint32_t *tp_key, uint8_t *tp_bits,
                                                              int *tp_cnt, unsigned long long *nvalid)
 {
     const int c = blockIdx.y;
     const int lane = threadIdx.x & 31;
+    const float *sc = score + (size_t)c * N;
+    const uint8_t *tb = tp + (size_t)c * N;
+    const bool vec = ((reinterpret_cast<uintptr_t>(sc) & 15) == 0) && ((reinterpret_cast<uintptr_t>(tb) & 15) == 0);
     int local_valid = 0;
-    const long long stride = (long long)gridDim.x * APC_NT;
-    const long long nround = (N + stride - 1) / stride;
-    for (long long it = 0; it < nround; ++it) {
-        const long long i = it * stride + (long long)blockIdx.x * APC_NT + threadIdx.x;
-        float s = -INFINITY; uint8_t t = 0;
-        if (i < N) { s = score[(size_t)c * N + i]; t = tp[(size_t)c * N + i]; }
-        const bool present = s > -INFINITY;
-        local_valid += present ? 1 : 0;
-        const bool is_tp = present && t != 0;
-        const unsigned m = __ballot_sync(0xffffffffu, is_tp);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&tp_cnt[c], __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (is_tp) {
-                const int slot = base + __popc(m & ((1u << lane) - 1));
-                if (slot < cap) { tp_key[(size_t)c * cap + slot] = apc_score_key(s); tp_bits[(size_t)c * cap + slot] = t; }
+    auto emit = [&](float s, uint8_t t) {
+        const int slot = atomicAdd(&tp_cnt[c], 1);
+        if (slot < cap) { tp_key[(size_t)c * cap + slot] = apc_score_key(s); tp_bits[(size_t)c * cap + slot] = t; }
+    };
+    for (long long base = ((long long)blockIdx.x * APC_NT + threadIdx.x) * APC_RPT; base < N; base += (long long)gridDim.x * APC_NT * APC_RPT) {
+        if (vec && base + APC_RPT <= N) {
+            float4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(sc + base) + q);
+            const uint4 tv = __ldg(reinterpret_cast<const uint4 *>(tb + base));
+            const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float f[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const bool present = f[r] > -INFINITY;
+                    local_valid += present ? 1 : 0;
+                    const uint8_t t = (uint8_t)((tw[q] >> (8 * r)) & 0xffu);
+                    if (present && t) emit(f[r], t);
+                }
+            }
+        } else {
+            for (int r = 0; r < APC_RPT && base + r < N; ++r) {
+                const float s = sc[base + r];
+                const uint8_t t = tb[base + r];
+                const bool present = s > -INFINITY;
+                local_valid += present ? 1 : 0;
+                if (present && t) emit(s, t);
             }
         }
     }
@@ -142,15 +161,27 @@ __global__ void __launch_bounds__(APC_NT) apc_hist_kernel(const float *__restric
     // positives): count those in a register instead of hammering one shared word.
     const int ntp = e[0];
     unsigned int tail = 0;
-    for (long long i = (long long)blockIdx.x * APC_NT + threadIdx.x; i < N; i += (long long)gridDim.x * APC_NT) {
-        const float s = score[(size_t)c * N + i];
-        if (!(s > -INFINITY)) continue;
+    const float *sc = score + (size_t)c * N;
+    auto place = [&](float s) {
+        if (!(s > -INFINITY)) return;
         const uint32_t key = apc_score_key(s);
         const int b = apc_bin(s);
         int lo = e[b + 1];
         const int hi = e[b];
         while (lo < hi && k[lo] < key) ++lo;
         if (lo >= ntp) ++tail; else atomicAdd(&h[lo], 1u);
+    };
+    // four records per thread and step (one 16-byte load), 32-bit indexing when the class fits
+    if (((reinterpret_cast<uintptr_t>(sc) & 15) == 0) && N < 0x7fffffffLL) {
+        const int n4 = (int)(N >> 2);
+        const int step = (int)(gridDim.x * APC_NT);
+        for (int i = (int)(blockIdx.x * APC_NT + threadIdx.x); i < n4; i += step) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(sc) + i);
+            place(v.x); place(v.y); place(v.z); place(v.w);
+        }
+        for (long long i = ((long long)n4 << 2) + (long long)blockIdx.x * APC_NT + threadIdx.x; i < N; i += (long long)gridDim.x * APC_NT) place(sc[i]);
+    } else {
+        for (long long i = (long long)blockIdx.x * APC_NT + threadIdx.x; i < N; i += (long long)gridDim.x * APC_NT) place(sc[i]);
     }
     for (int off = 16; off > 0; off >>= 1) tail += __shfl_xor_sync(0xffffffffu, tail, off);
     if ((threadIdx.x & 31) == 0 && tail) atomicAdd(&h[ntp], tail);
@@ -298,7 +329,7 @@ extern "C" int ovdet_apc_collect(const float *rec_score, const uint8_t *rec_tp, 
     OVDET_CUDA_TRY(cudaMemsetAsync(nvalid, 0, sizeof(int64_t) * C, st));
     if (N == 0) return OVDET_OK;
     OVDET_REQUIRE(rec_score && rec_tp, "null pointer");
-    int gx = (int)((N + APC_NT * 8 - 1) / (APC_NT * 8));
+    int gx = (int)((N + APC_NT * APC_RPT - 1) / (APC_NT * APC_RPT));
     if (gx < 1) gx = 1;
     apc_collect_kernel<<<dim3(gx, C), APC_NT, 0, st>>>(rec_score, rec_tp, N, cap, tp_key, tp_bits, tp_cnt,
                                                       reinterpret_cast<unsigned long long *>(nvalid));
