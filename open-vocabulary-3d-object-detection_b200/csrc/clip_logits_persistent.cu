@@ -23,8 +23,12 @@
 namespace ovdet {
 
 constexpr int PK_M = 128, PK_K = 64;
-constexpr int PK_THREADS = 640, PK_EPI = 512;   // 4 role warps + 16 epilogue warps
+#ifndef PK_EPI_WARPS
+#define PK_EPI_WARPS 16                          // epilogue warps (multiple of 4).  Measured at config 4: 16 -> 24.0 us, 28 (1024 threads, 64 regs) -> 25.8 us: the epilogue is throughput-, not latency-bound
+#endif
+constexpr int PK_EPI = 32 * PK_EPI_WARPS, PK_THREADS = 128 + PK_EPI;   // 4 role warps + the epilogue warps
 constexpr int PK_NG = PK_EPI / 128;              // column groups (epilogue warps per TMEM lane quarter)
+constexpr int PK_CPG = (16 + PK_NG - 1) / PK_NG; // 16-column chunks per group at BLOCK_N = 256
 constexpr int PK_MAX_NC = 8, PK_MAX_STAGES = 6;
 constexpr int PK_ACC_STRIDE = 256;   // TMEM columns between the two accumulators (512 allocated)
 
@@ -75,7 +79,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
         "bra WAITC_%=;\n\t"
         "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(PK_EPI) : "memory"); }
 
 __global__ void __launch_bounds__(PK_THREADS, 1)
 clip_logits_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PLogitsParams p)
@@ -172,7 +176,7 @@ clip_logits_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     } else if (warp >= 4) {
         // ===================== epilogue warps =====================
         const int et = threadIdx.x - 128;
-        const int grp = (warp - 4) >> 2;                   // column group: 16-column chunks grp, grp+4, grp+8, grp+12
+        const int grp = (warp - 4) >> 2;                   // column group: 16-column chunks grp, grp+NG, grp+2NG, ..
         const int row = (warp & 3) * 32 + lane;            // accumulator row == TMEM lane (quarter = warp % 4)
         const float LOG2E = 1.4426950408889634f;
         const int obj_c = p.N - 1 - n0;                    // tile column of the background class, if in this tile
@@ -188,7 +192,9 @@ clip_logits_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             const float a2 = rs * LOG2E;
             const uint32_t trow = tmem_base + (uint32_t)(acc * PK_ACC_STRIDE) + ((uint32_t)((warp & 3) * 32) << 16);
             float rmax = -INFINITY, rsum = 0.f, eobj = 0.f;
-            float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            float cm[PK_CPG];
+#pragma unroll
+            for (int ci = 0; ci < PK_CPG; ++ci) cm[ci] = -INFINITY;
 
             PSTAMP(0);
             mbar_wait(&tmem_full_bar[acc], ph);
@@ -196,7 +202,7 @@ clip_logits_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             PSTAMP(1);
             // ---- the only pass over TMEM: online (max, sum-exp); 2^(y - m_c) goes to the shared tile as bf16
 #pragma unroll
-            for (int ci = 0; ci < 4; ++ci) {
+            for (int ci = 0; ci < PK_CPG; ++ci) {
                 const int c0 = (grp + PK_NG * ci) * 16;
                 if (c0 >= p.block_n) continue;             // block_n is a multiple of 16: chunks are never partial in width
                 const int nv = min(16, p.N - (n0 + c0));   // valid columns (warp-uniform)
@@ -285,7 +291,7 @@ clip_logits_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __g
             }
             const float inv = 1.f / gsum;
 #pragma unroll
-            for (int ci = 0; ci < 4; ++ci) {
+            for (int ci = 0; ci < PK_CPG; ++ci) {
                 const int j = grp + PK_NG * ci, c0 = j * 16;
                 if (c0 >= p.block_n) continue;
                 const float f = cm[ci] > -INFINITY ? fast_exp2(cm[ci] - gmax) * inv : 0.f;
@@ -336,7 +342,7 @@ static bool pk_plan(int bn, int num_kb, PkPlan *pl)
 {
     pl->stage_bytes = (size_t)PK_M * PK_K * 2 + (((size_t)bn * PK_K * 2 + 1023) & ~(size_t)1023);
     pl->tile_bytes = (size_t)PK_M * (bn + 8) * 2;
-    const size_t budget = 227 * 1024 - 32 * 1024 - 1024 - pl->tile_bytes;   // static: barriers + stats 16K + part 4K + ftab 8.5K + colscale
+    const size_t budget = 227 * 1024 - 36 * 1024 - 1024 - pl->tile_bytes;   // static: barriers + stats 16K + part <= 7K + ftab 8.5K + colscale
     int stages = (int)(budget / pl->stage_bytes);
     if (stages > PK_MAX_STAGES) stages = PK_MAX_STAGES;
     if (stages > num_kb * 2) stages = num_kb * 2;
