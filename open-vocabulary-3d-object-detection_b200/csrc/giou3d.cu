@@ -560,14 +560,12 @@ template <typename ClipT, int PB> static int launch_giou(const GiouParams &p, cu
     if (force == 32) return launch_giou_tq<ClipT, PB, 32>(p, st);
     if (force == 16) return launch_giou_tq<ClipT, PB, 16>(p, st);
     if (force == 8) return launch_giou_tq<ClipT, PB, 8>(p, st);
-    // measured on B200 (profiles/r1_notes.md): when few pairs reach the clipper (prefilter on) the per-CTA staging of
-    // the GT chunk dominates and 32-row tiles win (10.9 us vs 17.3 us at config 1); when every pair is clipped
-    // (no prefilter) small tiles spread the clip work better (20 vs 15 Gpairs/s).
-    // 16-row tiles (<= 64 registers, 4 CTAs/SM, one wave at config 1) match 32-row tiles on the default path
-    // (9.7 vs 9.6 us) and beat them when every pair is clipped (20.3 vs 15.3 Gpairs/s); 32-row tiles amortise the
-    // GT-chunk staging better once the grid is many waves deep.
-    if (t32 < 148 * 8) return launch_giou_tq<ClipT, PB, 16>(p, st);
-    return launch_giou_tq<ClipT, PB, 32>(p, st);
+    // 16-row tiles everywhere (measured on B200, profiles/r1_notes.md): <= 64 registers, 4 CTAs/SM, config 1 is one wave of
+    // 512 CTAs; with the split mode and the cooperative clip they also beat 32-row tiles in the many-wave regime
+    // (4096 box sets: 115 vs 98 Gpairs/s as shipped, 95 vs 92 torch path, 33.5 vs 29.3 every pair clipped) and 8-row
+    // tiles everywhere (65 / 26 Gpairs/s).  OVDET_GIOU_TQ keeps the other heights reachable for experiments.
+    (void)t32;
+    return launch_giou_tq<ClipT, PB, 16>(p, st);
 }
 
 // ---------------------------------------------------------------------------
