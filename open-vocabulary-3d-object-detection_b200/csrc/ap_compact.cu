@@ -320,7 +320,8 @@ static bool apc_cap_ok(int cap) { return cap >= 1024 && cap <= APC_MAXCAP && (ca
 extern "C" int ovdet_apc_collect(const float *rec_score, const uint8_t *rec_tp, int C, int64_t N, int cap,
                                  uint32_t *tp_key, uint8_t *tp_bits, int32_t *tp_cnt, int64_t *nvalid, void *stream)
 {
-    OVDET_REQUIRE(C > 0 && N >= 0 && apc_cap_ok(cap), "bad size (cap must be a power of two in [1024, 16384])");
+    // a rank's own list may be short (lists of several ranks are concatenated to >= 1024 before ovdet_apc_sort)
+    OVDET_REQUIRE(C > 0 && N >= 0 && cap >= 32 && cap <= APC_MAXCAP && (cap & (cap - 1)) == 0, "bad size (cap must be a power of two in [32, 16384])");
     OVDET_REQUIRE(tp_key && tp_bits && tp_cnt && nvalid, "null pointer");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     OVDET_CUDA_TRY(cudaMemsetAsync(tp_key, 0xFF, sizeof(uint32_t) * (size_t)C * cap, st));

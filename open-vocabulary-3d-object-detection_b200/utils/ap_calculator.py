@@ -120,7 +120,8 @@ class APCalculator(object):
         self.class2type_map = class2type_map
         self.num_semcls = dataset_config.num_semcls if dataset_config is not None else None
         self.reduce_mode = "compact"   # "sort" forces the segmented radix sort + scan (full PR curves)
-        self.tp_list_cap = 2048        # per-class, per-rank TP-list capacity of the compact reducer (grows on overflow)
+        self.tp_list_cap = 2048        # per-class TP-list capacity of the compact reducer (split across ranks; grows on overflow)
+        self._cap_hint = {}            # world size -> per-rank capacity learned from the previous evaluation
         self.reset()
 
     def make_gt_list(self, gt_box_corners, gt_box_sem_cls_labels, gt_box_present):
@@ -190,16 +191,25 @@ class APCalculator(object):
             # no global sort: TP lists + one histogram pass; across ranks only the TP lists and the bucket
             # histogram travel (KBs) instead of the whole record stream.  Sync-free until the
             # single D2H of the packed result; an overflowing TP list retries with 4x the capacity.
-            cap = self.tp_list_cap
+            # Capacity of a rank's per-class TP list.  Scene-sharded ranks hold ~1/world of the TPs each, so the default
+            # is split across them (a short merged list keeps the sort / histogram kernels at their single-GPU cost);
+            # the reducer reports the largest count it saw, which sizes the retry after an overflow and the next call.
+            world = 1
+            if distributed:
+                import torch.distributed as tdist
+                world = tdist.get_world_size()
+            cap = self._cap_hint.get(world) or (max(128, self.tp_list_cap // world) if world > 1 else self.tp_list_cap)
             while ap is None:
                 res = E.ap_reduce_compact(rs, rt, npos, nthr, cap=cap, distributed=distributed)
                 if res is None:
                     break
-                ap_, recall_, ovf, _ = E.unpack_compact(res, nthr, rs.shape[0])
+                ap_, recall_, ovf, _, maxcnt = E.unpack_compact(res, nthr, rs.shape[0], with_max=True)
                 if ovf == 0:
                     ap, recall = ap_, recall_
+                    if maxcnt >= 0 and world > 1:
+                        self._cap_hint[world] = E._pow2_at_least(maxcnt + 1, 128)
                 else:
-                    cap *= 4
+                    cap = E._pow2_at_least(maxcnt + 1, 128) if maxcnt > cap else cap * 4
         if ap is None:   # sort-based path: all-gather the (score, tp) records, segmented radix sort + scan
             if distributed:
                 from ..dist import gather_records

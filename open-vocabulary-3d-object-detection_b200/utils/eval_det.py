@@ -103,9 +103,9 @@ def ap_reduce_compact(rec_score, rec_tp, npos, nthr, cap=4096, use_07_metric=Fal
     dev = rec_score.device
     Cn, N = rec_score.shape
     world = dist.get_world_size() if distributed else 1
-    cap = _pow2_at_least(int(cap))
+    cap = _pow2_at_least(int(cap), 32 if world > 1 else 1024)
     cap_total = _pow2_at_least(cap * world)
-    if cap_total > APC_MAXCAP:
+    if cap_total > APC_MAXCAP or (world == 1 and cap < 1024):
         return None
     L = C.lib()
     st = C.stream(dev)
@@ -130,67 +130,65 @@ def ap_reduce_compact(rec_score, rec_tp, npos, nthr, cap=4096, use_07_metric=Fal
             C.check(L.ovdet_apc_final(b_p, cnt_p, h_p, npos_p, nv_p, Cn, cap, nthr, int(bool(use_07_metric)), r_p,
                                       r_p + 8 * nthr * Cn, r_p + 16 * nthr * Cn, r_p + 16 * nthr * Cn + 8 * Cn, st))
         return res
-    # one int64 buffer for everything that is summed across ranks: npos | nvalid | overflow count
-    sums = torch.zeros((2 * Cn + 1,), dtype=torch.int64, device=dev)
-    sums[:Cn] = npos.to(device=dev, dtype=torch.int64)
-    nvalid = sums[Cn:2 * Cn]
-    # TP lists: keys (int32 view of u32) and bits share one byte buffer so that one all-gather moves both
-    lists = torch.empty((Cn, cap * 5), dtype=torch.uint8, device=dev)
+    # ---- several ranks: per-rank TP lists (keys | bits | count) travel in ONE all-gather, the bucket histogram and the
+    # npos / nvalid sums in ONE all-reduce; everything else is local.  `cap` is the per-rank list capacity.
+    row = cap * 5 + 8
+    lists = torch.zeros((Cn, row), dtype=torch.uint8, device=dev)
     kbuf = torch.empty((Cn, cap), dtype=torch.int32, device=dev)
     bbuf = torch.empty((Cn, cap), dtype=torch.uint8, device=dev)
     cnt = torch.empty((Cn,), dtype=torch.int32, device=dev)
+    sums = torch.zeros((2 * Cn,), dtype=torch.int64, device=dev)       # npos | nvalid
+    sums[:Cn] = npos.to(device=dev, dtype=torch.int64)
     with torch.cuda.device(dev):
         C.check(L.ovdet_apc_collect(C.ptr(rec_score), C.ptr(rec_tp), Cn, N, cap, C.ptr(kbuf), C.ptr(bbuf), C.ptr(cnt),
-                                    nvalid.data_ptr(), st))
-        sums[2 * Cn] = (cnt > cap).sum()
-        if world > 1:
-            lists[:, :cap * 4] = kbuf.view(torch.uint8)
-            lists[:, cap * 4:] = bbuf
-            glists = torch.empty((world * Cn, cap * 5), dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(glists, lists)
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-            g = glists.view(world, Cn, cap * 5).permute(1, 0, 2)                      # [C, W, 5cap]
-            gk = g[:, :, :cap * 4].contiguous().view(torch.int32).reshape(Cn, world * cap)
-            gb = g[:, :, cap * 4:].reshape(Cn, world * cap)
-        else:
-            gk, gb = kbuf, bbuf
-        if cap_total != gk.shape[1]:
-            key2 = torch.full((Cn, cap_total), -1, dtype=torch.int32, device=dev)     # 0xFFFFFFFF = empty slot
-            bits2 = torch.zeros((Cn, cap_total), dtype=torch.uint8, device=dev)
-            key2[:, :gk.shape[1]] = gk
-            bits2[:, :gb.shape[1]] = gb
-        else:
-            key2, bits2 = gk.contiguous(), gb.contiguous()
+                                    sums[Cn:].data_ptr(), st))
+        lists[:, :cap * 4] = kbuf.view(torch.uint8)
+        lists[:, cap * 4:cap * 5] = bbuf
+        lists[:, cap * 5:cap * 5 + 4] = cnt.view(torch.uint8).reshape(Cn, 4)
+        glists = torch.empty((world * Cn, row), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(glists, lists)
+        g = glists.view(world, Cn, row)
+        gcnt = g[:, :, cap * 5:cap * 5 + 4].contiguous().view(torch.int32)                 # [W, C, 1]
+        key2 = torch.full((Cn, cap_total), -1, dtype=torch.int32, device=dev)            # 0xFFFFFFFF = empty slot
+        bits2 = torch.zeros((Cn, cap_total), dtype=torch.uint8, device=dev)
+        key2[:, :world * cap] = g[:, :, :cap * 4].permute(1, 0, 2).contiguous().view(torch.int32).reshape(Cn, world * cap)
+        bits2[:, :world * cap] = g[:, :, cap * 4:cap * 5].permute(1, 0, 2).reshape(Cn, world * cap)
         C.check(L.ovdet_apc_sort(C.ptr(key2), C.ptr(bits2), Cn, cap_total, st))
         hist = torch.empty((Cn, cap_total + 1), dtype=torch.int32, device=dev)
         C.check(L.ovdet_apc_hist(C.ptr(rec_score), Cn, N, C.ptr(key2), cap_total, C.ptr(hist), st))
-        if world > 1:
-            dist.all_reduce(hist, op=dist.ReduceOp.SUM)
-        res = torch.empty((2 * nthr * Cn + 1 + Cn,), dtype=torch.float64, device=dev)
+        fused = torch.cat([hist.reshape(-1).to(torch.int64), sums])
+        dist.all_reduce(fused, op=dist.ReduceOp.SUM)
+        hist_g = fused[:Cn * (cap_total + 1)].to(torch.int32)
+        npos_g = fused[Cn * (cap_total + 1):Cn * (cap_total + 1) + Cn].contiguous()
+        nvalid_g = fused[Cn * (cap_total + 1) + Cn:].contiguous()
+        res = torch.empty((2 * nthr * Cn + 2 + Cn,), dtype=torch.float64, device=dev)
         ndet = torch.empty((Cn,), dtype=torch.int64, device=dev)
-        zero_cnt = torch.zeros((Cn,), dtype=torch.int32, device=dev)   # overflow is carried in `sums`, not here
-        npos_g = sums[:Cn].contiguous()
-        nvalid_g = sums[Cn:2 * Cn].contiguous()
-        C.check(L.ovdet_apc_final(C.ptr(bits2), C.ptr(zero_cnt), C.ptr(hist), C.ptr(npos_g), C.ptr(nvalid_g), Cn,
+        zero_cnt = torch.zeros((Cn,), dtype=torch.int32, device=dev)   # overflow is judged from the gathered counts
+        C.check(L.ovdet_apc_final(C.ptr(bits2), C.ptr(zero_cnt), C.ptr(hist_g), C.ptr(npos_g), C.ptr(nvalid_g), Cn,
                                   cap_total, nthr, int(bool(use_07_metric)), res.data_ptr(),
                                   res.data_ptr() + 8 * nthr * Cn, C.ptr(ndet), None, st))
-        res[2 * nthr * Cn] = sums[2 * Cn].to(torch.float64)
-        res[2 * nthr * Cn + 1:] = ndet.to(torch.float64)
+        k2 = 2 * nthr * Cn
+        res[k2] = (gcnt > cap).sum().to(torch.float64)
+        res[k2 + 1:k2 + 1 + Cn] = ndet.to(torch.float64)
+        res[k2 + 1 + Cn] = gcnt.max().to(torch.float64)
     return res
 
 
-def unpack_compact(res, nthr, Cn):
-    """Host view of ap_reduce_compact's packed result -> (ap [nthr,C], recall [nthr,C], overflow, n_det [C]).
-    One device-to-host copy.  (uint8 = the single-rank byte layout, float64 = the distributed one.)"""
+def unpack_compact(res, nthr, Cn, with_max=False):
+    """Host view of ap_reduce_compact's packed result -> (ap [nthr,C], recall [nthr,C], overflow, n_det [C]
+    [, largest per-rank per-class TP count, -1 if not reported]).  One device-to-host copy.
+    (uint8 = the single-rank byte layout, float64 = the distributed one.)"""
     k = nthr * Cn
     if res.dtype == torch.uint8:
         raw = res.cpu().numpy()
         f = raw[:16 * k].view(np.float64)
         nd = raw[16 * k:16 * k + 8 * Cn].view(np.int64)
         ovf = int(raw[16 * k + 8 * Cn:16 * k + 8 * Cn + 4].view(np.int32)[0])
-        return f[:k].reshape(nthr, Cn), f[k:].reshape(nthr, Cn), ovf, nd.copy()
+        out = (f[:k].reshape(nthr, Cn), f[k:].reshape(nthr, Cn), ovf, nd.copy())
+        return out + (-1,) if with_max else out
     r = res.cpu().numpy()
-    return r[:k].reshape(nthr, Cn), r[k:2 * k].reshape(nthr, Cn), int(r[2 * k]), r[2 * k + 1:].astype(np.int64)
+    out = (r[:k].reshape(nthr, Cn), r[k:2 * k].reshape(nthr, Cn), int(r[2 * k]), r[2 * k + 1:2 * k + 1 + Cn].astype(np.int64))
+    return out + (int(r[2 * k + 1 + Cn]),) if with_max else out
 
 
 def _pack(pred_all, gt_all):
