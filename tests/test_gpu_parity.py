@@ -63,7 +63,8 @@ def test_giou_vs_oracle(cfg):
     rot = cfg["heading"] > 0
     d1, d2, dn = c1.to(DEV), c2.to(DEV), nk.to(DEV)
     for mode, cap, pre, inter in (("tensor", 0, True, False), ("cython", 4, True, False), ("cython", 0, True, False),
-                                  ("tensor", 0, False, False), ("cython", 0, False, True), ("tensor", 0, True, True)):
+                                  ("tensor", 0, False, False), ("cython", 0, False, True), ("tensor", 0, True, True),
+                                  ("cython", 4, False, False), ("tensor", 2, True, False)):   # split mode: every eligible pair clipped / other caps
         want = oracle.generalized_box3d_iou(c1, c2, nk, rot, inter, mode=mode, prefilter=pre, k2_cap=cap or None)
         got = BU.generalized_box3d_iou(d1, d2, dn, rot, inter, mode=mode, prefilter=pre, k2_cap=cap).cpu().numpy()
         assert_close_giou(got, want, what=f"{mode} cap={cap} pre={pre} inter={inter}")
