@@ -270,9 +270,10 @@ def load_traffic(kernel):
     return None
 
 
-def cpu_giou_baseline(steps=3):
+def cpu_giou_baseline(steps=None, budget_s=10.0):
     """The reference's own compiled Cython loop (oracle/_ref) + restated torch glue, as shipped, on one decoder
-    layer's batch (8 x 128 x 64 = 65 536 nominal pairs); falls back to the C port when _ref is absent."""
+    layer's batch (8 x 128 x 64 = 65 536 nominal pairs); falls back to the C port when _ref is absent.
+    Bounded sample: repeated for ~budget_s seconds of CPU work (or exactly `steps` calls), median per call."""
     import oracle
     out, tgt = giou_inputs(100)
     c1, c2, nk = out["box_corners"][:B], tgt["gt_box_corners"][:B], tgt["nactual_gt"][:B]
@@ -281,13 +282,15 @@ def cpu_giou_baseline(steps=3):
          (lambda: oracle.generalized_box3d_iou(c1, c2, nk, True, False, mode="cython", k2_cap=4))
     fn()
     ts = []
-    for _ in range(steps):
+    t_start = time.perf_counter()
+    while (len(ts) < steps) if steps is not None else (time.perf_counter() - t_start < budget_s and len(ts) < 20000):
         t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+    steps = len(ts)
     t = float(np.median(ts))
     res = {"value": B * Q * G / t, "unit": "pairs/s", "cores": 1, "kind": "reference" if use_ref else "port",
            "sample": "one decoder layer (8x128x64 = 65 536 nominal pairs) of the step, as shipped (K2<=4 cap); "
                      + ("hot loop = reference box_intersection.pyx compiled in oracle/_ref, torch glue restated" if use_ref
-                        else "oracle C port (oracle/_ref absent)") + "; median of %d" % steps,
+                        else "oracle C port (oracle/_ref absent)") + "; median of %d calls (%.1f s of CPU work)" % (steps, sum(ts)),
            "ms_per_sample": t * 1e3, "torch_threads": torch.get_num_threads(), "host_cpus": os.cpu_count()}
     if use_ref:  # the intended (no-cap) semantics through the unmodified extension, 4 GT columns per call
         t0 = time.perf_counter()
@@ -366,7 +369,7 @@ def bench_ap(args, rank, world, dev, peaks):
     return res
 
 
-def cpu_ap_baseline(n_scenes=64):
+def cpu_ap_baseline(n_scenes=1024):
     import oracle
     out, tgt = ap_inputs(n_scenes)
     t0 = time.perf_counter()
