@@ -147,9 +147,9 @@ def timed_graph(fn, steps, world, dev):
 
 
 # ----------------------------------------------------------------------------- GIoU (headline)
-def giou_inputs(seed):
+def giou_inputs(seed, heading=np.pi):
     from ovdet_b200 import synth
-    out, tgt = synth.detection_batch(B=L_LAYERS * B, Q=Q, G=G, C=C_SUN, seed=seed, heading=np.pi)
+    out, tgt = synth.detection_batch(B=L_LAYERS * B, Q=Q, G=G, C=C_SUN, seed=seed, heading=heading)
     return out, tgt
 
 
@@ -194,6 +194,15 @@ def bench_giou(args, rank, world, dev, peaks):
     ms3 = timed_graph(lambda i: step(i, mode="tensor", k2_cap=0, prefilter=False), max(args.steps // 4, 5), world, dev)
     res["variants"]["exact_noprefilter_pairs_per_s"] = world * pairs * max(args.steps // 4, 5) / (ms3 * 1e-3)
 
+    # the |heading| <= 0.5 variant (many more pairs pass the axis-aligned prefilter and are clipped)
+    o5, t5 = giou_inputs(200, heading=0.5)
+    h5 = (o5["box_corners"].to(dev), t5["gt_box_corners"].to(dev), t5["nactual_gt"].to(dev), torch.empty((L_LAYERS * B, Q, G), device=dev))
+    for kw, name in ((dict(), "heading05_default_pairs_per_s"), (dict(mode="tensor", k2_cap=0), "heading05_tensor_nocap_pairs_per_s")):
+        f5 = lambda i: generalized_box3d_iou(h5[0], h5[1], h5[2], rotated_boxes=True, out=h5[3], **kw)
+        for i in range(3):
+            f5(i)
+        ms5 = timed_graph(f5, max(args.steps // 4, 5), world, dev)
+        res["variants"][name] = world * pairs * max(args.steps // 4, 5) / (ms5 * 1e-3)
     # launch floor of this timing method: the same entry point on a 1x1x1 problem (one CTA, ~no work)
     t1 = (torch.zeros((1, 1, 8, 3), device=dev), torch.zeros((1, 1, 8, 3), device=dev), torch.ones((1,), dtype=torch.int64, device=dev),
           torch.empty((1, 1, 1), device=dev))
@@ -410,7 +419,22 @@ def bench_extras(args, rank, world, dev, peaks):
     fl = 2 * 8192 * 640 * 1203
     ach = fl / (ms * 1e-3 / n) / 1e12
     ex["clip_logits"] = {"tflops": ach, "ms_per_step": ms / n, "frac_of_bf16_peak": ach / peaks["bf16_tflops"],
+                         "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                                      "frac": ach / peaks["bf16_tflops"], "traffic": load_traffic("clip_logits_persistent_kernel")},
                          "workload": "8192x640 @ 1203x640^T bf16 -> softmax probs bf16 + objectness (includes bf16 cast-free path)"}
+    # class-wise 3D NMS alone (10.9 ms/scene in the reference at K = 256)
+    from ovdet_b200.utils.nms import nms_batch
+    gN = torch.Generator().manual_seed(11)
+    SN, KN = 4096, 256
+    cN, sN, _ = synth.sample_boxes(gN, (SN, KN), "scannet", 0.0)
+    bN = torch.cat([(cN - sN / 2).double(), (cN + sN / 2).double(), torch.rand((SN, KN, 1), generator=gN).double(),
+                    torch.randint(0, 18, (SN, KN, 1), generator=gN).double()], -1).to(dev)
+    f = lambda i: nms_batch(bN, 0.25, samecls=True, want_order=False)
+    for i in range(2):
+        f(i)
+    ms = timed_graph(f, 5, world, dev)
+    ex["nms3d_samecls"] = {"scenes_per_s": world * SN * 5 / (ms * 1e-3), "ms_per_step": ms / 5,
+                           "workload": "%d scenes/rank x 256 boxes x 18 classes, nms_3d_faster_samecls thr 0.25 (keep mask)" % SN}
     # config 5: pseudo-label sweep, scene-sharded, no data-path collective
     S5 = 4096
     bx, pool = synth.pseudo_label_scenes(S5, P=256, pool=512, seed=5)

@@ -68,6 +68,14 @@ int ovdet_giou3d_decode_f32(const float *center1, const float *size1, const floa
                             const int64_t *nums_k2, int B, int K1, int K2, int k2_cap, unsigned flags,
                             float *out, float *corners1_out, void *stream);
 
+/* 3D box -> 2D image box of the RegionCLIP crop branch: project_box_3d_cuda
+ * (utils/image_util.py:117-134) with SUNRGBD_Calibration_cuda (:247-298), optionally followed by the clip to the
+ * image of criterion.py:387-391.  center/size [B,Q,3] (upright depth frame; size used as half extents like the
+ * reference), angle [B,Q], rtilt/kmat [B,3,3] row-major per scene, clip_wh [B,2] = (image width, height) or NULL,
+ * boxes2d [B,Q,4] = the reference's (x1, y1, x2, y2) = (min v, min u, max v, max u). */
+int ovdet_project_box3d_f32(const float *center, const float *size, const float *angle, const float *rtilt,
+                            const float *kmat, const float *clip_wh, int B, int Q, float *boxes2d, void *stream);
+
 /* GIoU backward: d loss / d corners1 for the fp32 torch-path GIoU (autograd of
  * generalized_box3d_iou_tensor, utils/box_util.py:517-618; flags = ROTATED | PREFILTER as in the forward).
  * grad_out [B,K1,K2] = d loss / d giou (zero entries are skipped: the loss only touches matched pairs,

@@ -27,6 +27,7 @@ SIGNATURES = {
     "ovdet_giou3d_f32": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_u, c_p, c_p]),
     "ovdet_box_corners_f32": (c_i, [c_p, c_p, c_p, c_i64, c_p, c_p]),
     "ovdet_giou3d_decode_f32": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_u, c_p, c_p, c_p]),
+    "ovdet_project_box3d_f32": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p]),
     "ovdet_giou3d_backward_f32": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_u, c_p, c_p]),
     "ovdet_box_intersection_f32": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "ovdet_box_intersection_host_f32": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i]),

@@ -662,3 +662,29 @@ def box_label_mode(points, labels, boxes, ignore_label=-100):
         else:
             out_m.append(-1); out_c.append(0)
     return np.array(out_m, np.int32), np.array(out_c, np.int32)
+
+
+def project_box_3d(Rtilt, K, center, size, heading_angle, image_wh=None):
+    """project_box_3d_cuda (utils/image_util.py:117-134) through SUNRGBD_Calibration_cuda.project_upright_depth_to_image
+    (:284-298), fp32 numpy, then the clip to the image of criterion.py:387-391 when image_wh = (w, h) is given.
+    center/size [Q,3], heading [Q] of one scene -> [Q,4] = (x1, y1, x2, y2) in the reference's (swapped) naming."""
+    f = np.float32
+    ctr, sz, ang = _np(center, f), _np(size, f), _np(heading_angle, f)
+    R, Km = _np(Rtilt, f), _np(K, f)
+    t = -ang
+    c, s = np.cos(t).astype(f), np.sin(t).astype(f)
+    sx = np.array([-1, 1, 1, -1, -1, 1, 1, -1], f); sy = np.array([1, 1, -1, -1, 1, 1, -1, -1], f); sz_ = np.array([1, 1, 1, 1, -1, -1, -1, -1], f)
+    x = sx[None] * sz[:, 0:1]; y = sy[None] * sz[:, 1:2]; z = sz_[None] * sz[:, 2:3]          # [Q,8]
+    px = c[:, None] * x - s[:, None] * y + ctr[:, 0:1]
+    py = s[:, None] * x + c[:, None] * y + ctr[:, 1:2]
+    pz = z + ctr[:, 2:3]
+    pc = np.stack([px, py, pz], -1)                                                            # [Q,8,3] upright depth
+    d = pc @ R                                                                                 # (Rtilt^T p)^T = p^T Rtilt
+    cam = np.stack([d[..., 0], -d[..., 2], d[..., 1]], -1)
+    uv = cam @ Km.T
+    u = uv[..., 0] / uv[..., 2]; v = uv[..., 1] / uv[..., 2]
+    box = np.stack([v.min(-1), u.min(-1), v.max(-1), u.max(-1)], -1).astype(f)
+    if image_wh is not None:
+        w, h = image_wh
+        box = np.minimum(np.maximum(box, 0), np.array([w, h, w, h], f))
+    return box

@@ -127,8 +127,36 @@ def golden_giou_grad(box_util):
     save("giou_grad.npz", **out)
 
 
+def golden_project(ref_root):
+    """project_box_3d_cuda + SUNRGBD_Calibration_cuda (utils/image_util.py) and the image clip of criterion.py:387-391."""
+    spec = importlib.util.spec_from_file_location("ref_image_util", os.path.join(ref_root, "utils", "image_util.py"))
+    iu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(iu)
+    g = torch.Generator().manual_seed(17)
+    B, Q = 3, 40
+    ctr = torch.stack([torch.rand(B, Q, generator=g) * 4 - 2, torch.rand(B, Q, generator=g) * 4 + 1.5, torch.rand(B, Q, generator=g) * 2 - 1], -1)
+    size = torch.rand(B, Q, 3, generator=g) * 0.8 + 0.15          # half extents, as the reference passes them
+    ang = torch.rand(B, Q, generator=g) * 6.28 - 3.14
+    out, outc, Rs, Ks, whs = [], [], [], [], []
+    for b in range(B):
+        tilt = float(torch.rand((), generator=g)) * 0.3 - 0.15
+        Rt = torch.tensor([[1, 0, 0], [0, np.cos(tilt), -np.sin(tilt)], [0, np.sin(tilt), np.cos(tilt)]], dtype=torch.float32)
+        K = torch.tensor([[529.5 + 10 * b, 0, 365.0], [0, 529.5 + 5 * b, 265.0], [0, 0, 1]], dtype=torch.float32)
+        calib = iu.SUNRGBD_Calibration_cuda(Rt, K)
+        bx = iu.project_box_3d_cuda(calib, ctr[b], size[b], ang[b])
+        w, h = 730, 530
+        mx = torch.broadcast_to(torch.tensor([[w, h, w, h]]), bx.size())
+        bc = torch.minimum(torch.clamp_min(bx, 0), mx)
+        out.append(bx.numpy()); outc.append(bc.numpy()); Rs.append(Rt.numpy()); Ks.append(K.numpy()); whs.append([w, h])
+    save("project.npz", center=ctr.numpy(), size=size.numpy(), angle=ang.numpy(), Rtilt=np.stack(Rs), K=np.stack(Ks),
+         image_wh=np.array(whs, np.float32), boxes=np.stack(out), boxes_clipped=np.stack(outc))
+
+
 def main():
     box_util, nms, eval_det, apc, lf, criterion, tools = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "project":   # regenerate only the projection fixture
+        golden_project(REF)
+        return
     torch.manual_seed(0)
     np.random.seed(0)
     if len(sys.argv) > 1 and sys.argv[1] == "grad":      # regenerate only the backward fixture

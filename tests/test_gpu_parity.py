@@ -536,6 +536,33 @@ def test_matcher_full_size_property():
         np.testing.assert_array_equal(np.sort(q), rr)
 
 
+# ------------------------------------------------------------------ 3D box -> image box (RegionCLIP crop branch)
+def test_project_box_3d_golden_and_oracle(golden):
+    from ovdet_b200.utils import image_util as IU
+    g = golden("project.npz")
+    R, K = cu(g["Rtilt"]), cu(g["K"])
+    got = IU.project_boxes_3d(R, K, cu(g["center"]), cu(g["size"]), cu(g["angle"])).cpu().numpy()
+    np.testing.assert_allclose(got, g["boxes"], rtol=2e-6, atol=2e-3)
+    gotc = IU.project_boxes_3d(R, K, cu(g["center"]), cu(g["size"]), cu(g["angle"]), image_wh=g["image_wh"]).cpu().numpy()
+    np.testing.assert_allclose(gotc, g["boxes_clipped"], rtol=2e-6, atol=2e-3)
+    # the reference's per-scene call surface
+    calib = IU.SUNRGBD_Calibration_cuda(R[1], K[1])
+    one = IU.project_box_3d_cuda(calib, cu(g["center"][1]), cu(g["size"][1]), cu(g["angle"][1])).cpu().numpy()
+    np.testing.assert_allclose(one, g["boxes"][1], rtol=2e-6, atol=2e-3)
+    # a larger random batch against the oracle
+    gen = torch.Generator().manual_seed(5)
+    B, Q = 16, 256
+    ctr = torch.stack([torch.rand(B, Q, generator=gen) * 4 - 2, torch.rand(B, Q, generator=gen) * 4 + 1.5, torch.rand(B, Q, generator=gen) * 2 - 1], -1)
+    size = torch.rand(B, Q, 3, generator=gen) * 0.8 + 0.15
+    ang = torch.rand(B, Q, generator=gen) * 6.28 - 3.14
+    Rt = torch.eye(3).repeat(B, 1, 1)
+    Km = torch.tensor([[529.5, 0, 365.0], [0, 529.5, 265.0], [0, 0, 1]]).repeat(B, 1, 1)
+    got = IU.project_boxes_3d(Rt.to(DEV), Km.to(DEV), ctr.to(DEV), size.to(DEV), ang.to(DEV)).cpu().numpy()
+    for b in range(B):
+        np.testing.assert_allclose(got[b], oracle.project_box_3d(Rt[b], Km[b], ctr[b], size[b], ang[b]), rtol=2e-6, atol=2e-3)
+    assert IU.project_boxes_3d(Rt[:0].to(DEV), Km[:0].to(DEV), ctr[:0].to(DEV), size[:0].to(DEV), ang[:0].to(DEV)).shape == (0, Q, 4)
+
+
 # ------------------------------------------------------------------ pseudo-label filter
 def test_lift_golden(golden):
     g = golden("lift.npz")
