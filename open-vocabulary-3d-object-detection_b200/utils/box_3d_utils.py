@@ -110,3 +110,20 @@ def lift_filter_scene(boxes, box_pool, nms_thresh=0.7, match_thresh=0.3, size_nm
     area = 2 * np.sum(scale * np.roll(scale, 1, axis=-1), axis=-1)
     rows = np.concatenate([pool[:, :6], np.stack([sc * vol, lab, vol, area], 1)], -1)[keep]
     return rows[np.argsort(-rows[:, 6], kind="stable")]
+
+
+def save_lifted_boxes(path, boxes):
+    """The on-disk form of lift_boxes.py:167-169: vertex-vertex rows [x1..z2, score, label, volume, area] ->
+    centre-size rows with score and label swapped, i.e. ``<scan>_bbox.npy`` = fp64 [N,10] =
+    (cx, cy, cz, sx, sy, sz, label, score, volume, area).  Returns the number of boxes written."""
+    b = np.asarray(boxes, np.float64)
+    if b.shape[0]:
+        b = vv2cs(b.copy())
+        b[:, [6, 7]] = b[:, [7, 6]]
+    np.save(path, b)
+    return int(b.shape[0])
+
+
+def lift_and_save_scene(path, boxes, box_pool, nms_thresh=0.7, match_thresh=0.3, size_nms_thresh=0.0):
+    """NMS -> pool match -> size-scored NMS (lift_boxes.py:139-165) and the file of :167-169 for one scene."""
+    return save_lifted_boxes(path, lift_filter_scene(boxes, box_pool, nms_thresh, match_thresh, size_nms_thresh))

@@ -576,6 +576,15 @@ def test_lift_golden(golden):
         got = B3.lift_filter_scene(bx[s], pool[s])
         np.testing.assert_allclose(got, g[f"final_{s}"], rtol=0, atol=0)
     np.testing.assert_allclose(B3.box_3d_iou(bx[0, 0, :6], pool[0]), g["iou_vv"][0], rtol=1e-14)
+    # the on-disk form (lift_boxes.py:167-169): centre-size rows, score and label swapped
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "scene0000_00_bbox.npy")
+        n = B3.lift_and_save_scene(path, bx[0], pool[0])
+        want = g["final_0"].copy()
+        want[:, 3:6] -= want[:, :3]; want[:, :3] += want[:, 3:6] / 2; want[:, [6, 7]] = want[:, [7, 6]]
+        np.testing.assert_allclose(np.load(path), want, rtol=0, atol=0)
+        assert n == want.shape[0]
 
 
 def test_lift_full_width_vs_oracle():
