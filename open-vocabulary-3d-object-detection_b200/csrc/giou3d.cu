@@ -11,9 +11,14 @@
 //            axis-aligned prefilter area, AABB enclosing volume, validity; pairs
 //            that need no polygon clip are finished here; the others are pushed
 //            (warp-aggregated) on a CTA-local queue.
-//   phase B  the queue is drained with all lanes busy: one Sutherland-Hodgman
-//            clip per lane, vertex lists in a conflict-free per-thread shared
-//            scratch, shoelace area streamed out of the last pass.
+//   phase B  the queue is drained.  Short queue (the shipped semantics): 8 lanes per
+//            pair, the polygon in registers, one vertex per lane -- the dependent chain
+//            of a clip pass is one vertex long.  Long queue (every pair clipped): one
+//            Sutherland-Hodgman clip per lane, vertex lists in a conflict-free per-thread
+//            shared scratch.  Both give bit-identical polygons; the shoelace is summed in
+//            the reference's term order.
+//   split    when at most 64 pairs of the tile are clip-eligible (k2_cap = 4 columns),
+//            the last two warps find and clip them WHILE the other six run phase A.
 // Results go to a shared [TQ][TG] tile and leave with coalesced row stores.
 // The pair work is ~60 (skip) to ~1200 (clip) instructions against 4 B written,
 // i.e. issue-bound, not HBM-bound: see DESIGN.md for the roofline used.
@@ -549,11 +554,9 @@ template <typename ClipT, int PB, int TQ> static int launch_giou_tq(const GiouPa
     return launch_giou_tq2<ClipT, PB, TQ, false>(p, st);
 }
 
-// Tile height by grid size: this workload is tiny (config 1 = 64 x 128 x 64 pairs), so latency, not
-// throughput, decides; use the smallest row tile that still leaves every SM several CTAs deep.
+// Tile height.  The workload is tiny (config 1 = 64 x 128 x 64 pairs): latency, not throughput, decides.
 template <typename ClipT, int PB> static int launch_giou(const GiouParams &p, cudaStream_t st)
 {
-    const long long t32 = (long long)p.B * ((p.K1 + 31) / 32);
     OVDET_REQUIRE((long long)p.B * ((p.K1 + 7) / 8) < 2147483647LL, "grid too large");
     static int force = -1;   // OVDET_GIOU_TQ=8|16|32 overrides the heuristic (profiling experiments)
     if (force < 0) { const char *e = getenv("OVDET_GIOU_TQ"); force = e ? atoi(e) : 0; }
@@ -564,7 +567,6 @@ template <typename ClipT, int PB> static int launch_giou(const GiouParams &p, cu
     // 512 CTAs; with the split mode and the cooperative clip they also beat 32-row tiles in the many-wave regime
     // (4096 box sets: 115 vs 98 Gpairs/s as shipped, 95 vs 92 torch path, 33.5 vs 29.3 every pair clipped) and 8-row
     // tiles everywhere (65 / 26 Gpairs/s).  OVDET_GIOU_TQ keeps the other heights reachable for experiments.
-    (void)t32;
     return launch_giou_tq<ClipT, PB, 16>(p, st);
 }
 
