@@ -297,23 +297,34 @@ __global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams
 
     for (int g0 = 0; g0 < p.K2; g0 += TG) {
         const int ng = min(TG, p.K2 - g0);
-        // ---- stage the query tile (first chunk only) and this GT chunk with one barrier, features with one more
-        if (g0 == 0) {
-            if (p.dec1.center) {   // fused decode: one thread per query box writes its 8 corners straight into the staging buffer
-                if (threadIdx.x < nq) {
-                    const size_t q = (size_t)b * p.K1 + q0 + threadIdx.x;
-                    decode_box(p.dec1.center + 3 * q, p.dec1.size + 3 * q, __ldg(p.dec1.angle + q), raw1 + threadIdx.x * 24);
-                    if (p.dec1.corners_out)
-                        for (int i = 0; i < 24; ++i) p.dec1.corners_out[q * 24 + i] = raw1[threadIdx.x * 24 + i];
-                }
-            } else stage_boxes(p.c1 + ((size_t)b * p.K1 + q0) * 24, nq, raw1, vec1);
-        }
-        stage_boxes(p.c2 + ((size_t)b * p.K2 + g0) * 24, ng, raw2, vec2);
+        // ---- box features.  Corner tensors: thread t loads ITS box (six 16-byte loads, 96 contiguous bytes) straight into
+        // registers and reduces it to the SoA features -- no staging buffer, one barrier.  Fused decode: the query box is
+        // built from (centre, size, heading) in the staging buffer first (it is also written out when asked for).
+        auto features_from_global = [&](const float *g, bool vec, float *f, int stride) {
+            float c[24];
+            if (vec) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { const float4 v = ldg4(g + 4 * i); c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 24; ++i) c[i] = __ldg(g + i);
+            }
+            box_features(c, f, stride);
+        };
         if (threadIdx.x == 0) qcount = 0;
-        __syncthreads();
+        if (threadIdx.x < TG) {
+            if (threadIdx.x < ng) features_from_global(p.c2 + ((size_t)b * p.K2 + g0 + threadIdx.x) * 24, vec2, f2 + threadIdx.x, TG);
+        } else if (g0 == 0 && threadIdx.x - TG < nq) {
+            const int r = threadIdx.x - TG;
+            if (p.dec1.center) {
+                const size_t q = (size_t)b * p.K1 + q0 + r;
+                decode_box(p.dec1.center + 3 * q, p.dec1.size + 3 * q, __ldg(p.dec1.angle + q), raw1 + r * 24);
+                if (p.dec1.corners_out)
+                    for (int i = 0; i < 24; ++i) p.dec1.corners_out[q * 24 + i] = raw1[r * 24 + i];
+                box_features(raw1 + r * 24, f1 + r, TQ);
+            } else features_from_global(p.c1 + ((size_t)b * p.K1 + q0 + r) * 24, vec1, f1 + r, TQ);
+        }
         GSTAMP(1);
-        if (threadIdx.x < TG) { if (threadIdx.x < ng) box_features(raw2 + threadIdx.x * 24, f2 + threadIdx.x, TG); }
-        else if (g0 == 0 && threadIdx.x - TG < nq) box_features(raw1 + (threadIdx.x - TG) * 24, f1 + (threadIdx.x - TG), TQ);
         __syncthreads();
         GSTAMP(2);
 
