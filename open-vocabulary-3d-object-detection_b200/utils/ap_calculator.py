@@ -122,6 +122,7 @@ class APCalculator(object):
         self.reduce_mode = "compact"   # "sort" forces the segmented radix sort + scan (full PR curves)
         self.tp_list_cap = 2048        # per-class TP-list capacity of the compact reducer (split across ranks; grows on overflow)
         self._cap_hint = {}            # world size -> per-rank capacity learned from the previous evaluation
+        self._fmt_keys = {}            # number of classes -> cached metric key strings
         self.reset()
 
     def make_gt_list(self, gt_box_corners, gt_box_sem_cls_labels, gt_box_present):
@@ -171,6 +172,8 @@ class APCalculator(object):
         """Concatenated class-major records of everything seen by ``step``."""
         if not self._scores:
             return None
+        if len(self._scores) == 1:     # one batch: no copy of the 5 B/record stream
+            return self._scores[0], self._tps[0], self._npos
         return torch.cat(self._scores, 1), torch.cat(self._tps, 1), self._npos
 
     def compute_metrics(self, distributed=False):
@@ -217,10 +220,25 @@ class APCalculator(object):
             ap, recall, ndet = E.ap_reduce(rs, rt, npos, nthr)
             ap, recall = ap.cpu().numpy(), recall.cpu().numpy()
         for ti, thr in enumerate(self.ap_iou_thresh):
-            apd = {c: ap[ti, c] for c in range(ap.shape[1])}
-            rcd = {c: recall[ti, c] for c in range(ap.shape[1])}
-            overall_ret[thr] = self._format(apd, rcd)
+            overall_ret[thr] = self._format_rows(np.asarray(ap[ti]), np.asarray(recall[ti]))
         return overall_ret
+
+    def _format_rows(self, ap_row, rec_row):
+        """_format for dense per-class rows (class id = column): same keys, order and value types, without rebuilding
+        the key strings and per-class dicts on every call (the formatting was ~10 % of a 0.6 ms evaluation)."""
+        n = ap_row.shape[0]
+        keys = self._fmt_keys.get(n)
+        if keys is None:
+            names = [self.class2type_map[k] if self.class2type_map else str(k) for k in range(n)]
+            keys = (["%s Average Precision" % nm for nm in names], ["%s Recall" % nm for nm in names])
+            self._fmt_keys[n] = keys
+        ret_dict = OrderedDict(zip(keys[0], ap_row))
+        ap_vals = ap_row.astype(np.float32)
+        ap_vals[np.isnan(ap_vals)] = 0
+        ret_dict["mAP"] = ap_vals.mean()
+        ret_dict.update(zip(keys[1], rec_row))
+        ret_dict["AR"] = np.mean(rec_row)
+        return ret_dict
 
     def _format(self, ap, last_rec):
         ret_dict = OrderedDict()
