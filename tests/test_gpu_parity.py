@@ -414,6 +414,24 @@ def test_ap_match_dense_fallback_and_crowded(thrs, max_gt):
             assert float(got[thr][k]) == pytest.approx(float(v), abs=1e-9), (thr, k)
 
 
+def test_ap_scannet_shape_three_thresholds():
+    """ScanNet-shaped evaluation (256 queries, 18 classes: the probability tile no longer fits the staging area of
+    ap_match, 256-thread NMS CTAs) with three IoU thresholds, in two step() calls of different batch sizes."""
+    S, Q, G, C = 20, 256, 64, 18
+    out, tgt = synth.detection_batch(B=S, Q=Q, G=G, C=C, seed=91, room="scannet", heading=0.0, max_gt=30)
+    thrs = (0.1, 0.25, 0.5)
+    calc = APC.APCalculator(_Cfg(C), ap_iou_thresh=list(thrs), exact_eval=False)
+    for lo, hi in ((0, 7), (7, S)):
+        calc.step(out["box_corners"][lo:hi].to(DEV), out["sem_cls_prob"][lo:hi].to(DEV), out["objectness_prob"][lo:hi].to(DEV), None,
+                  tgt["gt_box_corners"][lo:hi].to(DEV), tgt["gt_box_sem_cls_label"][lo:hi].to(DEV), tgt["gt_box_present"][lo:hi].to(DEV))
+    got = calc.compute_metrics()
+    want, _ = oracle.ap_metrics(out["box_corners"], out["sem_cls_prob"], out["objectness_prob"], tgt["gt_box_corners"],
+                                tgt["gt_box_sem_cls_label"], tgt["gt_box_present"], C, ap_iou_thresh=thrs)
+    for thr in thrs:
+        for k, v in want[thr].items():
+            assert float(got[thr][k]) == pytest.approx(float(v), abs=1e-9), (thr, k)
+
+
 def test_ap_reduce_properties_full_size():
     """C3-sized record stream (20 classes x 5050*128 slots): sortedness-free checks --
     recall == total TP / npos, AP in [0,1], AP invariant under a permutation of the records."""
