@@ -258,11 +258,12 @@ __global__ void __launch_bounds__(AM_NT) ap_match_kernel(MatchParams p)
     AMSTAMP(1);
 
     // records: score of every (class, slot), tp = 0.  The scene's [K, C] probability tile is staged through shared
-    // memory (aliasing the clip scratch, idle until step 2) with independent 16-byte loads, so that no thread walks 20
+    // memory (aliasing the feature / clip / candidate areas, idle until then) with independent 16-byte loads, so that no thread walks 20
     // dependent global loads; the stores are coalesced in k for each class.
     {
-        float *ptile = reinterpret_cast<float *>(scratch);
-        const size_t tile_cap = (sizeof(V2<double>) * 2 * SH_MAXV * AM_CLIP + sizeof(double) * AM_QCAP) / sizeof(float);
+        // everything below `best` (feature records, clip scratch, candidate IoUs) is idle until the barrier after this phase
+        float *ptile = reinterpret_cast<float *>(sm);
+        const size_t tile_cap = (size_t)(reinterpret_cast<unsigned char *>(best) - sm) / sizeof(float);
         const size_t kc = (size_t)p.K * p.C;
         const float *pg = p.probs ? p.probs + (size_t)s * kc : nullptr;
         const bool staged = pg && kc <= tile_cap;
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(AM_NT) ap_match_kernel(MatchParams p)
     }
     AMSTAMP(2);
     if (ng == 0 || nk == 0) return;   // no claims possible (uniform)
+    __syncthreads();                  // the probability tile aliases the feature records written next
 
     // stage features
     for (int i = tid; i < nk + ng; i += AM_NT) {
