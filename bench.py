@@ -422,6 +422,37 @@ def bench_extras(args, rank, world, dev, peaks):
                          "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                                       "frac": ach / peaks["bf16_tflops"], "traffic": load_traffic("clip_logits_persistent_kernel")},
                          "workload": "8192x640 @ 1203x640^T bf16 -> softmax probs bf16 + objectness (includes bf16 cast-free path)"}
+    # the reference's only native ABI, box_intersection(rect1, rect2, nonrot, nums_k2, inter_areas, approximate) on HOST
+    # numpy buffers (box_intersection.pyx:166-171): the drop-in against the reference's own compiled extension, same call
+    from ovdet_b200.utils.box_intersection import box_intersection as bi_ours
+    o1, t1 = synth.detection_batch(B=B, Q=Q, G=G, C=C_SUN, seed=100, heading=np.pi)
+    r1 = np.ascontiguousarray(o1["box_corners"][:, :, [3, 2, 1, 0]][..., [0, 2]].numpy(), dtype=np.float32)
+    r2 = np.ascontiguousarray(t1["gt_box_corners"][:, :, [3, 2, 1, 0]][..., [0, 2]].numpy(), dtype=np.float32)
+    lt = np.maximum(r1[:, :, None, 1], r2[:, None, :, 1]); rb = np.minimum(r1[:, :, None, 3], r2[:, None, :, 3])
+    wh = np.clip(rb - lt, 0, None)
+    nonrot = np.ascontiguousarray(wh[..., 0] * wh[..., 1], dtype=np.float32)
+    nk32 = t1["nactual_gt"].numpy().astype(np.int32)
+    areas = np.zeros_like(nonrot)
+    for _ in range(5):
+        bi_ours(r1, r2, nonrot, nk32, areas, True)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        bi_ours(r1, r2, nonrot, nk32, areas, True)
+    t_ours = (time.perf_counter() - t0) / 50
+    abi = {"ours_us_per_call": t_ours * 1e6, "calls": 50, "nominal_pairs": B * Q * G,
+           "workload": "box_intersection on host numpy buffers, one decoder layer (8x128x64), as shipped (k2 < 4), approximate=True"}
+    if not args.skip_cpu and rank == 0:
+        import oracle
+        ref = oracle.ref_box_intersection()
+        if ref is not None:
+            a2 = np.zeros_like(nonrot)
+            ref(r1, r2, nonrot, nk32, a2, True)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                ref(r1, r2, nonrot, nk32, a2, True)
+            abi["reference_cython_us_per_call"] = (time.perf_counter() - t0) / 20 * 1e6
+            abi["identical_output"] = bool(np.array_equal(a2, areas))
+    ex["box_intersection_abi"] = abi
     # class-wise 3D NMS alone (10.9 ms/scene in the reference at K = 256)
     from ovdet_b200.utils.nms import nms_batch
     gN = torch.Generator().manual_seed(11)

@@ -69,6 +69,16 @@ DeviceScratch &device_scratch()
     return ds;
 }
 
+int HostStaging::ensure_pinned(size_t bytes)
+{
+    if (bytes <= pinned_cap) return OVDET_OK;
+    if (pinned) { if (stream) OVDET_CUDA_TRY(cudaStreamSynchronize(stream)); OVDET_CUDA_TRY(cudaFreeHost(pinned)); pinned = nullptr; pinned_cap = 0; }
+    const size_t want = bytes + bytes / 2 + 4096;
+    OVDET_CUDA_TRY(cudaHostAlloc(&pinned, want, cudaHostAllocDefault));
+    pinned_cap = want;
+    return OVDET_OK;
+}
+
 HostStaging &host_staging()
 {
     static thread_local HostStaging hs;

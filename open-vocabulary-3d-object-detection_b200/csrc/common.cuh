@@ -42,7 +42,10 @@ struct HostStaging {
     cudaStream_t stream = nullptr;
     cudaStream_t stream_d2h = nullptr;   // second stream: result read-back of chunk i overlaps upload + kernel of chunk i+1
     cudaEvent_t ev[8] = {};
+    void *pinned = nullptr;      // grow-only pinned host buffer: small host arguments are packed here and travel in ONE copy
+    size_t pinned_cap = 0;
     int ensure(size_t bytes);
+    int ensure_pinned(size_t bytes);
 };
 HostStaging &host_staging();
 
