@@ -79,11 +79,13 @@ __global__ void __launch_bounds__(LS_NT) lsap_kernel(LsapParams p)
     for (int j = tid; j < nc; j += LS_NT) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
     __syncthreads();
 
+    // per-row state is reset once here and then together with the path walk of the previous row: two barriers per row
+    // besides the one per Dijkstra step (the original structure had four)
+    for (int i = tid; i < nr; i += LS_NT) SR[i] = 0;
+    for (int j = tid; j < nc; j += LS_NT) { SC[j] = 0; spc[j] = INFINITY; }
+    __syncthreads();
     int buf = 0;
     for (int cur = 0; cur < nr; ++cur) {
-        for (int i = tid; i < nr; i += LS_NT) SR[i] = 0;
-        for (int j = tid; j < nc; j += LS_NT) { SC[j] = 0; spc[j] = INFINITY; }
-        __syncthreads();
         double minVal = 0.0;
         int i = cur, sink = -1;
         while (sink == -1) {
@@ -118,7 +120,8 @@ __global__ void __launch_bounds__(LS_NT) lsap_kernel(LsapParams p)
             if ((j % LS_NT) == tid) SC[j] = 1;     // the owner marks its column scanned
             if (row4col[j] == -1) sink = j; else i = row4col[j];
         }
-        __syncthreads();
+        // no barrier here: everything the dual updates read across threads (SR, spc) was written before the barrier of
+        // the last step; SC / spc / v of a column are touched by its owner only
         if (sink < 0) break;
         // dual updates (Crouse 2016, step 4)
         if (tid == 0) u[cur] = __dadd_rn(u[cur], minVal);
@@ -126,8 +129,8 @@ __global__ void __launch_bounds__(LS_NT) lsap_kernel(LsapParams p)
             if (SR[r] && r != cur) u[r] = __dadd_rn(u[r], __dsub_rn(minVal, spc[col4row[r]]));
         for (int j = tid; j < nc; j += LS_NT)
             if (SC[j]) v[j] = __dsub_rn(v[j], __dsub_rn(minVal, spc[j]));
-        __syncthreads();
-        // augment along the alternating path
+        __syncthreads();   // duals done (they read spc / col4row / SR / SC)
+        // thread 0 augments along the alternating path (path[], row4col, col4row) while everybody resets the per-row state
         if (tid == 0) {
             int j = sink;
             while (true) {
@@ -137,6 +140,8 @@ __global__ void __launch_bounds__(LS_NT) lsap_kernel(LsapParams p)
                 if (r == cur) break;
             }
         }
+        for (int i2 = tid; i2 < nr; i2 += LS_NT) SR[i2] = 0;
+        for (int j = tid; j < nc; j += LS_NT) { SC[j] = 0; spc[j] = INFINITY; }
         __syncthreads();
     }
     __syncthreads();
