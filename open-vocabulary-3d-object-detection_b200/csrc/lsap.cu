@@ -147,9 +147,9 @@ __global__ void __launch_bounds__(LS_NT) lsap_kernel(LsapParams p)
                 Key kb = warp_min_key(key_of(best));
                 if (lane == 0) wbest[buf][warp] = kb;
                 __syncthreads();
-                kb = wbest[buf][0];
-#pragma unroll
-                for (int w = 1; w < LS_NT / 32; ++w) { const Key o = wbest[buf][w]; if (key_less(o, kb)) kb = o; }
+                // the 8 warp winners: lanes 0..7 of every warp take one each and the same three redux.sync finish the job
+                kb = lane < LS_NT / 32 ? wbest[buf][lane] : Key{~0ull, 0xffffffffu};
+                kb = warp_min_key(kb);
                 buf ^= 1;
                 best.v = dkey_inv(kb.kv); best.j = (int)(kb.kj & 0x7fffffffu); best.asg = (int)(kb.kj >> 31);
             }
