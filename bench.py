@@ -203,6 +203,15 @@ def bench_giou(args, rank, world, dev, peaks):
             f5(i)
         ms5 = timed_graph(f5, max(args.steps // 4, 5), world, dev)
         res["variants"][name] = world * pairs * max(args.steps // 4, 5) / (ms5 * 1e-3)
+    # config 2 shape: ScanNet, 256 queries, axis-aligned boxes (no clipping at all: one fp32 result per ~70 flops)
+    from ovdet_b200 import synth as _synth
+    o2, t2 = _synth.detection_batch(B=L_LAYERS * B, Q=256, G=G, C=18, seed=300, room="scannet", heading=0.0)
+    a2 = (o2["box_corners"].to(dev), t2["gt_box_corners"].to(dev), t2["nactual_gt"].to(dev), torch.empty((L_LAYERS * B, 256, G), device=dev))
+    f2_ = lambda i: generalized_box3d_iou(a2[0], a2[1], a2[2], rotated_boxes=False, out=a2[3])
+    for i in range(3):
+        f2_(i)
+    msa = timed_graph(f2_, max(args.steps // 4, 5), world, dev)
+    res["variants"]["axis_aligned_c2_pairs_per_s"] = world * L_LAYERS * B * 256 * G * max(args.steps // 4, 5) / (msa * 1e-3)
     # launch floor of this timing method: the same entry point on a 1x1x1 problem (one CTA, ~no work)
     t1 = (torch.zeros((1, 1, 8, 3), device=dev), torch.zeros((1, 1, 8, 3), device=dev), torch.ones((1,), dtype=torch.int64, device=dev),
           torch.empty((1, 1, 1), device=dev))
