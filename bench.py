@@ -494,6 +494,11 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    # all the host threads the reference can use: torchrun exports OMP_NUM_THREADS=1, which would cripple its torch glue
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     base = cpu_giou_baseline(steps=max(1, args.steps))
     line = {"impl": "reference", "metric": "3D GIoU pairs/s (SUN RGB-D-shaped step) & AP-eval scenes/s", "value": base["value"],
             "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
