@@ -1,0 +1,95 @@
+"""Randomised shapes and mode switches against the oracle (GPU): GIoU (every mode / cap / prefilter combination, ragged
+tiles, empty GT), the NMS family, the AP evaluation end to end and the matcher + LSAP.  Complements the fixed cases of
+test_gpu_parity.py; each seed draws ~230 cases and runs in a few seconds."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ovdet_b200  # noqa: E402,F401
+from ovdet_b200 import synth  # noqa: E402
+from ovdet_b200.utils import box_util as BU, nms as NMS, ap_calculator as APC  # noqa: E402
+from ovdet_b200.criterion import Matcher  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class Cfg:
+    def __init__(s, n):
+        s.num_semcls = n
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_fuzz_against_oracle(seed):
+    rng = np.random.default_rng(seed)
+    n_g = n_n = n_a = n_m = 0
+    # ---- GIoU
+    for it in range(120):
+        B = int(rng.integers(1, 5)); Q = int(rng.integers(1, 180)); G = int(rng.integers(1, 140))
+        heading = float(rng.choice([0.0, 0.3, 1.0, np.pi]))
+        out, tgt = synth.detection_batch(B=B, Q=Q, G=G, seed=int(rng.integers(1 << 30)), heading=heading, max_gt=G,
+                                         room=str(rng.choice(["sunrgbd", "scannet"])))
+        c1, c2, nk = out["box_corners"], tgt["gt_box_corners"], tgt["nactual_gt"].clone()
+        if rng.random() < 0.3: nk[int(rng.integers(B))] = 0
+        rot = bool(rng.random() < 0.8)
+        mode = str(rng.choice(["tensor", "cython"])); cap = int(rng.choice([0, 1, 4, 7])); pre = bool(rng.random() < 0.7); inter = bool(rng.random() < 0.2)
+        use_nk = rng.random() < 0.85
+        want = oracle.generalized_box3d_iou(c1, c2, nk if use_nk else None, rot, inter, mode=mode, prefilter=pre, k2_cap=cap or None)
+        got = BU.generalized_box3d_iou(c1.to(DEV), c2.to(DEV), nk.to(DEV) if use_nk else None, rot, inter, mode=mode, prefilter=pre, k2_cap=cap).cpu().numpy()
+        if not np.allclose(got, want, rtol=1e-5, atol=1e-6, equal_nan=True):
+            pytest.fail(str(("GIOU MISMATCH", dict(B=B, Q=Q, G=G, heading=heading, rot=rot, mode=mode, cap=cap, pre=pre, inter=inter, use_nk=use_nk), np.abs(got - want).max())))
+        n_g += 1
+    # ---- NMS
+    for it in range(60):
+        K = int(rng.integers(1, 700)); ncls = int(rng.integers(1, 40)); S = 2
+        g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+        c, s, _ = synth.sample_boxes(g, (S, K), "scannet", 0.0)
+        s = s * float(rng.uniform(0.8, 2.5))
+        score = torch.rand((S, K), generator=g).double()
+        cls = torch.randint(0, ncls, (S, K), generator=g).double()
+        bx = torch.cat([(c - s / 2).double(), (c + s / 2).double(), score[..., None], cls[..., None]], -1)
+        thr = float(rng.choice([0.0, 0.1, 0.25, 0.7])); old = bool(rng.random() < 0.3); same = bool(rng.random() < 0.7)
+        keep, order, npick = NMS.nms_batch(bx.to(DEV), thr, old_type=old, samecls=same, want_order=bool(rng.random() < 0.5) or True)
+        for i in range(S):
+            want = oracle.nms_3d_faster_samecls(bx[i].numpy(), thr, old) if same else oracle.nms_3d_faster(bx[i, :, :7].numpy(), thr, old)
+            if order[i, :int(npick[i])].cpu().tolist() != want:
+                pytest.fail(str(("NMS MISMATCH", dict(K=K, ncls=ncls, thr=thr, old=old, same=same))))
+        n_n += 1
+    # ---- AP end to end
+    for it in range(25):
+        S = int(rng.integers(1, 12)); Q = int(rng.choice([16, 64, 128, 200])); G = int(rng.choice([8, 64])); C = int(rng.choice([3, 10, 20]))
+        out, tgt = synth.detection_batch(B=S, Q=Q, G=G, C=C, seed=int(rng.integers(1 << 30)), heading=float(rng.choice([0.0, np.pi])), max_gt=int(rng.integers(1, G + 1)))
+        thrs = tuple(sorted(rng.choice([0.1, 0.25, 0.5, 0.75], size=int(rng.integers(1, 4)), replace=False).tolist()))
+        calc = APC.APCalculator(Cfg(C), ap_iou_thresh=list(thrs), exact_eval=False)
+        calc.step(out["box_corners"].to(DEV), out["sem_cls_prob"].to(DEV), out["objectness_prob"].to(DEV), None,
+                  tgt["gt_box_corners"].to(DEV), tgt["gt_box_sem_cls_label"].to(DEV), tgt["gt_box_present"].to(DEV))
+        got = calc.compute_metrics()
+        want, _ = oracle.ap_metrics(out["box_corners"], out["sem_cls_prob"], out["objectness_prob"], tgt["gt_box_corners"],
+                                    tgt["gt_box_sem_cls_label"], tgt["gt_box_present"], C, ap_iou_thresh=thrs)
+        for thr in thrs:
+            for k, v in want[thr].items():
+                a, b_ = float(got[thr][k]), float(v)
+                if not (abs(a - b_) < 1e-9 or (np.isnan(a) and np.isnan(b_))):
+                    pytest.fail(str(("AP MISMATCH", dict(S=S, Q=Q, G=G, C=C, thrs=thrs, key=k, got=a, want=b_))))
+        n_a += 1
+    # ---- matcher
+    for it in range(25):
+        B = int(rng.integers(1, 6)); Q = int(rng.choice([32, 128, 256, 300])); G = int(rng.choice([8, 64, 100])); C = 18
+        out, tgt = synth.detection_batch(B=B, Q=Q, G=G, C=C, seed=int(rng.integers(1 << 30)), heading=float(rng.choice([0.0, np.pi])), max_gt=G)
+        w = [float(x) for x in rng.uniform(0, 5, size=4)]
+        m = Matcher(*w)
+        o = {k: v.to(DEV) for k, v in out.items()}; t = {k: v.to(DEV) for k, v in tgt.items()}
+        rot = bool(rng.random() < 0.5)
+        res = m.match_from_boxes(o, t, rotated_boxes=rot)
+        cost = res["final_cost"].cpu().numpy()
+        _, inds_w, mask_w = oracle.matcher_assign(cost, tgt["nactual_gt"].numpy())
+        if not np.array_equal(res["per_prop_gt_inds"].cpu().numpy(), inds_w) or not np.array_equal(res["proposal_matched_mask"].cpu().numpy(), mask_w):
+            pytest.fail(str(("MATCHER MISMATCH", dict(B=B, Q=Q, G=G, w=w, rot=rot))))
+        n_m += 1
+    assert (n_g, n_n, n_a, n_m) == (120, 60, 25, 25)
