@@ -93,3 +93,19 @@ def test_fuzz_against_oracle(seed):
             pytest.fail(str(("MATCHER MISMATCH", dict(B=B, Q=Q, G=G, w=w, rot=rot))))
         n_m += 1
     assert (n_g, n_n, n_a, n_m) == (120, 60, 25, 25)
+
+
+@pytest.mark.parametrize("seed", [21])
+def test_fuzz_pseudo_label_filter(seed):
+    """lift_boxes' per-scene NMS -> pool match -> size NMS on random proposal / pool sizes and thresholds vs the oracle."""
+    from ovdet_b200.utils import box_3d_utils as B3
+    rng = np.random.default_rng(seed)
+    for it in range(40):
+        P = int(rng.integers(1, 257)); M = int(rng.integers(1, 513)); C = int(rng.integers(1, 19))
+        bx, pool = synth.pseudo_label_scenes(2, P=P, pool=M, C=C, seed=int(rng.integers(1 << 30)))
+        nms_t = float(rng.choice([0.25, 0.5, 0.7])); match_t = float(rng.choice([0.1, 0.3, 0.6])); size_t = float(rng.choice([0.0, 0.1]))
+        for s in range(2):
+            want = oracle.lift_filter_scene(bx[s].numpy(), pool[s].numpy(), nms_t, match_t, size_t)
+            got = B3.lift_filter_scene(bx[s].numpy(), pool[s].numpy(), nms_t, match_t, size_t)
+            assert got.shape == want.shape, (P, M, C, nms_t, match_t, size_t)
+            np.testing.assert_allclose(got, want, rtol=0, atol=0)
