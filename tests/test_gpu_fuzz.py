@@ -109,3 +109,19 @@ def test_fuzz_pseudo_label_filter(seed):
             got = B3.lift_filter_scene(bx[s].numpy(), pool[s].numpy(), nms_t, match_t, size_t)
             assert got.shape == want.shape, (P, M, C, nms_t, match_t, size_t)
             np.testing.assert_allclose(got, want, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("seed", [31])
+def test_fuzz_clip_logits_shapes(seed):
+    """Random (M, K, N) for the logits kernels: ragged M, N from a single tile to eight, every cluster size the
+    co-residency model can pick, both kernels (persistent for >= 2 rounds of M-tiles), with and without normalisation."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_gpu_parity as T
+    rng = np.random.default_rng(seed)
+    for it in range(12):
+        M = int(rng.choice([1, 77, 500, 1500, 3000, 6000])) + int(rng.integers(0, 50))
+        K = int(rng.choice([64, 128, 640]))
+        N = int(rng.choice([2, 19, 21, 100, 257, 600, 1203, 2048])) + (int(rng.integers(0, 7)) if it % 2 else 0)
+        N = min(max(N, 2), 2048)
+        l2 = bool(rng.random() < 0.3)
+        T._check_clip_logits(M, K, N, l2, (1.0 / 0.07) if l2 else float(rng.choice([0.5, 1.0])))
