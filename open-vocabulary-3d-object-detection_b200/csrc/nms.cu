@@ -563,12 +563,29 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
         }
         __syncthreads();
     }
+    // With a positive match threshold only OVERLAPPING pairs can match, and they are ~1 % of the P x M pairs: a
+    // conservative fp32 test (pick bounds rounded outwards against pool bounds rounded outwards; "certainly disjoint on
+    // some axis" implies the exact overlap is empty) runs at full fp32 rate, the few survivors go on a per-warp queue in
+    // pool order and only they get the fp64 IoU.  A pick with no survivor has IoU 0 everywhere and cannot match.
+    const bool prune = pool_staged && p.match_thr > 0.0 &&
+                       (size_t)np_ * 32 + (size_t)(blockDim.x >> 5) * np_ * 2 <= (size_t)(reinterpret_cast<unsigned char *>(sh.sidx) - sm);
+    float4 *plo = reinterpret_cast<float4 *>(sm);            // [np_] lower bounds rounded down (the NMS tables are idle here)
+    float4 *phi = plo + np_;                                 // [np_] upper bounds rounded up
+    unsigned short *wq = reinterpret_cast<unsigned short *>(phi + np_) + (size_t)warp * np_;   // this warp's candidate queue
+    if (prune) {
+        for (int j = threadIdx.x; j < np_; j += blockDim.x) {
+            const double *r = pl + (size_t)j * 6;
+            plo[j] = make_float4(__double2float_rd(r[0]), __double2float_rd(r[1]), __double2float_rd(r[2]), 0.f);
+            phi[j] = make_float4(__double2float_ru(r[3]), __double2float_ru(r[4]), __double2float_ru(r[5]), 0.f);
+        }
+        __syncthreads();
+    }
     for (int t = warp; t < npick; t += (blockDim.x >> 5)) {
         const double *bx = boxes + (size_t)order[t] * 8;
         const double b0 = bx[0], b1 = bx[1], b2 = bx[2], b3 = bx[3], b4 = bx[4], b5 = bx[5];
         const double qv = A::mul(A::mul(A::sub(b3, b0), A::sub(b4, b1)), A::sub(b5, b2));
         double bi = -INFINITY; int bj = 0x7fffffff;
-        for (int j = lane; j < np_; j += 32) {
+        auto exact_pair = [&](int j) {
             const double *r = (pool_staged ? pl : pool) + (size_t)j * 6;
             const double kv = pool_staged ? pkv[j] : A::mul(A::mul(A::sub(r[3], r[0]), A::sub(r[4], r[1])), A::sub(r[5], r[2]));
             const double e0 = A::max(A::sub(A::min(b3, r[3]), A::max(b0, r[0])), 0.0);
@@ -583,6 +600,27 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
                 iou = A::div(inter, A::add(A::sub(A::add(qv, kv), inter), 1e-5));
             }
             if (iou > bi) { bi = iou; bj = j; }  // np.argmax: first maximum
+        };
+        if (prune) {
+            const float lx = __double2float_rd(b0), ly = __double2float_rd(b1), lz = __double2float_rd(b2);
+            const float hx = __double2float_ru(b3), hy = __double2float_ru(b4), hz = __double2float_ru(b5);
+            int nq = 0;
+            for (int j0 = 0; j0 < np_; j0 += 32) {
+                const int j = j0 + lane;
+                bool maybe = false;
+                if (j < np_) {
+                    const float4 a = plo[j], c = phi[j];
+                    maybe = !(hx <= a.x || c.x <= lx || hy <= a.y || c.y <= ly || hz <= a.z || c.z <= lz);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, maybe);
+                if (maybe) wq[nq + __popc(m & ((1u << lane) - 1))] = (unsigned short)j;
+                nq += __popc(m);
+            }
+            __syncwarp();
+            for (int q = lane; q < nq; q += 32) exact_pair(wq[q]);   // ascending pool index within a lane: first maximum kept
+            __syncwarp();
+        } else {
+            for (int j = lane; j < np_; j += 32) exact_pair(j);
         }
         for (int off = 16; off > 0; off >>= 1) {
             const double oi = __shfl_xor_sync(0xffffffffu, bi, off);

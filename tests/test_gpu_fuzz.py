@@ -103,7 +103,7 @@ def test_fuzz_pseudo_label_filter(seed):
     for it in range(40):
         P = int(rng.integers(1, 257)); M = int(rng.integers(1, 513)); C = int(rng.integers(1, 19))
         bx, pool = synth.pseudo_label_scenes(2, P=P, pool=M, C=C, seed=int(rng.integers(1 << 30)))
-        nms_t = float(rng.choice([0.25, 0.5, 0.7])); match_t = float(rng.choice([0.1, 0.3, 0.6])); size_t = float(rng.choice([0.0, 0.1]))
+        nms_t = float(rng.choice([0.25, 0.5, 0.7])); match_t = float(rng.choice([0.0, 0.1, 0.3, 0.6])); size_t = float(rng.choice([0.0, 0.1]))
         for s in range(2):
             want = oracle.lift_filter_scene(bx[s].numpy(), pool[s].numpy(), nms_t, match_t, size_t)
             got = B3.lift_filter_scene(bx[s].numpy(), pool[s].numpy(), nms_t, match_t, size_t)
