@@ -524,8 +524,11 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
     using A = Ar<double>;
     const int s = blockIdx.x;
     NmsSmem sh = nms_carve(sm, p.Kmax);
-    unsigned int *best = reinterpret_cast<unsigned int *>(sm + nms_smem_bytes(p.Kmax));  // [M] earliest claiming pick
-    int *order = reinterpret_cast<int *>(best + p.M);  // [P] pick order of NMS #1
+    // [M] earliest claiming pick and [P] pick order of NMS #1 live in the sort-key array: it is dead once NMS #1 has sorted
+    // (the pick order is written after that) and NMS #2 only rewrites it after both are consumed.  (M + P) * 4 <= Kp * 8.
+    // Without these 3 KB a third CTA fits per SM at the config-5 shape.
+    unsigned int *best = reinterpret_cast<unsigned int *>(sh.skey);
+    int *order = reinterpret_cast<int *>(best + p.M);
     int nb = p.nboxes ? p.nboxes[s] : p.P;
     nb = nb < 0 ? 0 : (nb > p.P ? p.P : nb);
     int np_ = p.npool ? p.npool[s] : p.M;
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
     const double *pool = p.pool + (size_t)s * p.M * 6;
     double *olab = p.out_label + (size_t)s * p.M, *osc = p.out_score + (size_t)s * p.M;
     for (int k = threadIdx.x; k < p.P; k += blockDim.x) p.nms1_keep[(size_t)s * p.P + k] = 0;
-    for (int j = threadIdx.x; j < p.M; j += blockDim.x) { best[j] = 0xFFFFFFFFu; olab[j] = -100.0; osc[j] = 0.0; p.out_keep[(size_t)s * p.M + j] = 0; }
+    for (int j = threadIdx.x; j < p.M; j += blockDim.x) { olab[j] = -100.0; osc[j] = 0.0; p.out_keep[(size_t)s * p.M + j] = 0; }
     __syncthreads();
     // 1. class-wise NMS (lift_boxes.py:140; volume + 1e-8, box_3d_utils.py:74)
     ArraySrc src{boxes, 8, 3, nb, true};
@@ -545,6 +548,7 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
         for (int pos = threadIdx.x; pos < na; pos += blockDim.x)
             if (sh.picked[pos]) p.nms1_keep[(size_t)s * p.P + sh.sidx[pos]] = 1;
     }
+    for (int j = threadIdx.x; j < p.M; j += blockDim.x) best[j] = 0xFFFFFFFFu;
     __syncthreads();
     // 2. argmax-IoU match to the pool (lift_boxes.py:151-158): one warp per surviving box.  The pool boxes and their
     // volumes are staged once in shared memory (the suppression-word region, idle between the two NMS passes); a pair
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
     // some axis" implies the exact overlap is empty) runs at full fp32 rate, the few survivors go on a per-warp queue in
     // pool order and only they get the fp64 IoU.  A pick with no survivor has IoU 0 everywhere and cannot match.
     const bool prune = pool_staged && p.match_thr > 0.0 &&
-                       (size_t)np_ * 32 + (size_t)(blockDim.x >> 5) * np_ * 2 <= (size_t)(reinterpret_cast<unsigned char *>(sh.sidx) - sm);
+                       (size_t)np_ * 32 + (size_t)(blockDim.x >> 5) * np_ * 2 <= (size_t)(reinterpret_cast<unsigned char *>(sh.skey) - sm);
     float4 *plo = reinterpret_cast<float4 *>(sm);            // [np_] lower bounds rounded down (the NMS tables are idle here)
     float4 *phi = plo + np_;                                 // [np_] upper bounds rounded up
     unsigned short *wq = reinterpret_cast<unsigned short *>(phi + np_) + (size_t)warp * np_;   // this warp's candidate queue
@@ -702,7 +706,7 @@ extern "C" int ovdet_pseudo_filter_f64(const double *boxes, const double *pool, 
     OVDET_REQUIRE(P <= NMS_MAXK && M <= NMS_MAXK, "P and M must be <= 1024");
     PseudoParams p{boxes, pool, nboxes, npool, S, P, M, P > M ? P : M, nms_thr, match_thr, size_nms_thr,
                    nms1_keep, out_label, out_score, out_keep};
-    const size_t smem = nms_smem_bytes(p.Kmax) + sizeof(unsigned int) * (size_t)M + sizeof(int) * (size_t)P;
+    const size_t smem = nms_smem_bytes(p.Kmax);
     OVDET_CUDA_TRY(cudaFuncSetAttribute(pseudo_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pseudo_filter_kernel<<<S, NMS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("pseudo_filter_kernel");
