@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(EV_NT) box3d_iou_kernel(IouParams p)
 //   pass 2  same walk: TP iff this det holds the claim
 // Candidate pairs and their IoUs live in shared memory; the caller's workspace is only touched in the dense fallback.
 constexpr int AM_NT = 128;
-constexpr int AM_CLIP = 32;        // lanes of the dense (serial) clip path
-constexpr int AM_QCAP = 1024;      // candidate pairs held in shared memory (pair index + IoU)
+constexpr int AM_CLIP = 16;        // lanes of the dense (serial) clip path
+constexpr int AM_QCAP = 512;       // candidate pairs held in shared memory (pair index + IoU)
 
 struct __align__(16) AmBox { float qx[4], qz[4]; float ytop, ybot, lox, hix, loz, hiz; double vol; };   // 64 B
 
@@ -206,7 +206,7 @@ struct MatchParams {
 };
 #define AMSTAMP(i) do { if (p.dbg && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[(size_t)blockIdx.x * 8 + (i)] = t_; } } while (0)
 
-__global__ void __launch_bounds__(AM_NT) ap_match_kernel(MatchParams p)
+__global__ void __launch_bounds__(AM_NT, 8) ap_match_kernel(MatchParams p)
 {
     extern __shared__ __align__(16) unsigned char sm[];
     AmBox *dbox = reinterpret_cast<AmBox *>(sm);
