@@ -112,36 +112,47 @@ __global__ void __launch_bounds__(1024) apc_sort_kernel(uint32_t *tp_key, uint8_
 
 // ---- bucket of a record = number of TP-list keys strictly below its key (lower_bound over the sorted TP list).
 // A binary search costs log2(cap) dependent shared loads per record (ncu: 33 short-scoreboard stalls per issue).
-// Instead the score axis is cut into APC_BINS uniform bins; edge[b] = lower_bound(key(b / APC_BINS)) is computed
-// once per class (apc_edges_kernel), and a record of bin b only has to look at entries edge[b+1] .. edge[b] of the
-// list -- on average less than one.  bin() is monotone over all floats (scores <= 0 share bin 0, >= 1 the last).
+// Instead the KEY axis between the smallest and the largest key of the list is cut into <= APC_BINS equal bins
+// (bin = (key - kmin) >> shift; the key is the order-preserving image of the fp32 score, i.e. a piecewise-logarithmic
+// scale, which spreads the skewed score distributions of a detector evenly -- uniform bins in SCORE left ~10 entries
+// per occupied bin); edge[b] = lower_bound(kmin + (b << shift)) is computed once per class (apc_edges_kernel) and a
+// record only searches entries edge[b] .. edge[b+1].
 constexpr int APC_BINS = 4096;
+constexpr int APC_EHDR = 8;                           // u16 slots of the per-class header: kmin (2), shift, nb, ntp
+constexpr int APC_ESTRIDE = APC_BINS + 1 + APC_EHDR;
 
-__device__ __forceinline__ int apc_bin(float s)
-{
-    if (!(s > 0.f)) return 0;
-    if (s >= 1.f) return APC_BINS - 1;
-    return (int)(s * (float)APC_BINS);   // exact: power-of-two scale
-}
-
-// edge[c][b], b = 0..APC_BINS: entries of the sorted list with key < key(b / APC_BINS), i.e. score > b / APC_BINS;
-// edge[0] = number of real entries (everything scores above -inf), edge[APC_BINS] = 0 (nothing scores above +inf)
 __global__ void __launch_bounds__(1024) apc_edges_kernel(const uint32_t *__restrict__ tp_key, int cap, uint16_t *edge)
 {
     extern __shared__ __align__(16) unsigned char sm[];
     uint32_t *k = reinterpret_cast<uint32_t *>(sm);
+    __shared__ uint32_t kmin_s; __shared__ int shift_s, nb_s, ntp_s;
     const int c = blockIdx.x;
     for (int i = threadIdx.x; i < cap; i += 1024) k[i] = tp_key[(size_t)c * cap + i];
     __syncthreads();
-    for (int b = threadIdx.x; b <= APC_BINS; b += 1024) {
-        uint32_t key;
-        if (b == 0) key = 0xFFFFFFFFu;                  // above every real key (empty slots hold 0xFFFFFFFF themselves)
-        else if (b == APC_BINS) key = 0u;
-        else key = apc_score_key((float)b / (float)APC_BINS);
-        int lo = 0, n = cap;
-        while (n > 1) { const int half = n >> 1; lo += (k[lo + half - 1] < key) ? half : 0; n -= half; }
-        lo += (k[lo] < key) ? 1 : 0;
-        edge[(size_t)c * (APC_BINS + 1) + b] = (uint16_t)lo;
+    if (threadIdx.x == 0) {
+        int lo = 0, n = cap;   // number of real entries = first empty (0xFFFFFFFF) slot
+        while (n > 1) { const int half = n >> 1; lo += (k[lo + half - 1] < 0xFFFFFFFFu) ? half : 0; n -= half; }
+        const int ntp = lo + ((k[lo] < 0xFFFFFFFFu) ? 1 : 0);
+        uint32_t kmin = 0; int shift = 0, nb = 0;
+        if (ntp > 0) {
+            kmin = k[0];
+            const uint32_t span = k[ntp - 1] - kmin;
+            while ((span >> shift) >= (uint32_t)APC_BINS) ++shift;
+            nb = (int)(span >> shift) + 1;
+        }
+        kmin_s = kmin; shift_s = shift; nb_s = nb; ntp_s = ntp;
+        uint16_t *hdr = edge + (size_t)c * APC_ESTRIDE;
+        hdr[0] = (uint16_t)(kmin & 0xffffu); hdr[1] = (uint16_t)(kmin >> 16); hdr[2] = (uint16_t)shift; hdr[3] = (uint16_t)nb; hdr[4] = (uint16_t)ntp;
+    }
+    __syncthreads();
+    const int nb = nb_s, ntp = ntp_s, shift = shift_s;
+    const uint32_t kmin = kmin_s;
+    uint16_t *e = edge + (size_t)c * APC_ESTRIDE + APC_EHDR;
+    for (int b = threadIdx.x; b <= nb; b += 1024) {
+        const unsigned long long bound = (unsigned long long)kmin + ((unsigned long long)b << shift);
+        int lo = 0, hi = ntp;   // entries with key < bound
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((unsigned long long)k[mid] < bound) lo = mid + 1; else hi = mid; }
+        e[b] = (uint16_t)lo;
     }
 }
 
@@ -153,23 +164,30 @@ __global__ void __launch_bounds__(APC_NT) apc_hist_kernel(const float *__restric
     uint32_t *h = k + cap;                            // [cap + 1]
     uint16_t *e = reinterpret_cast<uint16_t *>(h + cap + 1);   // [APC_BINS + 1]
     const int c = blockIdx.y;
+    const uint16_t *eg = edge + (size_t)c * APC_ESTRIDE;
+    const uint32_t kmin = (uint32_t)eg[0] | ((uint32_t)eg[1] << 16);
+    const int shift = eg[2], nb = eg[3], ntp = eg[4];
     for (int i = threadIdx.x; i < cap; i += APC_NT) k[i] = tp_key[(size_t)c * cap + i];
     for (int i = threadIdx.x; i <= cap; i += APC_NT) h[i] = 0;
-    for (int i = threadIdx.x; i <= APC_BINS; i += APC_NT) e[i] = edge[(size_t)c * (APC_BINS + 1) + i];
+    for (int i = threadIdx.x; i <= nb; i += APC_NT) e[i] = eg[APC_EHDR + i];
     __syncthreads();
     // Every record scoring below all TPs lands in the one bucket after the last real entry (the bulk of the false
     // positives): count those in a register instead of hammering one shared word.
-    const int ntp = e[0];
+    const uint32_t kmax = ntp > 0 ? k[ntp - 1] : 0u;
     unsigned int tail = 0;
     const float *sc = score + (size_t)c * N;
     auto place = [&](float s) {
         if (!(s > -INFINITY)) return;
         const uint32_t key = apc_score_key(s);
-        const int b = apc_bin(s);
-        int lo = e[b + 1];
-        const int hi = e[b];
-        while (lo < hi && k[lo] < key) ++lo;
-        if (lo >= ntp) ++tail; else atomicAdd(&h[lo], 1u);
+        if (ntp == 0 || key > kmax) { ++tail; return; }
+        int lo = 0;
+        if (key > kmin) {
+            const int b = (int)((key - kmin) >> shift);
+            lo = e[b];
+            int hi = e[b + 1];
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] < key) lo = mid + 1; else hi = mid; }
+        }
+        atomicAdd(&h[lo], 1u);
     };
     // four records per thread and step (one 16-byte load), 32-bit indexing when the class fits
     if (((reinterpret_cast<uintptr_t>(sc) & 15) == 0) && N < 0x7fffffffLL) {
@@ -357,7 +375,7 @@ extern "C" int ovdet_apc_hist(const float *rec_score, int C, int64_t N, const ui
     OVDET_REQUIRE(rec_score, "null pointer");
     // per-class bin edges of the sorted list, in the library's grow-only device scratch
     uint16_t *edge = nullptr;
-    { void *ws = nullptr; int rc = device_scratch().acquire(sizeof(uint16_t) * (size_t)C * (APC_BINS + 1), st, &ws); if (rc) return rc; edge = static_cast<uint16_t *>(ws); }
+    { void *ws = nullptr; int rc = device_scratch().acquire(sizeof(uint16_t) * (size_t)C * APC_ESTRIDE, st, &ws); if (rc) return rc; edge = static_cast<uint16_t *>(ws); }
     OVDET_CUDA_TRY(cudaFuncSetAttribute(apc_edges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * cap)));
     apc_edges_kernel<<<C, 1024, sizeof(uint32_t) * cap, st>>>(tp_key, cap, edge);
     const size_t smem = sizeof(uint32_t) * (2 * (size_t)cap + 1) + sizeof(uint16_t) * (APC_BINS + 2);
