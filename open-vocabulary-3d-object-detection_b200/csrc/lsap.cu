@@ -95,11 +95,23 @@ __global__ void __launch_bounds__(LS_NT) lsap_kernel(LsapParams p)
     const int nr = transposed ? n : p.Q;
     const int nc = transposed ? p.Q : n;
     const int ldc = nc + 1;
-    if (p.stage_cost) {   // coalesced global read, conflict-free (odd stride) shared write
-        for (int idx = tid; idx < p.Q * n; idx += LS_NT) {
-            const int q = idx / n, g = idx - q * n;
-            const float c = __ldg(cb + (size_t)q * p.G + g);
-            if (transposed) sc[g * ldc + q] = c; else sc[q * ldc + g] = c;
+    if (p.stage_cost) {   // coalesced global read (16 bytes per thread when the rows allow it), conflict-free (odd stride) shared write
+        if ((p.G & 3) == 0 && (reinterpret_cast<uintptr_t>(cb) & 15) == 0) {
+            const int n4 = (n + 3) >> 2;
+            for (int idx = tid; idx < p.Q * n4; idx += LS_NT) {
+                const int q = idx / n4, g = (idx - q * n4) << 2;
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(cb + (size_t)q * p.G + g));   // g + 3 < G: columns >= n are just not stored
+                const float c4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (g + t < n) { if (transposed) sc[(g + t) * ldc + q] = c4[t]; else sc[q * ldc + g + t] = c4[t]; }
+            }
+        } else {
+            for (int idx = tid; idx < p.Q * n; idx += LS_NT) {
+                const int q = idx / n, g = idx - q * n;
+                const float c = __ldg(cb + (size_t)q * p.G + g);
+                if (transposed) sc[g * ldc + q] = c; else sc[q * ldc + g] = c;
+            }
         }
     }
     auto C = [&](int i, int j) -> double {
