@@ -410,13 +410,23 @@ __global__ void __launch_bounds__(NT, TQ == 32 ? 2 : 4) giou3d_kernel(GiouParams
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, need);
                 const int n = __popc(m);
-                for (int base = 0; base < n; base += 4) {
-                    const int k = base + (lane >> 3);
+                {   // one round (four pairs) per clip warp under phase A ...
+                    const int k = lane >> 3;
                     const bool act = k < n;
                     const int src = act ? (int)__fns(m, 0, k + 1) : 0;
                     const int sidx = cw + NCW * src;
                     const int r = sidx / clw, c = sidx - r * clw;
                     clip_pair_coop(r, c, act, lane & 7, lane & 24, scratch + (warp * 4 + (lane >> 3)) * 8);
+                }
+                if (n > 4) {   // ... the rest goes on the CTA queue and is drained by all 32 groups in phase B (clip-heavy tiles)
+                    const int rank = __popc(m & ((1u << lane) - 1));
+                    int basepos = 0;
+                    if (lane == 0) basepos = atomicAdd(&qcount, n - 4);
+                    basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                    if (need && rank >= 4) {
+                        const int r = idx / clw, c = idx - r * clw;
+                        queue[basepos + rank - 4] = (unsigned short)(r * TG + c);
+                    }
                 }
             } else {
                 for (int r = warp; r < nq; r += NWARP - NCW) phase_a_row(r);
