@@ -210,6 +210,77 @@ int ovdet_apc_final(const uint8_t *tp_bits, const int32_t *tp_cnt, const uint32_
                     const int64_t *nvalid, int C, int cap, int nthr, int use_07_metric,
                     double *ap, double *recall, int64_t *n_det, int32_t *overflow, void *stream);
 
+/* Fused AP front end: parse_predictions (utils/ap_calculator.py:39-238: argmax class, AABB from corners, NMS variant by
+ * `flags` as in ovdet_parse_predictions_f32, confidence gate) AND the AP matching of ovdet_ap_match
+ * (utils/eval_det.py:117-140) in one pass per scene: corners and class probabilities are read once, the keep mask never
+ * leaves the chip.  OVDET_FRONT_PER_CLASS = the per_class_proposal layout (score = prob*obj for every class,
+ * ap_calculator.py:196-210); without it a detection only appears in its argmax class with score = objectness, or the
+ * class confidence with OVDET_FRONT_CLS_CONF (:212-236).  rec_score [C, S*K] as in ovdet_ap_match; rec_tp may be NULL.
+ * tp_key/tp_bits [C, tp_cap] + tp_cnt i32 [C] (all three or none): every true-positive record is APPENDED as
+ * (descending-score key, threshold bits) -- the caller zeroes tp_cnt once per evaluation and may call this for several
+ * batches; tp_cnt may run past tp_cap (overflow, reported by ovdet_apx_reduce).  npos [C] int64 += GT count.
+ * keep_out [S,K] uint8 optional. */
+#define OVDET_FRONT_PER_CLASS 0x1000u
+#define OVDET_FRONT_CLS_CONF 0x2000u
+#define OVDET_FRONT_GT_PRESENT_F32 0x4000u   /* gt_present is the reference's fp32 mask [S,G] instead of uint8 */
+int ovdet_ap_front_f32(const float *corners, const float *probs, const float *obj, const uint8_t *nonempty,
+                       const float *gt_corners, const int64_t *gt_labels, const void *gt_present,
+                       int S, int K, int G, int C, double nms_iou, float conf_thresh, unsigned flags,
+                       const double *thr, int nthr, double *iou_ws, float *rec_score, uint8_t *rec_tp, int64_t *npos,
+                       uint32_t *tp_key, uint8_t *tp_bits, int32_t *tp_cnt, int tp_cap, uint8_t *keep_out, void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* Scene-sharded AP reduction with a device-side exchange (the one exchange step of the path;        */
+/* replaces the reference's all-gather of every output and input tensor, engine.py:207-209 via utils/dist.py:159-176).   */
+/* ------------------------------------------------------------------------- */
+/* Symmetric buffers: one allocation per rank, mapped into every peer process (CUDA IPC), so that kernels exchange the
+ * per-class TP lists and bucket histograms with plain stores over NVLink and flag words -- no collective launch.
+ *   alloc: cudaMalloc + zero fill;  export_handle: 64 opaque bytes to send to the peers (any transport);
+ *   open: map a peer's buffer from its handle (enables peer access);  close / free. */
+#define OVDET_SYMM_HANDLE_BYTES 64
+int ovdet_symm_alloc(size_t bytes, void **dev_ptr);
+int ovdet_symm_free(void *dev_ptr);
+int ovdet_symm_export(void *dev_ptr, void *handle_out);
+int ovdet_symm_open(const void *handle, void **peer_ptr);
+int ovdet_symm_close(void *peer_ptr);
+
+/* Sizes of the two workspaces of ovdet_apx_reduce: `local` (this rank only: merged lists, edges, histogram, counters,
+ * epoch word; zero it once) and `symm` (the symmetric buffer peers write into; zero-filled by ovdet_symm_alloc). */
+size_t ovdet_apx_local_bytes(int C, int cap_total);
+size_t ovdet_apx_symm_bytes(int C, int cap_total, int world);
+
+/* AP / recall of all classes and thresholds from this rank's record blocks and TP lists (ovdet_ap_front_f32; row
+ * stride cap_list), reduced over `world` scene-sharded ranks.  One call enqueues the whole chain on `stream`:
+ *   push    this rank's TP lists (keys, bits, count, npos) into every peer's symmetric buffer, then a flag per class
+ *   merge   per class: wait for the peers' flags, concatenate + bitonic-sort the lists (<= cap_total entries, a power of
+ *           two in [1024, 16384]), bin edges of the sorted list
+ *   hist    one streaming pass over the LOCAL records: bucket = position in the merged list; the last CTA of a class
+ *           pushes the class's partial histogram to every peer, then a flag
+ *   final   per (class, threshold): wait for the peers' histograms, sum them, prefix sums -> positions, precision
+ *           envelope, VOC AP (utils/eval_det.py:23-54, :143-153)
+ * blocks/block_n: host arrays of nblocks device pointers to rec_score blocks [C, block_n[i]] fp32.
+ * peers: host array of `world` device pointers = every rank's symmetric buffer as mapped in THIS process
+ * (peers[rank] = the local one); world == 1 needs neither `peers` nor a symmetric buffer unless OVDET_APX_FORCE_EXCHANGE
+ * asks for the exchange code path (push to self, flags, slot sums) anyway.
+ * result (device, fp64 [2*nthr*C + C + 3]): ap [nthr,C] | recall [nthr,C] | n_det [C] | overflow | max per-rank list
+ * count | largest merged list count; overflow > 0 means a merged list did not fit cap_total (the local lists are intact:
+ * retry with a larger cap_total) or a local list overflowed cap_list; overflow < 0 = a peer's flag never arrived (timeout).
+ * A symmetric buffer sized for a larger cap_total may be used with a smaller one.
+ * result_host: optional pinned host copy target (async D2H on `stream`; the caller synchronises).
+ * Every rank must call this the same number of times (an epoch word in `local` tags the flags). */
+#define OVDET_APX_FORCE_EXCHANGE 0x1u
+#define OVDET_APX_USE_07_METRIC 0x2u
+/* Stage selection (default = all three).  A consumer kernel spins on flags its peers raise, which is only safe when the
+ * peers run on OTHER GPUs (or have already finished): a harness that drives several ranks' buffers on ONE device must
+ * run the stages rank by rank -- all pushes, then all merge+hist, then all finals -- so that no kernel ever waits. */
+#define OVDET_APX_STAGE_PUSH 0x10u
+#define OVDET_APX_STAGE_MERGE_HIST 0x20u
+#define OVDET_APX_STAGE_FINAL 0x40u
+int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_n, int nblocks, int C,
+                     const uint32_t *tp_key, const uint8_t *tp_bits, const int32_t *tp_cnt, const int64_t *npos,
+                     int cap_list, int cap_total, int nthr, unsigned flags, int rank, int world,
+                     void *const *peers, void *local_ws, double *result, double *result_host, void *stream);
+
 /* ------------------------------------------------------------------------- */
 /* Open-vocabulary logits (models/model_3detr.py:237-238, :58-62;              */
 /* utils/ulip_losses.py:39-47): logits = scale * norm?(x) @ norm?(T)^T,        */

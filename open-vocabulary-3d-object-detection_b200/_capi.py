@@ -44,6 +44,15 @@ SIGNATURES = {
     "ovdet_apc_sort": (c_i, [c_p, c_p, c_i, c_i, c_p]),
     "ovdet_apc_hist": (c_i, [c_p, c_i, c_i64, c_p, c_i, c_p, c_p]),
     "ovdet_apc_final": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "ovdet_ap_front_f32": (c_i, [c_p] * 7 + [c_i] * 4 + [c_d, c_f, c_u, c_p, c_i] + [c_p] * 7 + [c_i, c_p, c_p]),
+    "ovdet_symm_alloc": (c_i, [c_sz, c_p]),
+    "ovdet_symm_free": (c_i, [c_p]),
+    "ovdet_symm_export": (c_i, [c_p, c_p]),
+    "ovdet_symm_open": (c_i, [c_p, c_p]),
+    "ovdet_symm_close": (c_i, [c_p]),
+    "ovdet_apx_local_bytes": (c_sz, [c_i, c_i]),
+    "ovdet_apx_symm_bytes": (c_sz, [c_i, c_i, c_i]),
+    "ovdet_apx_reduce": (c_i, [c_p, c_p, c_i, c_i] + [c_p] * 4 + [c_i, c_i, c_i, c_u, c_i, c_i] + [c_p] * 5),
     "ovdet_points_in_boxes_count": (c_i, [c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_p]),
     "ovdet_box_label_mode": (c_i, [c_p, c_p, c_i, c_p, c_i, c_i, c_d, c_p, c_p, c_p]),
     "ovdet_clip_logits_bf16": (c_i, [c_p, c_p, c_i, c_i, c_i, c_u, c_f, c_p, c_i, c_p, c_i, c_p, c_p]),
@@ -54,6 +63,10 @@ SIGNATURES = {
 GIOU_ROTATED, GIOU_PREFILTER, GIOU_INTER_ONLY, GIOU_CLIP_F64, GIOU_ENCL_HULL = 1, 2, 4, 8, 16
 NMS_2D, NMS_SAMECLS, NMS_OLD_TYPE, PARSE_NO_NMS = 1, 2, 4, 0x100
 LOGITS_L2NORM = 1
+FRONT_PER_CLASS, FRONT_CLS_CONF, FRONT_GT_PRESENT_F32 = 0x1000, 0x2000, 0x4000
+APX_FORCE_EXCHANGE, APX_USE_07_METRIC = 1, 2
+APX_STAGE_PUSH, APX_STAGE_MERGE_HIST, APX_STAGE_FINAL = 0x10, 0x20, 0x40
+SYMM_HANDLE_BYTES = 64
 
 _LIB = None
 
@@ -96,6 +109,30 @@ def ptr(t):
 
 def stream(device=None):
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def as_input(t, dtype, device):
+    """`t` as a contiguous, detached tensor of `dtype` on `device` -- the tensor itself when it already is one (the
+    usual case on the hot path: no torch op, no allocation)."""
+    if t.dtype is dtype and t.device == device and t.is_contiguous() and not t.requires_grad:
+        return t
+    return t.detach().to(device=device, dtype=dtype).contiguous()
+
+
+class on_device(object):
+    """``with on_device(dev):`` = torch.cuda.device(dev), skipped when `dev` is already current (saves ~10 us per call)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if device.index is None or torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*a)
 
 
 def require_cuda(*tensors):

@@ -410,3 +410,565 @@ extern "C" int ovdet_apc_final(const uint8_t *tp_bits, const int32_t *tp_cnt, co
     apc_final_kernel<<<dim3(C, nthr), 1024, smem, st>>>(p);
     return launch_ok("apc_final_kernel");
 }
+
+// =====================================================================================================================
+// Scene-sharded reduction with a device-side exchange (ovdet_apx_reduce): the same four stages, but
+//   * the TP lists come straight from the fused front end (ovdet_ap_front_f32), no collect pass;
+//   * ranks exchange by STORING into each other's symmetric buffer over NVLink (CUDA IPC mapping) and raising a flag
+//     word per (source rank, class) -- consumers spin on the flags of the class they own, so there is no collective
+//     launch, no host round trip, and class c of rank r can start as soon as ITS inputs have landed;
+//   * the two halves of the symmetric buffer alternate by evaluation (epoch parity), so a fast rank can never overwrite
+//     what a slow rank is still reading.
+// =====================================================================================================================
+namespace ovdet {
+
+constexpr int APX_MAXW = 16;
+
+struct ApxLayout {          // byte offsets inside one parity half of a symmetric buffer
+    size_t half, flags_l, flags_h, lists, list_stride, l_cnt, l_npos, l_key, l_bits, hist, hist_stride;
+    int hp;                 // u32 pitch of a histogram row (cap_total + 1 rounded up to 4)
+};
+static inline size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
+static ApxLayout apx_layout(int C, int cap, int W)
+{
+    ApxLayout L;
+    L.hp = (cap + 1 + 3) & ~3;
+    size_t o = 0;
+    L.flags_l = o; o += a16(sizeof(uint32_t) * (size_t)W * C);
+    L.flags_h = o; o += a16(sizeof(uint32_t) * (size_t)W * C);
+    size_t s = 0;
+    L.l_cnt = s; s += a16(sizeof(int32_t) * (size_t)C);
+    L.l_npos = s; s += a16(sizeof(int64_t) * (size_t)C);
+    L.l_key = s; s += a16(sizeof(uint32_t) * (size_t)C * cap);
+    L.l_bits = s; s += a16((size_t)C * cap);
+    L.list_stride = s;
+    L.lists = o; o += s * W;
+    L.hist_stride = a16(sizeof(uint32_t) * (size_t)C * L.hp);
+    L.hist = o; o += L.hist_stride * W;
+    L.half = (o + 255) & ~(size_t)255;
+    return L;
+}
+
+struct ApxLocal {           // byte offsets inside the rank-local workspace
+    size_t ctrl, done_hist, mcnt, npos_g, mkey, mbits, edge, hist, total;
+};
+// ctrl words: [0] epoch, [1] done_final, [2] overflow, [3] max per-rank count, [4] max merged count, [5] timeout
+static ApxLocal apx_local(int C, int cap)
+{
+    ApxLocal L;
+    const int hp = (cap + 1 + 3) & ~3;
+    size_t o = 0;
+    L.ctrl = o; o += 64;
+    L.done_hist = o; o += a16(sizeof(uint32_t) * (size_t)C);
+    L.mcnt = o; o += a16(sizeof(int32_t) * (size_t)C);
+    L.npos_g = o; o += a16(sizeof(int64_t) * (size_t)C);
+    L.mkey = o; o += a16(sizeof(uint32_t) * (size_t)C * cap);
+    L.mbits = o; o += a16((size_t)C * cap);
+    L.edge = o; o += a16(sizeof(uint16_t) * (size_t)C * APC_ESTRIDE);
+    L.hist = o; o += a16(sizeof(uint32_t) * (size_t)C * hp);
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin until *flag has reached `tag` (wrap-safe); gives up after ~4 s so that a missing peer cannot hang the GPU
+__device__ __forceinline__ bool wait_flag(const unsigned *flag, unsigned tag)
+{
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (unsigned it = 0;; ++it) {
+        if ((int)(ld_acquire_sys(flag) - tag) >= 0) return true;
+        if ((it & 1023u) == 1023u) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 4000000000ull) return false;
+        }
+    }
+}
+
+struct ApxPeers { unsigned char *base[APX_MAXW]; };
+
+struct ApxParams {
+    ApxPeers peers; ApxLayout sl; ApxLocal ll;
+    unsigned char *local;
+    const uint32_t *tp_key; const uint8_t *tp_bits; const int *tp_cnt; const long long *npos;
+    int C, cap_list, cap, nthr, use07, rank, W, exchange;
+    double *result;
+};
+
+__device__ __forceinline__ unsigned *apx_ctrl(const ApxParams &p) { return reinterpret_cast<unsigned *>(p.local + p.ll.ctrl); }
+
+// ---- stage 1: push this rank's lists to every peer.  grid (W, C)
+__global__ void __launch_bounds__(256) apx_push_lists_kernel(ApxParams p)
+{
+    const int dst = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    const unsigned tag = apx_ctrl(p)[0] + 1u;
+    unsigned char *half = p.peers.base[dst] + (size_t)(tag & 1u) * p.sl.half;
+    unsigned char *slot = half + p.sl.lists + (size_t)p.rank * p.sl.list_stride;
+    const int raw = p.tp_cnt[c];
+    const int n = min(min(raw, p.cap_list), p.cap);
+    const uint4 *ks = reinterpret_cast<const uint4 *>(p.tp_key + (size_t)c * p.cap_list);
+    uint4 *kd = reinterpret_cast<uint4 *>(slot + p.sl.l_key + sizeof(uint32_t) * (size_t)c * p.cap);
+    for (int i = tid; i < (n + 3) / 4; i += 256) kd[i] = ks[i];
+    const uint4 *bs = reinterpret_cast<const uint4 *>(p.tp_bits + (size_t)c * p.cap_list);
+    uint4 *bd = reinterpret_cast<uint4 *>(slot + p.sl.l_bits + (size_t)c * p.cap);
+    for (int i = tid; i < (n + 15) / 16; i += 256) bd[i] = bs[i];
+    if (tid == 0) {
+        reinterpret_cast<int *>(slot + p.sl.l_cnt)[c] = raw;
+        reinterpret_cast<long long *>(slot + p.sl.l_npos)[c] = p.npos[c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_l) + (size_t)p.rank * p.C + c, tag);
+}
+
+// ---- stage 2: per class, gather the W lists, sort, bin edges; zero the class's histogram.  grid C, 1024 threads
+__global__ void __launch_bounds__(1024) apx_merge_kernel(ApxParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint32_t *k = reinterpret_cast<uint32_t *>(sm);
+    uint8_t *b = reinterpret_cast<uint8_t *>(k + p.cap);
+    __shared__ int n_s[APX_MAXW], off_s[APX_MAXW + 1];
+    __shared__ uint32_t kmin_s; __shared__ int shift_s, nb_s, bad_s;
+    const int c = blockIdx.x, tid = threadIdx.x;
+    unsigned *ctrl = apx_ctrl(p);
+    const unsigned tag = ctrl[0] + 1u;
+    const unsigned char *half = p.exchange ? p.peers.base[p.rank] + (size_t)(tag & 1u) * p.sl.half : nullptr;
+    if (tid == 0) bad_s = 0;
+    __syncthreads();
+    if (p.exchange && tid < p.W) {
+        if (!wait_flag(reinterpret_cast<const unsigned *>(half + p.sl.flags_l) + (size_t)tid * p.C + c, tag)) bad_s = 1;
+    }
+    __syncthreads();
+    if (bad_s) { if (tid == 0) atomicExch(&ctrl[5], 1u); }   // carry on with whatever is there: the result is flagged invalid
+    if (tid == 0) {
+        int off = 0, mx = 0, raw_total = 0; long long np = 0;
+        for (int r = 0; r < p.W; ++r) {
+            int raw; long long q;
+            if (p.exchange) {
+                const unsigned char *slot = half + p.sl.lists + (size_t)r * p.sl.list_stride;
+                raw = reinterpret_cast<const int *>(slot + p.sl.l_cnt)[c];
+                q = reinterpret_cast<const long long *>(slot + p.sl.l_npos)[c];
+            } else { raw = p.tp_cnt[c]; q = p.npos[c]; }
+            mx = max(mx, raw); raw_total += raw; np += q;
+            int n = min(raw, min(p.cap_list, p.cap));   // what the producer could ship
+            n = min(n, p.cap - off);                    // what still fits
+            n_s[r] = n; off_s[r] = off; off += n;
+        }
+        off_s[p.W] = off;
+        reinterpret_cast<int *>(p.local + p.ll.mcnt)[c] = off;
+        reinterpret_cast<long long *>(p.local + p.ll.npos_g)[c] = np;
+        if (raw_total > p.cap || mx > p.cap_list) atomicExch(&ctrl[2], 1u);
+        atomicMax(&ctrl[3], (unsigned)mx);
+        atomicMax(&ctrl[4], (unsigned)raw_total);
+    }
+    __syncthreads();
+    const int total = off_s[p.W];
+    int n2 = 64;                                 // >= 64: the warp-local sort steps want whole warps
+    while (n2 < total) n2 <<= 1;                 // <= cap (a power of two >= 1024)
+    for (int r = 0; r < p.W; ++r) {
+        const uint32_t *ksrc; const uint8_t *bsrc;
+        if (p.exchange) {
+            const unsigned char *slot = half + p.sl.lists + (size_t)r * p.sl.list_stride;
+            ksrc = reinterpret_cast<const uint32_t *>(slot + p.sl.l_key) + (size_t)c * p.cap;
+            bsrc = slot + p.sl.l_bits + (size_t)c * p.cap;
+        } else { ksrc = p.tp_key + (size_t)c * p.cap_list; bsrc = p.tp_bits + (size_t)c * p.cap_list; }
+        const int n = n_s[r], o = off_s[r];
+        for (int i = tid; i < n; i += 1024) { k[o + i] = ksrc[i]; b[o + i] = bsrc[i]; }
+    }
+    for (int i = total + tid; i < n2; i += 1024) { k[i] = 0xFFFFFFFFu; b[i] = 0; }
+    __syncthreads();
+    // bitonic sort.  Thread t owns the compare-exchange pairs t, t + 1024, ...; for strides <= 32 the 32 pairs of a warp
+    // stay inside one 64-element chunk, so those steps only need a warp barrier (20 block barriers instead of 66 at 2048)
+    auto cmpx = [&](int t, int size, int stride) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const uint32_t ka = k[lo], kb = k[hi];
+        if (up ? (ka > kb) : (ka < kb)) {
+            k[lo] = kb; k[hi] = ka;
+            const uint8_t ba = b[lo]; b[lo] = b[hi]; b[hi] = ba;
+        }
+    };
+    for (int size = 2; size <= n2; size <<= 1) {
+        int stride = size >> 1;
+        for (; stride > 32; stride >>= 1) {
+            for (int t = tid; t < n2 / 2; t += 1024) cmpx(t, size, stride);
+            __syncthreads();
+        }
+        for (int t = tid; t < n2 / 2; t += 1024) {     // warp-uniform trip count (n2 / 2 is a multiple of 32 or < 32 with one warp)
+            for (int st = stride; st > 0; st >>= 1) { cmpx(t, size, st); __syncwarp(); }
+        }
+        __syncthreads();
+    }
+    uint32_t *mk = reinterpret_cast<uint32_t *>(p.local + p.ll.mkey) + (size_t)c * p.cap;
+    uint8_t *mb = p.local + p.ll.mbits + (size_t)c * p.cap;
+    for (int i = tid; i < p.cap; i += 1024) { mk[i] = i < n2 ? k[i] : 0xFFFFFFFFu; mb[i] = i < n2 ? b[i] : 0; }
+    // bin edges of the sorted list (see apc_edges_kernel)
+    if (tid == 0) {
+        uint32_t kmin = 0; int shift = 0, nb = 0;
+        if (total > 0) {
+            kmin = k[0];
+            const uint32_t span = k[total - 1] - kmin;
+            while ((span >> shift) >= (uint32_t)APC_BINS) ++shift;
+            nb = (int)(span >> shift) + 1;
+        }
+        kmin_s = kmin; shift_s = shift; nb_s = nb;
+        uint16_t *hdr = reinterpret_cast<uint16_t *>(p.local + p.ll.edge) + (size_t)c * APC_ESTRIDE;
+        hdr[0] = (uint16_t)(kmin & 0xffffu); hdr[1] = (uint16_t)(kmin >> 16); hdr[2] = (uint16_t)shift; hdr[3] = (uint16_t)nb; hdr[4] = (uint16_t)total;
+    }
+    __syncthreads();
+    {
+        const int nb = nb_s, shift = shift_s;
+        const uint32_t kmin = kmin_s;
+        uint16_t *e = reinterpret_cast<uint16_t *>(p.local + p.ll.edge) + (size_t)c * APC_ESTRIDE + APC_EHDR;
+        for (int bi = tid; bi <= nb; bi += 1024) {
+            const unsigned long long bound = (unsigned long long)kmin + ((unsigned long long)bi << shift);
+            int lo = 0, hi = total;   // entries with key < bound
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((unsigned long long)k[mid] < bound) lo = mid + 1; else hi = mid; }
+            e[bi] = (uint16_t)lo;
+        }
+    }
+    uint32_t *h = reinterpret_cast<uint32_t *>(p.local + p.ll.hist) + (size_t)c * p.sl.hp;
+    for (int i = tid; i < p.sl.hp; i += 1024) h[i] = 0;
+    if (tid == 0) reinterpret_cast<unsigned *>(p.local + p.ll.done_hist)[c] = 0;
+}
+
+// ---- stage 3: histogram of the local records over the merged list; the last CTA of a class ships the class's row
+__global__ void __launch_bounds__(APC_NT) apx_hist_kernel(ApxParams p, const float *__restrict__ score, long long N, int last_block)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int cap = p.cap;
+    uint32_t *k = reinterpret_cast<uint32_t *>(sm);   // [cap]
+    uint32_t *h = k + cap;                            // [cap + 1]
+    uint16_t *e = reinterpret_cast<uint16_t *>(h + cap + 1);   // [APC_BINS + 1]
+    __shared__ int last_s;
+    const int c = blockIdx.y;
+    const uint16_t *eg = reinterpret_cast<const uint16_t *>(p.local + p.ll.edge) + (size_t)c * APC_ESTRIDE;
+    const uint32_t *tp_key = reinterpret_cast<const uint32_t *>(p.local + p.ll.mkey);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(p.local + p.ll.hist) + (size_t)c * p.sl.hp;
+    const uint32_t kmin = (uint32_t)eg[0] | ((uint32_t)eg[1] << 16);
+    const int shift = eg[2], nb = eg[3], ntp = eg[4];
+    for (int i = threadIdx.x; i < ntp; i += APC_NT) k[i] = tp_key[(size_t)c * cap + i];
+    for (int i = threadIdx.x; i <= ntp; i += APC_NT) h[i] = 0;
+    for (int i = threadIdx.x; i <= nb; i += APC_NT) e[i] = eg[APC_EHDR + i];
+    __syncthreads();
+    const uint32_t kmax = ntp > 0 ? k[ntp - 1] : 0u;
+    unsigned int tail = 0;
+    const float *sc = score + (size_t)c * N;
+    // four records at a time, in lock step: bin look-up, then (rarely more than one) forward steps inside the bin's
+    // one- or two-entry range -- no per-record loop for the lanes of a warp to diverge on
+    auto place4 = [&](const float (&sv)[4]) {
+        uint32_t key[4]; int lo[4], hi[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool valid = sv[q] > -INFINITY;
+            key[q] = apc_score_key(sv[q]);
+            const bool below = valid && (ntp == 0 || key[q] > kmax);
+            tail += below ? 1u : 0u;
+            lo[q] = 0; hi[q] = -1;                       // hi < 0: nothing to count
+            if (valid && !below) {
+                hi[q] = 0;
+                if (key[q] > kmin) { const int bi = (int)((key[q] - kmin) >> shift); lo[q] = e[bi]; hi[q] = e[bi + 1]; }
+            }
+        }
+#pragma unroll
+        for (int st = 0; st < 2; ++st)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (lo[q] < hi[q] && k[lo[q]] < key[q]) ++lo[q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            while (lo[q] < hi[q] && k[lo[q]] < key[q]) ++lo[q];     // crowded bin: finish the scan
+            if (hi[q] >= 0) atomicAdd(&h[lo[q]], 1u);
+        }
+    };
+    auto place = [&](float s) { const float sv[4] = {s, -INFINITY, -INFINITY, -INFINITY}; place4(sv); };
+    if (((reinterpret_cast<uintptr_t>(sc) & 15) == 0) && N < 0x7fffffffLL) {
+        const int n4 = (int)(N >> 2);
+        const int step = (int)(gridDim.x * APC_NT);
+        for (int i = (int)(blockIdx.x * APC_NT + threadIdx.x); i < n4; i += step) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(sc) + i);
+            const float sv[4] = {v.x, v.y, v.z, v.w};
+            place4(sv);
+        }
+        for (long long i = ((long long)n4 << 2) + (long long)blockIdx.x * APC_NT + threadIdx.x; i < N; i += (long long)gridDim.x * APC_NT) place(sc[i]);
+    } else {
+        for (long long i = (long long)blockIdx.x * APC_NT + threadIdx.x; i < N; i += (long long)gridDim.x * APC_NT) place(sc[i]);
+    }
+    for (int off = 16; off > 0; off >>= 1) tail += __shfl_xor_sync(0xffffffffu, tail, off);
+    if ((threadIdx.x & 31) == 0 && tail) atomicAdd(&h[ntp], tail);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= ntp; i += APC_NT) { const uint32_t v = h[i]; if (v) atomicAdd(&hist[i], v); }
+    if (!(p.exchange && last_block)) return;
+    // the last CTA of this class to get here ships the finished row to every peer
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(reinterpret_cast<unsigned *>(p.local + p.ll.done_hist) + c, 1u);
+        last_s = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence();
+    const unsigned tag = apx_ctrl(p)[0] + 1u;
+    const uint4 *src = reinterpret_cast<const uint4 *>(hist);
+    const int n4 = p.sl.hp / 4;
+    for (int r = 0; r < p.W; ++r) {
+        unsigned char *half = p.peers.base[r] + (size_t)(tag & 1u) * p.sl.half;
+        uint4 *dst = reinterpret_cast<uint4 *>(half + p.sl.hist + (size_t)p.rank * p.sl.hist_stride + sizeof(uint32_t) * (size_t)c * p.sl.hp);
+        for (int i = threadIdx.x; i < n4; i += APC_NT) dst[i] = __ldcg(src + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < p.W) {
+        unsigned char *half = p.peers.base[threadIdx.x] + (size_t)(tag & 1u) * p.sl.half;
+        st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_h) + (size_t)p.rank * p.C + c, tag);
+    }
+}
+
+// ---- stage 4: per (class, threshold): sum the W histogram rows, positions, precision envelope, AP.  grid (C, nthr)
+__global__ void __launch_bounds__(1024) apx_final_kernel(ApxParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    unsigned int *H = reinterpret_cast<unsigned int *>(sm);   // [cap] inclusive prefix of hist = 1-based sorted position
+    unsigned int *ctp = H + p.cap;                            // [cap] inclusive count of TP(t) entries
+    __shared__ unsigned int wsum[32], carry_u;
+    __shared__ double wmax[32], red[32], carry_max_s;
+    __shared__ int bad_s, last_s;
+    const int c = blockIdx.x, t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cap = p.cap;
+    unsigned *ctrl = apx_ctrl(p);
+    const unsigned tag = ctrl[0] + 1u;
+    const unsigned char *half = p.exchange ? p.peers.base[p.rank] + (size_t)(tag & 1u) * p.sl.half : nullptr;
+    if (tid == 0) bad_s = 0;
+    __syncthreads();
+    if (p.exchange && tid < p.W) {
+        if (!wait_flag(reinterpret_cast<const unsigned *>(half + p.sl.flags_h) + (size_t)tid * p.C + c, tag)) bad_s = 1;
+    }
+    __syncthreads();
+    if (bad_s && tid == 0) atomicExch(&ctrl[5], 1u);
+    const double npos = (double)reinterpret_cast<const long long *>(p.local + p.ll.npos_g)[c];
+    const int ntp = reinterpret_cast<const int *>(p.local + p.ll.mcnt)[c];
+    const double eps = 2.220446049250313e-16;
+    const uint8_t *bits = p.local + p.ll.mbits + (size_t)c * cap;
+    const uint32_t *hl = reinterpret_cast<const uint32_t *>(p.local + p.ll.hist) + (size_t)c * p.sl.hp;
+    auto hist_at = [&](int i) -> unsigned int {
+        if (!p.exchange) return hl[i];
+        unsigned int v = 0;
+        for (int r = 0; r < p.W; ++r)
+            v += reinterpret_cast<const uint32_t *>(half + p.sl.hist + (size_t)r * p.sl.hist_stride)[(size_t)c * p.sl.hp + i];
+        return v;
+    };
+    // only the first n2 >= ntp entries matter (the rest of the list is padding); chunks of 1024
+    const int nch = max(1, (ntp + 1023) / 1024);
+    const int span = nch * 1024 <= cap ? nch * 1024 : cap;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (tid == 0) carry_u = 0;
+        __syncthreads();
+        for (int base = 0; base < span; base += 1024) {
+            const int i = base + tid;
+            const unsigned int v = pass == 0 ? hist_at(i) : (unsigned int)((bits[i] >> t) & 1u);
+            unsigned int x = v;
+            for (int off = 1; off < 32; off <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+            if (lane == 31) wsum[warp] = x;
+            __syncthreads();
+            if (tid < 32) {
+                unsigned int w = wsum[tid];
+                for (int off = 1; off < 32; off <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, w, off); if (tid >= off) w += y; }
+                wsum[tid] = w;
+            }
+            __syncthreads();
+            const unsigned int incl = carry_u + x + (warp ? wsum[warp - 1] : 0u);
+            (pass == 0 ? H : ctp)[i] = incl;
+            __syncthreads();
+            if (tid == 1023) carry_u = incl;
+            __syncthreads();
+        }
+    }
+    const unsigned int total_tp = ctp[span - 1];
+    // number of present records = all buckets, including the one behind the last list entry
+    unsigned long long nvalid = (unsigned long long)H[span - 1];
+    if (ntp >= span) nvalid += hist_at(ntp);   // ntp == span: the tail bucket sits just past the scanned range
+    if (tid == 0) carry_max_s = 0.0;
+    __syncthreads();
+    double ap_local = 0.0;
+    double p11[11];
+#pragma unroll
+    for (int kk = 0; kk < 11; ++kk) p11[kk] = 0.0;
+    for (int base = span - 1024; base >= 0; base -= 1024) {
+        const int i = base + tid;
+        const bool tp = (bits[i] >> t) & 1u;
+        const double ct = (double)ctp[i];
+        const double prec = tp ? __ddiv_rn(ct, fmax((double)H[i], eps)) : 0.0;   // precision at this TP record
+        const double rec = npos > 0.0 ? __ddiv_rn(ct, npos) : 0.0;
+        double m = prec;
+        for (int off = 1; off < 32; off <<= 1) { const double y = __shfl_down_sync(0xffffffffu, m, off); if (lane + off < 32) m = fmax(m, y); }
+        if (lane == 0) wmax[warp] = m;
+        __syncthreads();
+        if (tid < 32) {
+            double w = wmax[tid];
+            for (int off = 1; off < 32; off <<= 1) { const double y = __shfl_down_sync(0xffffffffu, w, off); if (tid + off < 32) w = fmax(w, y); }
+            wmax[tid] = w;
+        }
+        __syncthreads();
+        const double carry = carry_max_s;
+        double env = fmax(m, carry);
+        if (warp < 31) env = fmax(env, wmax[warp + 1]);
+        if (tp) {
+            const double rec_prev = npos > 0.0 ? __ddiv_rn(ct - 1.0, npos) : 0.0;
+            ap_local += __dmul_rn(__dsub_rn(rec, rec_prev), env);
+            if (p.use07) {
+#pragma unroll
+                for (int kk = 0; kk < 11; ++kk) if (rec >= kk * 0.1) p11[kk] = fmax(p11[kk], prec);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) carry_max_s = fmax(carry, wmax[0]);
+        __syncthreads();
+    }
+    double res;
+    if (!p.use07) {
+        double a = ap_local;
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+        if (lane == 0) red[warp] = a;
+        __syncthreads();
+        if (tid < 32) {
+            double w = red[tid];
+            for (int off = 16; off > 0; off >>= 1) w += __shfl_down_sync(0xffffffffu, w, off);
+            if (tid == 0) red[0] = w;
+        }
+        __syncthreads();
+        res = red[0];
+    } else {
+        res = 0.0;
+        for (int kk = 0; kk < 11; ++kk) {
+            double a = p11[kk];
+            for (int off = 16; off > 0; off >>= 1) a = fmax(a, __shfl_down_sync(0xffffffffu, a, off));
+            __syncthreads();
+            if (lane == 0) red[warp] = a;
+            __syncthreads();
+            if (tid < 32) {
+                double w = red[tid];
+                for (int off = 16; off > 0; off >>= 1) w = fmax(w, __shfl_down_sync(0xffffffffu, w, off));
+                if (tid == 0) red[0] = w;
+            }
+            __syncthreads();
+            res = res + red[0] / 11.0;
+        }
+    }
+    if (tid == 0) {
+        const size_t kx = (size_t)p.nthr * p.C;
+        p.result[(size_t)t * p.C + c] = nvalid > 0 ? res : 0.0;
+        p.result[kx + (size_t)t * p.C + c] = (nvalid > 0 && npos > 0.0) ? __ddiv_rn((double)total_tp, npos) : 0.0;
+        if (t == 0) p.result[2 * kx + c] = (double)nvalid;
+        __threadfence();
+        const unsigned tk = atomicAdd(&ctrl[1], 1u);
+        last_s = (tk == gridDim.x * gridDim.y - 1);
+        if (last_s) {   // everything of this evaluation is done on this rank: publish the status words, advance the epoch
+            __threadfence();
+            const unsigned ovf = atomicExch(&ctrl[2], 0u), mx = atomicExch(&ctrl[3], 0u), mt = atomicExch(&ctrl[4], 0u), to = atomicExch(&ctrl[5], 0u);
+            p.result[2 * kx + p.C] = to ? -1.0 : (double)ovf;
+            p.result[2 * kx + p.C + 1] = (double)mx;
+            p.result[2 * kx + p.C + 2] = (double)mt;
+            ctrl[1] = 0u;
+            __threadfence();
+            ctrl[0] = tag;
+        }
+    }
+}
+
+}  // namespace ovdet
+
+extern "C" size_t ovdet_apx_local_bytes(int C, int cap_total)
+{
+    if (C <= 0 || !apc_cap_ok(cap_total)) return 0;
+    return apx_local(C, cap_total).total;
+}
+
+extern "C" size_t ovdet_apx_symm_bytes(int C, int cap_total, int world)
+{
+    if (C <= 0 || !apc_cap_ok(cap_total) || world < 1 || world > APX_MAXW) return 0;
+    return 2 * apx_layout(C, cap_total, world).half;
+}
+
+extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_n, int nblocks, int C,
+                                const uint32_t *tp_key, const uint8_t *tp_bits, const int32_t *tp_cnt, const int64_t *npos,
+                                int cap_list, int cap_total, int nthr, unsigned flags, int rank, int world,
+                                void *const *peers, void *local_ws, double *result, double *result_host, void *stream)
+{
+    OVDET_REQUIRE(C > 0 && nblocks >= 0 && apc_cap_ok(cap_total) && nthr >= 1 && nthr <= 8, "bad size (cap_total must be a power of two in [1024, 16384])");
+    OVDET_REQUIRE(cap_list >= 16 && cap_list % 16 == 0, "cap_list must be a positive multiple of 16");
+    OVDET_REQUIRE(world >= 1 && world <= APX_MAXW && rank >= 0 && rank < world, "bad rank / world");
+    OVDET_REQUIRE(tp_key && tp_bits && tp_cnt && npos && local_ws && result, "null pointer");
+    OVDET_REQUIRE(nblocks == 0 || (blocks && block_n), "null block table");
+    const bool exchange = world > 1 || (flags & OVDET_APX_FORCE_EXCHANGE);
+    OVDET_REQUIRE(!exchange || peers, "the exchange needs the table of symmetric buffers");
+    ApxParams p;
+    memset(&p, 0, sizeof(p));
+    p.sl = apx_layout(C, cap_total, world);
+    p.ll = apx_local(C, cap_total);
+    if (exchange) for (int r = 0; r < world; ++r) { OVDET_REQUIRE(peers[r], "null symmetric buffer"); p.peers.base[r] = static_cast<unsigned char *>(peers[r]); }
+    p.local = static_cast<unsigned char *>(local_ws);
+    p.tp_key = tp_key; p.tp_bits = tp_bits; p.tp_cnt = tp_cnt; p.npos = reinterpret_cast<const long long *>(npos);
+    p.C = C; p.cap_list = cap_list; p.cap = cap_total; p.nthr = nthr; p.use07 = (flags & OVDET_APX_USE_07_METRIC) ? 1 : 0;
+    p.rank = rank; p.W = world; p.exchange = exchange ? 1 : 0; p.result = result;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned stages = flags & (OVDET_APX_STAGE_PUSH | OVDET_APX_STAGE_MERGE_HIST | OVDET_APX_STAGE_FINAL);
+    if (!stages) stages = OVDET_APX_STAGE_PUSH | OVDET_APX_STAGE_MERGE_HIST | OVDET_APX_STAGE_FINAL;
+    if (exchange && (stages & OVDET_APX_STAGE_PUSH)) {
+        apx_push_lists_kernel<<<dim3(world, C), 256, 0, st>>>(p);
+        { const int rc = launch_ok("apx_push_lists_kernel"); if (rc) return rc; }
+    }
+    if (stages & OVDET_APX_STAGE_MERGE_HIST) {
+        const size_t smem = (size_t)cap_total * 5;
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        apx_merge_kernel<<<C, 1024, smem, st>>>(p);
+        { const int rc = launch_ok("apx_merge_kernel"); if (rc) return rc; }
+    }
+    if (stages & OVDET_APX_STAGE_MERGE_HIST) {
+        const size_t smem = sizeof(uint32_t) * (2 * (size_t)cap_total + 1) + sizeof(uint16_t) * (APC_BINS + 2);
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = (int)(220 * 1024 / (smem + 1024));
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        const int gx_full = (148 * per_sm + C - 1) / C;
+        int launched = 0;
+        for (int b = 0; b < nblocks; ++b) {
+            const long long N = block_n[b];
+            OVDET_REQUIRE(N >= 0, "negative block size");
+            const bool last = (b == nblocks - 1);
+            if (N == 0 && !(exchange && last)) continue;
+            OVDET_REQUIRE(N == 0 || blocks[b], "null record block");
+            // a CTA pays ~3 x cap words of table set-up and flush: give it at least 8192 records when there are few
+            long long gx = (N + 8191) / 8192;
+            if (gx > gx_full) gx = gx_full;
+            if (gx < 1) gx = 1;
+            apx_hist_kernel<<<dim3((unsigned)gx, C), APC_NT, smem, st>>>(p, static_cast<const float *>(blocks[b]), N, last ? 1 : 0);
+            { const int rc = launch_ok("apx_hist_kernel"); if (rc) return rc; }
+            ++launched;
+        }
+        if (exchange && nblocks == 0) {   // nothing local: still ship the (zero) rows so that the peers' final stage can run
+            apx_hist_kernel<<<dim3(1, C), APC_NT, smem, st>>>(p, nullptr, 0, 1);
+            { const int rc = launch_ok("apx_hist_kernel"); if (rc) return rc; }
+        }
+        (void)launched;
+    }
+    if (stages & OVDET_APX_STAGE_FINAL) {
+        const size_t smem = sizeof(unsigned int) * 2 * (size_t)cap_total;
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        apx_final_kernel<<<dim3(C, nthr), 1024, smem, st>>>(p);
+        { const int rc = launch_ok("apx_final_kernel"); if (rc) return rc; }
+    }
+    if (result_host && (stages & OVDET_APX_STAGE_FINAL))
+        OVDET_CUDA_TRY(cudaMemcpyAsync(result_host, result, sizeof(double) * (2 * (size_t)nthr * C + C + 3), cudaMemcpyDeviceToHost, st));
+    return OVDET_OK;
+}

@@ -95,3 +95,50 @@ extern "C" int ovdet_device_count(void)
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
+
+// ---- symmetric buffers (CUDA IPC): one allocation per rank, mapped into every peer process, so that kernels can
+// exchange with plain stores over NVLink (csrc/ap_compact.cu, ovdet_apx_reduce)
+extern "C" int ovdet_symm_alloc(size_t bytes, void **dev_ptr)
+{
+    OVDET_REQUIRE(dev_ptr && bytes > 0, "null pointer / zero size");
+    void *p = nullptr;
+    OVDET_CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(p); return ovdet::cuda_fail(e, "cudaMemset(symmetric buffer)"); }
+    *dev_ptr = p;
+    return OVDET_OK;
+}
+
+extern "C" int ovdet_symm_free(void *dev_ptr)
+{
+    if (dev_ptr) OVDET_CUDA_TRY(cudaFree(dev_ptr));
+    return OVDET_OK;
+}
+
+extern "C" int ovdet_symm_export(void *dev_ptr, void *handle_out)
+{
+    OVDET_REQUIRE(dev_ptr && handle_out, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == OVDET_SYMM_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    OVDET_CUDA_TRY(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle_out, &h, sizeof(h));
+    return OVDET_OK;
+}
+
+extern "C" int ovdet_symm_open(const void *handle, void **peer_ptr)
+{
+    OVDET_REQUIRE(handle && peer_ptr, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    OVDET_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *peer_ptr = p;
+    return OVDET_OK;
+}
+
+extern "C" int ovdet_symm_close(void *peer_ptr)
+{
+    if (peer_ptr) OVDET_CUDA_TRY(cudaIpcCloseMemHandle(peer_ptr));
+    return OVDET_OK;
+}

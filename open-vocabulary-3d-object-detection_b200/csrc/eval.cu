@@ -18,7 +18,7 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "nms_core.cuh"
 
 namespace ovdet {
 
@@ -191,37 +191,66 @@ __device__ __forceinline__ double coop_area_f64(double vx, double vy, int n, int
     return n < 3 ? 0.0 : __dmul_rn(0.5, fabs(__dsub_rn(d1, d2)));
 }
 
-__host__ __device__ inline size_t am_smem_bytes(int K, int G, int nthr)
-{
-    return sizeof(AmBox) * ((size_t)K + G) + sizeof(V2<double>) * 2 * SH_MAXV * AM_CLIP + sizeof(double) * AM_QCAP +
-           sizeof(unsigned long long) * (size_t)G * nthr + sizeof(int) * ((size_t)K + 2 * (size_t)G) + sizeof(unsigned) * AM_QCAP + 64;
+__host__ __device__ inline size_t am_lower_bytes(int K, int G)
+{   // feature records, clip scratch, candidate IoUs: idle while the class-probability tile is in use
+    return sizeof(AmBox) * ((size_t)K + G) + sizeof(V2<double>) * 2 * SH_MAXV * AM_CLIP + sizeof(double) * AM_QCAP;
 }
+__host__ __device__ inline size_t am_upper_bytes(int K, int G, int nthr)
+{   // claim table, compaction tables, candidate queue: live from the first phase on
+    return sizeof(unsigned long long) * (size_t)G * nthr + sizeof(int) * ((size_t)K + 2 * (size_t)G) + (sizeof(unsigned) + sizeof(float)) * AM_QCAP + 64;
+}
+__host__ __device__ inline size_t am_smem_bytes(int K, int G, int nthr) { return am_lower_bytes(K, G) + am_upper_bytes(K, G, nthr); }
 
 struct MatchParams {
     const float *corners, *probs, *obj; const uint8_t *keep; const int32_t *det_cls;
     const float *gt_corners; const int64_t *gt_labels; const uint8_t *gt_present;
+    const float *gt_present_f32;   // the reference's float mask (datasets/*.py) read directly when gt_present is null
     int S, K, G, C, nthr; double thr[8];
     double *iou_ws; float *rec_score; uint8_t *rec_tp; unsigned long long *npos;
+    // optional TP list (csrc/ap_compact.cu): every record with a TP bit is appended as (score key, bits)
+    uint32_t *tp_key; uint8_t *tp_bits; int *tp_cnt; int tp_cap;
     unsigned long long *dbg;   // optional [S][8] globaltimer stamps of thread 0 (OVDET_APMATCH_DBG_PTR; null in production)
 };
 #define AMSTAMP(i) do { if (p.dbg && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[(size_t)blockIdx.x * 8 + (i)] = t_; } } while (0)
 
-__global__ void __launch_bounds__(AM_NT, 8) ap_match_kernel(MatchParams p)
+// One scene's inputs as the matching body sees them (generic pointers: global memory in ap_match_kernel, shared memory
+// for what the fused front end has just computed).
+struct AmScene {
+    const float *probs;        // [K,C] global, or null (single-class layouts)
+    const float *ptile;        // the same tile already staged in shared memory (row pitch ptile_pitch), or null
+    int ptile_pitch;
+    const float *score1;       // [K] objectness (per-class layout: multiplied with the class probability) or the det's score
+    const uint8_t *keep;       // [K]
+    const int32_t *det_cls;    // [K] or null
+};
+
+__device__ __forceinline__ uint32_t score_key(float s)
+{   // ascending key order == descending score; -inf (absent) sorts last
+    const uint32_t b = __float_as_uint(s);
+    const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ~ord;
+}
+
+// sm_lo: am_lower_bytes (aliases the tile the body stages itself; sc.ptile may overlap its tail beyond the feature records --
+// the tile is only read in the record phase, before anything but the feature records is written), sm_hi: am_upper_bytes.
+__device__ __forceinline__ void am_scene_body(const MatchParams &p, const AmScene &sc, unsigned char *sm_lo, unsigned char *sm_hi, const int s)
 {
-    extern __shared__ __align__(16) unsigned char sm[];
-    AmBox *dbox = reinterpret_cast<AmBox *>(sm);
+    AmBox *dbox = reinterpret_cast<AmBox *>(sm_lo);
     AmBox *gbox = dbox + p.K;
     V2<double> *scratch = reinterpret_cast<V2<double> *>(gbox + p.G);
     double *qiou = reinterpret_cast<double *>(scratch + 2 * SH_MAXV * AM_CLIP);   // IoU of the queued (surviving) pairs
-    unsigned long long *best = reinterpret_cast<unsigned long long *>(qiou + AM_QCAP);
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(sm_hi);
     int *kd = reinterpret_cast<int *>(best + (size_t)p.G * p.nthr);
     int *gl = kd + p.K;
     int *glab = gl + p.G;
     unsigned *queue = reinterpret_cast<unsigned *>(glab + p.G);
+    float *qscore = reinterpret_cast<float *>(queue + AM_QCAP);   // score of (det, class of the GT) per candidate: loaded early, used by the claims
     __shared__ int nk_s, ng_s, qn_s;
-    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t N = (size_t)p.S * p.K;
-    const uint8_t *keep = p.keep + (size_t)s * p.K;
+    const uint8_t *keep = sc.keep;
+    const float *corners = p.corners + (size_t)s * p.K * 24;
+    const float *gt_corners = p.gt_corners + (size_t)s * p.G * 24;
     AMSTAMP(0);
 
     // ordered compaction of kept detections (warp 0) / present GT (warp 1), ballot + popc
@@ -239,7 +268,7 @@ __global__ void __launch_bounds__(AM_NT, 8) ap_match_kernel(MatchParams p)
         int n = 0;
         for (int base = 0; base < p.G; base += 32) {
             const int g = base + lane;
-            const bool f = g < p.G && p.gt_present[(size_t)s * p.G + g];
+            const bool f = g < p.G && (p.gt_present ? p.gt_present[(size_t)s * p.G + g] != 0 : p.gt_present_f32[(size_t)s * p.G + g] != 0.f);
             const unsigned m = __ballot_sync(0xffffffffu, f);
             if (f) {
                 const int pos = n + __popc(m & ((1u << lane) - 1));
@@ -257,49 +286,49 @@ __global__ void __launch_bounds__(AM_NT, 8) ap_match_kernel(MatchParams p)
     const int nk = nk_s, ng = ng_s;
     AMSTAMP(1);
 
-    // records: score of every (class, slot), tp = 0.  The scene's [K, C] probability tile is staged through shared
-    // memory (aliasing the feature / clip / candidate areas, idle until then) with independent 16-byte loads, so that no thread walks 20
-    // dependent global loads; the stores are coalesced in k for each class.
+    // records: score of every (class, slot), tp = 0.  The scene's [K, C] probability tile goes through shared memory
+    // (staged here over the idle feature / clip / candidate areas unless the caller already holds it) with independent
+    // 16-byte loads, so that no thread walks C dependent global loads; the stores are coalesced in k for each class.
     {
-        // everything below `best` (feature records, clip scratch, candidate IoUs) is idle until the barrier after this phase
-        float *ptile = reinterpret_cast<float *>(sm);
-        const size_t tile_cap = (size_t)(reinterpret_cast<unsigned char *>(best) - sm) / sizeof(float);
+        const float *ptile = sc.ptile;
+        int pitch = sc.ptile_pitch;
         const size_t kc = (size_t)p.K * p.C;
-        const float *pg = p.probs ? p.probs + (size_t)s * kc : nullptr;
-        const bool staged = pg && kc <= tile_cap;
-        if (staged) {
+        const float *pg = sc.probs;
+        if (pg && !ptile && kc * sizeof(float) <= am_lower_bytes(p.K, p.G)) {
+            float *t = reinterpret_cast<float *>(sm_lo);
             if ((reinterpret_cast<uintptr_t>(pg) & 15) == 0 && (kc & 3) == 0) {
-                for (int i = tid; i < (int)(kc >> 2); i += AM_NT) reinterpret_cast<float4 *>(ptile)[i] = __ldg(reinterpret_cast<const float4 *>(pg) + i);
+                for (int i = tid; i < (int)(kc >> 2); i += AM_NT) reinterpret_cast<float4 *>(t)[i] = __ldg(reinterpret_cast<const float4 *>(pg) + i);
             } else {
-                for (int i = tid; i < (int)kc; i += AM_NT) ptile[i] = __ldg(pg + i);
+                for (int i = tid; i < (int)kc; i += AM_NT) t[i] = __ldg(pg + i);
             }
             __syncthreads();
+            ptile = t; pitch = p.C;
         }
         for (int k = tid; k < p.K; k += AM_NT) {
             const size_t slot = (size_t)s * p.K + k;
             const bool kept = keep[k];
-            const float ob = kept ? __ldg(p.obj + slot) : 0.f;
-            const int dc = (kept && p.det_cls) ? p.det_cls[slot] : -1;
+            const float ob = kept ? sc.score1[k] : 0.f;
+            const int dc = (kept && sc.det_cls) ? sc.det_cls[k] : -1;
             for (int c = 0; c < p.C; ++c) {
-                float sc = -INFINITY;
+                float v = -INFINITY;
                 if (kept) {
-                    if (p.det_cls) { if (dc == c) sc = ob; }
-                    else sc = __fmul_rn(staged ? ptile[(size_t)k * p.C + c] : __ldg(pg + (size_t)k * p.C + c), ob);
+                    if (sc.det_cls) { if (dc == c) v = ob; }
+                    else v = __fmul_rn(ptile ? ptile[(size_t)k * pitch + c] : __ldg(pg + (size_t)k * p.C + c), ob);
                 }
-                p.rec_score[(size_t)c * N + slot] = sc;
-                p.rec_tp[(size_t)c * N + slot] = 0;
+                p.rec_score[(size_t)c * N + slot] = v;
+                if (p.rec_tp) p.rec_tp[(size_t)c * N + slot] = 0;
             }
         }
     }
     AMSTAMP(2);
     if (ng == 0 || nk == 0) return;   // no claims possible (uniform)
-    __syncthreads();                  // the probability tile aliases the feature records written next
+    __syncthreads();                  // a tile staged here aliases the feature records written next
 
     // stage features
     for (int i = tid; i < nk + ng; i += AM_NT) {
         float c[24];
-        if (i < nk) { am_load_box(p.corners + ((size_t)s * p.K + kd[i]) * 24, c); am_features(c, dbox[i]); }
-        else { am_load_box(p.gt_corners + ((size_t)s * p.G + gl[i - nk]) * 24, c); am_features(c, gbox[i - nk]); }
+        if (i < nk) { am_load_box(corners + (size_t)kd[i] * 24, c); am_features(c, dbox[i]); }
+        else { am_load_box(gt_corners + (size_t)gl[i - nk] * 24, c); am_features(c, gbox[i - nk]); }
     }
     double thr_min = p.thr[0];
     for (int t = 1; t < p.nthr; ++t) thr_min = fmin(thr_min, p.thr[t]);
@@ -307,6 +336,20 @@ __global__ void __launch_bounds__(AM_NT, 8) ap_match_kernel(MatchParams p)
     if (tid == 0) { qn_s = 0; }
     __syncthreads();
     AMSTAMP(3);
+
+    // score of (det k, class c) exactly as the record loop wrote it
+    auto det_score = [&](int k, int c) -> float {
+        if (sc.det_cls) return sc.score1[k];
+        return __fmul_rn(__ldg(sc.probs + (size_t)k * p.C + c), sc.score1[k]);   // global: a staged tile is dead by now
+    };
+    auto emit_tp = [&](int k, int c, unsigned char tp, float score) {
+        const size_t slot = (size_t)s * p.K + k;
+        if (p.rec_tp) p.rec_tp[(size_t)c * N + slot] = tp;
+        if (p.tp_key) {
+            const int at = atomicAdd(&p.tp_cnt[c], 1);
+            if (at < p.tp_cap) { p.tp_key[(size_t)c * p.tp_cap + at] = score_key(score); p.tp_bits[(size_t)c * p.tp_cap + at] = tp; }
+        }
+    };
 
     // ---- sparse mode (thr_min >= 0): only pairs whose IoU could exceed the smallest threshold are clipped.
     // Exact rejects: no height overlap or disjoint BEV rectangles (IoU = 0); conservative reject: the IoU is at most
@@ -335,7 +378,12 @@ __global__ void __launch_bounds__(AM_NT, 8) ap_match_kernel(MatchParams p)
                 if (lane == 0) bp = atomicAdd(&qn_s, __popc(m));
                 bp = __shfl_sync(0xffffffffu, bp, 0);
                 const int q = bp + __popc(m & ((1u << lane) - 1));
-                if (need && q < AM_QCAP) { const int i = pi / ng; queue[q] = ((unsigned)i << 16) | (unsigned)(pi - i * ng); }   // K, G <= 32767
+                if (need && q < AM_QCAP) {   // K, G <= 32767
+                    const int i = pi / ng, j = pi - i * ng;
+                    queue[q] = ((unsigned)i << 16) | (unsigned)j;
+                    const int c = glab[j];
+                    qscore[q] = (c >= 0 && c < p.C) ? det_score(kd[i], c) : 0.f;   // the loads fly while the clipper runs
+                }
             }
         }
         __syncthreads();
@@ -389,8 +437,8 @@ __global__ void __launch_bounds__(AM_NT, 8) ap_match_kernel(MatchParams p)
                 const unsigned e = queue[q];
                 const int i = (int)(e >> 16), j = (int)(e & 0xffffu);
                 const int c = glab[j];
-                const size_t slot = (size_t)s * p.K + kd[i];
-                if (c < 0 || c >= p.C || (p.det_cls && p.det_cls[slot] != c)) continue;
+                const int k = kd[i];
+                if (c < 0 || c >= p.C || (sc.det_cls && sc.det_cls[k] != c)) continue;
                 bool first_max = true;   // jmax of (det, class c): first GT of the class attaining the maximum (eval_det.py:121-126)
                 for (int q2 = 0; q2 < qn; ++q2) {
                     const unsigned e2 = queue[q2];
@@ -402,9 +450,8 @@ __global__ void __launch_bounds__(AM_NT, 8) ap_match_kernel(MatchParams p)
                 }
                 if (!first_max) continue;
                 if (pass == 0) {
-                    const float sc = p.det_cls ? __ldg(p.obj + slot) : __fmul_rn(__ldg(p.probs + slot * p.C + c), __ldg(p.obj + slot));
                     // non-negative fp32 scores order like their bit patterns; lower det index wins ties
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(qscore[q]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
                     for (int t = 0; t < p.nthr; ++t)
                         if (v > p.thr[t]) atomicMax(&best[(size_t)j * p.nthr + t], key);
                 } else {
@@ -414,7 +461,7 @@ __global__ void __launch_bounds__(AM_NT, 8) ap_match_kernel(MatchParams p)
                             const unsigned long long w = best[(size_t)j * p.nthr + t];
                             if ((unsigned)(0xFFFFFFFFu - (unsigned)(w & 0xFFFFFFFFull)) == (unsigned)i) tp |= (unsigned char)(1u << t);
                         }
-                    if (tp) p.rec_tp[(size_t)c * N + slot] = tp;
+                    if (tp) emit_tp(k, c, tp, qscore[q]);
                 }
             }
             __syncthreads();
@@ -473,21 +520,20 @@ __global__ void __launch_bounds__(AM_NT, 8) ap_match_kernel(MatchParams p)
     __syncthreads();
     for (int pass = 0; pass < 2; ++pass) {
         for (int i = tid; i < nk; i += AM_NT) {
-            const size_t slot = (size_t)s * p.K + kd[i];
-            const int dc = p.det_cls ? p.det_cls[slot] : -1;
+            const int k = kd[i];
+            const int dc = sc.det_cls ? sc.det_cls[k] : -1;
             const double *row = iou + (size_t)i * ldi;
             for (int j = 0; j < ng; ++j) {
                 const double v = row[j];
                 if (!(v > thr_min)) continue;
                 const int c = glab[j];
-                if (c < 0 || c >= p.C || (p.det_cls && dc != c)) continue;
+                if (c < 0 || c >= p.C || (sc.det_cls && dc != c)) continue;
                 bool first_max = true;
                 for (int j2 = 0; j2 < ng; ++j2)
                     if (glab[j2] == c) { const double v2 = row[j2]; if (v2 > v || (v2 == v && j2 < j)) { first_max = false; break; } }
                 if (!first_max) continue;
                 if (pass == 0) {
-                    const float sc = p.det_cls ? __ldg(p.obj + slot) : __fmul_rn(__ldg(p.probs + slot * p.C + c), __ldg(p.obj + slot));
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(det_score(k, c)) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
                     for (int t = 0; t < p.nthr; ++t)
                         if (v > p.thr[t]) atomicMax(&best[(size_t)j * p.nthr + t], key);
                 } else {
@@ -497,7 +543,7 @@ __global__ void __launch_bounds__(AM_NT, 8) ap_match_kernel(MatchParams p)
                             const unsigned long long w = best[(size_t)j * p.nthr + t];
                             if ((unsigned)(0xFFFFFFFFu - (unsigned)(w & 0xFFFFFFFFull)) == (unsigned)i) tp |= (unsigned char)(1u << t);
                         }
-                    if (tp) p.rec_tp[(size_t)c * N + slot] = tp;
+                    if (tp) emit_tp(k, c, tp, det_score(k, c));
                 }
             }
         }
@@ -506,15 +552,129 @@ __global__ void __launch_bounds__(AM_NT, 8) ap_match_kernel(MatchParams p)
     AMSTAMP(5);
 }
 
+__global__ void __launch_bounds__(AM_NT, 8) ap_match_kernel(MatchParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int s = blockIdx.x;
+    AmScene sc;
+    sc.probs = p.probs ? p.probs + (size_t)s * p.K * p.C : nullptr;
+    sc.ptile = nullptr; sc.ptile_pitch = 0;
+    sc.score1 = p.obj + (size_t)s * p.K;
+    sc.keep = p.keep + (size_t)s * p.K;
+    sc.det_cls = p.det_cls ? p.det_cls + (size_t)s * p.K : nullptr;
+    am_scene_body(p, sc, sm, sm + am_lower_bytes(p.K, p.G), s);
+}
+
+// ---------------------------------------------------------------- fused AP front end
+// parse_predictions (argmax, AABB, NMS variant, confidence gate; utils/ap_calculator.py:39-238) and the AP matching of
+// the same scene (utils/eval_det.py:117-140) in ONE 128-thread CTA: corners and the class-probability tile are read from
+// HBM once, the keep mask / predicted class / class confidence never leave shared memory, no rec_tp stream is written
+// (true positives go straight on the per-class TP lists of the compact reducer).
+//   shared memory: [keep u8 K | cls i32 K | clsp f32 K] [union: NMS tables + probability tile  |  match lower area]
+//                  [match upper area]
+struct FrontParams {
+    MatchParams m;
+    const uint8_t *nonempty; double nms_iou; float conf; unsigned flags;   // parse_predictions' knobs (OVDET_NMS_*, OVDET_PARSE_NO_NMS, OVDET_FRONT_*)
+    uint8_t *keep_out;   // optional [S,K]
+    unsigned long long *dbg;   // optional [S][16] globaltimer stamps (OVDET_APFRONT_DBG_PTR; null in production)
+};
+
+__host__ __device__ inline size_t front_tile_bytes(int K, int C) { return sizeof(float) * (size_t)K * (C + 1); }
+__host__ __device__ inline size_t front_persist_bytes(int K) { return ((size_t)K * 9 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t front_union_bytes(int K, int G, int C, bool tile)
+{
+    const size_t a = nms_smem_bytes(K) + (tile ? front_tile_bytes(K, C) : 0), b = am_lower_bytes(K, G);
+    return ((a > b ? a : b) + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t front_smem_bytes(int K, int G, int C, int nthr, bool tile)
+{
+    return front_persist_bytes(K) + front_union_bytes(K, G, C, tile) + am_upper_bytes(K, G, nthr);
+}
+
+template <bool TILE>
+__global__ void __launch_bounds__(AM_NT, 7) ap_front_kernel(FrontParams fp)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    const MatchParams &p = fp.m;
+    const int s = blockIdx.x, K = p.K, C = p.C, tid = threadIdx.x;
+    int *cls_sm = reinterpret_cast<int *>(sm);
+    float *clsp_sm = reinterpret_cast<float *>(cls_sm + K);
+    uint8_t *keep_sm = reinterpret_cast<uint8_t *>(clsp_sm + K);
+    unsigned char *un = sm + front_persist_bytes(K);
+    unsigned char *hi = un + front_union_bytes(K, p.G, C, TILE);
+    NmsSmem sh = nms_carve(un, K);
+    float *ptile = TILE ? reinterpret_cast<float *>(un + nms_smem_bytes(K)) : nullptr;
+    const int pitch = C + 1;
+    const float *probs = p.probs + (size_t)s * K * C;
+    const float *obj = p.obj + (size_t)s * K;
+    const uint8_t *ne = fp.nonempty ? fp.nonempty + (size_t)s * K : nullptr;
+
+    NSTAMP(fp.dbg, 0);
+    // ---- argmax / max class probability (ap_calculator.py:59-61; np.argmax = first maximum)
+    if (TILE) {
+        const size_t kc = (size_t)K * C;
+        const float inv_c = 1.f / (float)C;
+        auto rowcol = [&](int e, int &r, int &c) {   // e / C without an integer divide (e < 2^21: the float estimate is off by at most one)
+            r = (int)(((float)e + 0.5f) * inv_c);
+            c = e - r * C;
+            if (c < 0) { --r; c += C; } else if (c >= C) { ++r; c -= C; }
+        };
+        if ((reinterpret_cast<uintptr_t>(probs) & 15) == 0 && (kc & 3) == 0) {
+            for (int i = tid; i < (int)(kc >> 2); i += AM_NT) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(probs) + i);
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+                int r, c;
+                rowcol(4 * i, r, c);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { ptile[r * pitch + c] = vv[q]; if (++c == C) { c = 0; ++r; } }
+            }
+        } else {
+            for (int e = tid; e < (int)kc; e += AM_NT) { int r, c; rowcol(e, r, c); ptile[r * pitch + c] = __ldg(probs + e); }
+        }
+        __syncthreads();
+    }
+    NSTAMP(fp.dbg, 1);
+    for (int k = tid; k < K; k += AM_NT) {
+        const float *row = TILE ? ptile + (size_t)k * pitch : nullptr;
+        float best = TILE ? row[0] : __ldg(probs + (size_t)k * C);
+        int bi = 0;
+        for (int c = 1; c < C; ++c) { const float v = TILE ? row[c] : __ldg(probs + (size_t)k * C + c); if (v > best) { best = v; bi = c; } }
+        cls_sm[k] = bi;
+        clsp_sm[k] = best;
+        keep_sm[k] = 0;
+    }
+    __syncthreads();
+    NSTAMP(fp.dbg, 10);
+    // ---- NMS variant + confidence gate -> keep (ap_calculator.py:86-189, :206-207)
+    if (fp.flags & OVDET_PARSE_NO_NMS) {
+        for (int k = tid; k < K; k += AM_NT) keep_sm[k] = (ne ? (ne[k] != 0) : 1) && (obj[k] > fp.conf);
+    } else {
+        const bool d2 = fp.flags & OVDET_NMS_2D;
+        CornerSrc src{p.corners + (size_t)s * K * 24, obj, ne, cls_sm, d2 ? 1 : 0};
+        nms_core(src, K, d2 ? 2 : 3, (fp.flags & OVDET_NMS_SAMECLS) != 0, (fp.flags & OVDET_NMS_OLD_TYPE) != 0, fp.nms_iou, 0.0, sh, nullptr, fp.dbg);
+        const int na = sh.misc[0];
+        for (int pos = tid; pos < na; pos += AM_NT)
+            if (sh.picked[pos]) { const int k = sh.sidx[pos]; keep_sm[k] = obj[k] > fp.conf; }
+    }
+    __syncthreads();
+    NSTAMP(fp.dbg, 11);
+    if (fp.keep_out) for (int k = tid; k < K; k += AM_NT) fp.keep_out[(size_t)s * K + k] = keep_sm[k];
+    // ---- matching on what is now in shared memory
+    AmScene sc;
+    const bool per_class = (fp.flags & OVDET_FRONT_PER_CLASS) != 0;
+    sc.probs = per_class ? probs : nullptr;
+    sc.ptile = (per_class && TILE) ? ptile : nullptr;
+    sc.ptile_pitch = pitch;
+    sc.score1 = (!per_class && (fp.flags & OVDET_FRONT_CLS_CONF)) ? clsp_sm : obj;
+    sc.keep = keep_sm;
+    sc.det_cls = per_class ? nullptr : cls_sm;
+    // the match areas alias the NMS tables (dead now) and grow into the tile behind them only after the record phase,
+    // its last reader
+    am_scene_body(p, sc, un, hi, s);
+}
+
 // ------------------------------------------------- segmented radix sort + AP
 constexpr int RS_NT = 256, RS_IPT = 8, RS_TILE = RS_NT * RS_IPT;
-
-__device__ __forceinline__ uint32_t score_key(float s)
-{   // ascending key order == descending score; -inf (absent) sorts last
-    const uint32_t b = __float_as_uint(s);
-    const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-    return ~ord;
-}
 
 __global__ void __launch_bounds__(RS_NT) rs_prep_kernel(const float *__restrict__ score, const uint8_t *__restrict__ tp,
                                                         uint32_t *keys, uint8_t *vals, unsigned long long *nvalid, long long N)
@@ -778,6 +938,24 @@ extern "C" int ovdet_box3d_iou_f64(const float *dets, const float *gts, const in
     return launch_ok("box3d_iou_kernel");
 }
 
+static int fill_match_params(MatchParams &p, const float *corners, const float *probs, const float *obj, const uint8_t *keep,
+                             const int32_t *det_cls, const float *gt_corners, const int64_t *gt_labels, const uint8_t *gt_present,
+                             int S, int K, int G, int C, const double *thr, int nthr,
+                             double *iou_ws, float *rec_score, uint8_t *rec_tp, int64_t *npos)
+{
+    OVDET_REQUIRE(G == 0 || (gt_corners && gt_labels && gt_present && iou_ws), "null GT pointer");
+    OVDET_REQUIRE(nthr >= 1 && nthr <= 8, "1..8 thresholds");
+    OVDET_REQUIRE(K <= 32767 && G <= 32767, "K, G must fit int16");
+    OVDET_REQUIRE((long long)K * G < 2147483647LL, "K*G too large");
+    p.corners = corners; p.probs = probs; p.obj = obj; p.keep = keep; p.det_cls = det_cls; p.gt_corners = gt_corners;
+    p.gt_labels = gt_labels; p.gt_present = gt_present; p.S = S; p.K = K; p.G = G; p.C = C; p.nthr = nthr;
+    for (int t = 0; t < nthr; ++t) p.thr[t] = thr[t];
+    p.iou_ws = iou_ws; p.rec_score = rec_score; p.rec_tp = rec_tp; p.npos = reinterpret_cast<unsigned long long *>(npos);
+    p.tp_key = nullptr; p.tp_bits = nullptr; p.tp_cnt = nullptr; p.tp_cap = 0; p.gt_present_f32 = nullptr;
+    { const char *e = getenv("OVDET_APMATCH_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
+    return OVDET_OK;
+}
+
 extern "C" int ovdet_ap_match(const float *corners, const float *probs, const float *obj, const uint8_t *keep,
                               const int32_t *det_cls, const float *gt_corners, const int64_t *gt_labels, const uint8_t *gt_present,
                               int S, int K, int G, int C, const double *thr, int nthr,
@@ -787,21 +965,48 @@ extern "C" int ovdet_ap_match(const float *corners, const float *probs, const fl
     if (S == 0) return OVDET_OK;
     OVDET_REQUIRE(corners && obj && keep && rec_score && rec_tp && npos && thr, "null pointer");
     OVDET_REQUIRE(probs || det_cls, "need probs (per-class proposals) or det_cls");
-    OVDET_REQUIRE(G == 0 || (gt_corners && gt_labels && gt_present && iou_ws), "null GT pointer");
-    OVDET_REQUIRE(nthr >= 1 && nthr <= 8, "1..8 thresholds");
-    OVDET_REQUIRE(K <= 32767 && G <= 32767, "K, G must fit int16");
     MatchParams p;
-    p.corners = corners; p.probs = probs; p.obj = obj; p.keep = keep; p.det_cls = det_cls; p.gt_corners = gt_corners;
-    p.gt_labels = gt_labels; p.gt_present = gt_present; p.S = S; p.K = K; p.G = G; p.C = C; p.nthr = nthr;
-    for (int t = 0; t < nthr; ++t) p.thr[t] = thr[t];
-    p.iou_ws = iou_ws; p.rec_score = rec_score; p.rec_tp = rec_tp; p.npos = reinterpret_cast<unsigned long long *>(npos);
-    { const char *e = getenv("OVDET_APMATCH_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
-    OVDET_REQUIRE((long long)K * G < 2147483647LL, "K*G too large");
+    { const int rc = fill_match_params(p, corners, probs, obj, keep, det_cls, gt_corners, gt_labels, gt_present, S, K, G, C, thr, nthr, iou_ws, rec_score, rec_tp, npos); if (rc) return rc; }
     const size_t smem = am_smem_bytes(K, G, nthr);
     OVDET_REQUIRE(smem <= 220 * 1024, "K + G too large for the shared-memory feature records");
     OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ap_match_kernel<<<S, AM_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("ap_match_kernel");
+}
+
+extern "C" int ovdet_ap_front_f32(const float *corners, const float *probs, const float *obj, const uint8_t *nonempty,
+                                  const float *gt_corners, const int64_t *gt_labels, const void *gt_present,
+                                  int S, int K, int G, int C, double nms_iou, float conf_thresh, unsigned flags,
+                                  const double *thr, int nthr, double *iou_ws, float *rec_score, uint8_t *rec_tp, int64_t *npos,
+                                  uint32_t *tp_key, uint8_t *tp_bits, int32_t *tp_cnt, int tp_cap, uint8_t *keep_out, void *stream)
+{
+    OVDET_REQUIRE(S >= 0 && K > 0 && G >= 0 && C > 0, "bad size");
+    if (S == 0) return OVDET_OK;
+    OVDET_REQUIRE(corners && probs && obj && rec_score && npos && thr, "null pointer");
+    OVDET_REQUIRE(K <= NMS_MAXK, "K must be <= 1024");
+    OVDET_REQUIRE((tp_key == nullptr) == (tp_bits == nullptr) && (tp_key == nullptr) == (tp_cnt == nullptr), "tp_key, tp_bits and tp_cnt go together");
+    OVDET_REQUIRE(tp_key == nullptr || tp_cap > 0, "tp_cap must be positive");
+    OVDET_REQUIRE(rec_tp || tp_key, "need rec_tp and/or a TP list to report the true positives");
+    FrontParams fp;
+    { const int rc = fill_match_params(fp.m, corners, probs, obj, nullptr, nullptr, gt_corners, gt_labels, static_cast<const uint8_t *>(gt_present), S, K, G, C, thr, nthr, iou_ws, rec_score, rec_tp, npos); if (rc) return rc; }
+    fp.m.tp_key = tp_key; fp.m.tp_bits = tp_bits; fp.m.tp_cnt = tp_cnt; fp.m.tp_cap = tp_cap;
+    if (flags & OVDET_FRONT_GT_PRESENT_F32) { fp.m.gt_present_f32 = reinterpret_cast<const float *>(gt_present); fp.m.gt_present = nullptr; }
+    fp.nonempty = nonempty; fp.nms_iou = nms_iou; fp.conf = conf_thresh; fp.flags = flags; fp.keep_out = keep_out;
+    { const char *e = getenv("OVDET_APFRONT_DBG_PTR"); fp.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
+    // the probability tile stays in shared memory from the argmax to the record phase (nothing reads it later, so the
+    // matching areas may grow into it) as long as the CTA stays small enough for >= 2 per SM
+    const bool tile = front_smem_bytes(K, G, C, nthr, true) <= 100 * 1024;
+    const size_t smem = front_smem_bytes(K, G, C, nthr, tile);
+    OVDET_REQUIRE(smem <= 220 * 1024, "K + G too large for the shared-memory tables");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (tile) {
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ap_front_kernel<true><<<S, AM_NT, smem, st>>>(fp);
+    } else {
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ap_front_kernel<false><<<S, AM_NT, smem, st>>>(fp);
+    }
+    return launch_ok("ap_front_kernel");
 }
 
 extern "C" size_t ovdet_ap_reduce_ws_bytes(int C, int64_t N)

@@ -39,15 +39,7 @@ def get_ap_config_dict(remove_empty_box=True, use_3d_nms=True, nms_iou=0.25, use
     }
 
 
-def _nms_flags(cfg):
-    if cfg.get("no_nms", False):
-        return C.PARSE_NO_NMS
-    f = C.NMS_OLD_TYPE if cfg["use_old_type_nms"] else 0
-    if not cfg["use_3d_nms"]:
-        return f | C.NMS_2D
-    if cfg["cls_nms"]:
-        f |= C.NMS_SAMECLS
-    return f
+_nms_flags = E.nms_flags
 
 
 def parse_predictions_device(predicted_boxes, sem_cls_probs, objectness_probs, config_dict, nonempty_box_mask=None):
@@ -109,7 +101,13 @@ def parse_predictions(predicted_boxes, sem_cls_probs, objectness_probs, point_cl
 
 
 class APCalculator(object):
-    """Calculating Average Precision (utils/ap_calculator.py:272-450), device-resident."""
+    """Calculating Average Precision (utils/ap_calculator.py:272-450), device-resident.
+
+    ``step`` = one launch of the fused front end (parse_predictions + AP matching) per batch; ``compute_metrics`` = one
+    call of the exchange reducer (merge of the TP lists, one histogram pass over the score records, AP) and a single
+    small device-to-host copy.  With ``distributed=True`` every rank steps over ITS scenes only and the ranks exchange
+    TP lists and bucket histograms through symmetric buffers inside those kernels (``ovdet_apx_reduce``); all ranks get
+    the metrics of all scenes, like ``engine.py:207-209`` where every rank evaluates the gathered world."""
 
     def __init__(self, dataset_config, ap_iou_thresh=[0.25, 0.5], class2type_map=None, exact_eval=True,
                  ap_config_dict=None):
@@ -119,10 +117,18 @@ class APCalculator(object):
         self.ap_config_dict = ap_config_dict
         self.class2type_map = class2type_map
         self.num_semcls = dataset_config.num_semcls if dataset_config is not None else None
-        self.reduce_mode = "compact"   # "sort" forces the segmented radix sort + scan (full PR curves)
-        self.tp_list_cap = 2048        # per-class TP-list capacity of the compact reducer (split across ranks; grows on overflow)
-        self._cap_hint = {}            # world size -> per-rank capacity learned from the previous evaluation
-        self._fmt_keys = {}            # number of classes -> cached metric key strings
+        self.reduce_mode = "compact"    # "sort" forces the segmented radix sort + scan (needs keep_tp_records)
+        self.keep_tp_records = False    # also keep the uint8 tp stream next to the scores (records(), sort mode, PR curves)
+        self.tp_list_cap = 2048         # merged per-class TP-list capacity the reducer starts with (grows on overflow)
+        self.local_list_cap = 16384     # capacity of this rank's own per-class lists
+        self.group = None               # process group of a distributed evaluation (None = the default group)
+        self.force_exchange = False     # run the exchange code path even on one rank (tests)
+        self._fmt_keys = {}             # number of classes -> cached metric key strings
+        self._lists = None
+        self._reducers = {}             # (classes, thresholds, capacity, world) -> ApxReducer
+        self._cap_hint = {}
+        self._iou_ws = None
+        self._thr_np = None
         self.reset()
 
     def make_gt_list(self, gt_box_corners, gt_box_sem_cls_labels, gt_box_present):
@@ -141,22 +147,23 @@ class APCalculator(object):
 
     def step(self, predicted_box_corners, sem_cls_probs, objectness_probs, point_cloud, gt_box_corners,
              gt_box_sem_cls_labels, gt_box_present):
-        """NMS + confidence gate + AP matching of one batch; keeps (score, tp) records only."""
+        """NMS + confidence gate + AP matching of one batch in one kernel; keeps the score records and the TP lists."""
         cfg = self.ap_config_dict
         Cn = self.num_semcls or sem_cls_probs.shape[-1]
+        C.require_cuda(predicted_box_corners)
+        dev = predicted_box_corners.device
+        if self._lists is None or self._lists.C != Cn or self._lists.device != dev or self._lists.cap_list != self.local_list_cap:
+            assert not self._blocks, "the number of classes / device changed in the middle of an evaluation"
+            self._lists = E.TpLists(Cn, dev, self.local_list_cap)
         ne = _nonempty_mask(predicted_box_corners, point_cloud, objectness_probs, cfg)
-        _, keep, cls, clsp = parse_predictions_device(predicted_box_corners, sem_cls_probs, objectness_probs, cfg, ne)
-        if cfg["per_class_proposal"]:
-            assert cfg["use_cls_confidence_only"] is False
-            rs, rt, npos = E.ap_match(predicted_box_corners, sem_cls_probs, objectness_probs, keep, gt_box_corners,
-                                      gt_box_sem_cls_labels, gt_box_present, Cn, self.ap_iou_thresh)
-        else:
-            score = clsp if cfg["use_cls_confidence_only"] else objectness_probs
-            rs, rt, npos = E.ap_match(predicted_box_corners, None, score, keep, gt_box_corners, gt_box_sem_cls_labels,
-                                      gt_box_present, Cn, self.ap_iou_thresh, det_cls=cls)
-        self._scores.append(rs)
-        self._tps.append(rt)
-        self._npos = npos if self._npos is None else self._npos + npos
+        if self._thr_np is None or self._thr_np[0] != tuple(self.ap_iou_thresh):
+            self._thr_np = (tuple(self.ap_iou_thresh), np.ascontiguousarray(np.asarray(self.ap_iou_thresh, np.float64)))
+        rs, rt, self._iou_ws = E.ap_front(predicted_box_corners, sem_cls_probs, objectness_probs, ne, gt_box_corners,
+                                          gt_box_sem_cls_labels, gt_box_present, Cn, self._thr_np[1], cfg, self._lists,
+                                          want_tp_records=self.keep_tp_records, iou_ws=self._iou_ws)
+        self._blocks.append(rs)
+        if rt is not None:
+            self._tps.append(rt)
         self.scan_cnt += predicted_box_corners.shape[0]
 
     def accumulate(self, batch_pred_map_cls, batch_gt_map_cls):
@@ -169,16 +176,30 @@ class APCalculator(object):
             self.scan_cnt += 1
 
     def records(self):
-        """Concatenated class-major records of everything seen by ``step``."""
-        if not self._scores:
+        """Concatenated class-major (score, tp) records of everything seen by ``step`` (needs ``keep_tp_records``)."""
+        if not self._blocks:
             return None
-        if len(self._scores) == 1:     # one batch: no copy of the 5 B/record stream
-            return self._scores[0], self._tps[0], self._npos
-        return torch.cat(self._scores, 1), torch.cat(self._tps, 1), self._npos
+        if len(self._tps) != len(self._blocks):
+            raise C.OvdetError("set keep_tp_records = True before step() to keep the tp record stream "
+                               "(records(), reduce_mode='sort', PR curves)")
+        if len(self._blocks) == 1:     # one batch: no copy of the 5 B/record stream
+            return self._blocks[0], self._tps[0], self._lists.npos.clone()
+        return torch.cat(self._blocks, 1), torch.cat(self._tps, 1), self._lists.npos.clone()
+
+    def _reducer(self, Cn, nthr, cap, world, dev):
+        key = (Cn, nthr, cap, world, bool(self.force_exchange), dev)
+        r = self._reducers.get(key)
+        if r is None:
+            rank = 0
+            if world > 1:
+                import torch.distributed as tdist
+                rank = tdist.get_rank(self.group)
+            r = E.ApxReducer(Cn, nthr, cap, dev, rank=rank, world=world, force_exchange=self.force_exchange, group=self.group)
+            self._reducers[key] = r
+        return r
 
     def compute_metrics(self, distributed=False):
-        """utils/ap_calculator.py:370-395.  ``distributed=True`` (scene-sharded ranks)
-        all-gathers the record lists and all-reduces npos first."""
+        """utils/ap_calculator.py:370-395.  ``distributed=True``: the ranks hold disjoint scenes; the result covers all."""
         nthr = len(self.ap_iou_thresh)
         overall_ret = OrderedDict()
         if self.pred_map_cls:  # host-list path fed through accumulate()
@@ -186,34 +207,35 @@ class APCalculator(object):
                 rec, prec, ap = E.eval_det(self.pred_map_cls, self.gt_map_cls, ovthresh=thr)
                 overall_ret[thr] = self._format(ap, {k: (v[-1] if hasattr(v, "__len__") and len(v) else 0) for k, v in rec.items()})
             return overall_ret
-        recs = self.records()
-        assert recs is not None, "no predictions accumulated"
-        rs, rt, npos = recs
+        assert self._lists is not None, "no predictions accumulated"
+        lists = self._lists
+        Cn, dev = lists.C, lists.device
+        world = 1
+        if distributed:
+            import torch.distributed as tdist
+            world = tdist.get_world_size(self.group)
         ap = None
         if self.reduce_mode == "compact":
-            # no global sort: TP lists + one histogram pass; across ranks only the TP lists and the bucket
-            # histogram travel (KBs) instead of the whole record stream.  Sync-free until the
-            # single D2H of the packed result; an overflowing TP list retries with 4x the capacity.
-            # Capacity of a rank's per-class TP list.  Scene-sharded ranks hold ~1/world of the TPs each, so the default
-            # is split across them (a short merged list keeps the sort / histogram kernels at their single-GPU cost);
-            # the reducer reports the largest count it saw, which sizes the retry after an overflow and the next call.
-            world = 1
-            if distributed:
-                import torch.distributed as tdist
-                world = tdist.get_world_size()
-            cap = self._cap_hint.get(world) or (max(128, self.tp_list_cap // world) if world > 1 else self.tp_list_cap)
-            while ap is None:
-                res = E.ap_reduce_compact(rs, rt, npos, nthr, cap=cap, distributed=distributed)
-                if res is None:
-                    break
-                ap_, recall_, ovf, _, maxcnt = E.unpack_compact(res, nthr, rs.shape[0], with_max=True)
+            # no global sort: merged TP lists + one histogram pass over the local score records; sync-free until the one
+            # D2H of the packed result.  A merged list that does not fit is reported by every rank alike: all retry with
+            # the capacity the kernels measured (new workspaces; collective when distributed).
+            cap = self._cap_hint.get(world) or E._pow2_at_least(self.tp_list_cap)
+            while cap <= E.APC_MAXCAP:
+                red = self._reducer(Cn, nthr, cap, world, dev)
+                red.launch(self._blocks, lists)
+                torch.cuda.current_stream(dev).synchronize()
+                ap_, recall_, _, ovf, max_rank, max_total = red.read()
+                if ovf < 0:
+                    raise C.OvdetError("AP exchange timed out waiting for a peer rank (did every rank call compute_metrics?)")
                 if ovf == 0:
                     ap, recall = ap_, recall_
-                    if maxcnt >= 0 and world > 1:
-                        self._cap_hint[world] = E._pow2_at_least(maxcnt + 1, 128)
-                else:
-                    cap = E._pow2_at_least(maxcnt + 1, 128) if maxcnt > cap else cap * 4
+                    self._cap_hint[world] = cap
+                    break
+                if max_rank > lists.cap_list:
+                    break    # this rank's own lists lost entries: only the record streams can still give the answer
+                cap = max(cap * 2, E._pow2_at_least(max_total))
         if ap is None:   # sort-based path: all-gather the (score, tp) records, segmented radix sort + scan
+            rs, rt, npos = self.records()
             if distributed:
                 from ..dist import gather_records
                 rs, rt, npos = gather_records(rs, rt, npos)
@@ -289,4 +311,12 @@ class APCalculator(object):
         self.gt_map_cls = {}
         self.pred_map_cls = {}
         self.scan_cnt = 0
-        self._scores, self._tps, self._npos = [], [], None
+        self._blocks, self._tps = [], []
+        if self._lists is not None:
+            self._lists.reset()
+
+    def close(self):
+        """Release the exchange workspaces (collective when distributed)."""
+        for r in self._reducers.values():
+            r.close()
+        self._reducers = {}

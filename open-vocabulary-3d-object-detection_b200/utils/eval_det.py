@@ -98,11 +98,13 @@ def ap_reduce_compact(rec_score, rec_tp, npos, nthr, cap=4096, use_07_metric=Fal
     returns one device tensor ``res`` fp64 [2*nthr*C + 1 + C] = ap | recall | overflow flag | n_det, to be read back by
     the caller in a single D2H copy; overflow != 0 means a TP list did not fit and the caller must retry with a
     larger ``cap`` or use the sort-based ap_reduce.  Returns None when world*cap exceeds the shared-memory sort."""
-    import torch.distributed as dist
     C.require_cuda(rec_score)
     dev = rec_score.device
     Cn, N = rec_score.shape
-    world = dist.get_world_size() if distributed else 1
+    world = 1
+    if distributed:
+        import torch.distributed as dist
+        world = dist.get_world_size()
     cap = _pow2_at_least(int(cap), 32 if world > 1 else 1024)
     cap_total = _pow2_at_least(cap * world)
     if cap_total > APC_MAXCAP or (world == 1 and cap < 1024):
@@ -130,48 +132,8 @@ def ap_reduce_compact(rec_score, rec_tp, npos, nthr, cap=4096, use_07_metric=Fal
             C.check(L.ovdet_apc_final(b_p, cnt_p, h_p, npos_p, nv_p, Cn, cap, nthr, int(bool(use_07_metric)), r_p,
                                       r_p + 8 * nthr * Cn, r_p + 16 * nthr * Cn, r_p + 16 * nthr * Cn + 8 * Cn, st))
         return res
-    # ---- several ranks: per-rank TP lists (keys | bits | count) travel in ONE all-gather, the bucket histogram and the
-    # npos / nvalid sums in ONE all-reduce; everything else is local.  `cap` is the per-rank list capacity.
-    row = cap * 5 + 8
-    lists = torch.zeros((Cn, row), dtype=torch.uint8, device=dev)
-    kbuf = torch.empty((Cn, cap), dtype=torch.int32, device=dev)
-    bbuf = torch.empty((Cn, cap), dtype=torch.uint8, device=dev)
-    cnt = torch.empty((Cn,), dtype=torch.int32, device=dev)
-    sums = torch.zeros((2 * Cn,), dtype=torch.int64, device=dev)       # npos | nvalid
-    sums[:Cn] = npos.to(device=dev, dtype=torch.int64)
-    with torch.cuda.device(dev):
-        C.check(L.ovdet_apc_collect(C.ptr(rec_score), C.ptr(rec_tp), Cn, N, cap, C.ptr(kbuf), C.ptr(bbuf), C.ptr(cnt),
-                                    sums[Cn:].data_ptr(), st))
-        lists[:, :cap * 4] = kbuf.view(torch.uint8)
-        lists[:, cap * 4:cap * 5] = bbuf
-        lists[:, cap * 5:cap * 5 + 4] = cnt.view(torch.uint8).reshape(Cn, 4)
-        glists = torch.empty((world * Cn, row), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(glists, lists)
-        g = glists.view(world, Cn, row)
-        gcnt = g[:, :, cap * 5:cap * 5 + 4].contiguous().view(torch.int32)                 # [W, C, 1]
-        key2 = torch.full((Cn, cap_total), -1, dtype=torch.int32, device=dev)            # 0xFFFFFFFF = empty slot
-        bits2 = torch.zeros((Cn, cap_total), dtype=torch.uint8, device=dev)
-        key2[:, :world * cap] = g[:, :, :cap * 4].permute(1, 0, 2).contiguous().view(torch.int32).reshape(Cn, world * cap)
-        bits2[:, :world * cap] = g[:, :, cap * 4:cap * 5].permute(1, 0, 2).reshape(Cn, world * cap)
-        C.check(L.ovdet_apc_sort(C.ptr(key2), C.ptr(bits2), Cn, cap_total, st))
-        hist = torch.empty((Cn, cap_total + 1), dtype=torch.int32, device=dev)
-        C.check(L.ovdet_apc_hist(C.ptr(rec_score), Cn, N, C.ptr(key2), cap_total, C.ptr(hist), st))
-        fused = torch.cat([hist.reshape(-1).to(torch.int64), sums])
-        dist.all_reduce(fused, op=dist.ReduceOp.SUM)
-        hist_g = fused[:Cn * (cap_total + 1)].to(torch.int32)
-        npos_g = fused[Cn * (cap_total + 1):Cn * (cap_total + 1) + Cn].contiguous()
-        nvalid_g = fused[Cn * (cap_total + 1) + Cn:].contiguous()
-        res = torch.empty((2 * nthr * Cn + 2 + Cn,), dtype=torch.float64, device=dev)
-        ndet = torch.empty((Cn,), dtype=torch.int64, device=dev)
-        zero_cnt = torch.zeros((Cn,), dtype=torch.int32, device=dev)   # overflow is judged from the gathered counts
-        C.check(L.ovdet_apc_final(C.ptr(bits2), C.ptr(zero_cnt), C.ptr(hist_g), C.ptr(npos_g), C.ptr(nvalid_g), Cn,
-                                  cap_total, nthr, int(bool(use_07_metric)), res.data_ptr(),
-                                  res.data_ptr() + 8 * nthr * Cn, C.ptr(ndet), None, st))
-        k2 = 2 * nthr * Cn
-        res[k2] = (gcnt > cap).sum().to(torch.float64)
-        res[k2 + 1:k2 + 1 + Cn] = ndet.to(torch.float64)
-        res[k2 + 1 + Cn] = gcnt.max().to(torch.float64)
-    return res
+    raise C.OvdetError("the scene-sharded reduction lives in ApxReducer (ovdet_apx_reduce): device-side exchange over "
+                       "symmetric buffers instead of collectives around this function")
 
 
 def unpack_compact(res, nthr, Cn, with_max=False):
@@ -189,6 +151,140 @@ def unpack_compact(res, nthr, Cn, with_max=False):
     r = res.cpu().numpy()
     out = (r[:k].reshape(nthr, Cn), r[k:2 * k].reshape(nthr, Cn), int(r[2 * k]), r[2 * k + 1:2 * k + 1 + Cn].astype(np.int64))
     return out + (int(r[2 * k + 1 + Cn]),) if with_max else out
+
+
+# ----------------------------------------------------------------------------- fused front end + exchange reducer
+def nms_flags(cfg):
+    """parse_predictions' NMS branch (utils/ap_calculator.py:86-189) as the kernels' flag word."""
+    if cfg.get("no_nms", False):
+        return C.PARSE_NO_NMS
+    f = C.NMS_OLD_TYPE if cfg["use_old_type_nms"] else 0
+    if not cfg["use_3d_nms"]:
+        return f | C.NMS_2D
+    if cfg["cls_nms"]:
+        f |= C.NMS_SAMECLS
+    return f
+
+
+class TpLists(object):
+    """Per-class true-positive lists of one rank (device): (descending-score key, threshold bits) appended by
+    ``ovdet_ap_front_f32``; ``counters`` holds tp_cnt i32 [C] and npos i64 [C] in one buffer (one memset to reset)."""
+
+    def __init__(self, num_classes, device, cap_list=16384):
+        self.C, self.cap_list, self.device = int(num_classes), int(cap_list), device
+        assert self.cap_list % 16 == 0
+        self.tp_key = torch.empty((self.C, self.cap_list), dtype=torch.int32, device=device)
+        self.tp_bits = torch.empty((self.C, self.cap_list), dtype=torch.uint8, device=device)
+        self._cnt_words = (self.C + 1) // 2 * 2                       # npos stays 8-byte aligned behind tp_cnt
+        self.counters = torch.zeros((self._cnt_words + 2 * self.C,), dtype=torch.int32, device=device)
+        self.tp_cnt_ptr = self.counters.data_ptr()
+        self.npos_ptr = self.counters.data_ptr() + 4 * self._cnt_words
+        self.key_ptr, self.bits_ptr = self.tp_key.data_ptr(), self.tp_bits.data_ptr()
+
+    def reset(self):
+        self.counters.zero_()
+
+    @property
+    def tp_cnt(self):
+        return self.counters[:self.C]
+
+    @property
+    def npos(self):
+        return self.counters[self._cnt_words:].view(torch.int64)
+
+
+def ap_front(corners, probs, obj, nonempty, gt_corners, gt_labels, gt_present, num_classes, thresholds, cfg, lists,
+             want_tp_records=False, iou_ws=None, stream=None):
+    """One launch per batch: parse_predictions + AP matching (``ovdet_ap_front_f32``).  Returns the batch's record block
+    ``rec_score`` fp32 [C, S*K] (and ``rec_tp`` uint8 when asked); true positives are appended to ``lists``."""
+    C.require_cuda(corners)
+    dev = corners.device
+    S, K = corners.shape[0], corners.shape[1]
+    G = gt_corners.shape[1]
+    Cn = int(num_classes)
+    corners, probs, obj, gt_corners = (C.as_input(t, torch.float32, dev) for t in (corners, probs, obj, gt_corners))
+    assert probs.shape[-1] == Cn, "sem_cls_probs must have num_semcls columns"
+    gt_labels = C.as_input(gt_labels, torch.int64, dev)
+    flags = nms_flags(cfg)
+    if gt_present.dtype is torch.float32:     # the reference's mask dtype: read as is
+        gt_present = C.as_input(gt_present, torch.float32, dev)
+        flags |= C.FRONT_GT_PRESENT_F32
+    elif gt_present.dtype is torch.uint8:
+        gt_present = C.as_input(gt_present, torch.uint8, dev)
+    else:
+        gt_present = (gt_present.to(dev) != 0).to(torch.uint8).contiguous()
+    ne = None if nonempty is None else (nonempty.to(dev) != 0).to(torch.uint8).contiguous()
+    thr = thresholds if isinstance(thresholds, np.ndarray) and thresholds.dtype == np.float64 else \
+        np.ascontiguousarray(np.asarray(thresholds, np.float64))
+    if cfg["per_class_proposal"]:
+        assert cfg["use_cls_confidence_only"] is False
+        flags |= C.FRONT_PER_CLASS
+    elif cfg["use_cls_confidence_only"]:
+        flags |= C.FRONT_CLS_CONF
+    rec_score = torch.empty((Cn, S * K), dtype=torch.float32, device=dev)
+    rec_tp = torch.empty((Cn, S * K), dtype=torch.uint8, device=dev) if want_tp_records else None
+    if iou_ws is None or iou_ws.numel() < S * K * max(G, 1):
+        iou_ws = torch.empty((S * K * max(G, 1),), dtype=torch.float64, device=dev)   # only touched by the dense fallback
+    with C.on_device(dev):
+        C.check(C.lib().ovdet_ap_front_f32(
+            corners.data_ptr(), probs.data_ptr(), obj.data_ptr(), C.ptr(ne), gt_corners.data_ptr(), gt_labels.data_ptr(),
+            gt_present.data_ptr(), S, K, G, Cn, float(cfg["nms_iou"]), float(cfg["conf_thresh"]), flags, thr.ctypes.data,
+            len(thr), iou_ws.data_ptr(), rec_score.data_ptr(), C.ptr(rec_tp), lists.npos_ptr, lists.key_ptr, lists.bits_ptr,
+            lists.tp_cnt_ptr, lists.cap_list, None, C.stream(dev) if stream is None else stream))
+    return rec_score, rec_tp, iou_ws
+
+
+class ApxReducer(object):
+    """Workspaces of ``ovdet_apx_reduce`` for one (classes, thresholds, merged-list capacity, rank set): the rank-local
+    scratch (with the epoch word) and, when several ranks take part, the symmetric buffer the peers store into.  Creating
+    one with ``world > 1`` is collective (IPC handle exchange)."""
+
+    def __init__(self, num_classes, nthr, cap_total, device, symm=None, rank=0, world=1, force_exchange=False, group=None):
+        from .. import dist as D
+        L = C.lib()
+        self.C, self.nthr, self.cap_total, self.device = int(num_classes), int(nthr), int(cap_total), device
+        self.rank, self.world = int(rank), int(world)
+        self.exchange = self.world > 1 or force_exchange
+        self.local = torch.zeros((L.ovdet_apx_local_bytes(self.C, self.cap_total),), dtype=torch.uint8, device=device)
+        self.symm, self._own_symm = symm, False
+        if self.exchange and self.symm is None:
+            with torch.cuda.device(device):
+                self.symm = D.SymmetricBuffer(L.ovdet_apx_symm_bytes(self.C, self.cap_total, self.world), group=group, device=device)
+            self._own_symm = True
+        self.nres = 2 * self.nthr * self.C + self.C + 3
+        self.result = torch.empty((self.nres,), dtype=torch.float64, device=device)
+        self.result_host = torch.empty((self.nres,), dtype=torch.float64).pin_memory()
+        self._res_np = self.result_host.numpy()
+        self._local_ptr, self._result_ptr, self._result_host_ptr = self.local.data_ptr(), self.result.data_ptr(), self.result_host.data_ptr()
+
+    def close(self):
+        if self._own_symm and self.symm is not None:
+            self.symm.close()
+            self.symm = None
+
+    def launch(self, blocks, lists, use_07_metric=False, stream=None, stages=0):
+        """Enqueue the whole reduction (and the D2H of the packed result) on the current stream; no host sync.
+        ``stages`` (C.APX_STAGE_*) restricts the call to some stages -- only for harnesses that drive several ranks'
+        buffers on one device, where a kernel must never wait for a peer that has not run yet."""
+        import ctypes
+        nb = len(blocks)
+        ptrs = (ctypes.c_void_p * max(nb, 1))(*[b.data_ptr() for b in blocks])
+        sizes = (ctypes.c_int64 * max(nb, 1))(*[b.shape[1] for b in blocks])
+        flags = (C.APX_FORCE_EXCHANGE if (self.exchange and self.world == 1) else 0) | (C.APX_USE_07_METRIC if use_07_metric else 0) | stages
+        with C.on_device(self.device):
+            C.check(C.lib().ovdet_apx_reduce(
+                ptrs, sizes, nb, self.C, lists.key_ptr, lists.bits_ptr, lists.tp_cnt_ptr, lists.npos_ptr,
+                lists.cap_list, self.cap_total, self.nthr, flags, self.rank, self.world,
+                self.symm.peers_array if self.exchange else None, self._local_ptr, self._result_ptr,
+                self._result_host_ptr, C.stream(self.device) if stream is None else stream))
+
+    def read(self):
+        """After a stream synchronise: (ap [nthr,C], recall [nthr,C], n_det [C], overflow, max rank count, max merged count)."""
+        r = self._res_np
+        k = self.nthr * self.C
+        return (r[:k].reshape(self.nthr, self.C).copy(), r[k:2 * k].reshape(self.nthr, self.C).copy(),
+                r[2 * k:2 * k + self.C].astype(np.int64), int(r[2 * k + self.C]), int(r[2 * k + self.C + 1]), int(r[2 * k + self.C + 2]))
+
 
 
 def _pack(pred_all, gt_all):
