@@ -39,6 +39,7 @@ extern "C" {
 int ovdet_version(void);                /* 100*major + minor */
 const char *ovdet_last_error(void);     /* thread-local, never NULL */
 int ovdet_device_count(void);           /* number of visible CUDA devices (0 if none) */
+int ovdet_stream_synchronize(void *stream); /* cudaStreamSynchronize: how a host shim waits for the result of the calls above */
 
 /* ------------------------------------------------------------------------- */
 /* Rotated / axis-aligned 3D GIoU                                             */

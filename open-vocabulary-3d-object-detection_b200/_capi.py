@@ -24,6 +24,7 @@ SIGNATURES = {
     "ovdet_version": (c_i, []),
     "ovdet_last_error": (ctypes.c_char_p, []),
     "ovdet_device_count": (c_i, []),
+    "ovdet_stream_synchronize": (c_i, [c_p]),
     "ovdet_giou3d_f32": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_u, c_p, c_p]),
     "ovdet_box_corners_f32": (c_i, [c_p, c_p, c_p, c_i64, c_p, c_p]),
     "ovdet_giou3d_decode_f32": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_u, c_p, c_p, c_p]),
@@ -108,7 +109,14 @@ def ptr(t):
 
 
 def stream(device=None):
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw handle (int) of torch's current CUDA stream on `device` (a torch.device with an index, or None = current)."""
+    idx = torch.cuda.current_device() if device is None or device.index is None else device.index
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
+def stream_synchronize(device=None):
+    """Block until the current stream of `device` has drained (one cudaStreamSynchronize through the C ABI)."""
+    check(lib().ovdet_stream_synchronize(stream(device)))
 
 
 def as_input(t, dtype, device):

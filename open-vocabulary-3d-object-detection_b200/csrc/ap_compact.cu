@@ -423,6 +423,9 @@ extern "C" int ovdet_apc_final(const uint8_t *tp_bits, const int32_t *tp_cnt, co
 namespace ovdet {
 
 constexpr int APX_MAXW = 16;
+constexpr int APX_BINS = 8192;     // bins of the key axis between the merged list's extremes (u16 entry: first list index | crowded << 15)
+constexpr int APX_EHDR = 4;        // u32 header words per class: kmin, shift, number of bins, list length
+constexpr size_t APX_ESTRIDE_BYTES = sizeof(uint32_t) * APX_EHDR + sizeof(uint16_t) * APX_BINS;
 
 struct ApxLayout {          // byte offsets inside one parity half of a symmetric buffer
     size_t half, flags_l, flags_h, lists, list_stride, l_cnt, l_npos, l_key, l_bits, hist, hist_stride;
@@ -464,7 +467,7 @@ static ApxLocal apx_local(int C, int cap)
     L.npos_g = o; o += a16(sizeof(int64_t) * (size_t)C);
     L.mkey = o; o += a16(sizeof(uint32_t) * (size_t)C * cap);
     L.mbits = o; o += a16((size_t)C * cap);
-    L.edge = o; o += a16(sizeof(uint16_t) * (size_t)C * APC_ESTRIDE);
+    L.edge = o; o += a16((size_t)C * APX_ESTRIDE_BYTES);
     L.hist = o; o += a16(sizeof(uint32_t) * (size_t)C * hp);
     L.total = o;
     return L;
@@ -535,8 +538,7 @@ __global__ void __launch_bounds__(256) apx_push_lists_kernel(ApxParams p)
 __global__ void __launch_bounds__(1024) apx_merge_kernel(ApxParams p)
 {
     extern __shared__ __align__(16) unsigned char sm[];
-    uint32_t *k = reinterpret_cast<uint32_t *>(sm);
-    uint8_t *b = reinterpret_cast<uint8_t *>(k + p.cap);
+    unsigned long long *v = reinterpret_cast<unsigned long long *>(sm);   // (key << 32) | bits: one 8-byte word per entry to compare and swap
     __shared__ int n_s[APX_MAXW], off_s[APX_MAXW + 1];
     __shared__ uint32_t kmin_s; __shared__ int shift_s, nb_s, bad_s;
     const int c = blockIdx.x, tid = threadIdx.x;
@@ -583,9 +585,9 @@ __global__ void __launch_bounds__(1024) apx_merge_kernel(ApxParams p)
             bsrc = slot + p.sl.l_bits + (size_t)c * p.cap;
         } else { ksrc = p.tp_key + (size_t)c * p.cap_list; bsrc = p.tp_bits + (size_t)c * p.cap_list; }
         const int n = n_s[r], o = off_s[r];
-        for (int i = tid; i < n; i += 1024) { k[o + i] = ksrc[i]; b[o + i] = bsrc[i]; }
+        for (int i = tid; i < n; i += 1024) v[o + i] = ((unsigned long long)ksrc[i] << 32) | bsrc[i];
     }
-    for (int i = total + tid; i < n2; i += 1024) { k[i] = 0xFFFFFFFFu; b[i] = 0; }
+    for (int i = total + tid; i < n2; i += 1024) v[i] = 0xFFFFFFFF00000000ull;
     __syncthreads();
     // bitonic sort.  Thread t owns the compare-exchange pairs t, t + 1024, ...; for strides <= 32 the 32 pairs of a warp
     // stay inside one 64-element chunk, so those steps only need a warp barrier (20 block barriers instead of 66 at 2048)
@@ -593,11 +595,8 @@ __global__ void __launch_bounds__(1024) apx_merge_kernel(ApxParams p)
         const int lo = 2 * t - (t & (stride - 1));
         const int hi = lo + stride;
         const bool up = ((lo & size) == 0);
-        const uint32_t ka = k[lo], kb = k[hi];
-        if (up ? (ka > kb) : (ka < kb)) {
-            k[lo] = kb; k[hi] = ka;
-            const uint8_t ba = b[lo]; b[lo] = b[hi]; b[hi] = ba;
-        }
+        const unsigned long long va = v[lo], vb = v[hi];
+        if (up ? (va > vb) : (va < vb)) { v[lo] = vb; v[hi] = va; }
     };
     for (int size = 2; size <= n2; size <<= 1) {
         int stride = size >> 1;
@@ -612,31 +611,40 @@ __global__ void __launch_bounds__(1024) apx_merge_kernel(ApxParams p)
     }
     uint32_t *mk = reinterpret_cast<uint32_t *>(p.local + p.ll.mkey) + (size_t)c * p.cap;
     uint8_t *mb = p.local + p.ll.mbits + (size_t)c * p.cap;
-    for (int i = tid; i < p.cap; i += 1024) { mk[i] = i < n2 ? k[i] : 0xFFFFFFFFu; mb[i] = i < n2 ? b[i] : 0; }
-    // bin edges of the sorted list (see apc_edges_kernel)
+    for (int i = tid; i < p.cap; i += 1024) { const unsigned long long x = i < n2 ? v[i] : 0xFFFFFFFF00000000ull; mk[i] = (uint32_t)(x >> 32); mb[i] = (uint8_t)x; }
+    // Bin table of the sorted list: the key axis between its extremes is cut into <= APX_BINS equal bins (the key is the
+    // order-preserving image of the fp32 score, i.e. a piecewise-logarithmic scale that spreads a detector's skewed scores
+    // evenly); entry b = index of the first list key >= the bin's lower bound, bit 15 set when the bin holds two or more
+    // list keys.  A record then finds its bucket with one table look-up and one compare (apx_hist_kernel).
+    unsigned char *eb = p.local + p.ll.edge + (size_t)c * APX_ESTRIDE_BYTES;
     if (tid == 0) {
         uint32_t kmin = 0; int shift = 0, nb = 0;
         if (total > 0) {
-            kmin = k[0];
-            const uint32_t span = k[total - 1] - kmin;
-            while ((span >> shift) >= (uint32_t)APC_BINS) ++shift;
+            kmin = (uint32_t)(v[0] >> 32);
+            const uint32_t span = (uint32_t)(v[total - 1] >> 32) - kmin;
+            while ((span >> shift) >= (uint32_t)APX_BINS) ++shift;
             nb = (int)(span >> shift) + 1;
         }
         kmin_s = kmin; shift_s = shift; nb_s = nb;
-        uint16_t *hdr = reinterpret_cast<uint16_t *>(p.local + p.ll.edge) + (size_t)c * APC_ESTRIDE;
-        hdr[0] = (uint16_t)(kmin & 0xffffu); hdr[1] = (uint16_t)(kmin >> 16); hdr[2] = (uint16_t)shift; hdr[3] = (uint16_t)nb; hdr[4] = (uint16_t)total;
+        uint32_t *hdr = reinterpret_cast<uint32_t *>(eb);
+        hdr[0] = kmin; hdr[1] = (uint32_t)shift; hdr[2] = (uint32_t)nb; hdr[3] = (uint32_t)total;
     }
     __syncthreads();
     {
         const int nb = nb_s, shift = shift_s;
         const uint32_t kmin = kmin_s;
-        uint16_t *e = reinterpret_cast<uint16_t *>(p.local + p.ll.edge) + (size_t)c * APC_ESTRIDE + APC_EHDR;
-        for (int bi = tid; bi <= nb; bi += 1024) {
-            const unsigned long long bound = (unsigned long long)kmin + ((unsigned long long)bi << shift);
-            int lo = 0, hi = total;   // entries with key < bound
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((unsigned long long)k[mid] < bound) lo = mid + 1; else hi = mid; }
-            e[bi] = (uint16_t)lo;
+        uint16_t *e = reinterpret_cast<uint16_t *>(eb + sizeof(uint32_t) * APX_EHDR);
+        auto lower = [&](unsigned long long bound) {   // entries with key < bound
+            int lo = 0, hi = total;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((v[mid] >> 32) < bound) lo = mid + 1; else hi = mid; }
+            return lo;
+        };
+        for (int bi = tid; bi < nb; bi += 1024) {
+            const unsigned long long b0 = (unsigned long long)kmin + ((unsigned long long)bi << shift);
+            const int lo = lower(b0), hi = lower(b0 + (1ull << shift));
+            e[bi] = (uint16_t)(lo | (hi - lo >= 2 ? 0x8000 : 0));
         }
+        if (tid == 0 && nb == 0) e[0] = 0;
     }
     uint32_t *h = reinterpret_cast<uint32_t *>(p.local + p.ll.hist) + (size_t)c * p.sl.hp;
     for (int i = tid; i < p.sl.hp; i += 1024) h[i] = 0;
@@ -648,48 +656,52 @@ __global__ void __launch_bounds__(APC_NT) apx_hist_kernel(ApxParams p, const flo
 {
     extern __shared__ __align__(16) unsigned char sm[];
     const int cap = p.cap;
-    uint32_t *k = reinterpret_cast<uint32_t *>(sm);   // [cap]
-    uint32_t *h = k + cap;                            // [cap + 1]
-    uint16_t *e = reinterpret_cast<uint16_t *>(h + cap + 1);   // [APC_BINS + 1]
+    uint32_t *k = reinterpret_cast<uint32_t *>(sm);   // [cap + 1] sorted keys of the merged list + a 0xFFFFFFFF sentinel
+    uint32_t *h = k + cap + 1;                        // [cap + 1] private histogram
+    uint16_t *bins = reinterpret_cast<uint16_t *>(h + cap + 1);   // [APX_BINS] bin -> first list entry | crowded << 15
     __shared__ int last_s;
     const int c = blockIdx.y;
-    const uint16_t *eg = reinterpret_cast<const uint16_t *>(p.local + p.ll.edge) + (size_t)c * APC_ESTRIDE;
+    const unsigned char *eb = p.local + p.ll.edge + (size_t)c * APX_ESTRIDE_BYTES;
+    const uint32_t *hdr = reinterpret_cast<const uint32_t *>(eb);
+    const uint16_t *eg = reinterpret_cast<const uint16_t *>(eb + sizeof(uint32_t) * APX_EHDR);
     const uint32_t *tp_key = reinterpret_cast<const uint32_t *>(p.local + p.ll.mkey);
     uint32_t *hist = reinterpret_cast<uint32_t *>(p.local + p.ll.hist) + (size_t)c * p.sl.hp;
-    const uint32_t kmin = (uint32_t)eg[0] | ((uint32_t)eg[1] << 16);
-    const int shift = eg[2], nb = eg[3], ntp = eg[4];
+    const uint32_t kmin = hdr[0];
+    const int shift = (int)hdr[1], nb = (int)hdr[2], ntp = (int)hdr[3];
     for (int i = threadIdx.x; i < ntp; i += APC_NT) k[i] = tp_key[(size_t)c * cap + i];
+    if (threadIdx.x == 0) k[ntp] = 0xFFFFFFFFu;
     for (int i = threadIdx.x; i <= ntp; i += APC_NT) h[i] = 0;
-    for (int i = threadIdx.x; i <= nb; i += APC_NT) e[i] = eg[APC_EHDR + i];
+    for (int i = threadIdx.x; i < (nb > 0 ? nb : 1); i += APC_NT) bins[i] = eg[i];
     __syncthreads();
-    const uint32_t kmax = ntp > 0 ? k[ntp - 1] : 0u;
+    // Every record scoring below all TPs lands in the one bucket after the last list entry (the bulk of the false
+    // positives): counted in a register instead of hammering one shared word.
+    const uint32_t kmax = ntp > 0 ? k[ntp - 1] : 0u;   // empty list: every valid key (>= 0x00800000) is "below"
+    const uint32_t last_bin = (uint32_t)(nb > 0 ? nb - 1 : 0);
     unsigned int tail = 0;
     const float *sc = score + (size_t)c * N;
-    // four records at a time, in lock step: bin look-up, then (rarely more than one) forward steps inside the bin's
-    // one- or two-entry range -- no per-record loop for the lanes of a warp to diverge on
+    // four records at a time in lock step: bin look-up, one compare against the bin's first list key (the sentinel /
+    // the next bin's key when the bin is empty: no effect), and only for a crowded bin a short forward scan
     auto place4 = [&](const float (&sv)[4]) {
-        uint32_t key[4]; int lo[4], hi[4];
+        uint32_t key[4], ent[4]; int lo[4]; bool cnt[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const bool valid = sv[q] > -INFINITY;
             key[q] = apc_score_key(sv[q]);
-            const bool below = valid && (ntp == 0 || key[q] > kmax);
-            tail += below ? 1u : 0u;
-            lo[q] = 0; hi[q] = -1;                       // hi < 0: nothing to count
-            if (valid && !below) {
-                hi[q] = 0;
-                if (key[q] > kmin) { const int bi = (int)((key[q] - kmin) >> shift); lo[q] = e[bi]; hi[q] = e[bi + 1]; }
-            }
+            const bool valid = sv[q] > -INFINITY, below = key[q] > kmax;
+            tail += (valid && below) ? 1u : 0u;
+            cnt[q] = valid && !below;
+            const uint32_t d = key[q] > kmin ? key[q] - kmin : 0u;
+            ent[q] = bins[min(d >> shift, last_bin)];
         }
 #pragma unroll
-        for (int st = 0; st < 2; ++st)
+        for (int q = 0; q < 4; ++q) { lo[q] = (int)(ent[q] & 0x7fffu); lo[q] += (k[lo[q]] < key[q]) ? 1 : 0; }
+        if (((ent[0] | ent[1] | ent[2] | ent[3]) & 0x8000u) != 0u) {   // some record sits in a crowded bin: finish its scan (the sentinel ends it)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) if (lo[q] < hi[q] && k[lo[q]] < key[q]) ++lo[q];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            while (lo[q] < hi[q] && k[lo[q]] < key[q]) ++lo[q];     // crowded bin: finish the scan
-            if (hi[q] >= 0) atomicAdd(&h[lo[q]], 1u);
+            for (int q = 0; q < 4; ++q)
+                if (ent[q] & 0x8000u) while (k[lo[q]] < key[q]) ++lo[q];
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (cnt[q]) atomicAdd(&h[lo[q]], 1u);
     };
     auto place = [&](float s) { const float sv[4] = {s, -INFINITY, -INFINITY, -INFINITY}; place4(sv); };
     if (((reinterpret_cast<uintptr_t>(sc) & 15) == 0) && N < 0x7fffffffLL) {
@@ -929,13 +941,13 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
         { const int rc = launch_ok("apx_push_lists_kernel"); if (rc) return rc; }
     }
     if (stages & OVDET_APX_STAGE_MERGE_HIST) {
-        const size_t smem = (size_t)cap_total * 5;
+        const size_t smem = (size_t)cap_total * 8;
         OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         apx_merge_kernel<<<C, 1024, smem, st>>>(p);
         { const int rc = launch_ok("apx_merge_kernel"); if (rc) return rc; }
     }
     if (stages & OVDET_APX_STAGE_MERGE_HIST) {
-        const size_t smem = sizeof(uint32_t) * (2 * (size_t)cap_total + 1) + sizeof(uint16_t) * (APC_BINS + 2);
+        const size_t smem = sizeof(uint32_t) * 2 * ((size_t)cap_total + 1) + sizeof(uint16_t) * APX_BINS;
         OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = (int)(220 * 1024 / (smem + 1024));
         if (per_sm > 8) per_sm = 8;

@@ -89,6 +89,11 @@ HostStaging &host_staging()
 
 extern "C" int ovdet_version(void) { return 1; }
 extern "C" const char *ovdet_last_error(void) { return ovdet::g_err; }
+extern "C" int ovdet_stream_synchronize(void *stream)
+{
+    OVDET_CUDA_TRY(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+    return OVDET_OK;
+}
 extern "C" int ovdet_device_count(void)
 {
     int n = 0;

@@ -223,7 +223,7 @@ class APCalculator(object):
             while cap <= E.APC_MAXCAP:
                 red = self._reducer(Cn, nthr, cap, world, dev)
                 red.launch(self._blocks, lists)
-                torch.cuda.current_stream(dev).synchronize()
+                C.stream_synchronize(dev)
                 ap_, recall_, _, ovf, max_rank, max_total = red.read()
                 if ovf < 0:
                     raise C.OvdetError("AP exchange timed out waiting for a peer rank (did every rank call compute_metrics?)")
@@ -256,10 +256,10 @@ class APCalculator(object):
             self._fmt_keys[n] = keys
         ret_dict = OrderedDict(zip(keys[0], ap_row))
         ap_vals = ap_row.astype(np.float32)
-        ap_vals[np.isnan(ap_vals)] = 0
-        ret_dict["mAP"] = ap_vals.mean()
+        ap_vals[ap_vals != ap_vals] = 0                      # NaN -> 0
+        ret_dict["mAP"] = np.add.reduce(ap_vals) / n         # == ap_vals.mean() (float32 pairwise sum / count) without _mean's Python
         ret_dict.update(zip(keys[1], rec_row))
-        ret_dict["AR"] = np.mean(rec_row)
+        ret_dict["AR"] = np.add.reduce(rec_row) / n          # == np.mean(rec_row)
         return ret_dict
 
     def _format(self, ap, last_rec):

@@ -1,4 +1,4 @@
-"""Per-CTA phase times of ap_front_kernel from globaltimer stamps (OVDET_APFRONT_DBG_PTR / OVDET_APMATCH_DBG_PTR)."""
+"""Per-CTA phase times of ap_front2_kernel from globaltimer stamps (OVDET_APFRONT_DBG_PTR)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -14,19 +14,14 @@ lists = ED.TpLists(20, dev)
 f = lambda: ED.ap_front(dv["box_corners"], dv["sem_cls_prob"], dv["objectness_prob"], None, dv["gt_box_corners"], dv["gt_box_sem_cls_label"], dv["gt_box_present"], 20, [0.25, 0.5], cfg, lists)
 f(); torch.cuda.synchronize()
 d1 = torch.zeros((S, 16), dtype=torch.int64, device=dev)
-d2 = torch.zeros((S, 8), dtype=torch.int64, device=dev)
-os.environ["OVDET_APFRONT_DBG_PTR"] = str(d1.data_ptr()); os.environ["OVDET_APMATCH_DBG_PTR"] = str(d2.data_ptr())
+os.environ["OVDET_APFRONT_DBG_PTR"] = str(d1.data_ptr())
 f(); torch.cuda.synchronize()
-a, b = d1.cpu().numpy().astype(np.float64), d2.cpu().numpy().astype(np.float64)
+a = d1.cpu().numpy().astype(np.float64)
 t0 = a[:, 0]
-names1 = [(1, "tile"), (10, "argmax"), (2, "nms:init"), (3, "nms:gather"), (4, "nms:group+rank"), (8, "nms:words"), (9, "nms:pick1"), (5, "nms:pick2"), (11, "keep")]
 prev = t0
-for i, nm in names1:
-    print("%-16s %7.2f us" % (nm, np.median(a[:, i] - prev) / 1e3)); prev = a[:, i]
-names2 = [(0, "match:start"), (1, "compact"), (2, "records"), (3, "features"), (4, "cands+clip"), (5, "claims")]
-for i, nm in names2:
-    ok = b[:, i] > 0
-    print("%-16s %7.2f us" % (nm, np.median((b[:, i] - prev)[ok]) / 1e3)); prev = np.where(ok, b[:, i], prev)
+for i, nm in [(7, "init+box"), (8, "probs+records"), (9, "GT"), (1, "barrier B1"), (10, "nms pairs"), (11, "nms rounds"), (2, "fixup"), (3, "enumerate"), (4, "clip"), (5, "claims")]:
+    ok = a[:, i] > 0
+    print("%-12s %7.2f us" % (nm, np.median((a[:, i] - prev)[ok]) / 1e3)); prev = np.where(ok, a[:, i], prev)
 print("CTA life median %.2f us, p95 %.2f; kernel span %.1f us" % (np.median(prev - t0) / 1e3, np.percentile(prev - t0, 95) / 1e3, (prev.max() - t0.min()) / 1e3))
-qn = (d2.cpu().numpy()[:, 6] & 0xffff)
+qn = d1.cpu().numpy()[:, 6]
 print("candidates per scene: mean %.1f max %d" % (qn.mean(), qn.max()))
