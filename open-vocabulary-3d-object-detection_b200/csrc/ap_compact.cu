@@ -652,10 +652,11 @@ __global__ void __launch_bounds__(1024) apx_merge_kernel(ApxParams p)
 }
 
 // ---- stage 3: histogram of the local records over the merged list; the last CTA of a class ships the class's row
-__global__ void __launch_bounds__(APC_NT) apx_hist_kernel(ApxParams p, const float *__restrict__ score, long long N, int last_block)
+__global__ void __launch_bounds__(1024) apx_hist_kernel(ApxParams p, const float *__restrict__ score, long long N, int last_block)
 {
     extern __shared__ __align__(16) unsigned char sm[];
     const int cap = p.cap;
+    const int NT = (int)blockDim.x;   // 256, or 1024 when the tables of a long merged list leave room for one CTA per SM only
     uint32_t *k = reinterpret_cast<uint32_t *>(sm);   // [cap + 1] sorted keys of the merged list + a 0xFFFFFFFF sentinel
     uint32_t *h = k + cap + 1;                        // [cap + 1] private histogram
     uint16_t *bins = reinterpret_cast<uint16_t *>(h + cap + 1);   // [APX_BINS] bin -> first list entry | crowded << 15
@@ -668,10 +669,10 @@ __global__ void __launch_bounds__(APC_NT) apx_hist_kernel(ApxParams p, const flo
     uint32_t *hist = reinterpret_cast<uint32_t *>(p.local + p.ll.hist) + (size_t)c * p.sl.hp;
     const uint32_t kmin = hdr[0];
     const int shift = (int)hdr[1], nb = (int)hdr[2], ntp = (int)hdr[3];
-    for (int i = threadIdx.x; i < ntp; i += APC_NT) k[i] = tp_key[(size_t)c * cap + i];
+    for (int i = threadIdx.x; i < ntp; i += NT) k[i] = tp_key[(size_t)c * cap + i];
     if (threadIdx.x == 0) k[ntp] = 0xFFFFFFFFu;
-    for (int i = threadIdx.x; i <= ntp; i += APC_NT) h[i] = 0;
-    for (int i = threadIdx.x; i < (nb > 0 ? nb : 1); i += APC_NT) bins[i] = eg[i];
+    for (int i = threadIdx.x; i <= ntp; i += NT) h[i] = 0;
+    for (int i = threadIdx.x; i < (nb > 0 ? nb : 1); i += NT) bins[i] = eg[i];
     __syncthreads();
     // Every record scoring below all TPs lands in the one bucket after the last list entry (the bulk of the false
     // positives): counted in a register instead of hammering one shared word.
@@ -706,20 +707,20 @@ __global__ void __launch_bounds__(APC_NT) apx_hist_kernel(ApxParams p, const flo
     auto place = [&](float s) { const float sv[4] = {s, -INFINITY, -INFINITY, -INFINITY}; place4(sv); };
     if (((reinterpret_cast<uintptr_t>(sc) & 15) == 0) && N < 0x7fffffffLL) {
         const int n4 = (int)(N >> 2);
-        const int step = (int)(gridDim.x * APC_NT);
-        for (int i = (int)(blockIdx.x * APC_NT + threadIdx.x); i < n4; i += step) {
+        const int step = (int)(gridDim.x * NT);
+        for (int i = (int)(blockIdx.x * NT + threadIdx.x); i < n4; i += step) {
             const float4 v = __ldg(reinterpret_cast<const float4 *>(sc) + i);
             const float sv[4] = {v.x, v.y, v.z, v.w};
             place4(sv);
         }
-        for (long long i = ((long long)n4 << 2) + (long long)blockIdx.x * APC_NT + threadIdx.x; i < N; i += (long long)gridDim.x * APC_NT) place(sc[i]);
+        for (long long i = ((long long)n4 << 2) + (long long)blockIdx.x * NT + threadIdx.x; i < N; i += (long long)gridDim.x * NT) place(sc[i]);
     } else {
-        for (long long i = (long long)blockIdx.x * APC_NT + threadIdx.x; i < N; i += (long long)gridDim.x * APC_NT) place(sc[i]);
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < N; i += (long long)gridDim.x * NT) place(sc[i]);
     }
     for (int off = 16; off > 0; off >>= 1) tail += __shfl_xor_sync(0xffffffffu, tail, off);
     if ((threadIdx.x & 31) == 0 && tail) atomicAdd(&h[ntp], tail);
     __syncthreads();
-    for (int i = threadIdx.x; i <= ntp; i += APC_NT) { const uint32_t v = h[i]; if (v) atomicAdd(&hist[i], v); }
+    for (int i = threadIdx.x; i <= ntp; i += NT) { const uint32_t v = h[i]; if (v) atomicAdd(&hist[i], v); }
     if (!(p.exchange && last_block)) return;
     // the last CTA of this class to get here ships the finished row to every peer
     __threadfence();
@@ -737,7 +738,7 @@ __global__ void __launch_bounds__(APC_NT) apx_hist_kernel(ApxParams p, const flo
     for (int r = 0; r < p.W; ++r) {
         unsigned char *half = p.peers.base[r] + (size_t)(tag & 1u) * p.sl.half;
         uint4 *dst = reinterpret_cast<uint4 *>(half + p.sl.hist + (size_t)p.rank * p.sl.hist_stride + sizeof(uint32_t) * (size_t)c * p.sl.hp);
-        for (int i = threadIdx.x; i < n4; i += APC_NT) dst[i] = __ldcg(src + i);
+        for (int i = threadIdx.x; i < n4; i += NT) dst[i] = __ldcg(src + i);
     }
     __threadfence_system();
     __syncthreads();
@@ -952,6 +953,7 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
         int per_sm = (int)(220 * 1024 / (smem + 1024));
         if (per_sm > 8) per_sm = 8;
         if (per_sm < 1) per_sm = 1;
+        const int hist_nt = per_sm >= 4 ? APC_NT : (per_sm >= 2 ? 512 : 1024);   // keep >= 1024 threads per SM
         const int gx_full = (148 * per_sm + C - 1) / C;
         int launched = 0;
         for (int b = 0; b < nblocks; ++b) {
@@ -964,12 +966,12 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
             long long gx = (N + 8191) / 8192;
             if (gx > gx_full) gx = gx_full;
             if (gx < 1) gx = 1;
-            apx_hist_kernel<<<dim3((unsigned)gx, C), APC_NT, smem, st>>>(p, static_cast<const float *>(blocks[b]), N, last ? 1 : 0);
+            apx_hist_kernel<<<dim3((unsigned)gx, C), hist_nt, smem, st>>>(p, static_cast<const float *>(blocks[b]), N, last ? 1 : 0);
             { const int rc = launch_ok("apx_hist_kernel"); if (rc) return rc; }
             ++launched;
         }
         if (exchange && nblocks == 0) {   // nothing local: still ship the (zero) rows so that the peers' final stage can run
-            apx_hist_kernel<<<dim3(1, C), APC_NT, smem, st>>>(p, nullptr, 0, 1);
+            apx_hist_kernel<<<dim3(1, C), hist_nt, smem, st>>>(p, nullptr, 0, 1);
             { const int rc = launch_ok("apx_hist_kernel"); if (rc) return rc; }
         }
         (void)launched;

@@ -30,7 +30,7 @@ def params_to_corners(center, size, angle):
 
 
 def _u(g, shape, lo, hi):
-    return torch.rand(shape, generator=g) * (hi - lo) + lo
+    return torch.rand(shape, generator=g, device=g.device) * (hi - lo) + lo
 
 
 def sample_boxes(g, shape, room="sunrgbd", heading=math.pi):
@@ -44,7 +44,7 @@ def sample_boxes(g, shape, room="sunrgbd", heading=math.pi):
         z = _u(g, (*shape, 1), 0.0, 2.5)
     center = torch.cat([xy, z], -1)
     size = _u(g, (*shape, 3), 0.3, 1.8)
-    ang = _u(g, shape, -heading, heading) if heading > 0 else torch.zeros(shape)
+    ang = _u(g, shape, -heading, heading) if heading > 0 else torch.zeros(shape, device=g.device)
     return center, size, ang
 
 
@@ -106,23 +106,25 @@ def clip_logits_inputs(M=8192, K=640, N=1203, seed=0):
     return x.to(torch.bfloat16), t.to(torch.bfloat16)
 
 
-def pseudo_label_scenes(S, P=256, pool=512, C=18, seed=0):
+def pseudo_label_scenes(S, P=256, pool=512, C=18, seed=0, device="cpu"):
     """C5: per scene P axis-aligned proposals [x1,y1,z1,x2,y2,z2,score,label] and a
     pool of `pool` AABBs (half of them jittered copies of proposals so that the
-    IoU>=0.3 match of lift_boxes.py:151-158 fires)."""
-    g = torch.Generator().manual_seed(seed)
+    IoU>=0.3 match of lift_boxes.py:151-158 fires).  `device`: where the generator runs (the stream of a CUDA
+    generator differs from the CPU one; a (seed, device type) pair is reproducible)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    dev = g.device
     c, s, _ = sample_boxes(g, (S, P), "scannet", 0.0)
-    score = torch.rand((S, P), generator=g)
-    label = torch.randint(0, C, (S, P), generator=g).float()
+    score = torch.rand((S, P), generator=g, device=dev)
+    label = torch.randint(0, C, (S, P), generator=g, device=dev).float()
     h = P // 2  # second half: near-duplicates of the first half (same label) so that NMS@0.7 suppresses
-    c[:, h:2 * h] = c[:, :h] + torch.randn((S, h, 3), generator=g) * 0.03
-    s[:, h:2 * h] = s[:, :h] * (torch.randn((S, h, 3), generator=g) * 0.03 + 1.0).clamp(0.8, 1.2)
+    c[:, h:2 * h] = c[:, :h] + torch.randn((S, h, 3), generator=g, device=dev) * 0.03
+    s[:, h:2 * h] = s[:, :h] * (torch.randn((S, h, 3), generator=g, device=dev) * 0.03 + 1.0).clamp(0.8, 1.2)
     label[:, h:2 * h] = label[:, :h]
     boxes = torch.cat([c - s / 2, c + s / 2, score[..., None], label[..., None]], -1)
     pc, ps, _ = sample_boxes(g, (S, pool), "scannet", 0.0)
     n = min(pool // 2, P)
-    pc[:, :n] = c[:, :n] + torch.randn((S, n, 3), generator=g) * 0.08
-    ps[:, :n] = s[:, :n] * (torch.randn((S, n, 3), generator=g) * 0.08 + 1.0).clamp(0.6, 1.4)
+    pc[:, :n] = c[:, :n] + torch.randn((S, n, 3), generator=g, device=dev) * 0.08
+    ps[:, :n] = s[:, :n] * (torch.randn((S, n, 3), generator=g, device=dev) * 0.08 + 1.0).clamp(0.6, 1.4)
     poolb = torch.cat([pc - ps / 2, pc + ps / 2], -1)
     return boxes.double().contiguous(), poolb.double().contiguous()
 

@@ -92,6 +92,42 @@ def lift_filter_batch(boxes, pool, nboxes=None, npool=None, nms_thresh=0.7, matc
     return {"nms1_keep": k1, "label": lab, "score": sc, "keep": keep}
 
 
+def lift_sweep(boxes, pool, nboxes=None, npool=None, nms_thresh=0.7, match_thresh=0.3, size_nms_thresh=0.0,
+               distributed=False, chunk=8192, out=None):
+    """The pseudo-label sweep of BASELINE config 5 over many scenes: the per-scene pipeline of lift_boxes.py:139-166
+    (its `__main__` maps it over all scans with ``mp.Pool``, :177-181) in chunks of ``chunk`` scenes per launch.
+    ``boxes`` / ``pool`` hold THIS rank's scenes (use ``dist.shard_range`` to cut the scan list; scenes are independent,
+    so there is no data-path collective).  Returns ``(result, total_kept)``: ``result`` as in ``lift_filter_batch``
+    (written into ``out`` when given), ``total_kept`` = number of pseudo-label boxes kept over ALL ranks -- the one
+    cross-rank value of the sweep (the "Acquired N boxes" / per-scan counts summed at :181; all-reduced when
+    ``distributed``)."""
+    from ..dist import all_reduce_count
+    C.require_cuda(boxes, pool)
+    S, P, M = boxes.shape[0], boxes.shape[1], pool.shape[1]
+    dev = boxes.device
+    if out is None:
+        out = {"nms1_keep": torch.empty((S, P), dtype=torch.uint8, device=dev), "label": torch.empty((S, M), dtype=torch.float64, device=dev),
+               "score": torch.empty((S, M), dtype=torch.float64, device=dev), "keep": torch.empty((S, M), dtype=torch.uint8, device=dev)}
+    b = boxes.detach().to(torch.float64).contiguous()
+    pl = pool.detach().to(torch.float64).contiguous()
+    nb = None if nboxes is None else torch.as_tensor(nboxes).to(device=dev, dtype=torch.int32).contiguous()
+    npl = None if npool is None else torch.as_tensor(npool).to(device=dev, dtype=torch.int32).contiguous()
+    L, st = C.lib(), C.stream(dev)
+    with C.on_device(dev):
+        for lo in range(0, S, chunk):
+            n = min(chunk, S - lo)
+            C.check(L.ovdet_pseudo_filter_f64(b[lo:].data_ptr(), pl[lo:].data_ptr(), None if nb is None else nb[lo:].data_ptr(),
+                                              None if npl is None else npl[lo:].data_ptr(), n, P, M, float(nms_thresh), float(match_thresh),
+                                              float(size_nms_thresh), out["nms1_keep"][lo:].data_ptr(), out["label"][lo:].data_ptr(),
+                                              out["score"][lo:].data_ptr(), out["keep"][lo:].data_ptr(), st))
+    kept = out["keep"].sum(dtype=torch.int64)      # stays on the device until the one count exchange
+    if distributed:
+        import torch.distributed as tdist
+        tdist.all_reduce(kept, op=tdist.ReduceOp.SUM)
+        return out, int(kept.item())
+    return out, all_reduce_count(int(kept.item()), dev)
+
+
 def lift_filter_scene(boxes, box_pool, nms_thresh=0.7, match_thresh=0.3, size_nms_thresh=0.0):
     """One scene, numpy in / numpy out, rows [x1..z2, score*volume, label, volume, area]
     ordered by the final NMS pick order -- what lift_boxes.py:159-165 leaves in `boxes`."""

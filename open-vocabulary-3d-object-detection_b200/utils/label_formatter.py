@@ -83,13 +83,23 @@ class LabelFormatter():
         np.save(os.path.join(self.output_path, scan_name) + "_bbox.npy", instance_bboxes)
         return numBox
 
-    def save(self):
-        return sum(self.gen_pseudo(i) for i in range(len(self.scene_list)))
+    def save(self, distributed=False):
+        """label_formatter.py:169-174.  The reference maps gen_pseudo over the scans with ``mp.Pool(cpu_count())``; here each
+        scan is one kernel launch, and with ``distributed=True`` the scans are cut across the ranks (``dist.shard_range``,
+        no data-path collective) and the kept-box counts are summed with one all-reduce."""
+        from ..dist import shard_range, all_reduce_count, is_distributed
+        n = len(self.scene_list)
+        lo, hi = shard_range(n) if (distributed and is_distributed()) else (0, n)
+        l = sum(self.gen_pseudo(i) for i in range(lo, hi))
+        return all_reduce_count(l, torch.device("cuda", torch.cuda.current_device())) if distributed else l
 
-    def process(self, k, th_s, th_o):
+    def process(self, k, th_s, th_o, distributed=False):
+        """label_formatter.py:176-179 -- the entry point generate_pseudo_label.py:209 calls with
+        (args.topk, args.conf_thresh, args.obj_thresh).  Returns the number of boxes acquired (the reference only prints it)."""
         self.compute(k, th_s, th_o)
-        l = self.save()
+        l = self.save(distributed=distributed)
         print("Done! Acquired {} boxes.".format(l))
+        return l
 
     def crop_pc(self, pc, box):
         """label_formatter.py:183-188 (host mask; kept for interface parity)."""
