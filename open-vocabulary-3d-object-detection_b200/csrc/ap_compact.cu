@@ -18,6 +18,7 @@
 // Results equal the sorted formulation on tie-free scores (same caveat as the reference's
 // unstable argsort).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -500,13 +501,33 @@ __device__ __forceinline__ bool wait_flag(const unsigned *flag, unsigned tag)
 
 struct ApxPeers { unsigned char *base[APX_MAXW]; };
 
+// Programmatic dependent launch: the kernels of the chain are launched with the stream-serialisation attribute, so a
+// successor's CTAs can take their SM slots while the predecessor is still running and start the moment it has finished
+// and flushed (griddepcontrol.wait) -- the launch latency of the three dependent stages disappears from the chain.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 struct ApxParams {
     ApxPeers peers; ApxLayout sl; ApxLocal ll;
     unsigned char *local;
     const uint32_t *tp_key; const uint8_t *tp_bits; const int *tp_cnt; const long long *npos;
     int C, cap_list, cap, nthr, use07, rank, W, exchange;
     double *result;
+    unsigned long long *dbg;   // optional [C][8] globaltimer stamps of the merge stage (OVDET_APX_DBG_PTR; null in production)
 };
+#define XSTAMP(i) do { if (p.dbg && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[(size_t)blockIdx.x * 8 + (i)] = t_; } } while (0)
 
 __device__ __forceinline__ unsigned *apx_ctrl(const ApxParams &p) { return reinterpret_cast<unsigned *>(p.local + p.ll.ctrl); }
 
@@ -514,6 +535,8 @@ __device__ __forceinline__ unsigned *apx_ctrl(const ApxParams &p) { return reint
 __global__ void __launch_bounds__(256) apx_push_lists_kernel(ApxParams p)
 {
     const int dst = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    pdl_wait();
+    pdl_release();
     const unsigned tag = apx_ctrl(p)[0] + 1u;
     unsigned char *half = p.peers.base[dst] + (size_t)(tag & 1u) * p.sl.half;
     unsigned char *slot = half + p.sl.lists + (size_t)p.rank * p.sl.list_stride;
@@ -535,13 +558,26 @@ __global__ void __launch_bounds__(256) apx_push_lists_kernel(ApxParams p)
 }
 
 // ---- stage 2: per class, gather the W lists, sort, bin edges; zero the class's histogram.  grid C, 1024 threads
-__global__ void __launch_bounds__(1024) apx_merge_kernel(ApxParams p)
+__global__ void __launch_bounds__(1024, 1) apx_merge_kernel(ApxParams p)
 {
     extern __shared__ __align__(16) unsigned char sm[];
-    unsigned long long *v = reinterpret_cast<unsigned long long *>(sm);   // (key << 32) | bits: one 8-byte word per entry to compare and swap
+    // two (key, bits) buffers for the radix passes (addressed by offset from one shared base: the compiler then knows
+    // every access is a shared-memory access), the per-element rank inside (warp, digit), the per-warp digit counts
+    const int cap = p.cap;
+    uint32_t *ksm = reinterpret_cast<uint32_t *>(sm);                 // [2][cap]
+    uint16_t *rnk = reinterpret_cast<uint16_t *>(ksm + 2 * cap);      // [cap]
+    uint16_t *whist = rnk + cap;                                      // [32 warps][256 digits]
+    uint8_t *bsm = reinterpret_cast<uint8_t *>(whist + 32 * 256);     // [2][cap]
+    uint16_t *lo16 = reinterpret_cast<uint16_t *>(bsm + 2 * cap);      // [APX_BINS + 1] first list index of every bin
+    __shared__ uint32_t dbase[256], wsum_s[8];
+    __shared__ int skip_s;
     __shared__ int n_s[APX_MAXW], off_s[APX_MAXW + 1];
-    __shared__ uint32_t kmin_s; __shared__ int shift_s, nb_s, bad_s;
+    __shared__ int bad_s;
     const int c = blockIdx.x, tid = threadIdx.x;
+    XSTAMP(0);
+    pdl_wait();
+    pdl_release();     // 20 CTAs: the histogram CTAs may take the other SMs now and wait there
+    XSTAMP(1);
     unsigned *ctrl = apx_ctrl(p);
     const unsigned tag = ctrl[0] + 1u;
     const unsigned char *half = p.exchange ? p.peers.base[p.rank] + (size_t)(tag & 1u) * p.sl.half : nullptr;
@@ -575,8 +611,7 @@ __global__ void __launch_bounds__(1024) apx_merge_kernel(ApxParams p)
     }
     __syncthreads();
     const int total = off_s[p.W];
-    int n2 = 64;                                 // >= 64: the warp-local sort steps want whole warps
-    while (n2 < total) n2 <<= 1;                 // <= cap (a power of two >= 1024)
+    XSTAMP(2);
     for (int r = 0; r < p.W; ++r) {
         const uint32_t *ksrc; const uint8_t *bsrc;
         if (p.exchange) {
@@ -585,70 +620,139 @@ __global__ void __launch_bounds__(1024) apx_merge_kernel(ApxParams p)
             bsrc = slot + p.sl.l_bits + (size_t)c * p.cap;
         } else { ksrc = p.tp_key + (size_t)c * p.cap_list; bsrc = p.tp_bits + (size_t)c * p.cap_list; }
         const int n = n_s[r], o = off_s[r];
-        for (int i = tid; i < n; i += 1024) v[o + i] = ((unsigned long long)ksrc[i] << 32) | bsrc[i];
+        for (int i = tid; i < n; i += 1024) { ksm[o + i] = ksrc[i]; bsm[o + i] = bsrc[i]; }
     }
-    for (int i = total + tid; i < n2; i += 1024) v[i] = 0xFFFFFFFF00000000ull;
-    __syncthreads();
-    // bitonic sort.  Thread t owns the compare-exchange pairs t, t + 1024, ...; for strides <= 32 the 32 pairs of a warp
-    // stay inside one 64-element chunk, so those steps only need a warp barrier (20 block barriers instead of 66 at 2048)
-    auto cmpx = [&](int t, int size, int stride) {
-        const int lo = 2 * t - (t & (stride - 1));
-        const int hi = lo + stride;
-        const bool up = ((lo & size) == 0);
-        const unsigned long long va = v[lo], vb = v[hi];
-        if (up ? (va > vb) : (va < vb)) { v[lo] = vb; v[hi] = va; }
-    };
-    for (int size = 2; size <= n2; size <<= 1) {
-        int stride = size >> 1;
-        for (; stride > 32; stride >>= 1) {
-            for (int t = tid; t < n2 / 2; t += 1024) cmpx(t, size, stride);
-            __syncthreads();
+    // Stable LSD radix sort of (key, bits) by 8-bit digits: the bits first (so that equal keys end up in a defined order
+    // whatever order the lists were appended in), then the four key bytes.  Warp w owns the contiguous elements
+    // [w*CH, (w+1)*CH): within a warp __match_any_sync ranks the elements of equal digit, one lane per digit bumps the
+    // warp's count; a scan over (digit, warp) then gives every element its destination.  O(n) per pass -- the bitonic
+    // network this replaces was 4x the instructions at 2 048 entries and 15x at 16 384.
+    const int lane = tid & 31, warp = tid >> 5;
+    const int CH = (((total + 31) >> 5) + 31) & ~31;
+    const int nwarp = CH ? (total + CH - 1) / CH : 0;      // warps that own elements
+    int cur = 0;
+    if (total <= 384) {
+        // short list (a rank's share of a small evaluation): one counting pass -- entry i goes to the number of entries
+        // that sort before it by (key, bits, position); every thread reads the same entry at a time (broadcast)
+        XSTAMP(6);
+        __syncthreads();
+        XSTAMP(7);
+        if (tid < total) {
+            const uint32_t ki = ksm[tid]; const uint8_t bi = bsm[tid];
+            const unsigned long long vi = ((unsigned long long)ki << 8) | bi;
+            int pos = 0;
+#pragma unroll 8
+            for (int j = 0; j < total; ++j) {   // unconditional broadcast loads and bitwise compares: nothing to branch on, the loads overlap
+                const unsigned long long vj = ((unsigned long long)ksm[j] << 8) | bsm[j];
+                pos += (int)(vj < vi) | ((int)(vj == vi) & (int)(j < tid));
+            }
+            ksm[cap + pos] = ki; bsm[cap + pos] = bi;
         }
-        for (int t = tid; t < n2 / 2; t += 1024) {     // warp-uniform trip count (n2 / 2 is a multiple of 32 or < 32 with one warp)
-            for (int st = stride; st > 0; st >>= 1) { cmpx(t, size, st); __syncwarp(); }
+        cur = 1;
+        __syncthreads();
+    } else
+    for (int pass = 0; pass < 5; ++pass) {
+        const int in0 = cur * cap, out0 = (cur ^ 1) * cap;
+        for (int i = tid; i < nwarp * 128; i += 1024) reinterpret_cast<uint32_t *>(whist)[i] = 0u;
+        if (tid == 0) skip_s = 0;
+        __syncthreads();
+        const int sh = 8 * (pass - 1);
+        for (int r = 0; r < CH; r += 32) {
+            const int i = warp * CH + r + lane;
+            const bool valid = i < total;
+            const unsigned d = valid ? (pass == 0 ? (unsigned)bsm[in0 + i] : ((ksm[in0 + i] >> sh) & 255u)) : (256u + lane);
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int lead = __ffs(peers) - 1;
+            unsigned old = 0;
+            if (valid && lane == lead) { old = whist[warp * 256 + d]; whist[warp * 256 + d] = (uint16_t)(old + __popc(peers)); }
+            __syncwarp();
+            old = __shfl_sync(0xffffffffu, old, lead);
+            if (valid) rnk[i] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
+        }
+        __syncthreads();
+        if (tid < 256) {   // digit tid: exclusive scan over the warps, then over the digits
+            unsigned run = 0;
+#pragma unroll 8
+            for (int w2 = 0; w2 < nwarp; ++w2) { const unsigned t = whist[w2 * 256 + tid]; whist[w2 * 256 + tid] = (uint16_t)run; run += t; }
+            if (run == (unsigned)total) skip_s = 1;   // every element has this digit: the pass would not move anything
+            unsigned x = run;
+            for (int off = 1; off < 32; off <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+            if (lane == 31) wsum_s[warp] = x;
+            dbase[tid] = x - run;   // exclusive inside the warp of digits
+        }
+        __syncthreads();
+        if (tid < 256) {
+            unsigned add = 0;
+            for (int w2 = 0; w2 < warp; ++w2) add += wsum_s[w2];
+            dbase[tid] += add;
+        }
+        __syncthreads();
+        if (!skip_s) {
+            for (int r = 0; r < CH; r += 32) {
+                const int i = warp * CH + r + lane;
+                if (i < total) {
+                    const uint32_t kk = ksm[in0 + i]; const uint8_t bb = bsm[in0 + i];
+                    const unsigned d = pass == 0 ? (unsigned)bb : ((kk >> sh) & 255u);
+                    const unsigned pos = dbase[d] + whist[warp * 256 + d] + rnk[i];
+                    ksm[out0 + pos] = kk; bsm[out0 + pos] = bb;
+                }
+            }
+            cur ^= 1;
         }
         __syncthreads();
     }
+    XSTAMP(3);
+    const uint32_t *ks = ksm + cur * cap; const uint8_t *bs = bsm + cur * cap;
     uint32_t *mk = reinterpret_cast<uint32_t *>(p.local + p.ll.mkey) + (size_t)c * p.cap;
     uint8_t *mb = p.local + p.ll.mbits + (size_t)c * p.cap;
-    for (int i = tid; i < p.cap; i += 1024) { const unsigned long long x = i < n2 ? v[i] : 0xFFFFFFFF00000000ull; mk[i] = (uint32_t)(x >> 32); mb[i] = (uint8_t)x; }
+    for (int i = tid; i < cap; i += 1024) { mk[i] = i < total ? ks[i] : 0xFFFFFFFFu; mb[i] = i < total ? bs[i] : 0; }
     // Bin table of the sorted list: the key axis between its extremes is cut into <= APX_BINS equal bins (the key is the
     // order-preserving image of the fp32 score, i.e. a piecewise-logarithmic scale that spreads a detector's skewed scores
     // evenly); entry b = index of the first list key >= the bin's lower bound, bit 15 set when the bin holds two or more
-    // list keys.  A record then finds its bucket with one table look-up and one compare (apx_hist_kernel).
+    // list keys.  A record then finds its bucket with one table look-up and one compare (apx_hist_kernel).  Built from
+    // the entries: the first entry of a bin writes that bin and the empty bins in front of it.
     unsigned char *eb = p.local + p.ll.edge + (size_t)c * APX_ESTRIDE_BYTES;
+    uint32_t kmin = 0; int shift = 0, nb = 0;
+    if (total > 0) {
+        kmin = ks[0];
+        const uint32_t span = ks[total - 1] - kmin;
+        while ((span >> shift) >= (uint32_t)APX_BINS) ++shift;
+        nb = (int)(span >> shift) + 1;
+    }
     if (tid == 0) {
-        uint32_t kmin = 0; int shift = 0, nb = 0;
-        if (total > 0) {
-            kmin = (uint32_t)(v[0] >> 32);
-            const uint32_t span = (uint32_t)(v[total - 1] >> 32) - kmin;
-            while ((span >> shift) >= (uint32_t)APX_BINS) ++shift;
-            nb = (int)(span >> shift) + 1;
-        }
-        kmin_s = kmin; shift_s = shift; nb_s = nb;
         uint32_t *hdr = reinterpret_cast<uint32_t *>(eb);
         hdr[0] = kmin; hdr[1] = (uint32_t)shift; hdr[2] = (uint32_t)nb; hdr[3] = (uint32_t)total;
     }
-    __syncthreads();
     {
-        const int nb = nb_s, shift = shift_s;
-        const uint32_t kmin = kmin_s;
+        // one thread per bin (a bin's first entry writing the run of empty bins in front of it would leave one thread
+        // with thousands of stores when the scores have a gap): binary search of the bin's lower bound in the sorted keys
         uint16_t *e = reinterpret_cast<uint16_t *>(eb + sizeof(uint32_t) * APX_EHDR);
-        auto lower = [&](unsigned long long bound) {   // entries with key < bound
-            int lo = 0, hi = total;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((v[mid] >> 32) < bound) lo = mid + 1; else hi = mid; }
-            return lo;
-        };
-        for (int bi = tid; bi < nb; bi += 1024) {
-            const unsigned long long b0 = (unsigned long long)kmin + ((unsigned long long)bi << shift);
-            const int lo = lower(b0), hi = lower(b0 + (1ull << shift));
-            e[bi] = (uint16_t)(lo | (hi - lo >= 2 ? 0x8000 : 0));
+        // branch-free lower bounds, the (up to 9) bins of a thread in lock step so that their shared loads overlap
+        constexpr int BPT = (APX_BINS + 1 + 1023) / 1024;
+        int top = 1;
+        while (top * 2 <= total) top *= 2;            // largest power of two <= total (1 when total <= 1)
+        unsigned long long bound[BPT]; int lo[BPT];
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) { bound[q] = (unsigned long long)kmin + ((unsigned long long)(tid + 1024 * q) << shift); lo[q] = 0; }
+        for (int step = total > 0 ? top : 0; step > 0; step >>= 1) {
+#pragma unroll
+            for (int q = 0; q < BPT; ++q) {
+                const int nx = lo[q] + step;
+                const uint32_t kv = ks[min(nx, total) - 1];                                  // unconditional load (total >= 1 here)
+                lo[q] = ((nx <= total) & ((unsigned long long)kv < bound[q])) ? nx : lo[q];   // entries with key < bound
+            }
         }
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) if (tid + 1024 * q <= nb) lo16[tid + 1024 * q] = (uint16_t)lo[q];
+        __syncthreads();
+        XSTAMP(4);
+        for (int bi = tid; bi < nb; bi += 1024) e[bi] = (uint16_t)(lo16[bi] | (lo16[bi + 1] - lo16[bi] >= 2 ? 0x8000 : 0));
         if (tid == 0 && nb == 0) e[0] = 0;
     }
     uint32_t *h = reinterpret_cast<uint32_t *>(p.local + p.ll.hist) + (size_t)c * p.sl.hp;
     for (int i = tid; i < p.sl.hp; i += 1024) h[i] = 0;
     if (tid == 0) reinterpret_cast<unsigned *>(p.local + p.ll.done_hist)[c] = 0;
+    XSTAMP(5);
 }
 
 // ---- stage 3: histogram of the local records over the merged list; the last CTA of a class ships the class's row
@@ -662,6 +766,8 @@ __global__ void __launch_bounds__(1024) apx_hist_kernel(ApxParams p, const float
     uint16_t *bins = reinterpret_cast<uint16_t *>(h + cap + 1);   // [APX_BINS] bin -> first list entry | crowded << 15
     __shared__ int last_s;
     const int c = blockIdx.y;
+    pdl_wait();
+    pdl_release();
     const unsigned char *eb = p.local + p.ll.edge + (size_t)c * APX_ESTRIDE_BYTES;
     const uint32_t *hdr = reinterpret_cast<const uint32_t *>(eb);
     const uint16_t *eg = reinterpret_cast<const uint16_t *>(eb + sizeof(uint32_t) * APX_EHDR);
@@ -749,16 +855,19 @@ __global__ void __launch_bounds__(1024) apx_hist_kernel(ApxParams p, const float
 }
 
 // ---- stage 4: per (class, threshold): sum the W histogram rows, positions, precision envelope, AP.  grid (C, nthr)
+// Thread t owns E = span / 1024 CONSECUTIVE list entries: the prefix sums (positions, cumulative TP) are a serial walk
+// over its own entries plus one block scan of the per-thread totals, the precision envelope (running maximum from the
+// right, utils/eval_det.py:45-46) a reverse walk plus one block suffix-max -- eight barriers whatever the list length.
 __global__ void __launch_bounds__(1024) apx_final_kernel(ApxParams p)
 {
     extern __shared__ __align__(16) unsigned char sm[];
-    unsigned int *H = reinterpret_cast<unsigned int *>(sm);   // [cap] inclusive prefix of hist = 1-based sorted position
-    unsigned int *ctp = H + p.cap;                            // [cap] inclusive count of TP(t) entries
-    __shared__ unsigned int wsum[32], carry_u;
-    __shared__ double wmax[32], red[32], carry_max_s;
+    unsigned int *Hs = reinterpret_cast<unsigned int *>(sm);   // [span] bucket counts summed over the ranks
+    uint8_t *Bs = reinterpret_cast<uint8_t *>(Hs + p.cap);     // [span] TP flag of the entry at this threshold
+    __shared__ unsigned int wsH[32], wsT[32];
+    __shared__ double wmax[32], red[32];
     __shared__ int bad_s, last_s;
     const int c = blockIdx.x, t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cap = p.cap;
+    pdl_wait();
     unsigned *ctrl = apx_ctrl(p);
     const unsigned tag = ctrl[0] + 1u;
     const unsigned char *half = p.exchange ? p.peers.base[p.rank] + (size_t)(tag & 1u) * p.sl.half : nullptr;
@@ -772,7 +881,7 @@ __global__ void __launch_bounds__(1024) apx_final_kernel(ApxParams p)
     const double npos = (double)reinterpret_cast<const long long *>(p.local + p.ll.npos_g)[c];
     const int ntp = reinterpret_cast<const int *>(p.local + p.ll.mcnt)[c];
     const double eps = 2.220446049250313e-16;
-    const uint8_t *bits = p.local + p.ll.mbits + (size_t)c * cap;
+    const uint8_t *bits = p.local + p.ll.mbits + (size_t)c * p.cap;
     const uint32_t *hl = reinterpret_cast<const uint32_t *>(p.local + p.ll.hist) + (size_t)c * p.sl.hp;
     auto hist_at = [&](int i) -> unsigned int {
         if (!p.exchange) return hl[i];
@@ -781,72 +890,84 @@ __global__ void __launch_bounds__(1024) apx_final_kernel(ApxParams p)
             v += reinterpret_cast<const uint32_t *>(half + p.sl.hist + (size_t)r * p.sl.hist_stride)[(size_t)c * p.sl.hp + i];
         return v;
     };
-    // only the first n2 >= ntp entries matter (the rest of the list is padding); chunks of 1024
     const int nch = max(1, (ntp + 1023) / 1024);
-    const int span = nch * 1024 <= cap ? nch * 1024 : cap;
-    for (int pass = 0; pass < 2; ++pass) {
-        if (tid == 0) carry_u = 0;
-        __syncthreads();
-        for (int base = 0; base < span; base += 1024) {
-            const int i = base + tid;
-            const unsigned int v = pass == 0 ? hist_at(i) : (unsigned int)((bits[i] >> t) & 1u);
-            unsigned int x = v;
-            for (int off = 1; off < 32; off <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
-            if (lane == 31) wsum[warp] = x;
-            __syncthreads();
-            if (tid < 32) {
-                unsigned int w = wsum[tid];
-                for (int off = 1; off < 32; off <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, w, off); if (tid >= off) w += y; }
-                wsum[tid] = w;
-            }
-            __syncthreads();
-            const unsigned int incl = carry_u + x + (warp ? wsum[warp - 1] : 0u);
-            (pass == 0 ? H : ctp)[i] = incl;
-            __syncthreads();
-            if (tid == 1023) carry_u = incl;
-            __syncthreads();
+    const int span = nch * 1024 <= p.cap ? nch * 1024 : p.cap;   // entries that matter (the rest of the list is padding)
+    const int E = span >> 10;
+    for (int i = tid; i < span; i += 1024) { Hs[i] = hist_at(i); Bs[i] = (uint8_t)((bits[i] >> t) & 1u); }
+    __syncthreads();
+    // ---- forward: per-thread totals, block exclusive scan
+    const int j0 = tid * E;
+    unsigned int sumH = 0, sumT = 0;
+    for (int j = 0; j < E; ++j) { sumH += Hs[j0 + j]; sumT += Bs[j0 + j]; }
+    unsigned int xH = sumH, xT = sumT;
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned int yH = __shfl_up_sync(0xffffffffu, xH, off), yT = __shfl_up_sync(0xffffffffu, xT, off);
+        if (lane >= off) { xH += yH; xT += yT; }
+    }
+    if (lane == 31) { wsH[warp] = xH; wsT[warp] = xT; }
+    __syncthreads();
+    if (tid < 32) {
+        unsigned int wH = wsH[tid], wT = wsT[tid];
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned int yH = __shfl_up_sync(0xffffffffu, wH, off), yT = __shfl_up_sync(0xffffffffu, wT, off);
+            if (tid >= off) { wH += yH; wT += yT; }
+        }
+        wsH[tid] = wH; wsT[tid] = wT;
+    }
+    __syncthreads();
+    const unsigned int exH = xH - sumH + (warp ? wsH[warp - 1] : 0u), exT = xT - sumT + (warp ? wsT[warp - 1] : 0u);
+    const unsigned int total_tp = wsT[31];
+    // number of present records = all buckets, including the one behind the last list entry
+    unsigned long long nvalid = (unsigned long long)wsH[31];
+    if (ntp >= span) nvalid += hist_at(ntp);   // ntp == span: the tail bucket sits just past the scanned range
+    // ---- my entries: precision at the TP records, its maximum
+    double pm = 0.0;
+    {
+        unsigned int H = exH, ct = exT;
+        for (int j = 0; j < E; ++j) {
+            H += Hs[j0 + j];
+            if (Bs[j0 + j]) { ++ct; pm = fmax(pm, __ddiv_rn((double)ct, fmax((double)H, eps))); }
         }
     }
-    const unsigned int total_tp = ctp[span - 1];
-    // number of present records = all buckets, including the one behind the last list entry
-    unsigned long long nvalid = (unsigned long long)H[span - 1];
-    if (ntp >= span) nvalid += hist_at(ntp);   // ntp == span: the tail bucket sits just past the scanned range
-    if (tid == 0) carry_max_s = 0.0;
+    // block suffix maximum (exclusive: threads after me)
+    double m = pm;
+    for (int off = 1; off < 32; off <<= 1) { const double y = __shfl_down_sync(0xffffffffu, m, off); if (lane + off < 32) m = fmax(m, y); }
+    if (lane == 0) wmax[warp] = m;
     __syncthreads();
+    if (tid < 32) {
+        double w = wmax[tid];
+        for (int off = 1; off < 32; off <<= 1) { const double y = __shfl_down_sync(0xffffffffu, w, off); if (tid + off < 32) w = fmax(w, y); }
+        wmax[tid] = w;
+    }
+    __syncthreads();
+    double env = warp < 31 ? wmax[warp + 1] : 0.0;                   // warps after mine
+    {
+        const double nx = __shfl_down_sync(0xffffffffu, m, 1);       // inclusive suffix max of the next lane = lanes after me
+        if (lane < 31) env = fmax(env, nx);
+    }
+    // ---- reverse walk: AP = sum over TP records of (recall step) x (max precision at or after the record)
     double ap_local = 0.0;
     double p11[11];
 #pragma unroll
     for (int kk = 0; kk < 11; ++kk) p11[kk] = 0.0;
-    for (int base = span - 1024; base >= 0; base -= 1024) {
-        const int i = base + tid;
-        const bool tp = (bits[i] >> t) & 1u;
-        const double ct = (double)ctp[i];
-        const double prec = tp ? __ddiv_rn(ct, fmax((double)H[i], eps)) : 0.0;   // precision at this TP record
-        const double rec = npos > 0.0 ? __ddiv_rn(ct, npos) : 0.0;
-        double m = prec;
-        for (int off = 1; off < 32; off <<= 1) { const double y = __shfl_down_sync(0xffffffffu, m, off); if (lane + off < 32) m = fmax(m, y); }
-        if (lane == 0) wmax[warp] = m;
-        __syncthreads();
-        if (tid < 32) {
-            double w = wmax[tid];
-            for (int off = 1; off < 32; off <<= 1) { const double y = __shfl_down_sync(0xffffffffu, w, off); if (tid + off < 32) w = fmax(w, y); }
-            wmax[tid] = w;
-        }
-        __syncthreads();
-        const double carry = carry_max_s;
-        double env = fmax(m, carry);
-        if (warp < 31) env = fmax(env, wmax[warp + 1]);
-        if (tp) {
-            const double rec_prev = npos > 0.0 ? __ddiv_rn(ct - 1.0, npos) : 0.0;
-            ap_local += __dmul_rn(__dsub_rn(rec, rec_prev), env);
-            if (p.use07) {
+    {
+        unsigned int H = exH + sumH, ct = exT + sumT;
+        for (int j = E - 1; j >= 0; --j) {
+            if (Bs[j0 + j]) {
+                const double ctd = (double)ct;
+                const double prec = __ddiv_rn(ctd, fmax((double)H, eps));
+                const double rec = npos > 0.0 ? __ddiv_rn(ctd, npos) : 0.0;
+                const double rec_prev = npos > 0.0 ? __ddiv_rn(ctd - 1.0, npos) : 0.0;
+                env = fmax(env, prec);
+                ap_local += __dmul_rn(__dsub_rn(rec, rec_prev), env);
+                if (p.use07) {
 #pragma unroll
-                for (int kk = 0; kk < 11; ++kk) if (rec >= kk * 0.1) p11[kk] = fmax(p11[kk], prec);
+                    for (int kk = 0; kk < 11; ++kk) if (rec >= kk * 0.1) p11[kk] = fmax(p11[kk], prec);
+                }
+                --ct;
             }
+            H -= Hs[j0 + j];
         }
-        __syncthreads();
-        if (tid == 0) carry_max_s = fmax(carry, wmax[0]);
-        __syncthreads();
     }
     double res;
     if (!p.use07) {
@@ -862,6 +983,8 @@ __global__ void __launch_bounds__(1024) apx_final_kernel(ApxParams p)
         __syncthreads();
         res = red[0];
     } else {
+        // VOC07: max precision over records with rec >= t; attained at a TP record unless t == 0, where the very
+        // first record counts too -- its precision is 1 if it is a TP (covered) else 0 (covered by the 0 init).
         res = 0.0;
         for (int kk = 0; kk < 11; ++kk) {
             double a = p11[kk];
@@ -888,7 +1011,10 @@ __global__ void __launch_bounds__(1024) apx_final_kernel(ApxParams p)
         last_s = (tk == gridDim.x * gridDim.y - 1);
         if (last_s) {   // everything of this evaluation is done on this rank: publish the status words, advance the epoch
             __threadfence();
-            const unsigned ovf = atomicExch(&ctrl[2], 0u), mx = atomicExch(&ctrl[3], 0u), mt = atomicExch(&ctrl[4], 0u), to = atomicExch(&ctrl[5], 0u);
+            // written by the merge stage (an earlier kernel): plain L2 reads, one 16-byte store to clear them
+            const uint2 s01 = __ldcg(reinterpret_cast<const uint2 *>(ctrl + 2)), s23 = __ldcg(reinterpret_cast<const uint2 *>(ctrl + 4));
+            const unsigned ovf = s01.x, mx = s01.y, mt = s23.x, to = s23.y;
+            ctrl[2] = 0u; ctrl[3] = 0u; ctrl[4] = 0u; ctrl[5] = 0u;
             p.result[2 * kx + p.C] = to ? -1.0 : (double)ovf;
             p.result[2 * kx + p.C + 1] = (double)mx;
             p.result[2 * kx + p.C + 2] = (double)mt;
@@ -934,17 +1060,18 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
     p.tp_key = tp_key; p.tp_bits = tp_bits; p.tp_cnt = tp_cnt; p.npos = reinterpret_cast<const long long *>(npos);
     p.C = C; p.cap_list = cap_list; p.cap = cap_total; p.nthr = nthr; p.use07 = (flags & OVDET_APX_USE_07_METRIC) ? 1 : 0;
     p.rank = rank; p.W = world; p.exchange = exchange ? 1 : 0; p.result = result;
+    { const char *e = getenv("OVDET_APX_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned stages = flags & (OVDET_APX_STAGE_PUSH | OVDET_APX_STAGE_MERGE_HIST | OVDET_APX_STAGE_FINAL);
     if (!stages) stages = OVDET_APX_STAGE_PUSH | OVDET_APX_STAGE_MERGE_HIST | OVDET_APX_STAGE_FINAL;
     if (exchange && (stages & OVDET_APX_STAGE_PUSH)) {
-        apx_push_lists_kernel<<<dim3(world, C), 256, 0, st>>>(p);
+        OVDET_CUDA_TRY(launch_pdl(apx_push_lists_kernel, dim3(world, C), dim3(256), 0, st, p));
         { const int rc = launch_ok("apx_push_lists_kernel"); if (rc) return rc; }
     }
     if (stages & OVDET_APX_STAGE_MERGE_HIST) {
-        const size_t smem = (size_t)cap_total * 8;
+        const size_t smem = (size_t)cap_total * 12 + sizeof(uint16_t) * (32 * 256 + APX_BINS + 8);
         OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        apx_merge_kernel<<<C, 1024, smem, st>>>(p);
+        OVDET_CUDA_TRY(launch_pdl(apx_merge_kernel, dim3(C), dim3(1024), smem, st, p));
         { const int rc = launch_ok("apx_merge_kernel"); if (rc) return rc; }
     }
     if (stages & OVDET_APX_STAGE_MERGE_HIST) {
@@ -966,20 +1093,20 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
             long long gx = (N + 8191) / 8192;
             if (gx > gx_full) gx = gx_full;
             if (gx < 1) gx = 1;
-            apx_hist_kernel<<<dim3((unsigned)gx, C), hist_nt, smem, st>>>(p, static_cast<const float *>(blocks[b]), N, last ? 1 : 0);
+            OVDET_CUDA_TRY(launch_pdl(apx_hist_kernel, dim3((unsigned)gx, C), dim3(hist_nt), smem, st, p, static_cast<const float *>(blocks[b]), (long long)N, last ? 1 : 0));
             { const int rc = launch_ok("apx_hist_kernel"); if (rc) return rc; }
             ++launched;
         }
         if (exchange && nblocks == 0) {   // nothing local: still ship the (zero) rows so that the peers' final stage can run
-            apx_hist_kernel<<<dim3(1, C), hist_nt, smem, st>>>(p, nullptr, 0, 1);
+            OVDET_CUDA_TRY(launch_pdl(apx_hist_kernel, dim3(1, C), dim3(hist_nt), smem, st, p, static_cast<const float *>(nullptr), 0LL, 1));
             { const int rc = launch_ok("apx_hist_kernel"); if (rc) return rc; }
         }
         (void)launched;
     }
     if (stages & OVDET_APX_STAGE_FINAL) {
-        const size_t smem = sizeof(unsigned int) * 2 * (size_t)cap_total;
+        const size_t smem = (sizeof(unsigned int) + 1) * (size_t)cap_total;
         OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        apx_final_kernel<<<dim3(C, nthr), 1024, smem, st>>>(p);
+        OVDET_CUDA_TRY(launch_pdl(apx_final_kernel, dim3(C, nthr), dim3(1024), smem, st, p));
         { const int rc = launch_ok("apx_final_kernel"); if (rc) return rc; }
     }
     if (result_host && (stages & OVDET_APX_STAGE_FINAL))

@@ -43,11 +43,34 @@ struct Front2Params {
     uint8_t *keep_out; unsigned long long *dbg;
 };
 
+// Shared-memory layout as BYTE OFFSETS from the CTA's dynamic shared base (uniform values the compiler keeps in uniform
+// registers or rematerialises; a struct of 19 generic pointers instead ended up in local memory and every shared access
+// paid a local load first).
 struct F2Smem {
-    AmBox *gbox, *cbox; V2<double> *scratch; double *qiou, *vol; unsigned long long *best;
-    float *box6, *score, *gvlo, *garea, *qscore; int *cls, *glab; unsigned *queue;   // box6: [lo0 lo1 lo2 hi0 hi1 hi2][K]
-    uint32_t *cmask, *alive, *picked, *done, *gmask;
+    unsigned char *base;
+    int o_cbox, o_scratch, o_qiou, o_vol, o_best, o_box6, o_score, o_gvlo, o_garea, o_qscore, o_cls, o_glab, o_queue, o_cmask,
+        o_alive, o_picked, o_done, o_gmask;
+    template <typename T> __device__ __forceinline__ T *at(int off) const { return reinterpret_cast<T *>(base + off); }
 };
+#define S_gbox (S.at<AmBox>(0))
+#define S_cbox (S.at<AmBox>(S.o_cbox))
+#define S_scratch (S.at<V2<double>>(S.o_scratch))
+#define S_qiou (S.at<double>(S.o_qiou))
+#define S_vol (S.at<double>(S.o_vol))
+#define S_best (S.at<unsigned long long>(S.o_best))
+#define S_box6 (S.at<float>(S.o_box6))
+#define S_score (S.at<float>(S.o_score))
+#define S_gvlo (S.at<float>(S.o_gvlo))
+#define S_garea (S.at<float>(S.o_garea))
+#define S_qscore (S.at<float>(S.o_qscore))
+#define S_cls (S.at<int>(S.o_cls))
+#define S_glab (S.at<int>(S.o_glab))
+#define S_queue (S.at<unsigned>(S.o_queue))
+#define S_cmask (S.at<uint32_t>(S.o_cmask))
+#define S_alive (S.at<uint32_t>(S.o_alive))
+#define S_picked (S.at<uint32_t>(S.o_picked))
+#define S_done (S.at<uint32_t>(S.o_done))
+#define S_gmask (S.at<uint32_t>(S.o_gmask))
 
 __host__ __device__ inline size_t f2_scratch_bytes(int nt)
 {
@@ -66,30 +89,30 @@ __host__ __device__ inline size_t f2_smem_bytes(int K, int G, int C, int nthr, i
     b += sizeof(uint32_t) * ((size_t)f2_cmask_classes(C, flags) * W + 3 * W + WG);
     return (b + 15) & ~(size_t)15;
 }
-__device__ inline F2Smem f2_carve(unsigned char *base, int K, int G, int C, int nthr, int nt, unsigned flags)
+__device__ __forceinline__ F2Smem f2_carve(unsigned char *base, int K, int G, int C, int nthr, int nt, unsigned flags)
 {
     const int W = (K + 31) / 32;
     F2Smem s;
-    s.gbox = reinterpret_cast<AmBox *>(base);
-    s.cbox = s.gbox + G;
-    s.scratch = reinterpret_cast<V2<double> *>(s.cbox + F2_COOP);
-    s.qiou = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(s.scratch) + f2_scratch_bytes(nt));
-    s.vol = s.qiou + F2_QCAP;
-    s.best = reinterpret_cast<unsigned long long *>(s.vol + K);
-    float *f = reinterpret_cast<float *>(s.best + (size_t)G * nthr);
-    s.box6 = f; f += 6 * (size_t)K;
-    s.score = f; f += K;
-    s.gvlo = f; f += G;
-    s.garea = f; f += G;
-    s.qscore = f; f += F2_QCAP;
-    s.cls = reinterpret_cast<int *>(f);
-    s.glab = s.cls + K;
-    s.queue = reinterpret_cast<unsigned *>(s.glab + G);
-    s.cmask = s.queue + F2_QCAP;
-    s.alive = s.cmask + (size_t)f2_cmask_classes(C, flags) * W;
-    s.picked = s.alive + W;
-    s.done = s.picked + W;
-    s.gmask = s.done + W;
+    s.base = base;
+    int o = (int)sizeof(AmBox) * G;
+    s.o_cbox = o; o += (int)sizeof(AmBox) * F2_COOP;
+    s.o_scratch = o; o += (int)f2_scratch_bytes(nt);
+    s.o_qiou = o; o += 8 * F2_QCAP;
+    s.o_vol = o; o += 8 * K;
+    s.o_best = o; o += 8 * G * nthr;
+    s.o_box6 = o; o += 24 * K;
+    s.o_score = o; o += 4 * K;
+    s.o_gvlo = o; o += 4 * G;
+    s.o_garea = o; o += 4 * G;
+    s.o_qscore = o; o += 4 * F2_QCAP;
+    s.o_cls = o; o += 4 * K;
+    s.o_glab = o; o += 4 * G;
+    s.o_queue = o; o += 4 * F2_QCAP;
+    s.o_cmask = o; o += 4 * f2_cmask_classes(C, flags) * W;
+    s.o_alive = o; o += 4 * W;
+    s.o_picked = o; o += 4 * W;
+    s.o_done = o; o += 4 * W;
+    s.o_gmask = o;
     return s;
 }
 
@@ -110,9 +133,12 @@ __device__ __noinline__ void f2_box_features(const float *g, AmBox *out)
 }
 
 struct CoopState { double vx, vy; int n; };
-__device__ __noinline__ CoopState f2_coop_pass(double ax, double ay, double bx, double by, CoopState st, int gl, int gshift, V2<double> *gbuf)
+// one Sutherland-Hodgman pass against edge (e-1 mod 4 -> e) of the GT quad; the quad is read from the feature record
+// here so that the caller keeps nothing but the polygon state alive across the call
+__device__ __noinline__ CoopState f2_coop_pass(const AmBox *gt, int e, CoopState st, int gl, int gshift, V2<double> *gbuf)
 {
-    st.n = coop_pass(ClipEdge<double>(ax, ay, bx, by), st.vx, st.vy, st.n, gl, gshift, gbuf);
+    const int a = (e + 3) & 3;
+    st.n = coop_pass(ClipEdge<double>((double)gt->qx[a], (double)gt->qz[a], (double)gt->qx[e], (double)gt->qz[e]), st.vx, st.vy, st.n, gl, gshift, gbuf);
     return st;
 }
 
@@ -161,9 +187,9 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) ap_front2_kernel(Front2
 
     {   // zero what is accumulated with atomics
         const int ncm = f2_cmask_classes(C, p.flags) * W;
-        for (int i = k; i < ncm; i += NT) S.cmask[i] = 0u;
-        for (int i = k; i < 2 * W; i += NT) S.picked[i] = 0u;   // picked | done are adjacent
-        for (int i = k; i < G * p.nthr; i += NT) S.best[i] = 0ull;
+        for (int i = k; i < ncm; i += NT) S_cmask[i] = 0u;
+        for (int i = k; i < 2 * W; i += NT) S_picked[i] = 0u;   // picked | done are adjacent
+        for (int i = k; i < G * p.nthr; i += NT) S_best[i] = 0ull;
         if (k == 0) qn_s = 0;
     }
     __syncthreads();
@@ -190,13 +216,11 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) ap_front2_kernel(Front2
             lox = fminf(fminf(c[0], c[3]), fminf(c[6], c[9])); hix = fmaxf(fmaxf(c[0], c[3]), fmaxf(c[6], c[9]));
             loz = fminf(fminf(c[2], c[5]), fminf(c[8], c[11])); hiz = fmaxf(fmaxf(c[2], c[5]), fmaxf(c[8], c[11]));
             // fp32 LOWER bound of the fp64 edge-length volume (box3d_vol): only used to widen the IoU upper bound
-            const int pa[3] = {0, 1, 0}, pb[3] = {1, 2, 4};
-            float v = 1.f;
-#pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const float dx = c[3 * pa[t]] - c[3 * pb[t]], dy = c[3 * pa[t] + 1] - c[3 * pb[t] + 1], dz = c[3 * pa[t] + 2] - c[3 * pb[t] + 2];
-                v *= sqrtf(dx * dx + dy * dy + dz * dz);
-            }
+            auto edge = [&](int a0, int b0) {   // |corner a0 - corner b0| (constant indices: c stays in registers)
+                const float dx = c[a0] - c[b0], dy = c[a0 + 1] - c[b0 + 1], dz = c[a0 + 2] - c[b0 + 2];
+                return sqrtf(dx * dx + dy * dy + dz * dz);
+            };
+            const float v = edge(0, 3) * edge(3, 6) * edge(0, 12);   // edges (0,1), (1,2), (0,4) of box3d_vol
             vlo = v * (1.f - 2e-5f);
             ahi = bev_area_hi(c);
         }
@@ -223,21 +247,21 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) ap_front2_kernel(Front2
         if (p.rec_tp) for (int c = 0; c < C; ++c) p.rec_tp[(size_t)c * N + slot] = 0;
         if (d2) { mn[1] = mn[2]; mx[1] = mx[2]; }   // 2D NMS works on the x and z extents (ap_calculator.py:92-104)
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { S.box6[a * K + k] = mn[a]; S.box6[(3 + a) * K + k] = mx[a]; }
+        for (int a = 0; a < 3; ++a) { S_box6[a * K + k] = mn[a]; S_box6[(3 + a) * K + k] = mx[a]; }
         {   // fp64 volume of the AABB as nms_3d_faster computes it (utils/nms.py:79-117 on the fp64 box rows)
             double v = A::sub((double)mx[0], (double)mn[0]);
             v = A::mul(v, A::sub((double)mx[1], (double)mn[1]));
             if (!d2) v = A::mul(v, A::sub((double)mx[2], (double)mn[2]));
-            S.vol[k] = v;
+            S_vol[k] = v;
         }
         F2STAMP(8);
-        S.score[k] = obj;
-        S.cls[k] = cls;
-        if (alive) atomicOr(&S.cmask[(size_t)(samecls ? cls : 0) * W + warp], mybit);
+        S_score[k] = obj;
+        S_cls[k] = cls;
+        if (alive) atomicOr(&S_cmask[(size_t)(samecls ? cls : 0) * W + warp], mybit);
     }
     {
         const unsigned m = __ballot_sync(0xffffffffu, alive);
-        if (lane == 0 && warp < W) S.alive[warp] = m;
+        if (lane == 0 && warp < W) S_alive[warp] = m;
     }
     // ---- present GT -> feature records (kept at their own index: the order of the present ones is what first-max needs)
     for (int g0 = warp * 32; g0 < G; g0 += NT) {
@@ -245,16 +269,16 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) ap_front2_kernel(Front2
         const size_t gs = (size_t)s * G + g;
         const bool present = g < G && (p.gt_present ? p.gt_present[gs] != 0 : p.gt_present_f32[gs] != 0.f);
         const unsigned m = __ballot_sync(0xffffffffu, present);
-        if (lane == 0) S.gmask[g0 >> 5] = m;
+        if (lane == 0) S_gmask[g0 >> 5] = m;
         if (present) {
-            f2_box_features(p.gt_corners + gs * 24, &S.gbox[g]);
+            f2_box_features(p.gt_corners + gs * 24, &S_gbox[g]);
             const long long lab = p.gt_labels[gs];
-            S.glab[g] = (lab >= 0 && lab < C) ? (int)lab : -1;
-            S.gvlo[g] = (float)S.gbox[g].vol * (1.f - 1e-6f);
+            S_glab[g] = (lab >= 0 && lab < C) ? (int)lab : -1;
+            S_gvlo[g] = (float)S_gbox[g].vol * (1.f - 1e-6f);
             {   // upper bound of the BEV area from the feature record's quad (vertex order reversed: same area)
-                const AmBox &b = S.gbox[g];
+                const AmBox &b = S_gbox[g];
                 const float q[12] = {b.qx[0], 0.f, b.qz[0], b.qx[1], 0.f, b.qz[1], b.qx[2], 0.f, b.qz[2], b.qx[3], 0.f, b.qz[3]};
-                S.garea[g] = bev_area_hi(q);
+                S_garea[g] = bev_area_hi(q);
             }
             if (lab >= 0 && lab < C) atomicAdd(&p.npos[lab], 1ull);
         }
@@ -277,8 +301,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) ap_front2_kernel(Front2
         if (alive) {
             // my bounds in the NMS axis order; all comparisons of bounds are exact in fp32 (the reference's fp64 values are
             // these floats widened), fp64 only for the few pairs that really overlap
-            const double vk = S.vol[k];
-            const uint32_t *cm = S.cmask + (size_t)(samecls ? cls : 0) * W;
+            const double vk = S_vol[k];
+            const uint32_t *cm = S_cmask + (size_t)(samecls ? cls : 0) * W;
 #pragma unroll
             for (int w = 0; w < F2_MAXW; ++w) {
                 if (w >= W) break;
@@ -288,17 +312,17 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) ap_front2_kernel(Front2
                     const int b = __ffs(m) - 1;
                     m &= m - 1;
                     const int j = 32 * w + b;
-                    const float sj = S.score[j];
+                    const float sj = S_score[j];
                     if (!(sj > obj || (sj == obj && j > k))) continue;   // only boxes picked before me can suppress me
                     float l[3], h[3];
                     bool empty = false;
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {   // (mn, mx) still hold my bounds in the NMS axis order
-                        l[a] = fmaxf(S.box6[a * K + j], mn[a]); h[a] = fminf(S.box6[(3 + a) * K + j], mx[a]);
+                        l[a] = fmaxf(S_box6[a * K + j], mn[a]); h[a] = fminf(S_box6[(3 + a) * K + j], mx[a]);
                         if (a < dims) empty |= !(h[a] > l[a]);   // <=> max(0, min(hi) - max(lo)) == 0 in fp64
                     }
                     if (empty) continue;   // inter == 0: overlap 0 or NaN, never > thr (thr >= 0 here)
-                    if (f2_nms_suppresses(l[0], h[0], l[1], h[1], l[2], h[2], S.vol[j], vk, dims, old_type, p.nms_iou)) sup[w] |= 1u << b;
+                    if (f2_nms_suppresses(l[0], h[0], l[1], h[1], l[2], h[2], S_vol[j], vk, dims, old_type, p.nms_iou)) sup[w] |= 1u << b;
                 }
             }
         }
@@ -309,13 +333,13 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) ap_front2_kernel(Front2
 #pragma unroll
             for (int w = 0; w < F2_MAXW; ++w) {
                 if (w >= W) break;
-                anyp |= sup[w] & S.picked[w];
-                pend |= sup[w] & ~S.done[w];
+                anyp |= sup[w] & S_picked[w];
+                pend |= sup[w] & ~S_done[w];
             }
             __syncthreads();   // everybody has read this round's state
             if (und) {
-                if (anyp) { atomicOr(&S.done[warp], mybit); und = false; }
-                else if (!pend) { atomicOr(&S.picked[warp], mybit); atomicOr(&S.done[warp], mybit); und = false; picked_me = true; }
+                if (anyp) { atomicOr(&S_done[warp], mybit); und = false; }
+                else if (!pend) { atomicOr(&S_picked[warp], mybit); atomicOr(&S_done[warp], mybit); und = false; picked_me = true; }
             }
             if (!__syncthreads_or(und ? 1 : 0)) break;
         }
@@ -337,19 +361,19 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) ap_front2_kernel(Front2
     const bool all_pairs = !(thr_min >= 0.0);
     const float thr_lo = all_pairs ? 0.f : (float)thr_min * (1.f - 1e-6f);
     int ng = 0;
-    for (int w = 0; w < WG; ++w) ng += __popc(S.gmask[w]);
+    for (int w = 0; w < WG; ++w) ng += __popc(S_gmask[w]);
     if (ng == 0) return;   // uniform
     const float *myrow = p.probs + slot * C;
     auto enumerate = [&](int k0, int k1) {
         if (!(keep && k >= k0 && k < k1)) return;
         for (int w = 0; w < WG; ++w) {
-            uint32_t m = S.gmask[w];
+            uint32_t m = S_gmask[w];
             while (m) {
                 const int g = 32 * w + __ffs(m) - 1;
                 m &= m - 1;
-                const int c = S.glab[g];
+                const int c = S_glab[g];
                 if (c < 0 || (!per_class && c != cls)) continue;   // can never match: not a candidate
-                const AmBox &b = S.gbox[g];
+                const AmBox &b = S_gbox[g];
                 const float hh = fminf(ytop, b.ytop) - fmaxf(ybot, b.ybot);
                 const float ox = fminf(hix, b.hix) - fmaxf(lox, b.lox), oz = fminf(hiz, b.hiz) - fmaxf(loz, b.loz);
                 bool need = false, zero = false;
@@ -359,15 +383,15 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) ap_front2_kernel(Front2
                 } else if (hh > 0.f && ox >= 0.f && oz >= 0.f) {
                     // IoU <= I / (V1 + V2 - I) with I = min(overlap of the BEV bounding rectangles, either BEV area) x height
                     // overlap >= the true intersection; fp32 with every rounding pushed to the safe side
-                    const float I = fminf(ox * oz, fminf(ahi, S.garea[g])) * hh * (1.f + 1e-5f);
-                    const float den = vlo + S.gvlo[g] - I;
+                    const float I = fminf(ox * oz, fminf(ahi, S_garea[g])) * hh * (1.f + 1e-5f);
+                    const float den = vlo + S_gvlo[g] - I;
                     need = !(den > 0.f) || I * (1.f + 1e-5f) >= thr_lo * den;
                 }
                 if (need) {
                     const int q = atomicAdd(&qn_s, 1);
                     if (q < F2_QCAP) {
-                        S.queue[q] = (zero ? 0x80000000u : 0u) | ((unsigned)k << 16) | (unsigned)g;
-                        S.qscore[q] = per_class ? __fmul_rn(__ldg(myrow + c), obj) : s1;
+                        S_queue[q] = (zero ? 0x80000000u : 0u) | ((unsigned)k << 16) | (unsigned)g;
+                        S_qscore[q] = per_class ? __fmul_rn(__ldg(myrow + c), obj) : s1;
                     }
                 }
             }
@@ -377,37 +401,31 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) ap_front2_kernel(Front2
         constexpr int NGROUP = NT / 8;
         if (qn <= F2_COOP) {
             for (int q = k; q < qn; q += NT) {
-                const unsigned e = S.queue[q];
-                if (e >> 31) { S.qiou[q] = 0.0; continue; }
-                f2_box_features(p.corners + ((size_t)s * K + ((e >> 16) & 0x3fffu)) * 24, &S.cbox[q]);
+                const unsigned e = S_queue[q];
+                if (e >> 31) { S_qiou[q] = 0.0; continue; }
+                f2_box_features(p.corners + ((size_t)s * K + ((e >> 16) & 0x3fffu)) * 24, &S_cbox[q]);
             }
             __syncthreads();
             const int gli = lane & 7, gshift = lane & 24, group = k >> 3;
-            V2<double> *gbuf = S.scratch + group * 8;
+            V2<double> *gbuf = S_scratch + group * 8;
             for (int base = 0; base < qn; base += NGROUP) {
                 if (base + warp * 4 >= qn) break;   // warp-uniform
                 const int qi = base + group;
                 unsigned e = 0x80000000u;
-                if (qi < qn) e = S.queue[qi];
+                if (qi < qn) e = S_queue[qi];
                 const bool act = !(e >> 31);
-                const AmBox &a = S.cbox[act ? qi : 0], &b = S.gbox[act ? (e & 0xffffu) : 0];
-                double cl[8];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) { cl[2 * t] = (double)b.qx[t]; cl[2 * t + 1] = (double)b.qz[t]; }
+                const AmBox &a = S_cbox[act ? qi : 0], &b = S_gbox[act ? (e & 0xffffu) : 0];
                 CoopState st{(double)a.qx[gli & 3], (double)a.qz[gli & 3], act ? 4 : 0};
-                st = f2_coop_pass(cl[6], cl[7], cl[0], cl[1], st, gli, gshift, gbuf);
-                st = f2_coop_pass(cl[0], cl[1], cl[2], cl[3], st, gli, gshift, gbuf);
-                st = f2_coop_pass(cl[2], cl[3], cl[4], cl[5], st, gli, gshift, gbuf);
-                st = f2_coop_pass(cl[4], cl[5], cl[6], cl[7], st, gli, gshift, gbuf);
+                for (int e = 0; e < 4; ++e) st = f2_coop_pass(&b, e, st, gli, gshift, gbuf);   // clip edges (3->0), (0->1), (1->2), (2->3)
                 const double ia = coop_area_f64(st.vx, st.vy, st.n, gli);
-                if (act && gli == 0) S.qiou[qi] = am_finish_iou(ia, a, b);
+                if (act && gli == 0) S_qiou[qi] = am_finish_iou(ia, a, b);
             }
         } else if (k < AM_CLIP) {
-            V2<double> *bufA = S.scratch + k, *bufB = S.scratch + SH_MAXV * AM_CLIP + k;
+            V2<double> *bufA = S_scratch + k, *bufB = S_scratch + SH_MAXV * AM_CLIP + k;
             for (int qi = k; qi < qn; qi += AM_CLIP) {
-                const unsigned e = S.queue[qi];
-                if (e >> 31) { S.qiou[qi] = 0.0; continue; }
-                S.qiou[qi] = f2_serial_iou(p.corners + ((size_t)s * K + ((e >> 16) & 0x3fffu)) * 24, &S.gbox[e & 0xffffu], bufA, bufB);
+                const unsigned e = S_queue[qi];
+                if (e >> 31) { S_qiou[qi] = 0.0; continue; }
+                S_qiou[qi] = f2_serial_iou(p.corners + ((size_t)s * K + ((e >> 16) & 0x3fffu)) * 24, &S_gbox[e & 0xffffu], bufA, bufB);
             }
         }
     };
@@ -415,35 +433,35 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) ap_front2_kernel(Front2
     // pass 1: a candidate is a true positive at threshold t iff it holds the claim (eval_det.py:117-140)
     auto claims = [&](int qn, int pass, bool recheck) {
         for (int q = k; q < qn; q += NT) {
-            const double v = S.qiou[q];
+            const double v = S_qiou[q];
             if (!(v > thr_min)) continue;
-            const unsigned e = S.queue[q];
+            const unsigned e = S_queue[q];
             const int i = (int)((e >> 16) & 0x3fffu), g = (int)(e & 0xffffu);
-            const int c = S.glab[g];
+            const int c = S_glab[g];
             if (pass == 0 || recheck) {   // (slab mode re-enumerates for the second sweep: the remembered flag is gone)
                 bool first_max = true;   // jmax of (det, class c): first GT of the class attaining the maximum (eval_det.py:121-126)
                 for (int q2 = 0; q2 < qn; ++q2) {
-                    const unsigned e2 = S.queue[q2];
+                    const unsigned e2 = S_queue[q2];
                     if ((int)((e2 >> 16) & 0x3fffu) != i) continue;
                     const int g2 = (int)(e2 & 0xffffu);
-                    if (S.glab[g2] != c) continue;
-                    const double v2 = S.qiou[q2];
+                    if (S_glab[g2] != c) continue;
+                    const double v2 = S_qiou[q2];
                     if (v2 > v || (v2 == v && g2 < g)) { first_max = false; break; }
                 }
                 if (!first_max) continue;
-                if (pass == 0) S.queue[q] = e | 0x40000000u;   // remembered for the true-positive pass on the same queue
+                if (pass == 0) S_queue[q] = e | 0x40000000u;   // remembered for the true-positive pass on the same queue
             }
             if (pass == 0) {
                 // non-negative fp32 scores order like their bit patterns; lower det index wins ties
-                const unsigned long long key = ((unsigned long long)__float_as_uint(S.qscore[q]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+                const unsigned long long key = ((unsigned long long)__float_as_uint(S_qscore[q]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
                 for (int t = 0; t < p.nthr; ++t)
-                    if (v > p.thr[t]) atomicMax(&S.best[(size_t)g * p.nthr + t], key);
+                    if (v > p.thr[t]) atomicMax(&S_best[(size_t)g * p.nthr + t], key);
             } else {
                 if (!recheck && !(e & 0x40000000u)) continue;
                 unsigned char tp = 0;
                 for (int t = 0; t < p.nthr; ++t)
                     if (v > p.thr[t]) {
-                        const unsigned long long w = S.best[(size_t)g * p.nthr + t];
+                        const unsigned long long w = S_best[(size_t)g * p.nthr + t];
                         if ((unsigned)(0xFFFFFFFFu - (unsigned)(w & 0xFFFFFFFFull)) == (unsigned)i) tp |= (unsigned char)(1u << t);
                     }
                 if (tp) {
@@ -451,7 +469,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 4) ap_front2_kernel(Front2
                     if (p.rec_tp) p.rec_tp[(size_t)c * N + dslot] = tp;
                     if (p.tp_key) {
                         const int at = atomicAdd(&p.tp_cnt[c], 1);
-                        if (at < p.tp_cap) { p.tp_key[(size_t)c * p.tp_cap + at] = score_key(S.qscore[q]); p.tp_bits[(size_t)c * p.tp_cap + at] = tp; }
+                        if (at < p.tp_cap) { p.tp_key[(size_t)c * p.tp_cap + at] = score_key(S_qscore[q]); p.tp_bits[(size_t)c * p.tp_cap + at] = tp; }
                     }
                 }
             }

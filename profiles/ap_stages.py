@@ -51,3 +51,11 @@ t1 = time.perf_counter()
 torch.cuda.synchronize()
 print("host us per reset+step (async)", (t1 - t0) / 50 * 1e6)
 print("mAP", float(m[0.25]["mAP"]), float(m[0.5]["mAP"]))
+if os.environ.get("APX_STAMPS"):
+    d = torch.zeros((20, 8), dtype=torch.int64, device=dev)
+    os.environ["OVDET_APX_DBG_PTR"] = str(d.data_ptr())
+    red.launch([rs], lists); torch.cuda.synchronize()
+    a = d.cpu().numpy().astype(np.float64)
+    print("merge: gather issue %.2f, gather wait %.2f, rank+rest %.2f us; total entries %s" % (np.median(a[:, 6] - a[:, 2]) / 1e3, np.median(a[:, 7] - a[:, 6]) / 1e3, np.median(a[:, 3] - a[:, 7]) / 1e3, lists.tp_cnt.cpu().numpy()[:6]))
+    for i, nm in [(1, "pdl wait"), (2, "counts (thread 0)"), (3, "gather+sort"), (4, "bin search"), (5, "table+zero")]:
+        print("merge %-18s %6.2f us" % (nm, np.median(a[:, i] - a[:, i - 1]) / 1e3))
