@@ -224,6 +224,7 @@ int ovdet_apc_final(const uint8_t *tp_bits, const int32_t *tp_cnt, const uint32_
 #define OVDET_FRONT_PER_CLASS 0x1000u
 #define OVDET_FRONT_CLS_CONF 0x2000u
 #define OVDET_FRONT_GT_PRESENT_F32 0x4000u   /* gt_present is the reference's fp32 mask [S,G] instead of uint8 */
+#define OVDET_FRONT_RESET 0x8000u            /* zero tp_cnt [C] and npos [C] on the stream first (start of an evaluation) */
 int ovdet_ap_front_f32(const float *corners, const float *probs, const float *obj, const uint8_t *nonempty,
                        const float *gt_corners, const int64_t *gt_labels, const void *gt_present,
                        int S, int K, int G, int C, double nms_iou, float conf_thresh, unsigned flags,

@@ -64,7 +64,7 @@ SIGNATURES = {
 GIOU_ROTATED, GIOU_PREFILTER, GIOU_INTER_ONLY, GIOU_CLIP_F64, GIOU_ENCL_HULL = 1, 2, 4, 8, 16
 NMS_2D, NMS_SAMECLS, NMS_OLD_TYPE, PARSE_NO_NMS = 1, 2, 4, 0x100
 LOGITS_L2NORM = 1
-FRONT_PER_CLASS, FRONT_CLS_CONF, FRONT_GT_PRESENT_F32 = 0x1000, 0x2000, 0x4000
+FRONT_PER_CLASS, FRONT_CLS_CONF, FRONT_GT_PRESENT_F32, FRONT_RESET = 0x1000, 0x2000, 0x4000, 0x8000
 APX_FORCE_EXCHANGE, APX_USE_07_METRIC = 1, 2
 APX_STAGE_PUSH, APX_STAGE_MERGE_HIST, APX_STAGE_FINAL = 0x10, 0x20, 0x40
 SYMM_HANDLE_BYTES = 64

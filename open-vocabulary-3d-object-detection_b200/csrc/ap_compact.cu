@@ -531,30 +531,136 @@ struct ApxParams {
 
 __device__ __forceinline__ unsigned *apx_ctrl(const ApxParams &p) { return reinterpret_cast<unsigned *>(p.local + p.ll.ctrl); }
 
-// ---- stage 1: push this rank's lists to every peer.  grid (W, C)
-__global__ void __launch_bounds__(256) apx_push_lists_kernel(ApxParams p)
+// Sort the (key, bits) entries [0, total) held in ksm[0..cap) / bsm[0..cap) by (key, bits, position); returns which half
+// (0 / 1) of the two-buffer arrays ksm[2][cap] / bsm[2][cap] holds the result.  All 1024 threads of the CTA call it.
+struct SortScratch { uint16_t *rnk, *whist; uint32_t *dbase, *wsum_s; int *skip_s; };
+__device__ __forceinline__ int cta_sort(uint32_t *ksm, uint8_t *bsm, const SortScratch &sc, int cap, int total)
 {
-    const int dst = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    uint16_t *rnk = sc.rnk, *whist = sc.whist;
+    uint32_t *dbase = sc.dbase, *wsum_s = sc.wsum_s;
+    int &skip_s = *sc.skip_s;
+    const int tid = threadIdx.x;
+    // Stable LSD radix sort of (key, bits) by 8-bit digits: the bits first (so that equal keys end up in a defined order
+    // whatever order the lists were appended in), then the four key bytes.  Warp w owns the contiguous elements
+    // [w*CH, (w+1)*CH): within a warp __match_any_sync ranks the elements of equal digit, one lane per digit bumps the
+    // warp's count; a scan over (digit, warp) then gives every element its destination.  O(n) per pass -- the bitonic
+    // network this replaces was 4x the instructions at 2 048 entries and 15x at 16 384.
+    const int lane = tid & 31, warp = tid >> 5;
+    const int CH = (((total + 31) >> 5) + 31) & ~31;
+    const int nwarp = CH ? (total + CH - 1) / CH : 0;      // warps that own elements
+    int cur = 0;
+    if (total <= 384) {
+        // short list (a rank's share of a small evaluation): one counting pass -- entry i goes to the number of entries
+        // that sort before it by (key, bits, position); every thread reads the same entry at a time (broadcast)
+        __syncthreads();
+        if (tid < total) {
+            const uint32_t ki = ksm[tid]; const uint8_t bi = bsm[tid];
+            const unsigned long long vi = ((unsigned long long)ki << 8) | bi;
+            int pos = 0;
+#pragma unroll 8
+            for (int j = 0; j < total; ++j) {   // unconditional broadcast loads and bitwise compares: nothing to branch on, the loads overlap
+                const unsigned long long vj = ((unsigned long long)ksm[j] << 8) | bsm[j];
+                pos += (int)(vj < vi) | ((int)(vj == vi) & (int)(j < tid));
+            }
+            ksm[cap + pos] = ki; bsm[cap + pos] = bi;
+        }
+        cur = 1;
+        __syncthreads();
+    } else
+    for (int pass = 0; pass < 5; ++pass) {
+        const int in0 = cur * cap, out0 = (cur ^ 1) * cap;
+        for (int i = tid; i < nwarp * 128; i += 1024) reinterpret_cast<uint32_t *>(whist)[i] = 0u;
+        if (tid == 0) skip_s = 0;
+        __syncthreads();
+        const int sh = 8 * (pass - 1);
+        for (int r = 0; r < CH; r += 32) {
+            const int i = warp * CH + r + lane;
+            const bool valid = i < total;
+            const unsigned d = valid ? (pass == 0 ? (unsigned)bsm[in0 + i] : ((ksm[in0 + i] >> sh) & 255u)) : (256u + lane);
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int lead = __ffs(peers) - 1;
+            unsigned old = 0;
+            if (valid && lane == lead) { old = whist[warp * 256 + d]; whist[warp * 256 + d] = (uint16_t)(old + __popc(peers)); }
+            __syncwarp();
+            old = __shfl_sync(0xffffffffu, old, lead);
+            if (valid) rnk[i] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
+        }
+        __syncthreads();
+        if (tid < 256) {   // digit tid: exclusive scan over the warps, then over the digits
+            unsigned run = 0;
+#pragma unroll 8
+            for (int w2 = 0; w2 < nwarp; ++w2) { const unsigned t = whist[w2 * 256 + tid]; whist[w2 * 256 + tid] = (uint16_t)run; run += t; }
+            if (run == (unsigned)total) skip_s = 1;   // every element has this digit: the pass would not move anything
+            unsigned x = run;
+            for (int off = 1; off < 32; off <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+            if (lane == 31) wsum_s[warp] = x;
+            dbase[tid] = x - run;   // exclusive inside the warp of digits
+        }
+        __syncthreads();
+        if (tid < 256) {
+            unsigned add = 0;
+            for (int w2 = 0; w2 < warp; ++w2) add += wsum_s[w2];
+            dbase[tid] += add;
+        }
+        __syncthreads();
+        if (!skip_s) {
+            for (int r = 0; r < CH; r += 32) {
+                const int i = warp * CH + r + lane;
+                if (i < total) {
+                    const uint32_t kk = ksm[in0 + i]; const uint8_t bb = bsm[in0 + i];
+                    const unsigned d = pass == 0 ? (unsigned)bb : ((kk >> sh) & 255u);
+                    const unsigned pos = dbase[d] + whist[warp * 256 + d] + rnk[i];
+                    ksm[out0 + pos] = kk; bsm[out0 + pos] = bb;
+                }
+            }
+            cur ^= 1;
+        }
+        __syncthreads();
+    }
+    return cur;
+}
+
+// ---- stage 1: SORT this rank's list of a class, then push it to every peer.  grid C, 1024 threads
+// Sorting on the sender means the eight ranks sort their eighth of the entries at the same time; the receivers only
+// have to merge sorted runs (stage 2), which is a handful of binary searches per entry instead of a 5-pass sort of all.
+__global__ void __launch_bounds__(1024, 1) apx_push_lists_kernel(ApxParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int cap = p.cap;
+    uint32_t *ksm = reinterpret_cast<uint32_t *>(sm);                 // [2][cap]
+    uint16_t *rnk = reinterpret_cast<uint16_t *>(ksm + 2 * cap);      // [cap]
+    uint16_t *whist = rnk + cap;                                      // [32 warps][256 digits]
+    uint8_t *bsm = reinterpret_cast<uint8_t *>(whist + 32 * 256);     // [2][cap]
+    __shared__ uint32_t dbase[256], wsum_s[8];
+    __shared__ int skip_s;
+    const int c = blockIdx.x, tid = threadIdx.x;
     pdl_wait();
     pdl_release();
     const unsigned tag = apx_ctrl(p)[0] + 1u;
-    unsigned char *half = p.peers.base[dst] + (size_t)(tag & 1u) * p.sl.half;
-    unsigned char *slot = half + p.sl.lists + (size_t)p.rank * p.sl.list_stride;
     const int raw = p.tp_cnt[c];
-    const int n = min(min(raw, p.cap_list), p.cap);
-    const uint4 *ks = reinterpret_cast<const uint4 *>(p.tp_key + (size_t)c * p.cap_list);
-    uint4 *kd = reinterpret_cast<uint4 *>(slot + p.sl.l_key + sizeof(uint32_t) * (size_t)c * p.cap);
-    for (int i = tid; i < (n + 3) / 4; i += 256) kd[i] = ks[i];
-    const uint4 *bs = reinterpret_cast<const uint4 *>(p.tp_bits + (size_t)c * p.cap_list);
-    uint4 *bd = reinterpret_cast<uint4 *>(slot + p.sl.l_bits + (size_t)c * p.cap);
-    for (int i = tid; i < (n + 15) / 16; i += 256) bd[i] = bs[i];
-    if (tid == 0) {
-        reinterpret_cast<int *>(slot + p.sl.l_cnt)[c] = raw;
-        reinterpret_cast<long long *>(slot + p.sl.l_npos)[c] = p.npos[c];
+    const int n = min(min(raw, p.cap_list), cap);
+    for (int i = tid; i < n; i += 1024) { ksm[i] = p.tp_key[(size_t)c * p.cap_list + i]; bsm[i] = p.tp_bits[(size_t)c * p.cap_list + i]; }
+    const int cur = cta_sort(ksm, bsm, SortScratch{rnk, whist, dbase, wsum_s, &skip_s}, cap, n);
+    const uint4 *ks = reinterpret_cast<const uint4 *>(ksm + cur * cap);
+    const uint4 *bs = reinterpret_cast<const uint4 *>(bsm + cur * cap);
+    const long long np = p.npos[c];
+    for (int dst = 0; dst < p.W; ++dst) {
+        unsigned char *slot = p.peers.base[dst] + (size_t)(tag & 1u) * p.sl.half + p.sl.lists + (size_t)p.rank * p.sl.list_stride;
+        uint4 *kd = reinterpret_cast<uint4 *>(slot + p.sl.l_key + sizeof(uint32_t) * (size_t)c * cap);
+        for (int i = tid; i < (n + 3) / 4; i += 1024) kd[i] = ks[i];
+        uint4 *bd = reinterpret_cast<uint4 *>(slot + p.sl.l_bits + (size_t)c * cap);
+        for (int i = tid; i < (n + 15) / 16; i += 1024) bd[i] = bs[i];
+        if (tid == 0) {
+            reinterpret_cast<int *>(slot + p.sl.l_cnt)[c] = raw;
+            reinterpret_cast<long long *>(slot + p.sl.l_npos)[c] = np;
+        }
     }
     __threadfence_system();
     __syncthreads();
-    if (tid == 0) st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_l) + (size_t)p.rank * p.C + c, tag);
+    if (tid < p.W) {
+        unsigned char *half = p.peers.base[tid] + (size_t)(tag & 1u) * p.sl.half;
+        st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_l) + (size_t)p.rank * p.C + c, tag);
+    }
 }
 
 // ---- stage 2: per class, gather the W lists, sort, bin edges; zero the class's histogram.  grid C, 1024 threads
@@ -622,83 +728,50 @@ __global__ void __launch_bounds__(1024, 1) apx_merge_kernel(ApxParams p)
         const int n = n_s[r], o = off_s[r];
         for (int i = tid; i < n; i += 1024) { ksm[o + i] = ksrc[i]; bsm[o + i] = bsrc[i]; }
     }
-    // Stable LSD radix sort of (key, bits) by 8-bit digits: the bits first (so that equal keys end up in a defined order
-    // whatever order the lists were appended in), then the four key bytes.  Warp w owns the contiguous elements
-    // [w*CH, (w+1)*CH): within a warp __match_any_sync ranks the elements of equal digit, one lane per digit bumps the
-    // warp's count; a scan over (digit, warp) then gives every element its destination.  O(n) per pass -- the bitonic
-    // network this replaces was 4x the instructions at 2 048 entries and 15x at 16 384.
-    const int lane = tid & 31, warp = tid >> 5;
-    const int CH = (((total + 31) >> 5) + 31) & ~31;
-    const int nwarp = CH ? (total + CH - 1) / CH : 0;      // warps that own elements
-    int cur = 0;
-    if (total <= 384) {
-        // short list (a rank's share of a small evaluation): one counting pass -- entry i goes to the number of entries
-        // that sort before it by (key, bits, position); every thread reads the same entry at a time (broadcast)
-        XSTAMP(6);
+    int cur;
+    if (!p.exchange) {
+        cur = cta_sort(ksm, bsm, SortScratch{rnk, whist, dbase, wsum_s, &skip_s}, cap, total);
+    } else {
+        // the W runs arrive sorted (stage 1): an entry's place in the merged order is its index in its own run plus, for
+        // every other run, the number of entries that sort before it -- ties broken by (bits, source rank), so the result
+        // does not depend on arrival order.  Four entries of a thread are searched in lock step (independent probes).
         __syncthreads();
-        XSTAMP(7);
-        if (tid < total) {
-            const uint32_t ki = ksm[tid]; const uint8_t bi = bsm[tid];
-            const unsigned long long vi = ((unsigned long long)ki << 8) | bi;
-            int pos = 0;
-#pragma unroll 8
-            for (int j = 0; j < total; ++j) {   // unconditional broadcast loads and bitwise compares: nothing to branch on, the loads overlap
-                const unsigned long long vj = ((unsigned long long)ksm[j] << 8) | bsm[j];
-                pos += (int)(vj < vi) | ((int)(vj == vi) & (int)(j < tid));
+        const int W = p.W;
+        for (int base = tid * 4; base < total; base += 4096) {
+            unsigned long long v[4]; int pos[4], own[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = min(base + q, total - 1);
+                v[q] = ((unsigned long long)ksm[i] << 8) | bsm[i];
+                int r = 0;
+                while (r + 1 < W && i >= off_s[r + 1]) ++r;
+                own[q] = r; pos[q] = i - off_s[r];
             }
-            ksm[cap + pos] = ki; bsm[cap + pos] = bi;
+            for (int r2 = 0; r2 < W; ++r2) {
+                const int o2 = off_s[r2], n2 = n_s[r2];
+                if (n2 == 0) continue;
+                int top = 1;
+                while (top * 2 <= n2) top *= 2;
+                int lo[4] = {0, 0, 0, 0};
+                for (int step = top; step > 0; step >>= 1) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int nx = lo[q] + step;
+                        const int j = o2 + min(nx, n2) - 1;
+                        const unsigned long long w = ((unsigned long long)ksm[j] << 8) | bsm[j];
+                        // entries of an earlier run go first on ties (<=), those of a later run after (<)
+                        const bool before = r2 < own[q] ? (w <= v[q]) : (w < v[q]);
+                        lo[q] = ((nx <= n2) & before) ? nx : lo[q];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pos[q] += (r2 != own[q]) ? lo[q] : 0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (base + q < total) { ksm[cap + pos[q]] = (uint32_t)(v[q] >> 8); bsm[cap + pos[q]] = (uint8_t)v[q]; }
         }
         cur = 1;
-        __syncthreads();
-    } else
-    for (int pass = 0; pass < 5; ++pass) {
-        const int in0 = cur * cap, out0 = (cur ^ 1) * cap;
-        for (int i = tid; i < nwarp * 128; i += 1024) reinterpret_cast<uint32_t *>(whist)[i] = 0u;
-        if (tid == 0) skip_s = 0;
-        __syncthreads();
-        const int sh = 8 * (pass - 1);
-        for (int r = 0; r < CH; r += 32) {
-            const int i = warp * CH + r + lane;
-            const bool valid = i < total;
-            const unsigned d = valid ? (pass == 0 ? (unsigned)bsm[in0 + i] : ((ksm[in0 + i] >> sh) & 255u)) : (256u + lane);
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
-            const int lead = __ffs(peers) - 1;
-            unsigned old = 0;
-            if (valid && lane == lead) { old = whist[warp * 256 + d]; whist[warp * 256 + d] = (uint16_t)(old + __popc(peers)); }
-            __syncwarp();
-            old = __shfl_sync(0xffffffffu, old, lead);
-            if (valid) rnk[i] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
-        }
-        __syncthreads();
-        if (tid < 256) {   // digit tid: exclusive scan over the warps, then over the digits
-            unsigned run = 0;
-#pragma unroll 8
-            for (int w2 = 0; w2 < nwarp; ++w2) { const unsigned t = whist[w2 * 256 + tid]; whist[w2 * 256 + tid] = (uint16_t)run; run += t; }
-            if (run == (unsigned)total) skip_s = 1;   // every element has this digit: the pass would not move anything
-            unsigned x = run;
-            for (int off = 1; off < 32; off <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
-            if (lane == 31) wsum_s[warp] = x;
-            dbase[tid] = x - run;   // exclusive inside the warp of digits
-        }
-        __syncthreads();
-        if (tid < 256) {
-            unsigned add = 0;
-            for (int w2 = 0; w2 < warp; ++w2) add += wsum_s[w2];
-            dbase[tid] += add;
-        }
-        __syncthreads();
-        if (!skip_s) {
-            for (int r = 0; r < CH; r += 32) {
-                const int i = warp * CH + r + lane;
-                if (i < total) {
-                    const uint32_t kk = ksm[in0 + i]; const uint8_t bb = bsm[in0 + i];
-                    const unsigned d = pass == 0 ? (unsigned)bb : ((kk >> sh) & 255u);
-                    const unsigned pos = dbase[d] + whist[warp * 256 + d] + rnk[i];
-                    ksm[out0 + pos] = kk; bsm[out0 + pos] = bb;
-                }
-            }
-            cur ^= 1;
-        }
         __syncthreads();
     }
     XSTAMP(3);
@@ -755,6 +828,37 @@ __global__ void __launch_bounds__(1024, 1) apx_merge_kernel(ApxParams p)
     XSTAMP(5);
 }
 
+// the last CTA of a class to finish its share of the LAST record block ships the class's finished histogram row to
+// every peer and raises the flag (called by all threads of the CTA after its flush to global memory)
+__device__ __forceinline__ void apx_hist_ship(const ApxParams &p, int c, uint32_t *hist, int last_block, int *last_s)
+{
+    const int NT = (int)blockDim.x;
+    if (!(p.exchange && last_block)) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(reinterpret_cast<unsigned *>(p.local + p.ll.done_hist) + c, 1u);
+        *last_s = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*last_s) return;
+    __threadfence();
+    const unsigned tag = apx_ctrl(p)[0] + 1u;
+    const uint4 *src = reinterpret_cast<const uint4 *>(hist);
+    const int n4 = p.sl.hp / 4;
+    for (int r = 0; r < p.W; ++r) {
+        unsigned char *half = p.peers.base[r] + (size_t)(tag & 1u) * p.sl.half;
+        uint4 *dst = reinterpret_cast<uint4 *>(half + p.sl.hist + (size_t)p.rank * p.sl.hist_stride + sizeof(uint32_t) * (size_t)c * p.sl.hp);
+        for (int i = threadIdx.x; i < n4; i += NT) dst[i] = __ldcg(src + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < p.W) {
+        unsigned char *half = p.peers.base[threadIdx.x] + (size_t)(tag & 1u) * p.sl.half;
+        st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_h) + (size_t)p.rank * p.C + c, tag);
+    }
+}
+
 // ---- stage 3: histogram of the local records over the merged list; the last CTA of a class ships the class's row
 __global__ void __launch_bounds__(1024) apx_hist_kernel(ApxParams p, const float *__restrict__ score, long long N, int last_block)
 {
@@ -778,7 +882,7 @@ __global__ void __launch_bounds__(1024) apx_hist_kernel(ApxParams p, const float
     for (int i = threadIdx.x; i < ntp; i += NT) k[i] = tp_key[(size_t)c * cap + i];
     if (threadIdx.x == 0) k[ntp] = 0xFFFFFFFFu;
     for (int i = threadIdx.x; i <= ntp; i += NT) h[i] = 0;
-    for (int i = threadIdx.x; i < (nb > 0 ? nb : 1); i += NT) bins[i] = eg[i];
+    for (int i = threadIdx.x; i < (nb + 1) / 2 + (nb == 0 ? 1 : 0); i += NT) reinterpret_cast<uint32_t *>(bins)[i] = reinterpret_cast<const uint32_t *>(eg)[i];   // two u16 entries per load
     __syncthreads();
     // Every record scoring below all TPs lands in the one bucket after the last list entry (the bulk of the false
     // positives): counted in a register instead of hammering one shared word.
@@ -827,31 +931,86 @@ __global__ void __launch_bounds__(1024) apx_hist_kernel(ApxParams p, const float
     if ((threadIdx.x & 31) == 0 && tail) atomicAdd(&h[ntp], tail);
     __syncthreads();
     for (int i = threadIdx.x; i <= ntp; i += NT) { const uint32_t v = h[i]; if (v) atomicAdd(&hist[i], v); }
-    if (!(p.exchange && last_block)) return;
-    // the last CTA of this class to get here ships the finished row to every peer
-    __threadfence();
+    apx_hist_ship(p, c, hist, last_block, &last_s);
+}
+
+// ---- stage 3, long merged list (> 4096 entries: several ranks' true positives): the private histogram packs two 16-bit
+// counters per shared word (a CTA never sees more than 60 000 records), so two 512-thread CTAs fit an SM next to the
+// 64 KB of list keys instead of one; a bin now holds 1-2 list keys on average, so the bucket is a short branch-free
+// binary search inside the bin's range.  (Keys left in global memory instead: 3x slower, every probe is an L1/L2 trip.)
+__global__ void __launch_bounds__(512) apx_hist_big_kernel(ApxParams p, const float *__restrict__ score, long long N, int last_block)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int cap = p.cap;
+    const int NT = (int)blockDim.x;
+    uint32_t *k = reinterpret_cast<uint32_t *>(sm);                         // [cap + 1] sorted keys of the merged list
+    uint32_t *hw = k + cap + 1;                                             // [(cap + 2) / 2] two u16 counters per word
+    uint16_t *bins = reinterpret_cast<uint16_t *>(hw + (cap + 2) / 2);      // [APX_BINS]
+    __shared__ int last_s;
+    const int c = blockIdx.y;
+    pdl_wait();
+    pdl_release();
+    const unsigned char *eb = p.local + p.ll.edge + (size_t)c * APX_ESTRIDE_BYTES;
+    const uint32_t *hdr = reinterpret_cast<const uint32_t *>(eb);
+    const uint16_t *eg = reinterpret_cast<const uint16_t *>(eb + sizeof(uint32_t) * APX_EHDR);
+    const uint32_t *kg = reinterpret_cast<const uint32_t *>(p.local + p.ll.mkey) + (size_t)c * cap;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(p.local + p.ll.hist) + (size_t)c * p.sl.hp;
+    const uint32_t kmin = hdr[0];
+    const int shift = (int)hdr[1], nb = (int)hdr[2], ntp = (int)hdr[3];
+    for (int i = threadIdx.x; i < ntp; i += NT) k[i] = kg[i];
+    for (int i = threadIdx.x; i < (ntp + 2) / 2; i += NT) hw[i] = 0;
+    for (int i = threadIdx.x; i < (nb + 1) / 2 + (nb == 0 ? 1 : 0); i += NT) reinterpret_cast<uint32_t *>(bins)[i] = reinterpret_cast<const uint32_t *>(eg)[i];
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(reinterpret_cast<unsigned *>(p.local + p.ll.done_hist) + c, 1u);
-        last_s = (t == gridDim.x - 1);
+    const uint32_t kmax = ntp > 0 ? k[ntp - 1] : 0u;
+    const uint32_t last_bin = (uint32_t)(nb > 0 ? nb - 1 : 0);
+    unsigned int tail = 0;
+    const float *sc = score + (size_t)c * N;
+    auto place4 = [&](const float (&sv)[4]) {
+        uint32_t key[4]; int lo[4], hi[4]; bool cnt[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            key[q] = apc_score_key(sv[q]);
+            const bool valid = sv[q] > -INFINITY, below = key[q] > kmax;
+            tail += (valid && below) ? 1u : 0u;
+            cnt[q] = valid && !below;
+            const uint32_t d = key[q] > kmin ? key[q] - kmin : 0u;
+            const uint32_t bi = min(d >> shift, last_bin);
+            lo[q] = (int)(bins[bi] & 0x7fffu);
+            hi[q] = bi + 1 < (uint32_t)nb ? (int)(bins[bi + 1] & 0x7fffu) : ntp;
+        }
+        // lower bound inside [lo, hi): three branch-free steps cover ranges of up to 7 entries
+#pragma unroll
+        for (int step = 4; step > 0; step >>= 1)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int nx = lo[q] + step;
+                const uint32_t kv = k[min(nx, hi[q]) - (hi[q] > 0 ? 1 : 0)];
+                lo[q] = ((nx <= hi[q]) & (kv < key[q])) ? nx : lo[q];
+            }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            while (cnt[q] && lo[q] < hi[q] && k[lo[q]] < key[q]) ++lo[q];   // a bin of more than 7 entries: finish the scan
+            if (cnt[q]) atomicAdd(&hw[lo[q] >> 1], 1u << ((lo[q] & 1) * 16));
+        }
+    };
+    auto place = [&](float s) { const float sv[4] = {s, -INFINITY, -INFINITY, -INFINITY}; place4(sv); };
+    if (((reinterpret_cast<uintptr_t>(sc) & 15) == 0) && N < 0x7fffffffLL) {
+        const int n4 = (int)(N >> 2);
+        const int step = (int)(gridDim.x * NT);
+        for (int i = (int)(blockIdx.x * NT + threadIdx.x); i < n4; i += step) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(sc) + i);
+            const float sv[4] = {v.x, v.y, v.z, v.w};
+            place4(sv);
+        }
+        for (long long i = ((long long)n4 << 2) + (long long)blockIdx.x * NT + threadIdx.x; i < N; i += (long long)gridDim.x * NT) place(sc[i]);
+    } else {
+        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < N; i += (long long)gridDim.x * NT) place(sc[i]);
     }
+    for (int off = 16; off > 0; off >>= 1) tail += __shfl_xor_sync(0xffffffffu, tail, off);
+    if ((threadIdx.x & 31) == 0 && tail) atomicAdd(&hist[ntp], tail);
     __syncthreads();
-    if (!last_s) return;
-    __threadfence();
-    const unsigned tag = apx_ctrl(p)[0] + 1u;
-    const uint4 *src = reinterpret_cast<const uint4 *>(hist);
-    const int n4 = p.sl.hp / 4;
-    for (int r = 0; r < p.W; ++r) {
-        unsigned char *half = p.peers.base[r] + (size_t)(tag & 1u) * p.sl.half;
-        uint4 *dst = reinterpret_cast<uint4 *>(half + p.sl.hist + (size_t)p.rank * p.sl.hist_stride + sizeof(uint32_t) * (size_t)c * p.sl.hp);
-        for (int i = threadIdx.x; i < n4; i += NT) dst[i] = __ldcg(src + i);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < p.W) {
-        unsigned char *half = p.peers.base[threadIdx.x] + (size_t)(tag & 1u) * p.sl.half;
-        st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_h) + (size_t)p.rank * p.C + c, tag);
-    }
+    for (int i = threadIdx.x; i <= ntp; i += NT) { const uint32_t v = (hw[i >> 1] >> ((i & 1) * 16)) & 0xffffu; if (v) atomicAdd(&hist[i], v); }
+    apx_hist_ship(p, c, hist, last_block, &last_s);
 }
 
 // ---- stage 4: per (class, threshold): sum the W histogram rows, positions, precision envelope, AP.  grid (C, nthr)
@@ -1065,7 +1224,9 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
     unsigned stages = flags & (OVDET_APX_STAGE_PUSH | OVDET_APX_STAGE_MERGE_HIST | OVDET_APX_STAGE_FINAL);
     if (!stages) stages = OVDET_APX_STAGE_PUSH | OVDET_APX_STAGE_MERGE_HIST | OVDET_APX_STAGE_FINAL;
     if (exchange && (stages & OVDET_APX_STAGE_PUSH)) {
-        OVDET_CUDA_TRY(launch_pdl(apx_push_lists_kernel, dim3(world, C), dim3(256), 0, st, p));
+        const size_t psmem = (size_t)cap_total * 12 + sizeof(uint16_t) * 32 * 256;
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_push_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        OVDET_CUDA_TRY(launch_pdl(apx_push_lists_kernel, dim3(C), dim3(1024), psmem, st, p));
         { const int rc = launch_ok("apx_push_lists_kernel"); if (rc) return rc; }
     }
     if (stages & OVDET_APX_STAGE_MERGE_HIST) {
@@ -1075,33 +1236,40 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
         { const int rc = launch_ok("apx_merge_kernel"); if (rc) return rc; }
     }
     if (stages & OVDET_APX_STAGE_MERGE_HIST) {
-        const size_t smem = sizeof(uint32_t) * 2 * ((size_t)cap_total + 1) + sizeof(uint16_t) * APX_BINS;
-        OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const bool big = cap_total > 4096;
+        const size_t smem = big ? sizeof(uint32_t) * ((size_t)cap_total + 1 + ((size_t)cap_total + 2) / 2) + sizeof(uint16_t) * APX_BINS
+                                : sizeof(uint32_t) * 2 * ((size_t)cap_total + 1) + sizeof(uint16_t) * APX_BINS;
+        if (big) OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_hist_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = (int)(220 * 1024 / (smem + 1024));
         if (per_sm > 8) per_sm = 8;
         if (per_sm < 1) per_sm = 1;
-        const int hist_nt = per_sm >= 4 ? APC_NT : (per_sm >= 2 ? 512 : 1024);   // keep >= 1024 threads per SM
         const int gx_full = (148 * per_sm + C - 1) / C;
-        int launched = 0;
+        auto launch_hist = [&](const float *blk, long long N, int last) -> int {
+            // a CTA pays the set-up of its tables (list keys, 16 KB of bins) and the flush of its histogram: with few records
+            // per class use 1024-thread CTAs (the set-up is spread over 4x the threads) of >= 16 records per thread
+            int nt = big ? 512 : APC_NT;
+            long long gx = (N + 8191) / 8192;
+            if (!big && gx < gx_full / 2) { nt = 1024; gx = (N + 16383) / 16384; }
+            if (gx > gx_full) gx = gx_full;
+            if (big && gx * 60000 < N) gx = (N + 59999) / 60000;   // 16-bit private counters: < 65 536 records per CTA
+            if (gx < 1) gx = 1;
+            if (big) OVDET_CUDA_TRY(launch_pdl(apx_hist_big_kernel, dim3((unsigned)gx, C), dim3(nt), smem, st, p, blk, N, last));
+            else OVDET_CUDA_TRY(launch_pdl(apx_hist_kernel, dim3((unsigned)gx, C), dim3(nt), smem, st, p, blk, N, last));
+            return OVDET_OK;
+        };
         for (int b = 0; b < nblocks; ++b) {
             const long long N = block_n[b];
             OVDET_REQUIRE(N >= 0, "negative block size");
             const bool last = (b == nblocks - 1);
             if (N == 0 && !(exchange && last)) continue;
             OVDET_REQUIRE(N == 0 || blocks[b], "null record block");
-            // a CTA pays ~3 x cap words of table set-up and flush: give it at least 8192 records when there are few
-            long long gx = (N + 8191) / 8192;
-            if (gx > gx_full) gx = gx_full;
-            if (gx < 1) gx = 1;
-            OVDET_CUDA_TRY(launch_pdl(apx_hist_kernel, dim3((unsigned)gx, C), dim3(hist_nt), smem, st, p, static_cast<const float *>(blocks[b]), (long long)N, last ? 1 : 0));
-            { const int rc = launch_ok("apx_hist_kernel"); if (rc) return rc; }
-            ++launched;
+            { const int rc = launch_hist(static_cast<const float *>(blocks[b]), N, last ? 1 : 0); if (rc) return rc; }
         }
         if (exchange && nblocks == 0) {   // nothing local: still ship the (zero) rows so that the peers' final stage can run
-            OVDET_CUDA_TRY(launch_pdl(apx_hist_kernel, dim3(1, C), dim3(hist_nt), smem, st, p, static_cast<const float *>(nullptr), 0LL, 1));
-            { const int rc = launch_ok("apx_hist_kernel"); if (rc) return rc; }
+            const int rc = launch_hist(nullptr, 0, 1);
+            if (rc) return rc;
         }
-        (void)launched;
     }
     if (stages & OVDET_APX_STAGE_FINAL) {
         const size_t smem = (sizeof(unsigned int) + 1) * (size_t)cap_total;

@@ -521,6 +521,11 @@ extern "C" int ovdet_ap_front_f32(const float *corners, const float *probs, cons
     OVDET_REQUIRE((tp_key == nullptr) == (tp_bits == nullptr) && (tp_key == nullptr) == (tp_cnt == nullptr), "tp_key, tp_bits and tp_cnt go together");
     OVDET_REQUIRE(tp_key == nullptr || tp_cap > 0, "tp_cap must be positive");
     OVDET_REQUIRE(rec_tp || tp_key, "need rec_tp and/or a TP list to report the true positives");
+    if (flags & OVDET_FRONT_RESET) {   // start of an evaluation: the lists' counters and the GT counts, one memset each
+        if (tp_cnt) OVDET_CUDA_TRY(cudaMemsetAsync(tp_cnt, 0, sizeof(int32_t) * C, reinterpret_cast<cudaStream_t>(stream)));
+        OVDET_CUDA_TRY(cudaMemsetAsync(npos, 0, sizeof(int64_t) * C, reinterpret_cast<cudaStream_t>(stream)));
+        flags &= ~OVDET_FRONT_RESET;
+    }
     const int nt = K <= 128 ? 128 : 256;
     const bool lean = K <= 256 && G <= 32767 && ((flags & OVDET_PARSE_NO_NMS) || nms_iou >= 0.0) && !getenv("OVDET_APFRONT_GENERIC") &&
                       f2_smem_bytes(K, G, C, nthr, nt, flags) <= 100 * 1024;

@@ -209,6 +209,7 @@ class APCalculator(object):
             return overall_ret
         assert self._lists is not None, "no predictions accumulated"
         lists = self._lists
+        lists.flush_reset()     # reset() without a step since: the counters are still the previous evaluation's
         Cn, dev = lists.C, lists.device
         world = 1
         if distributed:

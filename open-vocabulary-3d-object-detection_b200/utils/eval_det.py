@@ -180,9 +180,17 @@ class TpLists(object):
         self.tp_cnt_ptr = self.counters.data_ptr()
         self.npos_ptr = self.counters.data_ptr() + 4 * self._cnt_words
         self.key_ptr, self.bits_ptr = self.tp_key.data_ptr(), self.tp_bits.data_ptr()
+        self.dirty = False      # counters must be zeroed before the next append
 
     def reset(self):
-        self.counters.zero_()
+        """Counters back to zero -- lazily: the next ``ap_front`` launch does it on its stream (no separate torch op)."""
+        self.dirty = True
+
+    def flush_reset(self):
+        """Apply a pending reset now (for readers of the counters that come before any further append)."""
+        if self.dirty:
+            self.counters.zero_()
+            self.dirty = False
 
     @property
     def tp_cnt(self):
@@ -206,6 +214,9 @@ def ap_front(corners, probs, obj, nonempty, gt_corners, gt_labels, gt_present, n
     assert probs.shape[-1] == Cn, "sem_cls_probs must have num_semcls columns"
     gt_labels = C.as_input(gt_labels, torch.int64, dev)
     flags = nms_flags(cfg)
+    if lists.dirty:
+        flags |= C.FRONT_RESET
+        lists.dirty = False
     if gt_present.dtype is torch.float32:     # the reference's mask dtype: read as is
         gt_present = C.as_input(gt_present, torch.float32, dev)
         flags |= C.FRONT_GT_PRESENT_F32
@@ -280,9 +291,9 @@ class ApxReducer(object):
 
     def read(self):
         """After a stream synchronise: (ap [nthr,C], recall [nthr,C], n_det [C], overflow, max rank count, max merged count)."""
-        r = self._res_np
+        r = self._res_np.copy()     # one 800-byte copy out of the pinned buffer; the rest are views
         k = self.nthr * self.C
-        return (r[:k].reshape(self.nthr, self.C).copy(), r[k:2 * k].reshape(self.nthr, self.C).copy(),
+        return (r[:k].reshape(self.nthr, self.C), r[k:2 * k].reshape(self.nthr, self.C),
                 r[2 * k:2 * k + self.C].astype(np.int64), int(r[2 * k + self.C]), int(r[2 * k + self.C + 1]), int(r[2 * k + self.C + 2]))
 
 

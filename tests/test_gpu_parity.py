@@ -603,8 +603,8 @@ def _apx_virtual_ranks(out, tgt, C, thrs, nranks, cap_total=1024, rounds=2, cfg=
     return res
 
 
-@pytest.mark.parametrize("nranks,S", [(1, 61), (2, 61), (3, 61), (8, 61), (3, 2)])
-def test_ap_exchange_virtual_ranks(nranks, S):
+@pytest.mark.parametrize("nranks,S,cap_total", [(1, 61, 1024), (2, 61, 1024), (3, 61, 1024), (8, 61, 1024), (3, 2, 1024), (4, 61, 8192)])
+def test_ap_exchange_virtual_ranks(nranks, S, cap_total):
     """The distributed AP path (device-side exchange of TP lists and bucket histograms through symmetric buffers) on ONE
     GPU with virtual ranks, against the oracle's evaluation of all scenes; every rank must report the same numbers.
     61 scenes: ragged shards; 2 scenes on 3 ranks: a rank without any scene still takes part in the exchange."""
@@ -613,7 +613,7 @@ def test_ap_exchange_virtual_ranks(nranks, S):
     out, tgt = synth.detection_batch(B=S, Q=Q, G=G, C=C, seed=123, heading=np.pi, max_gt=12)
     want, _ = oracle.ap_metrics(out["box_corners"], out["sem_cls_prob"], out["objectness_prob"], tgt["gt_box_corners"],
                                 tgt["gt_box_sem_cls_label"], tgt["gt_box_present"], C, ap_iou_thresh=thrs)
-    res = _apx_virtual_ranks(out, tgt, C, thrs, nranks)
+    res = _apx_virtual_ranks(out, tgt, C, thrs, nranks, cap_total=cap_total)
     for r, (ap, recall, ndet, ovf, max_rank, max_total) in enumerate(res):
         assert ovf == 0, (r, ovf)
         for ti, thr in enumerate(thrs):
@@ -645,6 +645,12 @@ def test_ap_exchange_overflow_and_force_exchange():
     got = calc.compute_metrics()
     assert calc._cap_hint[1] >= 2048          # grew after the overflow
     got2 = calc.compute_metrics()             # idempotent; second call starts from the learned capacity
+    calc._cap_hint.clear()
+    calc.tp_list_cap = 8192                   # a long-list capacity: the dense-list histogram kernel (keys in global memory,
+    got3 = calc.compute_metrics()             # packed 16-bit private counters) must give the same numbers
+    for thr in thrs:
+        for k in got[thr]:
+            assert float(got3[thr][k]) == float(got[thr][k]), (thr, k)
     # 51 200 records per class hold ~30 exactly equal fp32 scores, some next to a true positive: the reference's argsort
     # is unstable there (utils/eval_det.py:108), the oracle breaks ties by index, the reducer counts every tie before the
     # TP (the only order-free choice, so the result cannot depend on the sharding) -- a 1/N^2 ~ 1e-9 effect on AP
