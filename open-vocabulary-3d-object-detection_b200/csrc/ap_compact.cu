@@ -527,7 +527,8 @@ struct ApxParams {
     double *result;
     unsigned long long *dbg;   // optional [C][8] globaltimer stamps of the merge stage (OVDET_APX_DBG_PTR; null in production)
 };
-#define XSTAMP(i) do { if (p.dbg && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[(size_t)blockIdx.x * 8 + (i)] = t_; } } while (0)
+#define XSTAMPC(cls, i) do { if (p.dbg && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[(size_t)(cls) * 32 + (i)] = t_; } } while (0)
+#define XSTAMP(i) XSTAMPC(blockIdx.x, i)
 
 __device__ __forceinline__ unsigned *apx_ctrl(const ApxParams &p) { return reinterpret_cast<unsigned *>(p.local + p.ll.ctrl); }
 
@@ -634,13 +635,16 @@ __global__ void __launch_bounds__(1024, 1) apx_push_lists_kernel(ApxParams p)
     __shared__ uint32_t dbase[256], wsum_s[8];
     __shared__ int skip_s;
     const int c = blockIdx.x, tid = threadIdx.x;
+    XSTAMPC(c, 8);
     pdl_wait();
     pdl_release();
+    XSTAMPC(c, 9);
     const unsigned tag = apx_ctrl(p)[0] + 1u;
     const int raw = p.tp_cnt[c];
     const int n = min(min(raw, p.cap_list), cap);
     for (int i = tid; i < n; i += 1024) { ksm[i] = p.tp_key[(size_t)c * p.cap_list + i]; bsm[i] = p.tp_bits[(size_t)c * p.cap_list + i]; }
     const int cur = cta_sort(ksm, bsm, SortScratch{rnk, whist, dbase, wsum_s, &skip_s}, cap, n);
+    XSTAMPC(c, 10);
     const uint4 *ks = reinterpret_cast<const uint4 *>(ksm + cur * cap);
     const uint4 *bs = reinterpret_cast<const uint4 *>(bsm + cur * cap);
     const long long np = p.npos[c];
@@ -661,6 +665,7 @@ __global__ void __launch_bounds__(1024, 1) apx_push_lists_kernel(ApxParams p)
         unsigned char *half = p.peers.base[tid] + (size_t)(tag & 1u) * p.sl.half;
         st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_l) + (size_t)p.rank * p.C + c, tag);
     }
+    XSTAMPC(c, 11);
 }
 
 // ---- stage 2: per class, gather the W lists, sort, bin edges; zero the class's histogram.  grid C, 1024 threads
@@ -694,6 +699,7 @@ __global__ void __launch_bounds__(1024, 1) apx_merge_kernel(ApxParams p)
     }
     __syncthreads();
     if (bad_s) { if (tid == 0) atomicExch(&ctrl[5], 1u); }   // carry on with whatever is there: the result is flagged invalid
+    XSTAMP(6);
     if (tid == 0) {
         int off = 0, mx = 0, raw_total = 0; long long np = 0;
         for (int r = 0; r < p.W; ++r) {
@@ -828,35 +834,161 @@ __global__ void __launch_bounds__(1024, 1) apx_merge_kernel(ApxParams p)
     XSTAMP(5);
 }
 
-// the last CTA of a class to finish its share of the LAST record block ships the class's finished histogram row to
-// every peer and raises the flag (called by all threads of the CTA after its flush to global memory)
-__device__ __forceinline__ void apx_hist_ship(const ApxParams &p, int c, uint32_t *hist, int last_block, int *last_s)
+// ---- stage 2 (several ranks): merge the W sorted runs of a class with a CLUSTER of 8 CTAs.  One SM's shared-memory
+// bandwidth was the limit (151 us for 12 500 entries: every probe of every binary search is a shared load); each CTA
+// of the cluster holds all runs as 8-byte (key << 8 | bits) words and places one eighth of the entries, writing them
+// straight to their final position in global memory; after a cluster barrier each CTA reads the merged keys back and
+// builds one eighth of the bin table.
+constexpr int APX_CL = 8;
+__device__ __forceinline__ void cluster_sync_all()
 {
-    const int NT = (int)blockDim.x;
-    if (!(p.exchange && last_block)) return;
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(APX_CL, 1, 1) __launch_bounds__(1024, 1) apx_merge_runs_kernel(ApxParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int cap = p.cap;
+    unsigned long long *v = reinterpret_cast<unsigned long long *>(sm);   // [cap] all runs, (key << 8) | bits
+    uint32_t *ksm = reinterpret_cast<uint32_t *>(sm);                     // later: the merged keys, [cap]
+    uint16_t *lo16 = reinterpret_cast<uint16_t *>(sm + sizeof(unsigned long long) * (size_t)cap);   // [APX_BINS / APX_CL + 8]
+    __shared__ int n_s[APX_MAXW], off_s[APX_MAXW + 1];
+    __shared__ int bad_s;
+    const int c = blockIdx.x / APX_CL, part = blockIdx.x % APX_CL, tid = threadIdx.x;
+    if (part == 0) XSTAMPC(c, 0);
+    pdl_wait();
+    pdl_release();
+    unsigned *ctrl = apx_ctrl(p);
+    const unsigned tag = ctrl[0] + 1u;
+    const unsigned char *half = p.peers.base[p.rank] + (size_t)(tag & 1u) * p.sl.half;
+    if (tid == 0) bad_s = 0;
+    __syncthreads();
+    if (tid < p.W) {
+        if (!wait_flag(reinterpret_cast<const unsigned *>(half + p.sl.flags_l) + (size_t)tid * p.C + c, tag)) bad_s = 1;
+    }
+    __syncthreads();
+    if (bad_s && tid == 0) atomicExch(&ctrl[5], 1u);   // carry on with whatever is there: the result is flagged invalid
+    if (part == 0) XSTAMPC(c, 6);
+    if (tid == 0) {
+        int off = 0, mx = 0, raw_total = 0; long long np = 0;
+        for (int r = 0; r < p.W; ++r) {
+            const unsigned char *slot = half + p.sl.lists + (size_t)r * p.sl.list_stride;
+            const int raw = reinterpret_cast<const int *>(slot + p.sl.l_cnt)[c];
+            np += reinterpret_cast<const long long *>(slot + p.sl.l_npos)[c];
+            mx = max(mx, raw); raw_total += raw;
+            int n = min(raw, min(p.cap_list, cap));   // what the producer could ship
+            n = min(n, cap - off);                    // what still fits
+            n_s[r] = n; off_s[r] = off; off += n;
+        }
+        off_s[p.W] = off;
+        if (part == 0) {
+            reinterpret_cast<int *>(p.local + p.ll.mcnt)[c] = off;
+            reinterpret_cast<long long *>(p.local + p.ll.npos_g)[c] = np;
+            if (raw_total > cap || mx > p.cap_list) atomicExch(&ctrl[2], 1u);
+            atomicMax(&ctrl[3], (unsigned)mx);
+            atomicMax(&ctrl[4], (unsigned)raw_total);
+        }
+    }
+    __syncthreads();
+    const int total = off_s[p.W], W = p.W;
+    if (part == 0) XSTAMPC(c, 2);
+    for (int r = 0; r < W; ++r) {
+        const unsigned char *slot = half + p.sl.lists + (size_t)r * p.sl.list_stride;
+        const uint32_t *ksrc = reinterpret_cast<const uint32_t *>(slot + p.sl.l_key) + (size_t)c * cap;
+        const uint8_t *bsrc = slot + p.sl.l_bits + (size_t)c * cap;
+        const int n = n_s[r], o = off_s[r];
+        for (int i = tid; i < n; i += 1024) v[o + i] = ((unsigned long long)ksrc[i] << 8) | bsrc[i];
+    }
+    __syncthreads();
+    uint32_t *mk = reinterpret_cast<uint32_t *>(p.local + p.ll.mkey) + (size_t)c * cap;
+    uint8_t *mb = p.local + p.ll.mbits + (size_t)c * cap;
+    // my eighth of the entries: place = index in the own run + entries of every other run that sort before it; ties by
+    // (bits, source rank).  Four entries of a thread are searched in lock step (independent probes).
+    const int s0 = (int)((long long)total * part / APX_CL), s1 = (int)((long long)total * (part + 1) / APX_CL);
+    for (int base = s0 + tid * 4; base < s1; base += 4096) {
+        unsigned long long x[4]; int pos[4], own[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = min(base + q, s1 - 1);
+            x[q] = v[i];
+            int r = 0;
+            while (r + 1 < W && i >= off_s[r + 1]) ++r;
+            own[q] = r; pos[q] = i - off_s[r];
+        }
+        for (int r2 = 0; r2 < W; ++r2) {
+            const int o2 = off_s[r2], n2 = n_s[r2];
+            if (n2 == 0) continue;
+            int top = 1;
+            while (top * 2 <= n2) top *= 2;
+            int lo[4] = {0, 0, 0, 0};
+            for (int step = top; step > 0; step >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int nx = lo[q] + step;
+                    const unsigned long long w = v[o2 + min(nx, n2) - 1];
+                    const bool before = r2 < own[q] ? (w <= x[q]) : (w < x[q]);   // an earlier run goes first on ties
+                    lo[q] = ((nx <= n2) & before) ? nx : lo[q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pos[q] += (r2 != own[q]) ? lo[q] : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (base + q < s1) { mk[pos[q]] = (uint32_t)(x[q] >> 8); mb[pos[q]] = (uint8_t)x[q]; }
+    }
+    // padding behind the list, the class's histogram row: an eighth each
+    for (int i = total + part * 1024 + tid; i < cap; i += APX_CL * 1024) { mk[i] = 0xFFFFFFFFu; mb[i] = 0; }
+    uint32_t *h = reinterpret_cast<uint32_t *>(p.local + p.ll.hist) + (size_t)c * p.sl.hp;
+    for (int i = part * 1024 + tid; i < p.sl.hp; i += APX_CL * 1024) h[i] = 0;
+    if (part == 0 && tid == 0) reinterpret_cast<unsigned *>(p.local + p.ll.done_hist)[c] = 0;
     __threadfence();
+    cluster_sync_all();
+    if (part == 0) XSTAMPC(c, 3);
+    // ---- bin table (see apx_merge_kernel): the merged keys back into shared memory, an eighth of the bins per CTA
+    for (int i = tid; i < total; i += 1024) ksm[i] = __ldcg(mk + i);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(reinterpret_cast<unsigned *>(p.local + p.ll.done_hist) + c, 1u);
-        *last_s = (t == gridDim.x - 1);
+    unsigned char *eb = p.local + p.ll.edge + (size_t)c * APX_ESTRIDE_BYTES;
+    uint32_t kmin = 0; int shift = 0, nb = 0;
+    if (total > 0) {
+        kmin = ksm[0];
+        const uint32_t span = ksm[total - 1] - kmin;
+        while ((span >> shift) >= (uint32_t)APX_BINS) ++shift;
+        nb = (int)(span >> shift) + 1;
     }
-    __syncthreads();
-    if (!*last_s) return;
-    __threadfence();
-    const unsigned tag = apx_ctrl(p)[0] + 1u;
-    const uint4 *src = reinterpret_cast<const uint4 *>(hist);
-    const int n4 = p.sl.hp / 4;
-    for (int r = 0; r < p.W; ++r) {
-        unsigned char *half = p.peers.base[r] + (size_t)(tag & 1u) * p.sl.half;
-        uint4 *dst = reinterpret_cast<uint4 *>(half + p.sl.hist + (size_t)p.rank * p.sl.hist_stride + sizeof(uint32_t) * (size_t)c * p.sl.hp);
-        for (int i = threadIdx.x; i < n4; i += NT) dst[i] = __ldcg(src + i);
+    if (part == 0 && tid == 0) {
+        uint32_t *hdr = reinterpret_cast<uint32_t *>(eb);
+        hdr[0] = kmin; hdr[1] = (uint32_t)shift; hdr[2] = (uint32_t)nb; hdr[3] = (uint32_t)total;
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < p.W) {
-        unsigned char *half = p.peers.base[threadIdx.x] + (size_t)(tag & 1u) * p.sl.half;
-        st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_h) + (size_t)p.rank * p.C + c, tag);
+    {
+        uint16_t *e = reinterpret_cast<uint16_t *>(eb + sizeof(uint32_t) * APX_EHDR);
+        const int b0 = part * (APX_BINS / APX_CL);                       // my bins [b0, b0 + 1024): thread t takes bin b0 + t
+        int top = 1;
+        while (top * 2 <= total) top *= 2;
+        const int bi = b0 + tid;
+        const unsigned long long bound = (unsigned long long)kmin + ((unsigned long long)bi << shift);
+        int lo = 0;
+        for (int step = total > 0 ? top : 0; step > 0; step >>= 1) {
+            const int nx = lo + step;
+            const uint32_t kv = ksm[min(nx, total) - 1];
+            lo = ((nx <= total) & ((unsigned long long)kv < bound)) ? nx : lo;   // entries with key < bound
+        }
+        lo16[tid] = (uint16_t)lo;
+        if (tid == 0) {   // the bound of the bin after my last one
+            const unsigned long long bnd = (unsigned long long)kmin + ((unsigned long long)(b0 + 1024) << shift);
+            int l2 = 0;
+            for (int step = total > 0 ? top : 0; step > 0; step >>= 1) {
+                const int nx = l2 + step;
+                const uint32_t kv = ksm[min(nx, total) - 1];
+                l2 = ((nx <= total) & ((unsigned long long)kv < bnd)) ? nx : l2;
+            }
+            lo16[1024] = (uint16_t)l2;
+        }
+        __syncthreads();
+        if (bi < nb) e[bi] = (uint16_t)(lo16[tid] | (lo16[tid + 1] - lo16[tid] >= 2 ? 0x8000 : 0));
+        if (part == 0 && tid == 0 && nb == 0) e[0] = 0;
     }
+    if (part == 0) XSTAMPC(c, 5);
 }
 
 // ---- stage 3: histogram of the local records over the merged list; the last CTA of a class ships the class's row
@@ -931,7 +1063,7 @@ __global__ void __launch_bounds__(1024) apx_hist_kernel(ApxParams p, const float
     if ((threadIdx.x & 31) == 0 && tail) atomicAdd(&h[ntp], tail);
     __syncthreads();
     for (int i = threadIdx.x; i <= ntp; i += NT) { const uint32_t v = h[i]; if (v) atomicAdd(&hist[i], v); }
-    apx_hist_ship(p, c, hist, last_block, &last_s);
+    (void)last_block; (void)last_s;   // shipping to the peers is a separate stage (apx_ship_hist_kernel): one CTA per (class, peer)
 }
 
 // ---- stage 3, long merged list (> 4096 entries: several ranks' true positives): the private histogram packs two 16-bit
@@ -1010,7 +1142,29 @@ __global__ void __launch_bounds__(512) apx_hist_big_kernel(ApxParams p, const fl
     if ((threadIdx.x & 31) == 0 && tail) atomicAdd(&hist[ntp], tail);
     __syncthreads();
     for (int i = threadIdx.x; i <= ntp; i += NT) { const uint32_t v = (hw[i >> 1] >> ((i & 1) * 16)) & 0xffffu; if (v) atomicAdd(&hist[i], v); }
-    apx_hist_ship(p, c, hist, last_block, &last_s);
+    (void)last_block; (void)last_s;   // shipping to the peers is a separate stage (apx_ship_hist_kernel): one CTA per (class, peer)
+}
+
+// ---- stage 3b: ship the finished histogram rows.  grid (W, C): CTA (dst, c) copies row c into peer dst's slot of this
+// rank and raises the flag -- 160 CTAs move what one "last CTA" per class used to push alone (33 us at 16 384 buckets).
+__global__ void __launch_bounds__(256) apx_ship_hist_kernel(ApxParams p)
+{
+    const int dst = blockIdx.x, c = blockIdx.y;
+    pdl_wait();
+    pdl_release();
+    if (dst == 0) XSTAMPC(c, 12);
+    const unsigned tag = apx_ctrl(p)[0] + 1u;
+    const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(p.local + p.ll.hist) + (size_t)c * p.sl.hp);
+    const int ntp = reinterpret_cast<const int *>(p.local + p.ll.mcnt)[c];
+    const int span = min(max(1, (ntp + 1023) / 1024) * 1024, p.cap);      // what the final stage scans (plus the bucket behind it)
+    const int n4 = min(p.sl.hp, span + 4) / 4;
+    unsigned char *half = p.peers.base[dst] + (size_t)(tag & 1u) * p.sl.half;
+    uint4 *out = reinterpret_cast<uint4 *>(half + p.sl.hist + (size_t)p.rank * p.sl.hist_stride + sizeof(uint32_t) * (size_t)c * p.sl.hp);
+    for (int i = threadIdx.x; i < n4; i += 256) out[i] = __ldcg(src + i);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_h) + (size_t)p.rank * p.C + c, tag);
+    if (dst == 0) XSTAMPC(c, 13);
 }
 
 // ---- stage 4: per (class, threshold): sum the W histogram rows, positions, precision envelope, AP.  grid (C, nthr)
@@ -1026,7 +1180,9 @@ __global__ void __launch_bounds__(1024) apx_final_kernel(ApxParams p)
     __shared__ double wmax[32], red[32];
     __shared__ int bad_s, last_s;
     const int c = blockIdx.x, t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (t == 0) XSTAMPC(c, 16);
     pdl_wait();
+    if (t == 0) XSTAMPC(c, 17);
     unsigned *ctrl = apx_ctrl(p);
     const unsigned tag = ctrl[0] + 1u;
     const unsigned char *half = p.exchange ? p.peers.base[p.rank] + (size_t)(tag & 1u) * p.sl.half : nullptr;
@@ -1037,6 +1193,7 @@ __global__ void __launch_bounds__(1024) apx_final_kernel(ApxParams p)
     }
     __syncthreads();
     if (bad_s && tid == 0) atomicExch(&ctrl[5], 1u);
+    if (t == 0) XSTAMPC(c, 18);
     const double npos = (double)reinterpret_cast<const long long *>(p.local + p.ll.npos_g)[c];
     const int ntp = reinterpret_cast<const int *>(p.local + p.ll.mcnt)[c];
     const double eps = 2.220446049250313e-16;
@@ -1160,6 +1317,7 @@ __global__ void __launch_bounds__(1024) apx_final_kernel(ApxParams p)
             res = res + red[0] / 11.0;
         }
     }
+    if (t == 0) XSTAMPC(c, 19);
     if (tid == 0) {
         const size_t kx = (size_t)p.nthr * p.C;
         p.result[(size_t)t * p.C + c] = nvalid > 0 ? res : 0.0;
@@ -1229,11 +1387,17 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
         OVDET_CUDA_TRY(launch_pdl(apx_push_lists_kernel, dim3(C), dim3(1024), psmem, st, p));
         { const int rc = launch_ok("apx_push_lists_kernel"); if (rc) return rc; }
     }
-    if (stages & OVDET_APX_STAGE_MERGE_HIST) {
+    if ((stages & OVDET_APX_STAGE_MERGE_HIST) && !exchange) {
         const size_t smem = (size_t)cap_total * 12 + sizeof(uint16_t) * (32 * 256 + APX_BINS + 8);
         OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         OVDET_CUDA_TRY(launch_pdl(apx_merge_kernel, dim3(C), dim3(1024), smem, st, p));
         { const int rc = launch_ok("apx_merge_kernel"); if (rc) return rc; }
+    }
+    if ((stages & OVDET_APX_STAGE_MERGE_HIST) && exchange) {   // the runs arrive sorted: a cluster of 8 CTAs per class merges them
+        const size_t smem = (size_t)cap_total * 8 + sizeof(uint16_t) * (APX_BINS / APX_CL + 8);
+        OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_merge_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OVDET_CUDA_TRY(launch_pdl(apx_merge_runs_kernel, dim3(APX_CL * C), dim3(1024), smem, st, p));   // cluster dims are compiled in
+        { const int rc = launch_ok("apx_merge_runs_kernel"); if (rc) return rc; }
     }
     if (stages & OVDET_APX_STAGE_MERGE_HIST) {
         const bool big = cap_total > 4096;
@@ -1266,9 +1430,9 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
             OVDET_REQUIRE(N == 0 || blocks[b], "null record block");
             { const int rc = launch_hist(static_cast<const float *>(blocks[b]), N, last ? 1 : 0); if (rc) return rc; }
         }
-        if (exchange && nblocks == 0) {   // nothing local: still ship the (zero) rows so that the peers' final stage can run
-            const int rc = launch_hist(nullptr, 0, 1);
-            if (rc) return rc;
+        if (exchange) {   // every rank ships its rows (all zero when it had no records) so that the peers' final stage can run
+            OVDET_CUDA_TRY(launch_pdl(apx_ship_hist_kernel, dim3(world, C), dim3(256), 0, st, p));
+            { const int rc = launch_ok("apx_ship_hist_kernel"); if (rc) return rc; }
         }
     }
     if (stages & OVDET_APX_STAGE_FINAL) {

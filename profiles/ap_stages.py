@@ -52,7 +52,7 @@ torch.cuda.synchronize()
 print("host us per reset+step (async)", (t1 - t0) / 50 * 1e6)
 print("mAP", float(m[0.25]["mAP"]), float(m[0.5]["mAP"]))
 if os.environ.get("APX_STAMPS"):
-    d = torch.zeros((20, 8), dtype=torch.int64, device=dev)
+    d = torch.zeros((20, 32), dtype=torch.int64, device=dev)
     os.environ["OVDET_APX_DBG_PTR"] = str(d.data_ptr())
     red.launch([rs], lists); torch.cuda.synchronize()
     a = d.cpu().numpy().astype(np.float64)
