@@ -121,7 +121,9 @@ int ovdet_box3d_iou_f64(const float *dets, const float *gts, const int32_t *nd, 
  * center_dist == NULL: L1 distance of center_q [B,Q,3] / center_g [B,G,3]
  * (torch.cdist(.., p=1), criterion.py:357-359) is computed in the kernel.
  * gious == NULL: GIoU is computed in the kernel from corners1/corners2 with
- * (giou_flags, k2_cap) as in ovdet_giou3d_f32 and optionally written to gious_out. */
+ * (giou_flags, k2_cap) as in ovdet_giou3d_f32 and optionally written to gious_out.
+ * gt_labels outside [0, C) are clamped into range (the reference's torch.gather, criterion.py:46-48, would raise a device
+ * assert there); padded GT columns beyond nactual_gt carry label 0 in the reference's batches, so this never triggers on them. */
 int ovdet_matcher_cost_f32(const float *sem_cls_prob, const float *objectness, const float *center_dist,
                            const float *center_q, const float *center_g, const float *gious,
                            const float *corners1, const float *corners2, const int64_t *gt_labels,
@@ -132,7 +134,9 @@ int ovdet_matcher_cost_f32(const float *sem_cls_prob, const float *objectness, c
 /* Per-sample linear sum assignment on cost[b, :, :nactual_gt[b]] (criterion.py:76-86,
  * scipy.optimize.linear_sum_assignment semantics, fp64 internally).
  * per_prop_gt_inds [B,Q] int64, proposal_matched_mask [B,Q] fp32 (both fully
- * written, zeros where unmatched), col_to_row [B,G] int32 (-1 beyond nactual_gt). */
+ * written, zeros where unmatched), col_to_row [B,G] int32 (-1 beyond nactual_gt).
+ * scipy raises ValueError on NaN / -inf entries and on infeasible problems; such a sample is left unsolved and MARKED:
+ * proposal_matched_mask[b,:] = -1, col_to_row[b,:] = -2 (+inf entries are legal: forbidden pairs). */
 int ovdet_lsap_f32(const float *cost, const int64_t *nactual_gt, int B, int Q, int G,
                    int64_t *per_prop_gt_inds, float *proposal_matched_mask, int32_t *col_to_row, void *stream);
 
@@ -142,6 +146,8 @@ int ovdet_lsap_f32(const float *cost, const int64_t *nactual_gt, int B, int Q, i
 #define OVDET_NMS_2D 0x01u        /* nms_2d_faster: boxes = x1,y1,x2,y2,score */
 #define OVDET_NMS_SAMECLS 0x02u   /* only suppress same-class boxes (cls column after score) */
 #define OVDET_NMS_OLD_TYPE 0x04u  /* overlap = inter / vol_j */
+#define OVDET_NMS_LHS 0x08u       /* tools variant, `lhs=True` (3DOVDet_tools/utils/box_3d_utils.py:113-116): the better-scoring half of
+                                     the boxes a pick suppresses is picked as well (and still removed) */
 /* boxes [S,K,ncols] fp64 (dims*2 coords, score, [cls], ...); counts [S] int32 or
  * NULL (=K); vol_eps added to each volume (1e-8 for the tools variant, else 0).
  * keep [S,K] uint8; pick_order [S,K] int32 = indices in the reference's pick
@@ -179,6 +185,17 @@ int ovdet_ap_match(const float *corners, const float *probs, const float *obj, c
                    const int32_t *det_cls, const float *gt_corners, const int64_t *gt_labels, const uint8_t *gt_present,
                    int S, int K, int G, int C, const double *thr, int nthr,
                    double *iou_ws, float *rec_score, uint8_t *rec_tp, int64_t *npos, void *stream);
+
+/* The same matching on a PRECOMPUTED IoU matrix iou [S,K,G] fp64 (any IoU definition): what eval_det_cls does with a
+ * caller-supplied get_iou_func.  ovdet_aabb_iou_f64 fills the matrix with the tools' axis-aligned IoU, get_iou / calc_iou
+ * (3DOVDet_tools/utils/evaluation/eval_det.py:63-77, evaluation/box_util.py:287-309): dets [S,D,6], gts [S,G,6] fp64 =
+ * (centre, lengths), result clamped to [0, 1]; nd / ng [S] int32 counts or NULL. */
+int ovdet_aabb_iou_f64(const double *dets, const double *gts, const int32_t *nd, const int32_t *ng,
+                       int S, int D, int G, double *out, void *stream);
+int ovdet_ap_match_iou(const double *iou, const float *probs, const float *obj, const uint8_t *keep,
+                       const int32_t *det_cls, const int64_t *gt_labels, const uint8_t *gt_present,
+                       int S, int K, int G, int C, const double *thr, int nthr,
+                       float *rec_score, uint8_t *rec_tp, int64_t *npos, void *stream);
 
 /* Per-class AP from records (eval_det.py:108-153 + voc_ap :23-54): sort each
  * class segment by descending score, cumulative TP/FP, precision/recall, AP.

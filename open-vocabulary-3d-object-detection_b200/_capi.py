@@ -39,6 +39,8 @@ SIGNATURES = {
     "ovdet_nms_f64": (c_i, [c_p, c_p, c_i, c_i, c_i, c_d, c_d, c_u, c_p, c_p, c_p, c_p]),
     "ovdet_parse_predictions_f32": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_d, c_f, c_u, c_p, c_p, c_p, c_p, c_p]),
     "ovdet_ap_match": (c_i, [c_p] * 8 + [c_i] * 4 + [c_p, c_i] + [c_p] * 5),
+    "ovdet_aabb_iou_f64": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
+    "ovdet_ap_match_iou": (c_i, [c_p] * 7 + [c_i] * 4 + [c_p, c_i] + [c_p] * 4),
     "ovdet_ap_reduce_ws_bytes": (c_sz, [c_i, c_i64]),
     "ovdet_ap_reduce": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "ovdet_apc_collect": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_p, c_p, c_p, c_p, c_p]),
@@ -62,7 +64,7 @@ SIGNATURES = {
 
 # flag words (include/ovdet_b200.h)
 GIOU_ROTATED, GIOU_PREFILTER, GIOU_INTER_ONLY, GIOU_CLIP_F64, GIOU_ENCL_HULL = 1, 2, 4, 8, 16
-NMS_2D, NMS_SAMECLS, NMS_OLD_TYPE, PARSE_NO_NMS = 1, 2, 4, 0x100
+NMS_2D, NMS_SAMECLS, NMS_OLD_TYPE, NMS_LHS, PARSE_NO_NMS = 1, 2, 4, 8, 0x100
 LOGITS_L2NORM = 1
 FRONT_PER_CLASS, FRONT_CLS_CONF, FRONT_GT_PRESENT_F32, FRONT_RESET = 0x1000, 0x2000, 0x4000, 0x8000
 APX_FORCE_EXCHANGE, APX_USE_07_METRIC = 1, 2

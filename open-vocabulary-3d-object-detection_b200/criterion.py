@@ -40,7 +40,10 @@ def matcher_cost(sem_cls_prob, objectness_prob, gt_labels, weights, center_dist=
 
 def lsap(cost, nactual_gt):
     """Per-sample assignment on cost[b, :, :nactual_gt[b]].  Returns
-    (per_prop_gt_inds int64 [B,Q], proposal_matched_mask fp32 [B,Q], col_to_row int32 [B,G])."""
+    (per_prop_gt_inds int64 [B,Q], proposal_matched_mask fp32 [B,Q], col_to_row int32 [B,G]).
+    A sample whose cost slab holds NaN / -inf, or that has no feasible assignment, is not solved: its mask is -1
+    everywhere and its col_to_row row -2 (scipy raises ValueError there; ``Matcher`` does too as soon as the
+    assignments are read on the host -- the stream-ordered outputs cannot raise by themselves)."""
     C.require_cuda(cost)
     dev = cost.device
     cost = cost.detach().to(torch.float32).contiguous()
@@ -58,6 +61,10 @@ def _assignments(c2r, nactual_gt, device):
     """The reference's per-sample [rows, cols] LongTensors (criterion.py:79-86; scipy
     returns rows ascending).  One small D2H of the [B,G] column->row table."""
     c2r_h = c2r.cpu()
+    if (c2r_h == -2).any():
+        # what scipy.optimize.linear_sum_assignment does at criterion.py:79 on such a cost matrix
+        raise ValueError("matrix contains invalid numeric entries (sample %d): NaN / -inf in the matcher cost, or an "
+                         "infeasible assignment" % int((c2r_h == -2).any(1).nonzero()[0]))
     n_h = nactual_gt.cpu().tolist()
     out = []
     for b, n in enumerate(n_h):

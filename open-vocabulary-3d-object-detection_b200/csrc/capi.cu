@@ -41,6 +41,18 @@ int DeviceScratch::acquire(size_t bytes, cudaStream_t stream, void **out)
 {
     if (!last_use) OVDET_CUDA_TRY(cudaEventCreateWithFlags(&last_use, cudaEventDisableTiming));
     if (bytes > cap) {
+        // growing frees the old buffer: a CUDA graph captured earlier has its address baked in, and a capture in progress
+        // cannot synchronise on the event -- refuse rather than hand out memory a replay would find freed
+        cudaStreamCaptureStatus cs0 = cudaStreamCaptureStatusNone;
+        OVDET_CUDA_TRY(cudaStreamIsCapturing(stream, &cs0));
+        if (cs0 != cudaStreamCaptureStatusNone) {
+            set_error("the library scratch buffer would have to grow (%zu > %zu bytes) inside a stream capture; run the call once eagerly at this size before capturing", bytes, cap);
+            return OVDET_ERR_UNSUPPORTED;
+        }
+        if (pinned_by_graph) {
+            set_error("the library scratch buffer is referenced by a captured CUDA graph and cannot grow (%zu > %zu bytes); run the larger problem before capturing", bytes, cap);
+            return OVDET_ERR_UNSUPPORTED;
+        }
         if (dev) { OVDET_CUDA_TRY(cudaEventSynchronize(last_use)); OVDET_CUDA_TRY(cudaFree(dev)); dev = nullptr; cap = 0; }
         const size_t want = bytes + bytes / 2 + 4096;
         OVDET_CUDA_TRY(cudaMalloc(&dev, want));
@@ -50,6 +62,7 @@ int DeviceScratch::acquire(size_t bytes, cudaStream_t stream, void **out)
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         OVDET_CUDA_TRY(cudaStreamIsCapturing(stream, &cs));
         if (cs == cudaStreamCaptureStatusNone) OVDET_CUDA_TRY(cudaStreamWaitEvent(stream, last_use, 0));
+        else pinned_by_graph = true;   // the graph keeps the address: from now on the buffer never moves
     }
     *out = dev;
     return OVDET_OK;
@@ -63,10 +76,19 @@ int DeviceScratch::release(cudaStream_t stream)
     return OVDET_OK;
 }
 
+// Library state is per (host thread, CUDA device): a buffer allocated on device A must never be handed to a kernel
+// running on device B (a process that drives several GPUs calls the same entry points under different current devices).
+static int current_device_slot()
+{
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; }
+    return (d >= 0 && d < OVDET_MAX_DEVICES) ? d : 0;
+}
+
 DeviceScratch &device_scratch()
 {
-    static thread_local DeviceScratch ds;
-    return ds;
+    static thread_local DeviceScratch ds[OVDET_MAX_DEVICES];
+    return ds[current_device_slot()];
 }
 
 int HostStaging::ensure_pinned(size_t bytes)
@@ -81,8 +103,8 @@ int HostStaging::ensure_pinned(size_t bytes)
 
 HostStaging &host_staging()
 {
-    static thread_local HostStaging hs;
-    return hs;
+    static thread_local HostStaging hs[OVDET_MAX_DEVICES];
+    return hs[current_device_slot()];
 }
 
 }  // namespace ovdet

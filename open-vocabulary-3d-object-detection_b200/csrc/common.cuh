@@ -34,7 +34,7 @@ static inline int launch_ok(const char *what)
     return OVDET_OK;
 }
 
-// Grow-only device scratch owned by the library, one per host thread, used only
+// Grow-only device scratch owned by the library, one per (host thread, device), used only
 // by the *_host entry points (the device-pointer API never allocates).
 struct HostStaging {
     void *dev = nullptr;
@@ -50,14 +50,17 @@ struct HostStaging {
 HostStaging &host_staging();
 
 // Grow-only device scratch for kernels that need a small internal table (logits row norms, AP bin edges): one per
-// host thread, reused across calls.  cudaMallocAsync is not used for this: with the default pool's release threshold of
+// (host thread, device), reused across calls.  Captured CUDA graphs pin the buffer: once handed out inside a stream
+// capture it can no longer grow (acquire() then fails loudly instead of freeing what a replay would touch).  cudaMallocAsync is not used for this: with the default pool's release threshold of
 // zero every synchronisation returns the memory to the OS and the next call pays a multi-millisecond re-map.
 // Stream order across calls is kept with an event: acquire() makes `stream` wait for the previous user, release()
 // records the new last use.
+constexpr int OVDET_MAX_DEVICES = 64;   // library scratch / staging objects are kept per (host thread, device)
 struct DeviceScratch {
     void *dev = nullptr;
     size_t cap = 0;
     cudaEvent_t last_use = nullptr;
+    bool pinned_by_graph = false;   // handed out inside a stream capture: the address is baked into a graph, never free it
     int acquire(size_t bytes, cudaStream_t stream, void **out);
     int release(cudaStream_t stream);
 };

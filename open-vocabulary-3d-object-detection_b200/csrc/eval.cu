@@ -90,6 +90,41 @@ __device__ __forceinline__ double exact_iou(const float *c1, const float *c2, V2
 
 constexpr int EV_NT = 256;
 
+// Axis-aligned IoU of the tools' evaluation (3DOVDet_tools/utils/evaluation/box_util.py:287-309 calc_iou, clamped to
+// [0, 1] by get_iou, eval_det.py:63-77): boxes are (centre, lengths), fp64, numpy's operation order.
+struct AabbParams { const double *dets, *gts; const int32_t *nd, *ng; int S, D, G; double *out; long long total; };
+
+__global__ void __launch_bounds__(EV_NT) aabb_iou_kernel(AabbParams p)
+{
+    using A = Ar<double>;
+    for (long long idx = (long long)blockIdx.x * EV_NT + threadIdx.x; idx < p.total; idx += (long long)gridDim.x * EV_NT) {
+        const int g = (int)(idx % p.G);
+        const long long sd = idx / p.G;
+        const int d = (int)(sd % p.D), s = (int)(sd / p.D);
+        double r = 0.0;
+        if ((!p.nd || d < p.nd[s]) && (!p.ng || g < p.ng[s])) {
+            const double *a = p.dets + sd * 6, *b = p.gts + ((long long)s * p.G + g) * 6;
+            double e[3];
+            bool pos = true;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double ha = A::div(a[3 + k], 2.0), hb = A::div(b[3 + k], 2.0);
+                const double min_max = A::min(A::add(a[k], ha), A::add(b[k], hb)), max_min = A::max(A::sub(a[k], ha), A::sub(b[k], hb));
+                pos = pos && (min_max > max_min);
+                e[k] = A::sub(min_max, max_min);
+            }
+            if (pos) {
+                const double inter = A::mul(A::mul(e[0], e[1]), e[2]);
+                const double va = A::mul(A::mul(a[3], a[4]), a[5]), vb = A::mul(A::mul(b[3], b[4]), b[5]);
+                r = A::div(inter, A::sub(A::add(va, vb), inter));
+                if (r < 0.0) r = 0.0;
+                if (r > 1.0) r = 1.0;
+            }
+        }
+        p.out[idx] = r;
+    }
+}
+
 struct IouParams {
     const float *dets, *gts; const int32_t *nd, *ng;
     int S, D, G; double *out, *out2d; long long total;
@@ -135,6 +170,7 @@ struct MatchParams {
     const float *gt_present_f32;   // the reference's float mask (datasets/*.py) read directly when gt_present is null
     int S, K, G, C, nthr; double thr[8];
     double *iou_ws; float *rec_score; uint8_t *rec_tp; unsigned long long *npos;
+    const double *iou_given;   // [S,K,G] precomputed IoU matrix (original det / GT indices): skip the geometry (ovdet_ap_match_iou)
     // optional TP list (csrc/ap_compact.cu): every record with a TP bit is appended as (score key, bits)
     uint32_t *tp_key; uint8_t *tp_bits; int *tp_cnt; int tp_cap;
     unsigned long long *dbg;   // optional [S][8] globaltimer stamps of thread 0 (OVDET_APMATCH_DBG_PTR; null in production)
@@ -245,8 +281,9 @@ __device__ __forceinline__ void am_scene_body(const MatchParams &p, const AmScen
     if (ng == 0 || nk == 0) return;   // no claims possible (uniform)
     __syncthreads();                  // a tile staged here aliases the feature records written next
 
+    const bool given = p.iou_given != nullptr;
     // stage features
-    for (int i = tid; i < nk + ng; i += AM_NT) {
+    if (!given) for (int i = tid; i < nk + ng; i += AM_NT) {
         float c[24];
         if (i < nk) { am_load_box(corners + (size_t)kd[i] * 24, c); am_features(c, dbox[i]); }
         else { am_load_box(gt_corners + (size_t)gl[i - nk] * 24, c); am_features(c, gbox[i - nk]); }
@@ -277,7 +314,7 @@ __device__ __forceinline__ void am_scene_body(const MatchParams &p, const AmScen
     // ub = I/(V1+V2-I) with I = (overlap of the BEV bounding rectangles) x (height overlap) >= the true intersection;
     // a pair with ub(1+1e-6) < thr_min can neither be a TP nor change which GT is a detection's arg-max among those
     // above the threshold, so its IoU is never needed.  Survivors (with their IoU) form a short list in shared memory.
-    bool dense = !(thr_min >= 0.0);
+    bool dense = given || !(thr_min >= 0.0);
     if (!dense) {
         for (int base = 0; base < npair; base += AM_NT) {
             const int pi = base + tid;
@@ -393,9 +430,9 @@ __device__ __forceinline__ void am_scene_body(const MatchParams &p, const AmScen
 
     // ---- dense mode (a negative threshold, or more than AM_QCAP candidate pairs): the full IoU matrix in the caller's
     // workspace, exact rejects only, pairs processed in slabs of AM_QCAP
-    double *iou = p.iou_ws + (size_t)s * p.K * p.G;
+    double *iou = given ? nullptr : p.iou_ws + (size_t)s * p.K * p.G;
     const int ldi = p.G;
-    for (int slab = 0; slab < npair; slab += AM_QCAP) {
+    for (int slab = 0; !given && slab < npair; slab += AM_QCAP) {
         __syncthreads();
         if (tid == 0) qn_s = 0;
         __syncthreads();
@@ -443,15 +480,17 @@ __device__ __forceinline__ void am_scene_body(const MatchParams &p, const AmScen
         for (int i = tid; i < nk; i += AM_NT) {
             const int k = kd[i];
             const int dc = sc.det_cls ? sc.det_cls[k] : -1;
-            const double *row = iou + (size_t)i * ldi;
+            // a given matrix is indexed by the ORIGINAL detection / GT positions, the one computed here by the compacted ones
+            const double *row = given ? p.iou_given + ((size_t)s * p.K + k) * p.G : iou + (size_t)i * ldi;
+            auto col = [&](int jj) { return given ? gl[jj] : jj; };
             for (int j = 0; j < ng; ++j) {
-                const double v = row[j];
+                const double v = row[col(j)];
                 if (!(v > thr_min)) continue;
                 const int c = glab[j];
                 if (c < 0 || c >= p.C || (sc.det_cls && dc != c)) continue;
                 bool first_max = true;
                 for (int j2 = 0; j2 < ng; ++j2)
-                    if (glab[j2] == c) { const double v2 = row[j2]; if (v2 > v || (v2 == v && j2 < j)) { first_max = false; break; } }
+                    if (glab[j2] == c) { const double v2 = row[col(j2)]; if (v2 > v || (v2 == v && j2 < j)) { first_max = false; break; } }
                 if (!first_max) continue;
                 if (pass == 0) {
                     const unsigned long long key = ((unsigned long long)__float_as_uint(det_score(k, c)) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
@@ -878,7 +917,7 @@ static int fill_match_params(MatchParams &p, const float *corners, const float *
     p.gt_labels = gt_labels; p.gt_present = gt_present; p.S = S; p.K = K; p.G = G; p.C = C; p.nthr = nthr;
     for (int t = 0; t < nthr; ++t) p.thr[t] = thr[t];
     p.iou_ws = iou_ws; p.rec_score = rec_score; p.rec_tp = rec_tp; p.npos = reinterpret_cast<unsigned long long *>(npos);
-    p.tp_key = nullptr; p.tp_bits = nullptr; p.tp_cnt = nullptr; p.tp_cap = 0; p.gt_present_f32 = nullptr;
+    p.tp_key = nullptr; p.tp_bits = nullptr; p.tp_cnt = nullptr; p.tp_cap = 0; p.gt_present_f32 = nullptr; p.iou_given = nullptr;
     { const char *e = getenv("OVDET_APMATCH_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
     return OVDET_OK;
 }
@@ -896,6 +935,41 @@ extern "C" int ovdet_ap_match(const float *corners, const float *probs, const fl
     { const int rc = fill_match_params(p, corners, probs, obj, keep, det_cls, gt_corners, gt_labels, gt_present, S, K, G, C, thr, nthr, iou_ws, rec_score, rec_tp, npos); if (rc) return rc; }
     const size_t smem = am_smem_bytes(K, G, nthr);
     OVDET_REQUIRE(smem <= 220 * 1024, "K + G too large for the shared-memory feature records");
+    OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ap_match_kernel<<<S, AM_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return launch_ok("ap_match_kernel");
+}
+
+extern "C" int ovdet_aabb_iou_f64(const double *dets, const double *gts, const int32_t *nd, const int32_t *ng,
+                                  int S, int D, int G, double *out, void *stream)
+{
+    OVDET_REQUIRE(S >= 0 && D >= 0 && G >= 0, "negative size");
+    if (S == 0 || D == 0 || G == 0) return OVDET_OK;
+    OVDET_REQUIRE(dets && gts && out, "null pointer");
+    AabbParams p{dets, gts, nd, ng, S, D, G, out, (long long)S * D * G};
+    long long blocks = (p.total + EV_NT - 1) / EV_NT;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    aabb_iou_kernel<<<(unsigned)blocks, EV_NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    return launch_ok("aabb_iou_kernel");
+}
+
+extern "C" int ovdet_ap_match_iou(const double *iou, const float *probs, const float *obj, const uint8_t *keep,
+                                  const int32_t *det_cls, const int64_t *gt_labels, const uint8_t *gt_present,
+                                  int S, int K, int G, int C, const double *thr, int nthr,
+                                  float *rec_score, uint8_t *rec_tp, int64_t *npos, void *stream)
+{
+    OVDET_REQUIRE(S >= 0 && K > 0 && G >= 0 && C > 0, "bad size");
+    if (S == 0) return OVDET_OK;
+    OVDET_REQUIRE(obj && keep && rec_score && rec_tp && npos && thr, "null pointer");
+    OVDET_REQUIRE(probs || det_cls, "need probs (per-class proposals) or det_cls");
+    OVDET_REQUIRE(G == 0 || iou, "null IoU matrix");
+    MatchParams p;
+    double dummy = 0.0;
+    { const int rc = fill_match_params(p, nullptr, probs, obj, keep, det_cls, reinterpret_cast<const float *>(&dummy), gt_labels, gt_present, S, K, G, C, thr, nthr, &dummy, rec_score, rec_tp, npos); if (rc) return rc; }
+    p.gt_corners = nullptr; p.iou_ws = nullptr;
+    p.iou_given = G > 0 ? iou : &dummy;   // G == 0: nothing is ever read
+    const size_t smem = am_smem_bytes(K, G, nthr);
+    OVDET_REQUIRE(smem <= 220 * 1024, "K + G too large for the shared-memory tables");
     OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ap_match_kernel<<<S, AM_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("ap_match_kernel");

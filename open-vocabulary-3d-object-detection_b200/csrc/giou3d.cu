@@ -551,7 +551,11 @@ template <typename ClipT, int PB, int TQ, bool HULL> static int launch_giou_tq2(
     p.tiles_per_b = (p.K1 + TQ - 1) / TQ;
     { const char *e = getenv("OVDET_GIOU_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
     const size_t smem = giou_smem_bytes<ClipT, PB, TQ>();
-    static bool attr_set = false;
+    static bool attr_set_dev[OVDET_MAX_DEVICES] = {};   // the attribute is per device: set it once on each
+    int dev_ = 0;
+    OVDET_CUDA_TRY(cudaGetDevice(&dev_));
+    bool untracked = false;   // a device index beyond the table: set the attribute on every call
+    bool &attr_set = (dev_ >= 0 && dev_ < OVDET_MAX_DEVICES) ? attr_set_dev[dev_] : untracked;
     if (!attr_set) {
         OVDET_CUDA_TRY(cudaFuncSetAttribute(giou3d_kernel<ClipT, PB, TQ, HULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -779,7 +783,11 @@ extern "C" int ovdet_box_intersection_f32(const float *rect1, const float *rect2
     p.B = B; p.K1 = K1; p.K2 = K2; p.k2_loop = k2_loop; p.approximate = approximate;
     p.total = (long long)B * K1 * K2;
     const size_t smem = sizeof(V2<double>) * 2 * SH_MAXV * NT;
-    static bool attr_set = false;
+    static bool attr_set_dev[OVDET_MAX_DEVICES] = {};   // the attribute is per device: set it once on each
+    int dev_ = 0;
+    OVDET_CUDA_TRY(cudaGetDevice(&dev_));
+    bool untracked = false;   // a device index beyond the table: set the attribute on every call
+    bool &attr_set = (dev_ >= 0 && dev_ < OVDET_MAX_DEVICES) ? attr_set_dev[dev_] : untracked;
     if (!attr_set) {
         OVDET_CUDA_TRY(cudaFuncSetAttribute(box_intersection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;

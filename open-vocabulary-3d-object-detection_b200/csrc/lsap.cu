@@ -95,6 +95,10 @@ __global__ void __launch_bounds__(LS_NT) lsap_kernel(LsapParams p)
     const int nr = transposed ? n : p.Q;
     const int nc = transposed ? p.Q : n;
     const int ldc = nc + 1;
+    // scipy.optimize.linear_sum_assignment raises ValueError on NaN / -inf entries ("matrix contains invalid numeric
+    // entries") and on infeasible problems: such a sample is not solved here either -- its mask is set to -1 and its
+    // col_to_row entries to -2, which the Python shim turns into the same exception (criterion.lsap)
+    bool bad = false;
     if (p.stage_cost) {   // coalesced global read (16 bytes per thread when the rows allow it), conflict-free (odd stride) shared write
         if ((p.G & 3) == 0 && (reinterpret_cast<uintptr_t>(cb) & 15) == 0) {
             const int n4 = (n + 3) >> 2;
@@ -104,16 +108,25 @@ __global__ void __launch_bounds__(LS_NT) lsap_kernel(LsapParams p)
                 const float c4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
-                    if (g + t < n) { if (transposed) sc[(g + t) * ldc + q] = c4[t]; else sc[q * ldc + g + t] = c4[t]; }
+                    if (g + t < n) { bad |= !(c4[t] > -INFINITY) ; if (transposed) sc[(g + t) * ldc + q] = c4[t]; else sc[q * ldc + g + t] = c4[t]; }
             }
         } else {
             for (int idx = tid; idx < p.Q * n; idx += LS_NT) {
                 const int q = idx / n, g = idx - q * n;
                 const float c = __ldg(cb + (size_t)q * p.G + g);
+                bad |= !(c > -INFINITY);
                 if (transposed) sc[g * ldc + q] = c; else sc[q * ldc + g] = c;
             }
         }
     }
+    else {
+        for (int idx = tid; idx < p.Q * n; idx += LS_NT) { const int q = idx / n, g = idx - q * n; bad |= !(__ldg(cb + (size_t)q * p.G + g) > -INFINITY); }
+    }
+    auto fail = [&]() {
+        for (int q = tid; q < p.Q; q += LS_NT) p.mask[(size_t)b * p.Q + q] = -1.f;
+        if (p.col_to_row) for (int g = tid; g < p.G; g += LS_NT) p.col_to_row[(size_t)b * p.G + g] = -2;
+    };
+    if (__syncthreads_or(bad ? 1 : 0)) { fail(); return; }   // NaN or -inf somewhere in cost[b, :, :n]
     auto C = [&](int i, int j) -> double {
         if (p.stage_cost) return (double)sc[i * ldc + j];
         return transposed ? (double)__ldg(cb + (size_t)j * p.G + i) : (double)__ldg(cb + (size_t)i * p.G + j);
@@ -215,6 +228,11 @@ __global__ void __launch_bounds__(LS_NT) lsap_kernel(LsapParams p)
     }
     __syncthreads();
     LSTAMP(2);
+    {   // a row without a column: the search ran out of finite costs (+inf rows): infeasible
+        bool unassigned = false;
+        for (int r = tid; r < nr; r += LS_NT) unassigned |= col4row[r] < 0;
+        if (__syncthreads_or(unassigned ? 1 : 0)) { fail(); return; }
+    }
     if (p.dbg && tid == 0) p.dbg[(size_t)b * 4 + 3] = ((unsigned long long)n << 32) | (unsigned)nsteps;
     for (int r = tid; r < nr; r += LS_NT) {
         const int c = col4row[r];

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(NMS_NT) nms_kernel(NmsParams p)
     }
     __syncthreads();
     nms_core(src, p.K, dims, samecls, p.flags & OVDET_NMS_OLD_TYPE, p.thr, p.eps, sh,
-             p.pick_order ? p.pick_order + (size_t)s * p.K : nullptr);
+             p.pick_order ? p.pick_order + (size_t)s * p.K : nullptr, nullptr, (p.flags & OVDET_NMS_LHS) != 0);
     const int na = sh.misc[0];
     for (int pos = threadIdx.x; pos < na; pos += blockDim.x)
         if (sh.picked[pos]) p.keep[(size_t)s * p.K + sh.sidx[pos]] = 1;

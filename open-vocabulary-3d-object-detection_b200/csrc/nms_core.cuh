@@ -63,7 +63,7 @@ __device__ inline NmsSmem nms_carve(unsigned char *base, int K)
 // s.misc[1] = npick.  `order_out` (may be null) gets original indices in pick order.
 template <typename Src>
 __device__ void nms_core(const Src &src, int K, int dims, bool samecls, bool old_type, double thr, double eps,
-                         NmsSmem &s, int32_t *order_out, unsigned long long *dbg = nullptr)
+                         NmsSmem &s, int32_t *order_out, unsigned long long *dbg = nullptr, bool lhs = false)
 {
     using A = Ar<double>;
     const int tid = threadIdx.x;
@@ -82,7 +82,7 @@ __device__ void nms_core(const Src &src, int K, int dims, bool samecls, bool old
     // ---- 0. mode.  Class-wise NMS with thr >= 0 and dense class ids (0..255) splits into independent per-class
     // problems (steps 3'/4'); if the caller does not need the global pick order either, no global sort is needed at all:
     // boxes stay at their original positions and are ordered inside their class only (`identity`).
-    bool classwise = fast && samecls;
+    bool classwise = fast && samecls && !lhs;   // the lhs re-pick needs the global score order of the suppressed boxes
     if (classwise) {
         bool bad = false;
         for (int k = tid; k < K; k += NT)
@@ -312,7 +312,28 @@ __device__ void nms_core(const Src &src, int K, int dims, bool samecls, bool old
                     if (order_out) order_out[np] = s.sidx[i];
                 }
                 ++np;
-                if (lane < W) removed |= s.mask[(size_t)i * W + lane];
+                const uint32_t row = lane < W ? s.mask[(size_t)i * W + lane] : 0u;
+                if (lhs) {
+                    // tools variant (3DOVDet_tools/utils/box_3d_utils.py:113-116): the better-scoring half of the boxes this
+                    // pick suppresses is picked too (in descending score = ascending position), and still leaves the race
+                    const uint32_t newly = row & ~removed;
+                    const int cnt = __popc(newly);
+                    int incl = cnt;
+                    for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += y; }
+                    const int half = __shfl_sync(0xffffffffu, incl, 31) / 2;
+                    int rank = incl - cnt;
+                    uint32_t m = newly;
+                    while (m && rank < half) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int pos = 32 * lane + b;
+                        s.picked[pos] = 1;
+                        if (order_out) order_out[np + rank] = s.sidx[pos];
+                        ++rank;
+                    }
+                    np += half;
+                }
+                removed |= row;
             }
         }
         if (lane == 0) s.misc[1] = np;

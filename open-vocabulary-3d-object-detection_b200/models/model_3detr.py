@@ -40,6 +40,29 @@ def clip_logits(x, text, l2norm=False, scale=1.0, want_logits=False, want_prob=T
     return lg, pr, obj.reshape(lead)
 
 
+class _ClipLogitsFn(torch.autograd.Function):
+    """Differentiable form of the classification head: the forward is the fused kernel (fp32 logits + bf16 probabilities
+    + objectness), the backward is the one the frozen ``nn.Linear`` of the reference has w.r.t. its input,
+    dX = scale * dLogits @ T (the text matrix is frozen, models/model_3detr.py:151-154).  Probabilities and objectness
+    are outputs of convenience (matcher / evaluation inputs) and carry no gradient -- the reference's losses
+    differentiate ``sem_cls_logits`` (criterion.py: loss_sem_cls)."""
+
+    @staticmethod
+    def forward(ctx, x, text, scale):
+        lg, pr, ob = clip_logits(x, text, False, scale, want_logits=True, want_prob=True)
+        ctx.save_for_backward(text)
+        ctx.scale, ctx.xdtype = float(scale), x.dtype
+        ctx.mark_non_differentiable(pr, ob)
+        return lg, pr, ob
+
+    @staticmethod
+    def backward(ctx, g_lg, g_pr, g_ob):
+        (text,) = ctx.saved_tensors
+        n = g_lg.shape[-1]
+        gx = (g_lg.reshape(-1, n).to(torch.float32) @ text.to(torch.float32)) * ctx.scale
+        return gx.reshape(*g_lg.shape[:-1], text.shape[1]).to(ctx.xdtype), None, None
+
+
 class BoxProcessor(object):
     """The classification part of models/model_3detr.py:19-69."""
 
@@ -64,8 +87,26 @@ class ClipTextClassifier(nn.Module):
         self.l2norm = l2norm
         self.logit_scale = logit_scale
 
-    @torch.no_grad()
-    def forward(self, visual_embeds, want_logits=False):
-        """visual_embeds [..., 640] -> dict(sem_cls_logits, sem_cls_prob, objectness_prob)."""
-        lg, pr, ob = clip_logits(visual_embeds, self.weight, self.l2norm, self.logit_scale, want_logits=want_logits)
-        return {"sem_cls_logits": lg, "sem_cls_prob": pr, "objectness_prob": ob}
+    def forward(self, visual_embeds, want_logits=False, prob_dtype=None):
+        """visual_embeds [..., 640] -> dict(sem_cls_logits, sem_cls_prob, objectness_prob).
+
+        Only the weight is frozen in the reference: when ``visual_embeds`` requires grad (training), ``sem_cls_logits``
+        is returned in fp32 WITH its graph (dX = dLogits @ T), so swapping this module in does not cut the gradient
+        into ``visual_embed_head``.  ``sem_cls_prob`` comes from the kernel in bf16 (8 bits of mantissa: scores
+        prob * objectness are then quantised to ~0.4 % relative, which can tie neighbouring detections in AP ranking
+        and the matcher's class cost); pass ``prob_dtype=torch.float32`` to get the probabilities recomputed in fp32
+        from the fp32 logits instead (one extra softmax kernel), as the reference has them."""
+        if torch.is_grad_enabled() and visual_embeds.requires_grad:
+            if self.l2norm:
+                raise C.OvdetError("the differentiable path covers the reference's head (no normalisation, models/model_3detr.py:237-238)")
+            lg, pr, ob = _ClipLogitsFn.apply(visual_embeds, self.weight, float(self.logit_scale))
+        else:
+            with torch.no_grad():
+                lg, pr, ob = clip_logits(visual_embeds, self.weight, self.l2norm, self.logit_scale,
+                                         want_logits=want_logits or prob_dtype is torch.float32)
+        if prob_dtype is torch.float32:
+            p32 = torch.softmax(lg.detach(), dim=-1)
+            pr, ob = p32[..., :-1], 1 - p32[..., -1]
+        elif prob_dtype is not None and pr is not None:
+            pr = pr.to(prob_dtype)
+        return {"sem_cls_logits": lg if (want_logits or lg is not None and lg.requires_grad) else None, "sem_cls_prob": pr, "objectness_prob": ob}

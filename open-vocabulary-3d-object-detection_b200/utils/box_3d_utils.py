@@ -33,9 +33,8 @@ def box_3d_iou(box_q, box_k, typ="vv", eps=1e-5):
 def nms_3d_faster(boxes, overlap_threshold, old_type=False, eps=1e-8, use_size=False, use_size_score=False,
                   class_wise=False, size_typ=None, lhs=False):
     """box_3d_utils.py:60-120.  Returns ``boxes[pick]``.  As in the reference,
-    ``use_size_score`` multiplies the caller's score column in place (:78-79)."""
-    if lhs:
-        raise NotImplementedError("lhs re-pick option (box_3d_utils.py:113-116) is not built")
+    ``use_size_score`` multiplies the caller's score column in place (:78-79); ``lhs`` re-picks the better-scoring
+    half of the boxes each pick suppresses (:113-116)."""
     assert size_typ in [None, "Volume", "Area"]
     boxes = np.asarray(boxes)
     if boxes.shape[0] == 0:
@@ -49,7 +48,7 @@ def nms_3d_faster(boxes, overlap_threshold, old_type=False, eps=1e-8, use_size=F
             boxes[:, 6] *= size
             work[:, 6] = boxes[:, 6]
     b = torch.as_tensor(np.ascontiguousarray(work), device="cuda")[None]
-    _, order, npick = nms_batch(b, overlap_threshold, old_type, 3, class_wise, vol_eps=eps)
+    _, order, npick = nms_batch(b, overlap_threshold, old_type, 3, class_wise, vol_eps=eps, lhs=lhs)
     n = int(npick[0].item())
     return boxes[order[0, :n].cpu().numpy().astype(np.int64)]
 

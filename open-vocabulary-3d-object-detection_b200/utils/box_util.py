@@ -11,9 +11,10 @@ Reference quirks are explicit switches, defaulting to the reference's behaviour:
   fp32 polygon/area, and the shipped ``K2 = rect2.shape[2]`` bug
   (utils/box_intersection.pyx:180): only GT columns < 4 are clipped.  Override
   with ``k2_cap=0`` (no cap) or set ``ovdet_b200.utils.box_util.DEFAULT_K2_CAP``.
-* ``needs_grad=True`` (the TorchScript path, :725-730) -> all-fp32 clip, no cap.
-  Only the forward value is provided; the backward is not built
-  and inputs that require grad raise.
+* ``needs_grad=True`` (the TorchScript path, :725-730) -> all-fp32 clip, no cap.  When ``corners1`` requires
+  grad the call is differentiable (``_GIoU3D``: forward kernel + the sparse backward kernel of csrc/giou3d_bwd.cu,
+  SURVEY.md 8f-4) and, like the reference's ``with torch.enable_grad()``, tracks gradients even inside an outer
+  ``no_grad``.  No gradient w.r.t. ``corners2`` (the ground truth carries none in criterion.py:274-296).
 * ``prefilter`` (default True): skip pairs whose axis-aligned BEV overlap is 0
   (:587-588), which is wrong for rotated boxes but is what the reference does.
 * ``enclosing``: "aabb" (live reference, :466-514) or "hull" (utils/box_ops3d.py:533-571).
@@ -93,38 +94,53 @@ def generalized_box3d_iou(corners1, corners2, nums_k2, rotated_boxes=True, retur
     (utils/box_util.py:717-737).  CUDA tensors run stream-ordered with no host
     sync; CPU tensors go through the host-buffer C entry point (H2D, kernel, D2H)."""
     _check_shapes(corners1, corners2)
-    if needs_grad and (corners1.requires_grad or corners2.requires_grad) and torch.is_grad_enabled():
-        # the reference's TorchScript path under enable_grad (:725-730): differentiable w.r.t. the predicted corners
+    if needs_grad and (corners1.requires_grad or corners2.requires_grad):
+        # the reference's TorchScript path runs under `with torch.enable_grad()` (:725-730): differentiable w.r.t. the
+        # predicted corners even when the caller sits inside no_grad
         if corners2.requires_grad:
             raise NotImplementedError("no gradient w.r.t. corners2 (ground truth) is produced")
         if return_inter_vols_only or enclosing != "aabb" or (mode not in (None, "tensor")) or not corners1.is_cuda or k2_cap:
             raise NotImplementedError("the backward exists for the fp32 torch-path GIoU on CUDA tensors only")
         nk_t = None if nums_k2 is None else torch.as_tensor(nums_k2)
-        return _GIoU3D.apply(corners1, corners2, nk_t, bool(rotated_boxes), bool(prefilter))
+        with torch.enable_grad():
+            return _GIoU3D.apply(corners1, corners2, nk_t, bool(rotated_boxes), bool(prefilter))
     if mode is None:
         mode = "tensor" if needs_grad else "cython"
     if k2_cap is None:
         k2_cap = DEFAULT_K2_CAP if mode == "cython" else 0
     flags = giou_flags(rotated_boxes, return_inter_vols_only, mode, prefilter, enclosing)
     B, K1, K2 = corners1.shape[0], corners1.shape[1], corners2.shape[1]
-    c1 = corners1.detach().to(torch.float32).contiguous()
-    c2 = corners2.detach().to(torch.float32).contiguous()
-    nk = None
-    if nums_k2 is not None:
-        nk = torch.as_tensor(nums_k2).detach().to(device=c1.device, dtype=torch.int64).contiguous()
-        assert nk.numel() == B
-    if out is None:
-        out = torch.empty((B, K1, K2), dtype=torch.float32, device=c1.device)
-    else:  # caller-owned result buffer (e.g. pinned host memory for the host-buffer path)
-        assert out.shape == (B, K1, K2) and out.dtype == torch.float32 and out.is_contiguous() and out.device == c1.device
+    dev = corners1.device
+    c1 = C.as_input(corners1, torch.float32, dev)
     L = C.lib()
     if c1.is_cuda:
-        C.require_cuda(c2)
-        with torch.cuda.device(c1.device):
-            C.check(L.ovdet_giou3d_f32(C.ptr(c1), C.ptr(c2), C.ptr(nk), B, K1, K2, int(k2_cap), flags, C.ptr(out),
-                                       C.stream(c1.device)))
-    else:
-        C.check(L.ovdet_giou3d_host_f32(C.ptr(c1), C.ptr(c2.cpu()), C.ptr(nk), B, K1, K2, int(k2_cap), flags, C.ptr(out)))
+        C.require_cuda(corners2)
+        c2 = C.as_input(corners2, torch.float32, dev)
+        nk = None
+        if nums_k2 is not None:
+            nk = C.as_input(nums_k2 if isinstance(nums_k2, torch.Tensor) else torch.as_tensor(nums_k2), torch.int64, dev)
+            assert nk.numel() == B
+        if out is None:
+            out = torch.empty((B, K1, K2), dtype=torch.float32, device=dev)
+        else:  # caller-owned result buffer
+            assert out.shape == (B, K1, K2) and out.dtype == torch.float32 and out.is_contiguous() and out.device == dev
+        with C.on_device(dev):
+            C.check(L.ovdet_giou3d_f32(c1.data_ptr(), c2.data_ptr(), None if nk is None else nk.data_ptr(), B, K1, K2, int(k2_cap), flags,
+                                       out.data_ptr(), C.stream(dev)))
+        return out
+    # host buffers: everything the C entry point sees must live on the host and outlive the call (locals, not temporaries)
+    cpu = torch.device("cpu")
+    c2 = C.as_input(corners2, torch.float32, cpu)
+    nk = None
+    if nums_k2 is not None:
+        nk = C.as_input(nums_k2 if isinstance(nums_k2, torch.Tensor) else torch.as_tensor(nums_k2), torch.int64, cpu)
+        assert nk.numel() == B
+    if out is None:
+        out = torch.empty((B, K1, K2), dtype=torch.float32)
+    else:  # e.g. pinned host memory
+        assert out.shape == (B, K1, K2) and out.dtype == torch.float32 and out.is_contiguous() and not out.is_cuda
+    C.check(L.ovdet_giou3d_host_f32(c1.data_ptr(), c2.data_ptr(), None if nk is None else nk.data_ptr(), B, K1, K2, int(k2_cap), flags,
+                                    out.data_ptr()))
     return out
 
 

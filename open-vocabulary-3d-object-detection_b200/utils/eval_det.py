@@ -347,30 +347,98 @@ def _eval_packed(pred_all, gt_all, ovthresh, use_07_metric):
     return out_rec, out_prec, out_ap
 
 
+def calc_iou(box_a, box_b):
+    """3DOVDet_tools/utils/evaluation/box_util.py:287-309: IoU of two axis-aligned boxes given as (centre, lengths).
+    Host scalar form for interface parity -- the evaluation itself runs ``ovdet_aabb_iou_f64`` on all pairs at once."""
+    box_a, box_b = np.asarray(box_a), np.asarray(box_b)
+    min_max = np.array([box_a[0:3] + box_a[3:6] / 2, box_b[0:3] + box_b[3:6] / 2]).min(0)
+    max_min = np.array([box_a[0:3] - box_a[3:6] / 2, box_b[0:3] - box_b[3:6] / 2]).max(0)
+    if not ((min_max > max_min).all()):
+        return 0.0
+    intersection = (min_max - max_min).prod()
+    union = box_a[3:6].prod() + box_b[3:6].prod() - intersection
+    return 1.0 * intersection / union
+
+
+def get_iou(bb1, bb2):
+    """3DOVDet_tools/utils/evaluation/eval_det.py:63-77: ``calc_iou`` clamped to [0, 1] -- the tools' default
+    ``get_iou_func`` (axis-aligned evaluation of the lifted pseudo-label boxes)."""
+    return min(max(calc_iou(bb1, bb2), 0), 1)
+
+
+def _eval_packed_aabb(pred_all, gt_all, ovthresh, use_07_metric):
+    """eval_det with get_iou_func=get_iou: boxes are 6-vectors (centre, lengths), fp64."""
+    imgs = list(dict.fromkeys(list(pred_all.keys()) + list(gt_all.keys())))
+    classes = list(dict.fromkeys([cl for img in pred_all for cl, _, _ in pred_all[img]] + [cl for img in gt_all for cl, _ in gt_all[img]]))
+    cidx = {c: i for i, c in enumerate(classes)}
+    S = len(imgs)
+    K = max([len(pred_all.get(i, [])) for i in imgs] + [1])
+    G = max([len(gt_all.get(i, [])) for i in imgs] + [1])
+    det = np.zeros((S, K, 6), np.float64); score = np.zeros((S, K), np.float32); dcls = np.zeros((S, K), np.int32)
+    keep = np.zeros((S, K), np.uint8); gtb = np.zeros((S, G, 6), np.float64); glab = np.zeros((S, G), np.int64); gpres = np.zeros((S, G), np.uint8)
+    for si, img in enumerate(imgs):
+        for k, (cl, box, sc) in enumerate(pred_all.get(img, [])):
+            det[si, k] = np.asarray(box, np.float64)[:6]; score[si, k] = sc; dcls[si, k] = cidx[cl]; keep[si, k] = 1
+        for g, (cl, box) in enumerate(gt_all.get(img, [])):
+            gtb[si, g] = np.asarray(box, np.float64)[:6]; glab[si, g] = cidx[cl]; gpres[si, g] = 1
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = lambda a: torch.as_tensor(a, device=dev)
+    dd, gg, sc_d, dc_d, kp_d, gl_d, gp_d = t(det), t(gtb), t(score), t(dcls), t(keep), t(glab), t(gpres)
+    Cn = len(classes)
+    iou = torch.empty((S, K, G), dtype=torch.float64, device=dev)
+    rs = torch.empty((Cn, S * K), dtype=torch.float32, device=dev)
+    rt = torch.empty((Cn, S * K), dtype=torch.uint8, device=dev)
+    npos = torch.zeros((Cn,), dtype=torch.int64, device=dev)
+    thr = np.asarray([ovthresh], np.float64)
+    L = C.lib()
+    with C.on_device(dev):
+        C.check(L.ovdet_aabb_iou_f64(dd.data_ptr(), gg.data_ptr(), None, None, S, K, G, iou.data_ptr(), C.stream(dev)))
+        C.check(L.ovdet_ap_match_iou(iou.data_ptr(), None, sc_d.data_ptr(), kp_d.data_ptr(), dc_d.data_ptr(), gl_d.data_ptr(), gp_d.data_ptr(),
+                                     S, K, G, Cn, thr.ctypes.data, 1, rs.data_ptr(), rt.data_ptr(), npos.data_ptr(), C.stream(dev)))
+    ap, recall, ndet, rec, prec = ap_reduce(rs, rt, npos, 1, use_07_metric, curves=True)
+    ap, ndet, rec, prec = ap.cpu().numpy(), ndet.cpu().numpy(), rec.cpu().numpy(), prec.cpu().numpy()
+    pred_classes = set(cl for img in pred_all for cl, _, _ in pred_all[img])
+    out_rec, out_prec, out_ap = {}, {}, {}
+    for ci, cl in enumerate(classes):
+        if cl in pred_classes:
+            n = int(ndet[ci])
+            out_rec[cl], out_prec[cl], out_ap[cl] = rec[0, ci, :n].copy(), prec[0, ci, :n].copy(), float(ap[0, ci])
+        else:
+            out_rec[cl], out_prec[cl], out_ap[cl] = 0, 0, 0
+    return out_rec, out_prec, out_ap
+
+
 def get_iou_obb(bb1, bb2):
     """utils/eval_det.py:57-59."""
     from .box_util import box3d_iou
     return box3d_iou(bb1, bb2)[0]
 
 
+def _iou_path(get_iou_func):
+    """The two IoU definitions the reference evaluates with: ``get_iou_obb`` (exact rotated IoU of 8-corner boxes, the
+    default of utils/eval_det.py) and ``get_iou`` / ``calc_iou`` (axis-aligned IoU of (centre, lengths) boxes, the default
+    of 3DOVDet_tools/utils/evaluation/eval_det.py:86).  Arbitrary Python callables cannot run on the device."""
+    if get_iou_func is None or get_iou_func is get_iou_obb:
+        return _eval_packed
+    if get_iou_func is get_iou or get_iou_func is calc_iou:
+        return _eval_packed_aabb
+    raise NotImplementedError("get_iou_func must be get_iou_obb (rotated) or get_iou / calc_iou (axis-aligned) of this module")
+
+
 def eval_det_cls(pred, gt, ovthresh=0.25, use_07_metric=False, get_iou_func=get_iou_obb):
     """utils/eval_det.py:66-155: pred {img: [(bbox, score)]}, gt {img: [bbox]} ->
     (rec, prec, ap) with rec/prec sorted by descending score."""
-    if get_iou_func is not get_iou_obb:
-        raise NotImplementedError("only get_iou_obb (exact rotated IoU) is built on the GPU path")
     pred_all = {img: [(0, b, s) for b, s in lst] for img, lst in pred.items()}
     gt_all = {img: [(0, b) for b in lst] for img, lst in gt.items()}
     if not any(len(v) for v in pred_all.values()):
         return np.zeros(0), np.zeros(0), voc_ap(np.zeros(0), np.zeros(0), use_07_metric)
-    rec, prec, ap = _eval_packed(pred_all, gt_all, ovthresh, use_07_metric)
+    rec, prec, ap = _iou_path(get_iou_func)(pred_all, gt_all, ovthresh, use_07_metric)
     return rec[0], prec[0], ap[0]
 
 
 def eval_det(pred_all, gt_all, ovthresh=0.25, use_07_metric=False, get_iou_func=get_iou_obb):
     """utils/eval_det.py:164-208 / :214-272 -> ({cls: rec}, {cls: prec}, {cls: ap})."""
-    if get_iou_func is not None and get_iou_func is not get_iou_obb:
-        raise NotImplementedError("only get_iou_obb (exact rotated IoU) is built on the GPU path")
-    return _eval_packed(pred_all, gt_all, ovthresh, use_07_metric)
+    return _iou_path(get_iou_func)(pred_all, gt_all, ovthresh, use_07_metric)
 
 
 eval_det_multiprocessing = eval_det  # the per-class Pool(10) of :253-261 is one kernel launch here

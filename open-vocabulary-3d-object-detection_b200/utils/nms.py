@@ -12,7 +12,7 @@ import torch
 from .. import _capi as C
 
 
-def nms_batch(boxes, overlap_threshold, old_type=False, dims=3, samecls=False, counts=None, vol_eps=0.0, want_order=True):
+def nms_batch(boxes, overlap_threshold, old_type=False, dims=3, samecls=False, counts=None, vol_eps=0.0, want_order=True, lhs=False):
     """boxes: CUDA fp64 [S,K,ncols] (2*dims coords, score, [cls]).  Returns
     (keep uint8 [S,K], pick_order int32 [S,K] (-1 padded) or None, npick int32 [S]).  ``want_order=False`` lets the
     class-wise kernel skip the global score sort (the keep mask is the same)."""
@@ -23,7 +23,7 @@ def nms_batch(boxes, overlap_threshold, old_type=False, dims=3, samecls=False, c
     order = torch.empty((S, K), dtype=torch.int32, device=b.device) if want_order else None
     npick = torch.zeros((S,), dtype=torch.int32, device=b.device)
     cnt = None if counts is None else torch.as_tensor(counts).to(device=b.device, dtype=torch.int32).contiguous()
-    flags = (C.NMS_2D if dims == 2 else 0) | (C.NMS_SAMECLS if samecls else 0) | (C.NMS_OLD_TYPE if old_type else 0)
+    flags = (C.NMS_2D if dims == 2 else 0) | (C.NMS_SAMECLS if samecls else 0) | (C.NMS_OLD_TYPE if old_type else 0) | (C.NMS_LHS if lhs else 0)
     with torch.cuda.device(b.device):
         C.check(C.lib().ovdet_nms_f64(C.ptr(b), C.ptr(cnt), S, K, ncols, float(overlap_threshold), float(vol_eps), flags,
                                       C.ptr(keep), C.ptr(order), C.ptr(npick), C.stream(b.device)))

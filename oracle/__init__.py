@@ -350,6 +350,81 @@ def tools_nms_3d_faster(boxes, overlap_threshold, old_type=False, eps=1e-8, use_
     return boxes[np.array(pick, dtype=np.int64)] if len(pick) else boxes[:0]
 
 
+def tools_nms_3d_faster_lhs(boxes, overlap_threshold, old_type=False, eps=1e-8, class_wise=False, lhs=True):
+    """3DOVDet_tools/utils/box_3d_utils.py:60-120 WITH the ``lhs`` option (:113-116), restated in numpy: after each pick
+    the better-scoring half of the boxes it suppresses is appended to the picks as well (and removed with the rest).
+    Returns the pick indices.  Stable ascending sort on (score, index): only defined for tie-free scores."""
+    b = np.asarray(boxes, np.float64)
+    vol = (b[:, 3] - b[:, 0]) * (b[:, 4] - b[:, 1]) * (b[:, 5] - b[:, 2]) + eps
+    order = list(np.argsort(b[:, 6], kind="stable"))
+    pick = []
+    while order:
+        i = order[-1]
+        rest = order[:-1]
+        pick.append(int(i))
+        sup = []
+        for pos, j in enumerate(rest):
+            l = max(0.0, min(b[i, 3], b[j, 3]) - max(b[i, 0], b[j, 0]))
+            w = max(0.0, min(b[i, 4], b[j, 4]) - max(b[i, 1], b[j, 1]))
+            h = max(0.0, min(b[i, 5], b[j, 5]) - max(b[i, 2], b[j, 2]))
+            inter = l * w * h
+            o = inter / vol[j] if old_type else inter / (vol[i] + vol[j] - inter)
+            if class_wise:
+                o = o * (1.0 if b[i, 7] == b[j, 7] else 0.0)
+            if o > overlap_threshold:
+                sup.append(pos)
+        if lhs:
+            for count in range(len(sup) // 2):
+                pick.append(int(rest[sup[len(sup) - count - 1]]))
+        gone = set(sup)
+        order = [j for pos, j in enumerate(rest) if pos not in gone]
+    return pick
+
+
+def calc_iou_aabb(box_a, box_b):
+    """3DOVDet_tools/utils/evaluation/box_util.py:287-309 + the [0, 1] clamp of get_iou (evaluation/eval_det.py:63-77)."""
+    a, b = np.asarray(box_a, np.float64), np.asarray(box_b, np.float64)
+    hi = np.minimum(a[0:3] + a[3:6] / 2, b[0:3] + b[3:6] / 2)
+    lo = np.maximum(a[0:3] - a[3:6] / 2, b[0:3] - b[3:6] / 2)
+    if not (hi > lo).all():
+        return 0.0
+    d = hi - lo
+    inter = d[0] * d[1] * d[2]
+    iou = inter / (a[3] * a[4] * a[5] + b[3] * b[4] * b[5] - inter)
+    return min(max(iou, 0.0), 1.0)
+
+
+def eval_det_cls_aabb(pred, gt, ovthresh=0.25, use_07_metric=False):
+    """3DOVDet_tools/utils/evaluation/eval_det.py:86-170 with its default get_iou_func=get_iou (axis-aligned boxes as
+    (centre, lengths)): pred {img: [(box6, score)]}, gt {img: [box6]} -> (rec, prec, ap).  Python loops: small cases."""
+    recs, npos = {}, 0
+    for img, lst in gt.items():
+        recs[img] = [np.asarray(x, np.float64) for x in lst], [False] * len(lst)
+        npos += len(lst)
+    ids, conf, bbs = [], [], []
+    for img, lst in pred.items():
+        for box, score in lst:
+            ids.append(img); conf.append(score); bbs.append(np.asarray(box, np.float64))
+    order = np.argsort(-np.asarray(conf, np.float64), kind="stable")
+    tp, fp = np.zeros(len(ids)), np.zeros(len(ids))
+    for d, o in enumerate(order):
+        gtb, taken = recs.get(ids[o], ([], []))
+        ovmax, jmax = -np.inf, -1
+        for j, g in enumerate(gtb):
+            iou = calc_iou_aabb(bbs[o], g)
+            if iou > ovmax:
+                ovmax, jmax = iou, j
+        if ovmax > ovthresh and not taken[jmax]:
+            tp[d] = 1.0
+            taken[jmax] = True
+        else:
+            fp[d] = 1.0
+    fp, tp = np.cumsum(fp), np.cumsum(tp)
+    rec = tp / np.maximum(float(npos), np.finfo(np.float64).eps)
+    prec = tp / np.maximum(tp + fp, np.finfo(np.float64).eps)
+    return rec, prec, voc_ap(rec, prec, use_07_metric)
+
+
 def voc_ap(rec, prec, use_07_metric=False):
     """utils/eval_det.py:23-54."""
     r = np.ascontiguousarray(rec, np.float64)

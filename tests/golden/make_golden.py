@@ -127,6 +127,56 @@ def golden_giou_grad(box_util):
     save("giou_grad.npz", **out)
 
 
+def golden_holes():
+    """Fixtures for the two API corners added in round 2, from the reference's own tools modules: the ``lhs`` re-pick of
+    3DOVDet_tools/utils/box_3d_utils.py:113-116 and the axis-aligned evaluation of
+    3DOVDet_tools/utils/evaluation/eval_det.py:86 (get_iou_func=get_iou -> evaluation/box_util.py:287-309)."""
+    sys.path.insert(0, os.path.join(REF, "3DOVDet_tools/utils"))
+    import evaluation.eval_det as ted
+    spec = importlib.util.spec_from_file_location("ref_box_3d_utils2", os.path.join(REF, "3DOVDet_tools/utils/box_3d_utils.py"))
+    tools = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tools)
+    rng = np.random.default_rng(7)
+    out = {}
+    for tag, cw in (("plain", False), ("cls", True)):
+        K = 96
+        c = rng.uniform(0, 4, (K, 3)); sz = rng.uniform(0.5, 2.0, (K, 3))
+        b = np.concatenate([c - sz / 2, c + sz / 2, rng.permutation(K)[:, None] / K + 0.001, rng.integers(0, 4, (K, 1)).astype(float)], 1)
+        picked = tools.nms_3d_faster(b.copy(), 0.1, class_wise=cw, lhs=True)
+        out["lhs_boxes_" + tag] = b
+        out["lhs_pick_" + tag] = np.array([int(np.where((b == row).all(1))[0][0]) for row in picked])
+    S = 12
+    pred, gt = {}, {}
+    for s in range(S):
+        ng = int(rng.integers(0, 6))
+        g = [np.concatenate([rng.uniform(0, 5, 3), rng.uniform(0.5, 2, 3)]) for _ in range(ng)]
+        gt[s] = g
+        p = []
+        for gb in g:
+            for _ in range(int(rng.integers(1, 4))):
+                p.append((np.concatenate([gb[:3] + rng.normal(0, 0.25, 3), gb[3:] * rng.uniform(0.7, 1.3, 3)]), float(rng.uniform(0.05, 1))))
+        for _ in range(int(rng.integers(0, 8))):
+            p.append((np.concatenate([rng.uniform(0, 5, 3), rng.uniform(0.5, 2, 3)]), float(rng.uniform(0.05, 1))))
+        pred[s] = p
+    for thr in (0.25, 0.5):
+        rec, prec, ap = ted.eval_det_cls(pred, gt, thr, False, ted.get_iou)
+        out[f"aabb_rec_{thr}"] = rec; out[f"aabb_prec_{thr}"] = prec; out[f"aabb_ap_{thr}"] = np.array(ap)
+    out["aabb_ap07"] = np.array(ted.eval_det_cls(pred, gt, 0.25, True, ted.get_iou)[2])
+    K = max(len(v) for v in pred.values()); G = max(len(v) for v in gt.values())
+    pb = np.zeros((S, K, 7)); pn = np.zeros(S, np.int64); gb = np.zeros((S, max(G, 1), 6)); gn = np.zeros(S, np.int64)
+    for s in range(S):
+        pn[s] = len(pred[s]); gn[s] = len(gt[s])
+        for k, (b, sc) in enumerate(pred[s]):
+            pb[s, k, :6] = b; pb[s, k, 6] = sc
+        for j, b in enumerate(gt[s]):
+            gb[s, j] = b
+    out.update(aabb_pred=pb, aabb_npred=pn, aabb_gt=gb, aabb_ngt=gn)
+    a = np.concatenate([rng.uniform(0, 3, 3), rng.uniform(0.5, 2, 3)])
+    b2 = np.concatenate([a[:3] + 0.3, a[3:] * 1.1])
+    out.update(calc_iou_a=a, calc_iou_b=b2, calc_iou=np.array(ted.get_iou(a, b2)))
+    save("holes.npz", **out)
+
+
 def golden_project(ref_root):
     """project_box_3d_cuda + SUNRGBD_Calibration_cuda (utils/image_util.py) and the image clip of criterion.py:387-391."""
     spec = importlib.util.spec_from_file_location("ref_image_util", os.path.join(ref_root, "utils", "image_util.py"))
@@ -153,7 +203,12 @@ def golden_project(ref_root):
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "holes":     # only the lhs-NMS / axis-aligned-evaluation fixture
+        golden_holes()
+        return
     box_util, nms, eval_det, apc, lf, criterion, tools = import_reference()
+    if len(sys.argv) <= 1:
+        golden_holes()
     if len(sys.argv) > 1 and sys.argv[1] == "project":   # regenerate only the projection fixture
         golden_project(REF)
         return

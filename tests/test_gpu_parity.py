@@ -20,6 +20,7 @@ from ovdet_b200.utils import ap_calculator as APC  # noqa: E402
 from ovdet_b200.utils import box_3d_utils as B3  # noqa: E402
 from ovdet_b200.utils.box_intersection import box_intersection  # noqa: E402
 from ovdet_b200.criterion import Matcher, matcher_cost, lsap  # noqa: E402
+from scipy.optimize import linear_sum_assignment as scipy_lsa  # noqa: E402
 
 DEV = "cuda"
 
@@ -660,6 +661,49 @@ def test_ap_exchange_overflow_and_force_exchange():
             assert float(got2[thr][k]) == float(got[thr][k])
     calc.close()
 
+
+def test_tools_lhs_nms_golden(golden):
+    """tools nms_3d_faster(lhs=True) (3DOVDet_tools/utils/box_3d_utils.py:113-116): reference fixture + random fuzz vs the oracle."""
+    g = golden("holes.npz")
+    for tag, cw in (("plain", False), ("cls", True)):
+        b = g["lhs_boxes_" + tag]
+        got = B3.nms_3d_faster(b.copy(), 0.1, class_wise=cw, lhs=True)
+        np.testing.assert_array_equal(got, b[g["lhs_pick_" + tag]])
+    rng = np.random.default_rng(3)
+    for K in (1, 2, 33, 130, 257):
+        c = rng.uniform(0, 3, (K, 3)); sz = rng.uniform(0.4, 1.6, (K, 3))
+        b = np.concatenate([c - sz / 2, c + sz / 2, (rng.permutation(K)[:, None] + 1.0) / K, rng.integers(0, 3, (K, 1)).astype(float)], 1)
+        for cw in (False, True):
+            for thr in (0.05, 0.3):
+                want = oracle.tools_nms_3d_faster_lhs(b, thr, class_wise=cw)
+                np.testing.assert_array_equal(B3.nms_3d_faster(b.copy(), thr, class_wise=cw, lhs=True), b[want])
+
+
+def test_aabb_eval_golden(golden):
+    """eval_det_cls with the tools' axis-aligned get_iou (3DOVDet_tools/utils/evaluation/eval_det.py:86,
+    evaluation/box_util.py:287-309) against the reference-generated PR curves."""
+    g = golden("holes.npz")
+    pred = {s: [(g["aabb_pred"][s, k, :6], float(g["aabb_pred"][s, k, 6])) for k in range(int(g["aabb_npred"][s]))] for s in range(g["aabb_pred"].shape[0])}
+    gt = {s: [g["aabb_gt"][s, j] for j in range(int(g["aabb_ngt"][s]))] for s in range(g["aabb_gt"].shape[0])}
+    assert ED.get_iou(g["calc_iou_a"], g["calc_iou_b"]) == pytest.approx(float(g["calc_iou"]), abs=1e-15)
+    for thr in (0.25, 0.5):
+        rec, prec, ap = ED.eval_det_cls(pred, gt, thr, False, ED.get_iou)
+        np.testing.assert_allclose(rec, g[f"aabb_rec_{thr}"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(prec, g[f"aabb_prec_{thr}"], rtol=0, atol=1e-12)
+        assert ap == pytest.approx(float(g[f"aabb_ap_{thr}"]), abs=1e-12)
+    assert ED.eval_det_cls(pred, gt, 0.25, True, ED.get_iou)[2] == pytest.approx(float(g["aabb_ap07"]), abs=1e-12)
+    # the multi-class dict API
+    pa = {s: [(k % 2, b, sc) for k, (b, sc) in enumerate(lst)] for s, lst in pred.items()}
+    ga = {s: [(j % 2, b) for j, b in enumerate(lst)] for s, lst in gt.items()}
+    rec, prec, ap = ED.eval_det(pa, ga, 0.25, get_iou_func=ED.get_iou)
+    for cl in (0, 1):
+        want = oracle.eval_det_cls_aabb({s: [(b, sc) for c_, b, sc in lst if c_ == cl] for s, lst in pa.items()},
+                                        {s: [b for c_, b in lst if c_ == cl] for s, lst in ga.items()}, 0.25)
+        np.testing.assert_allclose(rec[cl], want[0], rtol=0, atol=1e-12)
+        assert ap[cl] == pytest.approx(want[2], abs=1e-12)
+    with pytest.raises(NotImplementedError):
+        ED.eval_det_cls(pred, gt, 0.25, False, lambda a, b: 0.0)
+
 # ------------------------------------------------------------------ matcher
 @pytest.mark.parametrize("tag", ["sunrgbd", "scannet"])
 def test_matcher_golden(golden, tag):
@@ -897,3 +941,67 @@ def test_box_decode_and_fused_giou():
     np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
     assert_close_giou(a.cpu().numpy(), oracle.generalized_box3d_iou(want, tgt["gt_box_corners"], tgt["nactual_gt"], True, False, mode="tensor"),
                       rtol=1e-4, atol=1e-5, what="fused decode vs oracle on torch-decoded corners")
+
+
+# ------------------------------------------------------------------ round-2 behaviour fixes
+def test_lsap_marks_invalid_cost_and_matcher_raises():
+    """scipy.optimize.linear_sum_assignment raises ValueError on NaN / -inf (criterion.py:79): the kernel leaves such a
+    sample unsolved and marked, the Matcher raises when the assignments are read; +inf entries stay legal."""
+    B, Q, G = 3, 16, 6
+    g = torch.Generator().manual_seed(0)
+    cost = torch.rand((B, Q, G), generator=g).to(DEV)
+    n = torch.tensor([6, 4, 5], device=DEV)
+    cost[1, 3, 2] = float("nan")
+    cost[1, 0, 5] = float("nan")        # column 5 >= nactual_gt[1]: outside the slab, must not matter on its own
+    cost[2, :, 1] = float("inf")        # a forbidden column is infeasible only if ALL its entries are inf
+    cost[2, 4, 1] = 0.3
+    inds, mask, c2r = lsap(cost, n)
+    assert (mask[1] == -1).all() and (c2r[1] == -2).all()
+    for b in (0, 2):
+        nb = int(n[b])
+        r, c = scipy_lsa(cost[b, :, :nb].cpu().numpy())
+        assert (mask[b].cpu().numpy() == np.isin(np.arange(Q), r)).all()
+        assert (inds[b].cpu().numpy()[r] == c).all()
+    from ovdet_b200.criterion import _assignments
+    with pytest.raises(ValueError):
+        _assignments(c2r, n, cost.device)
+    cost[2, :, 1] = float("inf")        # now column 1 cannot be assigned at all
+    _, mask2, c2r2 = lsap(cost, n)
+    assert (mask2[2] == -1).all() and (c2r2[2] == -2).all()
+
+
+def test_clip_text_classifier_keeps_the_gradient():
+    """Only the text matrix is frozen in the reference (models/model_3detr.py:151-154): the gradient must reach the visual
+    embedding.  dX = dLogits @ T against torch autograd of the same bf16-rounded operands in fp32."""
+    from ovdet_b200.models.model_3detr import ClipTextClassifier
+    x, t = synth.clip_logits_inputs(256, 640, 21, seed=3)
+    head = ClipTextClassifier(t.to(DEV))
+    xd = (x.float() * 0.25).to(DEV).requires_grad_(True)
+    out = head(xd)
+    assert out["sem_cls_logits"] is not None and out["sem_cls_logits"].requires_grad and not out["sem_cls_prob"].requires_grad
+    w = torch.randn(out["sem_cls_logits"].shape, generator=torch.Generator().manual_seed(1)).to(DEV)
+    (out["sem_cls_logits"] * w).sum().backward()
+    xr = xd.detach().to(torch.bfloat16).float().requires_grad_(True)
+    ((xr @ t.to(DEV).float().t()) * w).sum().backward()
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), xr.grad.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    with torch.no_grad():
+        o2 = head(xd, prob_dtype=torch.float32)
+    assert o2["sem_cls_prob"].dtype == torch.float32 and o2["sem_cls_logits"] is None
+    ref = torch.softmax(xd.detach().to(torch.bfloat16).float() @ t.to(DEV).float().t(), -1)
+    np.testing.assert_allclose(o2["sem_cls_prob"].cpu().numpy(), ref[:, :-1].cpu().numpy(), rtol=2e-3, atol=2e-4)
+
+
+def test_giou_needs_grad_tracks_under_no_grad_and_host_mixed_inputs():
+    """The reference wraps the needs_grad path in torch.enable_grad() (utils/box_util.py:725-730); host-buffer calls must
+    keep every converted input alive (corners1 on the host, corners2 on the device)."""
+    out, tgt = synth.detection_batch(B=2, Q=16, G=8, C=5, seed=9, heading=0.4, max_gt=8)
+    c1 = out["box_corners"].to(DEV).requires_grad_(True)
+    with torch.no_grad():
+        g = BU.generalized_box3d_iou(c1, tgt["gt_box_corners"].to(DEV), tgt["nactual_gt"].to(DEV), needs_grad=True)
+    assert g.requires_grad
+    g.sum().backward()
+    assert c1.grad is not None and torch.isfinite(c1.grad).all()
+    want = oracle.generalized_box3d_iou(out["box_corners"], tgt["gt_box_corners"], tgt["nactual_gt"], True, False, mode="cython", k2_cap=4)
+    got = BU.generalized_box3d_iou(out["box_corners"], tgt["gt_box_corners"].to(DEV), tgt["nactual_gt"].to(DEV))
+    assert not got.is_cuda
+    assert_close_giou(got.numpy(), want, what="host corners1, device corners2")
