@@ -140,6 +140,16 @@ int ovdet_matcher_cost_f32(const float *sem_cls_prob, const float *objectness, c
 int ovdet_lsap_f32(const float *cost, const int64_t *nactual_gt, int B, int Q, int G,
                    int64_t *per_prop_gt_inds, float *proposal_matched_mask, int32_t *col_to_row, void *stream);
 
+/* The whole matcher step of a decoder layer (criterion.py:348-361 + :33-92), or of all layers batched along B, in ONE call:
+ * ovdet_matcher_cost_f32 (GIoU computed in the kernel from the corners, L1 centre distance from the centres) followed by
+ * ovdet_lsap_f32 on the same stream.  Arguments as in those two. */
+int ovdet_matcher_step_f32(const float *sem_cls_prob, const float *objectness, const float *center_q, const float *center_g,
+                           const float *corners1, const float *corners2, const int64_t *gt_labels,
+                           const int64_t *nactual_gt, int B, int Q, int G, int C,
+                           float w_class, float w_obj, float w_center, float w_giou,
+                           unsigned giou_flags, int k2_cap, float *gious_out, float *cost,
+                           int64_t *per_prop_gt_inds, float *proposal_matched_mask, int32_t *col_to_row, void *stream);
+
 /* ------------------------------------------------------------------------- */
 /* Greedy NMS (utils/nms.py:43-162, 3DOVDet_tools/utils/box_3d_utils.py:60-120) */
 /* ------------------------------------------------------------------------- */

@@ -35,6 +35,7 @@ SIGNATURES = {
     "ovdet_giou3d_host_f32": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_u, c_p]),
     "ovdet_box3d_iou_f64": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     "ovdet_matcher_cost_f32": (c_i, [c_p] * 10 + [c_i] * 4 + [c_f] * 4 + [c_u, c_i, c_p, c_p, c_p]),
+    "ovdet_matcher_step_f32": (c_i, [c_p] * 8 + [c_i] * 4 + [c_f] * 4 + [c_u, c_i] + [c_p] * 6),
     "ovdet_lsap_f32": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "ovdet_nms_f64": (c_i, [c_p, c_p, c_i, c_i, c_i, c_d, c_d, c_u, c_p, c_p, c_p, c_p]),
     "ovdet_parse_predictions_f32": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_d, c_f, c_u, c_p, c_p, c_p, c_p, c_p]),

@@ -108,13 +108,31 @@ class Matcher(nn.Module):
         if k2_cap is None:
             k2_cap = DEFAULT_K2_CAP if mode == "cython" else 0
         flags = giou_flags(rotated_boxes, False, mode, prefilter, "aabb")
-        cost, gious = matcher_cost(outputs["sem_cls_prob"], outputs["objectness_prob"], targets["gt_box_sem_cls_label"],
-                                   self._weights(), center_q=outputs["center_normalized"],
-                                   center_g=targets["gt_box_centers_normalized"], corners1=outputs["box_corners"],
-                                   corners2=targets["gt_box_corners"], nactual_gt=targets["nactual_gt"], flags=flags,
-                                   k2_cap=k2_cap, want_gious=True)
+        prob = outputs["sem_cls_prob"]
+        C.require_cuda(prob)
+        dev = prob.device
+        f32 = lambda t: C.as_input(t, torch.float32, dev)
+        prob, obj, cq, cg = f32(prob), f32(outputs["objectness_prob"]), f32(outputs["center_normalized"]), f32(targets["gt_box_centers_normalized"])
+        c1, c2 = f32(outputs["box_corners"]), f32(targets["gt_box_corners"])
+        lab = C.as_input(targets["gt_box_sem_cls_label"], torch.int64, dev)
+        nk = C.as_input(targets["nactual_gt"], torch.int64, dev)
+        B, Q, Cn = prob.shape
+        G = lab.shape[1]
+        # one allocation for the three fp32 [B,Q,G]-sized / [B,Q] outputs, one for the integer ones
+        fbuf = torch.empty((2 * B * Q * G + B * Q,), dtype=torch.float32, device=dev)
+        cost, gious, mask = fbuf[:B * Q * G].view(B, Q, G), fbuf[B * Q * G:2 * B * Q * G].view(B, Q, G), fbuf[2 * B * Q * G:].view(B, Q)
+        inds = torch.empty((B, Q), dtype=torch.int64, device=dev)
+        c2r = torch.empty((B, G), dtype=torch.int32, device=dev)
+        wc, wo, wce, wg = [float(w) for w in self._weights()]
+        with C.on_device(dev):
+            C.check(C.lib().ovdet_matcher_step_f32(prob.data_ptr(), obj.data_ptr(), cq.data_ptr(), cg.data_ptr(), c1.data_ptr(), c2.data_ptr(),
+                                                   lab.data_ptr(), nk.data_ptr(), B, Q, G, Cn, wc, wo, wce, wg, int(flags), int(k2_cap),
+                                                   gious.data_ptr(), cost.data_ptr(), inds.data_ptr(), mask.data_ptr(), c2r.data_ptr(), C.stream(dev)))
         outputs["gious"] = gious
-        return self._solve(cost, targets["nactual_gt"], return_assignments)
+        ret = {"per_prop_gt_inds": inds, "proposal_matched_mask": mask, "final_cost": cost}
+        if return_assignments:
+            ret["assignments"] = _assignments(c2r, nk, dev)
+        return ret
 
     def _solve(self, cost, nactual_gt, return_assignments):
         inds, mask, c2r = lsap(cost, nactual_gt)

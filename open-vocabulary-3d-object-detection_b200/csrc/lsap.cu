@@ -268,3 +268,27 @@ extern "C" int ovdet_lsap_f32(const float *cost, const int64_t *nactual_gt, int 
     lsap_kernel<<<B, LS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("lsap_kernel");
 }
+
+// One call for what criterion.py:348-361 + Matcher.forward do per decoder layer (or for all layers batched along B): the
+// fused GIoU + L1-centre + class + objectness cost kernel, then the per-sample assignment -- two launches, one trip
+// through the host shim.
+extern "C" int ovdet_matcher_cost_f32(const float *sem_cls_prob, const float *objectness, const float *center_dist,
+                                      const float *center_q, const float *center_g, const float *gious,
+                                      const float *corners1, const float *corners2, const int64_t *gt_labels,
+                                      const int64_t *nactual_gt, int B, int Q, int G, int C,
+                                      float w_class, float w_obj, float w_center, float w_giou,
+                                      unsigned giou_flags, int k2_cap, float *gious_out, float *cost, void *stream);
+
+extern "C" int ovdet_matcher_step_f32(const float *sem_cls_prob, const float *objectness, const float *center_q, const float *center_g,
+                                      const float *corners1, const float *corners2, const int64_t *gt_labels,
+                                      const int64_t *nactual_gt, int B, int Q, int G, int C,
+                                      float w_class, float w_obj, float w_center, float w_giou,
+                                      unsigned giou_flags, int k2_cap, float *gious_out, float *cost,
+                                      int64_t *per_prop_gt_inds, float *proposal_matched_mask, int32_t *col_to_row, void *stream)
+{
+    OVDET_REQUIRE(cost && per_prop_gt_inds && proposal_matched_mask, "null output");
+    int rc = ovdet_matcher_cost_f32(sem_cls_prob, objectness, nullptr, center_q, center_g, nullptr, corners1, corners2, gt_labels, nactual_gt,
+                                    B, Q, G, C, w_class, w_obj, w_center, w_giou, giou_flags, k2_cap, gious_out, cost, stream);
+    if (rc) return rc;
+    return ovdet_lsap_f32(cost, nactual_gt, B, Q, G, per_prop_gt_inds, proposal_matched_mask, col_to_row, stream);
+}

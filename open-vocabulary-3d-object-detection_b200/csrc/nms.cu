@@ -181,6 +181,7 @@ struct PseudoParams {
     const double *boxes, *pool; const int32_t *nboxes, *npool;
     int S, P, M, Kmax; double nms_thr, match_thr, size_thr;
     uint8_t *nms1_keep; double *out_label, *out_score; uint8_t *out_keep;
+    unsigned long long *dbg;   // optional [S][16] globaltimer stamps (OVDET_PSEUDO_DBG_PTR; null in production)
 };
 
 __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
     for (int k = threadIdx.x; k < p.P; k += blockDim.x) p.nms1_keep[(size_t)s * p.P + k] = 0;
     for (int j = threadIdx.x; j < p.M; j += blockDim.x) { olab[j] = -100.0; osc[j] = 0.0; p.out_keep[(size_t)s * p.M + j] = 0; }
     __syncthreads();
+    NSTAMP(p.dbg, 0);
     // 1. class-wise NMS (lift_boxes.py:140; volume + 1e-8, box_3d_utils.py:74)
     ArraySrc src{boxes, 8, 3, nb, true};
     nms_core(src, p.P, 3, true, false, p.nms_thr, 1e-8, sh, order);
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
     }
     for (int j = threadIdx.x; j < p.M; j += blockDim.x) best[j] = 0xFFFFFFFFu;
     __syncthreads();
+    NSTAMP(p.dbg, 1);
     // 2. argmax-IoU match to the pool (lift_boxes.py:151-158): one warp per surviving box.  The pool boxes and their
     // volumes are staged once in shared memory (the suppression-word region, idle between the two NMS passes); a pair
     // with an empty overlap on some axis has IoU = +0 / positive = 0 exactly, so its fp64 divide is skipped.
@@ -236,30 +239,79 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
     // conservative fp32 test (pick bounds rounded outwards against pool bounds rounded outwards; "certainly disjoint on
     // some axis" implies the exact overlap is empty) runs at full fp32 rate, the few survivors go on a per-warp queue in
     // pool order and only they get the fp64 IoU.  A pick with no survivor has IoU 0 everywhere and cannot match.
+    constexpr int NSLAB = 16;
+    const int W16 = (np_ + 31) >> 5;
     const bool prune = pool_staged && p.match_thr > 0.0 &&
-                       (size_t)np_ * 32 + (size_t)(blockDim.x >> 5) * np_ * 2 <= (size_t)(reinterpret_cast<unsigned char *>(sh.skey) - sm);
+                       (size_t)np_ * 32 + sizeof(uint32_t) * 2 * NSLAB * (W16 + 1) + 64 <=
+                           (size_t)(reinterpret_cast<unsigned char *>(sh.skey) - sm);
     float4 *plo = reinterpret_cast<float4 *>(sm);            // [np_] lower bounds rounded down (the NMS tables are idle here)
     float4 *phi = plo + np_;                                 // [np_] upper bounds rounded up
-    unsigned short *wq = reinterpret_cast<unsigned short *>(phi + np_) + (size_t)warp * np_;   // this warp's candidate queue
+    // Slab masks: the pool's x and y extents are cut into 16 slabs each; xs[s] / ys[s] = bitmask of the pool boxes that
+    // reach into slab s.  A pick only looks at (OR of its x slabs) & (OR of its y slabs) -- ~5 % of the pool -- instead
+    // of testing all 512 boxes; the conservative fp32 test and the fp64 IoU then run on those few.
+    uint32_t *xs = reinterpret_cast<uint32_t *>(phi + np_);
+    uint32_t *ys = xs + NSLAB * W16;
+    float *ext = reinterpret_cast<float *>(ys + NSLAB * W16);   // xmin, inv_x, ymin, inv_y
     if (prune) {
         for (int j = threadIdx.x; j < np_; j += blockDim.x) {
             const double *r = pl + (size_t)j * 6;
-            plo[j] = make_float4(__double2float_rd(r[0]), __double2float_rd(r[1]), __double2float_rd(r[2]), 0.f);
+            plo[j] = make_float4(__double2float_rd(r[0]), __double2float_rd(r[1]), __double2float_rd(r[2]), __double2float_rd(pkv[j]) * (1.f - 1e-6f));   // .w: lower bound of the volume
             phi[j] = make_float4(__double2float_ru(r[3]), __double2float_ru(r[4]), __double2float_ru(r[5]), 0.f);
+        }
+        for (int i = threadIdx.x; i < 2 * NSLAB * W16; i += blockDim.x) xs[i] = 0u;
+        __syncthreads();
+        if (warp == 0) {
+            float x0 = INFINITY, x1 = -INFINITY, y0 = INFINITY, y1 = -INFINITY;
+            for (int j = lane; j < np_; j += 32) { x0 = fminf(x0, plo[j].x); x1 = fmaxf(x1, phi[j].x); y0 = fminf(y0, plo[j].y); y1 = fmaxf(y1, phi[j].y); }
+            for (int off = 16; off > 0; off >>= 1) {
+                x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, off)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, off));
+                y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, off)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, off));
+            }
+            if (lane == 0) { ext[0] = x0; ext[1] = x1 > x0 ? NSLAB / (x1 - x0) : 0.f; ext[2] = y0; ext[3] = y1 > y0 ? NSLAB / (y1 - y0) : 0.f; }
         }
         __syncthreads();
     }
-    for (int t = warp; t < npick; t += (blockDim.x >> 5)) {
-        const double *bx = boxes + (size_t)order[t] * 8;
-        const double b0 = bx[0], b1 = bx[1], b2 = bx[2], b3 = bx[3], b4 = bx[4], b5 = bx[5];
+    // slab of a coordinate: one monotone function for box and pick bounds alike, so overlapping intervals share a slab
+    auto slab = [&](float v, float mn, float inv) { const float t = (v - mn) * inv; return t >= (float)(NSLAB - 1) ? NSLAB - 1 : (t > 0.f ? (int)t : 0); };
+    if (prune) {
+        const float xmn = ext[0], xin = ext[1], ymn = ext[2], yin = ext[3];
+        for (int j = threadIdx.x; j < np_; j += blockDim.x) {
+            const float4 a = plo[j], c = phi[j];
+            const uint32_t bit = 1u << (j & 31);
+            for (int sl = slab(a.x, xmn, xin); sl <= slab(c.x, xmn, xin); ++sl) atomicOr(&xs[sl * W16 + (j >> 5)], bit);
+            for (int sl = slab(a.y, ymn, yin); sl <= slab(c.y, ymn, yin); ++sl) atomicOr(&ys[sl * W16 + (j >> 5)], bit);
+        }
+        __syncthreads();
+    }
+    NSTAMP(p.dbg, 2);
+    // A group of GL lanes per surviving box: 8 lanes (two mask words each, four boxes per warp) when the pool fits 16 mask
+    // words, else the whole warp.  The boxes' coordinates are staged in shared memory in pick order first, so that a
+    // group does not start every box with a dependent global load.
+    const int GL = (prune && W16 <= 16) ? 8 : 32;
+    double *pk = reinterpret_cast<double *>(ext + 4);          // [npick][6]
+    const bool picks_staged = prune && (size_t)(reinterpret_cast<unsigned char *>(pk + (size_t)npick * 6) - sm) <= (size_t)(reinterpret_cast<unsigned char *>(sh.skey) - sm);
+    if (picks_staged) {
+        for (int i = threadIdx.x; i < npick * 6; i += blockDim.x) { const int t = i / 6; pk[i] = boxes[(size_t)order[t] * 8 + (i - 6 * t)]; }
+        __syncthreads();
+    }
+    const int ngroups = blockDim.x / GL, group = threadIdx.x / GL, gl = threadIdx.x & (GL - 1);
+    for (int t0 = 0; t0 < npick; t0 += ngroups) {
+        const int t = t0 + group;
+        const bool act = t < npick;
+        const double *bx = boxes + (size_t)order[act ? t : 0] * 8;
+        const double *bc = picks_staged ? pk + (size_t)(act ? t : 0) * 6 : bx;
+        const double b0 = bc[0], b1 = bc[1], b2 = bc[2], b3 = bc[3], b4 = bc[4], b5 = bc[5];
         const double qv = A::mul(A::mul(A::sub(b3, b0), A::sub(b4, b1)), A::sub(b5, b2));
         double bi = -INFINITY; int bj = 0x7fffffff;
         auto exact_pair = [&](int j) {
             const double *r = (pool_staged ? pl : pool) + (size_t)j * 6;
             const double kv = pool_staged ? pkv[j] : A::mul(A::mul(A::sub(r[3], r[0]), A::sub(r[4], r[1])), A::sub(r[5], r[2]));
-            const double e0 = A::max(A::sub(A::min(b3, r[3]), A::max(b0, r[0])), 0.0);
-            const double e1 = A::max(A::sub(A::min(b4, r[4]), A::max(b1, r[1])), 0.0);
-            const double e2 = A::max(A::sub(A::min(b5, r[5]), A::max(b2, r[2])), 0.0);
+            // compare-and-select min / max (the library's fmin / fmax spend ~10 instructions on NaN handling per call)
+            auto dmin = [](double x, double y) { return x < y ? x : y; };
+            auto dmax = [](double x, double y) { return x > y ? x : y; };
+            const double e0 = dmax(A::sub(dmin(b3, r[3]), dmax(b0, r[0])), 0.0);
+            const double e1 = dmax(A::sub(dmin(b4, r[4]), dmax(b1, r[1])), 0.0);
+            const double e2 = dmax(A::sub(dmin(b5, r[5]), dmax(b2, r[2])), 0.0);
             double iou;
             if (e0 == 0.0 || e1 == 0.0 || e2 == 0.0) {
                 const double den = A::add(A::add(qv, kv), 1e-5);   // inter = +0: (qv + kv - 0) + 1e-5
@@ -268,35 +320,41 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
                 const double inter = A::mul(A::mul(e0, e1), e2);
                 iou = A::div(inter, A::add(A::sub(A::add(qv, kv), inter), 1e-5));
             }
-            if (iou > bi) { bi = iou; bj = j; }  // np.argmax: first maximum
+            if (iou > bi || (iou == bi && j < bj)) { bi = iou; bj = j; }  // np.argmax: first maximum (whatever order the candidates come in)
         };
         if (prune) {
             const float lx = __double2float_rd(b0), ly = __double2float_rd(b1), lz = __double2float_rd(b2);
             const float hx = __double2float_ru(b3), hy = __double2float_ru(b4), hz = __double2float_ru(b5);
-            int nq = 0;
-            for (int j0 = 0; j0 < np_; j0 += 32) {
-                const int j = j0 + lane;
-                bool maybe = false;
-                if (j < np_) {
-                    const float4 a = plo[j], c = phi[j];
-                    maybe = !(hx <= a.x || c.x <= lx || hy <= a.y || c.y <= ly || hz <= a.z || c.z <= lz);
+            const float qv_lo = __double2float_rd(qv) * (1.f - 1e-6f), thr_lo = __double2float_rd(p.match_thr) * (1.f - 1e-6f);
+            // candidate words from the slab masks (lane w of the group owns pool boxes 32w .. 32w+31), then the conservative fp32 test
+            if (act) for (int w = gl; w < W16; w += GL) {   // (one word per lane unless the pool is longer than 32 * GL)
+                uint32_t cx = 0u, cy = 0u;
+                for (int sl = slab(lx, ext[0], ext[1]); sl <= slab(hx, ext[0], ext[1]); ++sl) cx |= xs[sl * W16 + w];
+                for (int sl = slab(ly, ext[2], ext[3]); sl <= slab(hy, ext[2], ext[3]); ++sl) cy |= ys[sl * W16 + w];
+                uint32_t m = cx & cy;
+                while (m) {
+                    const int bb = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float4 a = plo[32 * w + bb], c = phi[32 * w + bb];
+                    // fp32 UPPER bound of the IoU from outward-rounded bounds (overlap too large, volumes too small): a pair that
+                    // cannot reach the match threshold can neither match nor be the arg-max of a box that does; the few
+                    // survivors (spread over the group's lanes) go straight to the exact fp64 IoU
+                    const float ex = fminf(hx, c.x) - fmaxf(lx, a.x), ey = fminf(hy, c.y) - fmaxf(ly, a.y), ez = fminf(hz, c.z) - fmaxf(lz, a.z);
+                    if (ex > 0.f && ey > 0.f && ez > 0.f) {
+                        const float ih = ex * ey * ez * (1.f + 1e-5f), den = qv_lo + a.w - ih;
+                        if (!(den > 0.f) || ih * (1.f + 1e-5f) >= thr_lo * den) exact_pair(32 * w + bb);
+                    }
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, maybe);
-                if (maybe) wq[nq + __popc(m & ((1u << lane) - 1))] = (unsigned short)j;
-                nq += __popc(m);
             }
-            __syncwarp();
-            for (int q = lane; q < nq; q += 32) exact_pair(wq[q]);   // ascending pool index within a lane: first maximum kept
-            __syncwarp();
-        } else {
-            for (int j = lane; j < np_; j += 32) exact_pair(j);
+        } else if (act) {
+            for (int j = gl; j < np_; j += GL) exact_pair(j);
         }
-        for (int off = 16; off > 0; off >>= 1) {
-            const double oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+        for (int off = GL / 2; off > 0; off >>= 1) {
+            const double oi = __shfl_xor_sync(0xffffffffu, bi, off, GL);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, off, GL);
             if (oi > bi || (oi == bi && oj < bj)) { bi = oi; bj = oj; }
         }
-        if (lane == 0 && bj != 0x7fffffff && !(bi < p.match_thr)) {
+        if (act && gl == 0 && bj != 0x7fffffff && !(bi < p.match_thr)) {
             const double sc = bx[6];
             // `box[-2] > tmp_score[index]` with tmp_score starting at 0: boxes arrive in pick order
             // (= descending score), so the earliest claimant with score > 0 wins and is never replaced.
@@ -313,12 +371,15 @@ __global__ void __launch_bounds__(NMS_NT) pseudo_filter_kernel(PseudoParams p)
         }
     }
     __syncthreads();
+    NSTAMP(p.dbg, 3);
     // 3. size-scored class-wise NMS over the labelled pool boxes (lift_boxes.py:165)
     PoolSrc psrc{pool, olab, osc, np_};
     nms_core(psrc, p.M, 3, true, false, p.size_thr, 1e-8, sh, nullptr);
     const int na = sh.misc[0];
     for (int pos = threadIdx.x; pos < na; pos += blockDim.x)
         if (sh.picked[pos]) p.out_keep[(size_t)s * p.M + sh.sidx[pos]] = 1;
+    NSTAMP(p.dbg, 4);
+    if (p.dbg && threadIdx.x == 0) p.dbg[(size_t)blockIdx.x * 16 + 5] = (unsigned long long)npick;
 }
 
 }  // namespace ovdet
@@ -370,7 +431,8 @@ extern "C" int ovdet_pseudo_filter_f64(const double *boxes, const double *pool, 
     OVDET_REQUIRE(boxes && pool && nms1_keep && out_label && out_score && out_keep, "null pointer");
     OVDET_REQUIRE(P <= NMS_MAXK && M <= NMS_MAXK, "P and M must be <= 1024");
     PseudoParams p{boxes, pool, nboxes, npool, S, P, M, P > M ? P : M, nms_thr, match_thr, size_nms_thr,
-                   nms1_keep, out_label, out_score, out_keep};
+                   nms1_keep, out_label, out_score, out_keep, nullptr};
+    { const char *e = getenv("OVDET_PSEUDO_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
     const size_t smem = nms_smem_bytes(p.Kmax);
     OVDET_CUDA_TRY(cudaFuncSetAttribute(pseudo_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pseudo_filter_kernel<<<S, NMS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
