@@ -247,7 +247,7 @@ def bench_giou(args, rank, world, dev, peaks):
     nclip = clipped_pairs(*dsets[0][:3])
     res = {"value": value, "ms_per_step": ms / args.steps, "launches": args.steps, "ms_per_step_python_loop": ms_loop / args.steps,
            "clipped_pairs_per_step": nclip,
-           "roofline": hbm_roofline(GIOU_BYTES_PER_PAIR * pairs, per_launch_s, peaks, "giou3d_kernel<double",
+           "roofline": hbm_roofline(GIOU_BYTES_PER_PAIR * pairs, per_launch_s, peaks, "giou3d_default",
                                     "contract roofline (bytes are the only resource the headline step is quoted against); the pair maths is "
                                     "ALU/issue-bound and at this size launch-bound: %d of %d pairs reach the clipper under the shipped "
                                     "semantics -- see variants.clip_dominated for the ALU-side figure" % (nclip, pairs))}
@@ -482,14 +482,14 @@ def bench_ap(args, rank, world, dev, peaks):
         front(i)
     ms_front = timed_region(front, steps, world, dev) / steps
     rs = front(0)[0]
-    kern = {"ap_front": hbm_roofline(AP_BYTES_PER_SCENE * nloc, ms_front * 1e-3, peaks, "ap_front2_kernel",
+    kern = {"ap_front": hbm_roofline(AP_BYTES_PER_SCENE * nloc, ms_front * 1e-3, peaks, "ap_front2",
                                      "parse_predictions + AP matching of %d scenes in one launch; issue/latency-bound (short dependent phases per scene)" % nloc)}
     if world == 1:   # the reducer's stages wait for the peers when distributed: timed alone only on one rank
         red = list(calc._reducers.values())[-1]
         for i in range(3):
             red.launch([rs], lists)
         ms_red = timed_region(lambda i: red.launch([rs], lists), steps, world, dev) / steps
-        kern["apx_reduce"] = hbm_roofline(4.0 * C_SUN * Q * nloc, ms_red * 1e-3, peaks, "apx_hist_kernel",
+        kern["apx_reduce"] = hbm_roofline(4.0 * C_SUN * Q * nloc, ms_red * 1e-3, peaks, "apx_hist",
                                           "merge + histogram + final: one streaming read of the score records (4 B each); the chain is "
                                           "three dependent launches, the merge is one CTA per class")
         kern["apx_reduce"]["us_chain"] = ms_red * 1e3
@@ -566,7 +566,7 @@ def bench_extras(args, rank, world, dev, peaks):
     mbytes = 4 * nb2 * 256 * 18 + 4 * nb2 * 256 + 12 * nb2 * (256 + G) + 8 * nb2 * G + 96 * nb2 * (256 + G) + 4 * nb2 * 256 * G   # SURVEY 8d x 8 layers
     ex["matcher_scannet"] = {"pairs_per_s": world * nb2 * 256 * G * n / (ms * 1e-3), "ms_per_step": ms / n,
                              "workload": "8 layers x B8 x 256 queries x 64 GT, fused cost kernel + on-device LSAP",
-                             "roofline": hbm_roofline(mbytes, ms * 1e-3 / n, peaks, "lsap_kernel",
+                             "roofline": hbm_roofline(mbytes, ms * 1e-3 / n, peaks, "lsap",
                                                       "cost kernel + LSAP; the step is the LSAP's latency (one CTA per sample, a serial chain of "
                                                       "augmenting-path steps), not bytes")}
     # config 4: open-vocab logits
@@ -580,8 +580,8 @@ def bench_extras(args, rank, world, dev, peaks):
     ach = fl / (ms * 1e-3 / n) / 1e12
     ex["clip_logits"] = {"tflops": ach, "ms_per_step": ms / n, "frac_of_bf16_peak": ach / peaks["bf16_tflops"],
                          "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                                      "frac": ach / peaks["bf16_tflops"], "traffic": ncu_field("clip_logits_persistent_kernel", "dram_bytes_per_launch"),
-                                      "ncu_tensor_pct": ncu_field("clip_logits_persistent_kernel", "tensor_pct")},
+                                      "frac": ach / peaks["bf16_tflops"], "traffic": ncu_field("clip_logits", "dram_bytes_per_launch"),
+                                      "ncu_tensor_pct": ncu_field("clip_logits", "tensor_pct")},
                          "workload": "8192x640 @ 1203x640^T bf16 -> softmax probs bf16 + objectness (includes bf16 cast-free path)"}
     # the reference's only native ABI, box_intersection(rect1, rect2, nonrot, nums_k2, inter_areas, approximate) on HOST
     # numpy buffers (box_intersection.pyx:166-171): the drop-in against the reference's own compiled extension, same call
@@ -627,7 +627,7 @@ def bench_extras(args, rank, world, dev, peaks):
     ms = timed_graph(f, 5, world, dev)
     ex["nms3d_samecls"] = {"scenes_per_s": world * SN * 5 / (ms * 1e-3), "ms_per_step": ms / 5,
                            "workload": "%d scenes/rank x 256 boxes x 18 classes, nms_3d_faster_samecls thr 0.25 (keep mask)" % SN,
-                           "roofline": hbm_roofline((KN * 64 + KN) * SN, ms * 1e-3 / 5, peaks, "nms_kernel",
+                           "roofline": hbm_roofline((KN * 64 + KN) * SN, ms * 1e-3 / 5, peaks, "nms_samecls",
                                                     "bytes as the kernel is fed here: fp64 rows [x1..z2, score, cls] (64 B/box) in, one keep byte out "
                                                     "(SURVEY 8d's fp32 figure is 8 192 + 1 280 B/scene); sum n_c^2/2 fp64 pair tests per scene: issue-bound")}
     del bN
@@ -655,7 +655,7 @@ def bench_extras(args, rank, world, dev, peaks):
     ex["pseudo_label"] = {"scenes_per_s": S5 * k5 / (ms * 1e-3), "ms_per_step": ms / k5, "scaling": "strong", "kept_boxes": kept[0],
                           "workload": "100 000 scenes in total (%d on this rank) x 256 proposals x 512 pool boxes: NMS 0.7 -> IoU>=0.3 match -> "
                                       "size NMS; scene-sharded, one all-reduce of the kept-box count" % bxd.shape[0],
-                          "roofline": hbm_roofline(pbytes * bxd.shape[0], ms * 1e-3 / k5, peaks, "pseudo_filter_kernel",
+                          "roofline": hbm_roofline(pbytes * bxd.shape[0], ms * 1e-3 / k5, peaks, "pseudo_filter",
                                                    "per-rank bytes / per-sweep time; two class-wise NMS passes + the pool match per scene: issue-bound")}
     del bxd, pd, outbuf
     return ex

@@ -60,9 +60,12 @@ def gather_records(rec_score, rec_tp, npos):
 
 def all_reduce_count(n, device):
     """Sum of a per-rank integer (kept-box counts of the pseudo-label sweep, label_formatter.py:174,179)."""
+    if not is_distributed():
+        return int(n)
+    if dist.get_backend() != "nccl":      # gloo (CPU tests): the collective runs on host tensors
+        device = torch.device("cpu")
     t = torch.tensor([int(n)], dtype=torch.int64, device=device)
-    if is_distributed():
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return int(t.item())
 
 

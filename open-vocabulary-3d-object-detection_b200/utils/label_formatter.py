@@ -91,7 +91,8 @@ class LabelFormatter():
         n = len(self.scene_list)
         lo, hi = shard_range(n) if (distributed and is_distributed()) else (0, n)
         l = sum(self.gen_pseudo(i) for i in range(lo, hi))
-        return all_reduce_count(l, torch.device("cuda", torch.cuda.current_device())) if distributed else l
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        return all_reduce_count(l, dev) if distributed else l
 
     def process(self, k, th_s, th_o, distributed=False):
         """label_formatter.py:176-179 -- the entry point generate_pseudo_label.py:209 calls with

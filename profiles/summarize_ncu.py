@@ -32,16 +32,19 @@ def to_bytes(v, unit):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
 
 
-def main(path, out_json=None):
+def main(path, out_json=None, labels_json=None):
     rows = list(csv.reader(open(path)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
+    labels = json.load(open(labels_json)) if labels_json else []
     summary = {}
     seen = {}
-    for r in rows[2:]:
+    for li, r in enumerate(rows[2:]):
         name = r[idx["Kernel Name"]].split("(")[0].replace("ovdet::", "").replace("void ", "")
         seen[name] = seen.get(name, 0) + 1
         key = name if seen[name] == 1 else "%s#%d" % (name, seen[name])
+        if li < len(labels):        # profiles/prof_driver.py's label of this launch, then the kernel name
+            key = "%s | %s" % (labels[li], name)
         d = {}
         for short, m in METRICS:
             if m not in idx:
@@ -71,4 +74,4 @@ def main(path, out_json=None):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None, sys.argv[3] if len(sys.argv) > 3 else None)

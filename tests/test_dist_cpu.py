@@ -1,5 +1,7 @@
-"""CPU, world_size 2, gloo: the scene-sharded AP exchange (dist.gather_records)
-reproduces the single-process records, and AP computed from them is unchanged."""
+"""CPU, world_size 2, gloo: the host side of the scene-sharded paths -- the record all-gather of the sort fallback
+(dist.gather_records) reproduces the single-process records and their AP; the handle exchange of the symmetric buffers,
+the count all-reduce and the scan sharding of the pseudo-label sweep.  (The device-side exchange itself -- push / flag /
+merge kernels -- is tested on the GPU with virtual ranks: tests/test_gpu_parity.py::test_ap_exchange_virtual_ranks.)"""
 import os
 import socket
 
@@ -61,6 +63,18 @@ def _worker_impl(rank, world, port, q):
         hi -= 137
     npos_local = tp[:, lo:hi].sum(1).to(torch.int64) + 2
     gs, gt, npos = D.gather_records(score[:, lo:hi].contiguous(), tp[:, lo:hi].contiguous(), npos_local)
+    # the plumbing of the device-side exchange that runs on the host: the IPC handles of the symmetric buffers travel as
+    # one small byte string per rank (dist.exchange_bytes), kept-box counts of the sharded sweeps as one all-reduce
+    handles = D.exchange_bytes(bytes([rank + 1]) * 64)
+    assert handles == [bytes([1]) * 64, bytes([2]) * 64]
+    assert D.all_reduce_count(10 + rank, torch.device("cpu")) == 21
+    # LabelFormatter.save(distributed=True): scans cut across the ranks, counts summed (label_formatter.py:169-174)
+    from ovdet_b200.utils.label_formatter import LabelFormatter
+    fmt = LabelFormatter("", "", "", ["scan%d" % i for i in range(7)])
+    seen = []
+    fmt.gen_pseudo = lambda i: (seen.append(i), i + 1)[1]        # scan i "acquires" i + 1 boxes
+    total = fmt.save(distributed=True)
+    assert total == sum(range(1, 8)) and seen == list(range(*D.shard_range(7)))
     if rank == 0:
         q.put((gs.numpy(), gt.numpy(), npos.numpy()))
     dist.barrier()
