@@ -280,17 +280,20 @@ size_t ovdet_apx_symm_bytes(int C, int cap_total, int world);
 
 /* AP / recall of all classes and thresholds from this rank's record blocks and TP lists (ovdet_ap_front_f32; row
  * stride cap_list), reduced over `world` scene-sharded ranks.  One call enqueues the whole chain on `stream`:
- *   push    this rank's TP lists (keys, bits, count, npos) into every peer's symmetric buffer, then a flag per class
- *   merge   per class: wait for the peers' flags, concatenate + bitonic-sort the lists (<= cap_total entries, a power of
- *           two in [1024, 16384]), bin edges of the sorted list
- *   hist    one streaming pass over the LOCAL records: bucket = position in the merged list; the last CTA of a class
- *           pushes the class's partial histogram to every peer, then a flag
+ *   push    this rank's TP list of every class is SORTED in R slices (one CTA each; R = 1 today) and every sorted
+ *           run (keys, bits, count, npos) is stored into every peer's symmetric buffer, then a flag per (run, class)
+ *   merge   per class, a cluster of 8 CTAs: wait for the world * R run flags, rank every entry among the other runs by
+ *           binary search (merged position = sum of ranks; <= cap_total entries, a power of two in [1024, 16384]),
+ *           then the bin edges of the sorted list
+ *   hist    one streaming pass over the LOCAL records: bucket = position in the merged list; a (peer, class) grid then
+ *           ships the class's partial histogram to every peer, with a flag
  *   final   per (class, threshold): wait for the peers' histograms, sum them, prefix sums -> positions, precision
  *           envelope, VOC AP (utils/eval_det.py:23-54, :143-153)
  * blocks/block_n: host arrays of nblocks device pointers to rec_score blocks [C, block_n[i]] fp32.
  * peers: host array of `world` device pointers = every rank's symmetric buffer as mapped in THIS process
- * (peers[rank] = the local one); world == 1 needs neither `peers` nor a symmetric buffer unless OVDET_APX_FORCE_EXCHANGE
- * asks for the exchange code path (push to self, flags, slot sums) anyway.
+ * (peers[rank] = the local one).  With world == 1 `peers` may be NULL (one CTA per class sorts the whole list) or point
+ * at ONE plain device buffer of ovdet_apx_symm_bytes(C, cap_total, 1) zeroed bytes, which selects the push + cluster
+ * merge above; OVDET_APX_FORCE_EXCHANGE additionally runs the histogram exchange (push to self, slot sums).
  * result (device, fp64 [2*nthr*C + C + 3]): ap [nthr,C] | recall [nthr,C] | n_det [C] | overflow | max per-rank list
  * count | largest merged list count; overflow > 0 means a merged list did not fit cap_total (the local lists are intact:
  * retry with a larger cap_total) or a local list overflowed cap_list; overflow < 0 = a peer's flag never arrived (timeout).

@@ -429,24 +429,31 @@ constexpr int APX_EHDR = 4;        // u32 header words per class: kmin, shift, n
 constexpr size_t APX_ESTRIDE_BYTES = sizeof(uint32_t) * APX_EHDR + sizeof(uint16_t) * APX_BINS;
 
 struct ApxLayout {          // byte offsets inside one parity half of a symmetric buffer
-    size_t half, flags_l, flags_h, lists, list_stride, l_cnt, l_npos, l_key, l_bits, hist, hist_stride;
+    size_t half, flags_l, flags_h, lists, list_stride, l_cnt, l_raw, l_npos, l_key, l_bits, hist, hist_stride;
     int hp;                 // u32 pitch of a histogram row (cap_total + 1 rounded up to 4)
 };
 static inline size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
+// Every rank ships its list of a class as R sorted RUNS; run (rank, sub) lives in list slot rank * R + sub of every
+// receiver.  R > 1 spreads a rank's sort over R CTAs, but measured on one B200 (5 050 scenes, 20 classes, R = 8) the
+// 160-CTA push + 160-CTA cluster merge finished the merged lists at 52-70 us against 29 us for one radix-sorting CTA per
+// class: two waves of one-CTA-per-SM kernels and a system-scope fence per run cost more than the sort saves.  So R = 1.
+static int apx_runs_per_rank(int W) { (void)W; return 1; }
 static ApxLayout apx_layout(int C, int cap, int W)
 {
     ApxLayout L;
+    const int NR = W * apx_runs_per_rank(W);
     L.hp = (cap + 1 + 3) & ~3;
     size_t o = 0;
-    L.flags_l = o; o += a16(sizeof(uint32_t) * (size_t)W * C);
+    L.flags_l = o; o += a16(sizeof(uint32_t) * (size_t)NR * C);
     L.flags_h = o; o += a16(sizeof(uint32_t) * (size_t)W * C);
     size_t s = 0;
     L.l_cnt = s; s += a16(sizeof(int32_t) * (size_t)C);
+    L.l_raw = s; s += a16(sizeof(int32_t) * (size_t)C);
     L.l_npos = s; s += a16(sizeof(int64_t) * (size_t)C);
     L.l_key = s; s += a16(sizeof(uint32_t) * (size_t)C * cap);
     L.l_bits = s; s += a16((size_t)C * cap);
     L.list_stride = s;
-    L.lists = o; o += s * W;
+    L.lists = o; o += s * NR;
     L.hist_stride = a16(sizeof(uint32_t) * (size_t)C * L.hp);
     L.hist = o; o += L.hist_stride * W;
     L.half = (o + 255) & ~(size_t)255;
@@ -523,7 +530,7 @@ struct ApxParams {
     ApxPeers peers; ApxLayout sl; ApxLocal ll;
     unsigned char *local;
     const uint32_t *tp_key; const uint8_t *tp_bits; const int *tp_cnt; const long long *npos;
-    int C, cap_list, cap, nthr, use07, rank, W, exchange;
+    int C, cap_list, cap, nthr, use07, rank, W, R, exchange;   // R = sorted runs per rank (list slots = W * R)
     double *result;
     unsigned long long *dbg;   // optional [C][8] globaltimer stamps of the merge stage (OVDET_APX_DBG_PTR; null in production)
 };
@@ -621,9 +628,9 @@ __device__ __forceinline__ int cta_sort(uint32_t *ksm, uint8_t *bsm, const SortS
     return cur;
 }
 
-// ---- stage 1: SORT this rank's list of a class, then push it to every peer.  grid C, 1024 threads
-// Sorting on the sender means the eight ranks sort their eighth of the entries at the same time; the receivers only
-// have to merge sorted runs (stage 2), which is a handful of binary searches per entry instead of a 5-pass sort of all.
+// ---- stage 1: SORT this rank's list of a class in R slices, push every sorted run to all peers.  grid (R, C), 1024 threads
+// Sorting on the senders means W * R CTAs per class sort an (W * R)-th of the entries each, at the same time; the
+// receivers only have to merge sorted runs (stage 2): a handful of binary searches per entry instead of a 5-pass sort of all.
 __global__ void __launch_bounds__(1024, 1) apx_push_lists_kernel(ApxParams p)
 {
     extern __shared__ __align__(16) unsigned char sm[];
@@ -634,28 +641,31 @@ __global__ void __launch_bounds__(1024, 1) apx_push_lists_kernel(ApxParams p)
     uint8_t *bsm = reinterpret_cast<uint8_t *>(whist + 32 * 256);     // [2][cap]
     __shared__ uint32_t dbase[256], wsum_s[8];
     __shared__ int skip_s;
-    const int c = blockIdx.x, tid = threadIdx.x;
-    XSTAMPC(c, 8);
+    const int sub = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    if (sub == 0) XSTAMPC(c, 8);
     pdl_wait();
     pdl_release();
-    XSTAMPC(c, 9);
+    if (sub == 0) XSTAMPC(c, 9);
     const unsigned tag = apx_ctrl(p)[0] + 1u;
     const int raw = p.tp_cnt[c];
-    const int n = min(min(raw, p.cap_list), cap);
-    for (int i = tid; i < n; i += 1024) { ksm[i] = p.tp_key[(size_t)c * p.cap_list + i]; bsm[i] = p.tp_bits[(size_t)c * p.cap_list + i]; }
+    const int nall = min(min(raw, p.cap_list), cap);
+    const int i0 = (int)((long long)nall * sub / p.R), n = (int)((long long)nall * (sub + 1) / p.R) - i0;   // my slice of the list
+    for (int i = tid; i < n; i += 1024) { ksm[i] = p.tp_key[(size_t)c * p.cap_list + i0 + i]; bsm[i] = p.tp_bits[(size_t)c * p.cap_list + i0 + i]; }
     const int cur = cta_sort(ksm, bsm, SortScratch{rnk, whist, dbase, wsum_s, &skip_s}, cap, n);
-    XSTAMPC(c, 10);
+    if (sub == 0) XSTAMPC(c, 10);
     const uint4 *ks = reinterpret_cast<const uint4 *>(ksm + cur * cap);
     const uint4 *bs = reinterpret_cast<const uint4 *>(bsm + cur * cap);
-    const long long np = p.npos[c];
+    const long long np = sub == 0 ? p.npos[c] : 0;
+    const int run = p.rank * p.R + sub;
     for (int dst = 0; dst < p.W; ++dst) {
-        unsigned char *slot = p.peers.base[dst] + (size_t)(tag & 1u) * p.sl.half + p.sl.lists + (size_t)p.rank * p.sl.list_stride;
+        unsigned char *slot = p.peers.base[dst] + (size_t)(tag & 1u) * p.sl.half + p.sl.lists + (size_t)run * p.sl.list_stride;
         uint4 *kd = reinterpret_cast<uint4 *>(slot + p.sl.l_key + sizeof(uint32_t) * (size_t)c * cap);
         for (int i = tid; i < (n + 3) / 4; i += 1024) kd[i] = ks[i];
         uint4 *bd = reinterpret_cast<uint4 *>(slot + p.sl.l_bits + (size_t)c * cap);
         for (int i = tid; i < (n + 15) / 16; i += 1024) bd[i] = bs[i];
         if (tid == 0) {
-            reinterpret_cast<int *>(slot + p.sl.l_cnt)[c] = raw;
+            reinterpret_cast<int *>(slot + p.sl.l_cnt)[c] = n;
+            reinterpret_cast<int *>(slot + p.sl.l_raw)[c] = sub == 0 ? raw : 0;   // the rank's true count (overflow check), once
             reinterpret_cast<long long *>(slot + p.sl.l_npos)[c] = np;
         }
     }
@@ -663,9 +673,9 @@ __global__ void __launch_bounds__(1024, 1) apx_push_lists_kernel(ApxParams p)
     __syncthreads();
     if (tid < p.W) {
         unsigned char *half = p.peers.base[tid] + (size_t)(tag & 1u) * p.sl.half;
-        st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_l) + (size_t)p.rank * p.C + c, tag);
+        st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_l) + (size_t)run * p.C + c, tag);
     }
-    XSTAMPC(c, 11);
+    if (sub == 0) XSTAMPC(c, 11);
 }
 
 // ---- stage 2: per class, gather the W lists, sort, bin edges; zero the class's histogram.  grid C, 1024 threads
@@ -706,7 +716,7 @@ __global__ void __launch_bounds__(1024, 1) apx_merge_kernel(ApxParams p)
             int raw; long long q;
             if (p.exchange) {
                 const unsigned char *slot = half + p.sl.lists + (size_t)r * p.sl.list_stride;
-                raw = reinterpret_cast<const int *>(slot + p.sl.l_cnt)[c];
+                raw = reinterpret_cast<const int *>(slot + p.sl.l_raw)[c];
                 q = reinterpret_cast<const long long *>(slot + p.sl.l_npos)[c];
             } else { raw = p.tp_cnt[c]; q = p.npos[c]; }
             mx = max(mx, raw); raw_total += raw; np += q;
@@ -863,7 +873,8 @@ __global__ void __cluster_dims__(APX_CL, 1, 1) __launch_bounds__(1024, 1) apx_me
     const unsigned char *half = p.peers.base[p.rank] + (size_t)(tag & 1u) * p.sl.half;
     if (tid == 0) bad_s = 0;
     __syncthreads();
-    if (tid < p.W) {
+    const int NR = p.W * p.R;   // sorted runs to merge
+    if (tid < NR) {
         if (!wait_flag(reinterpret_cast<const unsigned *>(half + p.sl.flags_l) + (size_t)tid * p.C + c, tag)) bad_s = 1;
     }
     __syncthreads();
@@ -871,16 +882,16 @@ __global__ void __cluster_dims__(APX_CL, 1, 1) __launch_bounds__(1024, 1) apx_me
     if (part == 0) XSTAMPC(c, 6);
     if (tid == 0) {
         int off = 0, mx = 0, raw_total = 0; long long np = 0;
-        for (int r = 0; r < p.W; ++r) {
+        for (int r = 0; r < NR; ++r) {
             const unsigned char *slot = half + p.sl.lists + (size_t)r * p.sl.list_stride;
-            const int raw = reinterpret_cast<const int *>(slot + p.sl.l_cnt)[c];
+            const int raw = reinterpret_cast<const int *>(slot + p.sl.l_raw)[c];   // the source rank's true count (its first run carries it)
             np += reinterpret_cast<const long long *>(slot + p.sl.l_npos)[c];
             mx = max(mx, raw); raw_total += raw;
-            int n = min(raw, min(p.cap_list, cap));   // what the producer could ship
+            int n = reinterpret_cast<const int *>(slot + p.sl.l_cnt)[c];           // entries in this run
             n = min(n, cap - off);                    // what still fits
             n_s[r] = n; off_s[r] = off; off += n;
         }
-        off_s[p.W] = off;
+        off_s[NR] = off;
         if (part == 0) {
             reinterpret_cast<int *>(p.local + p.ll.mcnt)[c] = off;
             reinterpret_cast<long long *>(p.local + p.ll.npos_g)[c] = np;
@@ -890,7 +901,7 @@ __global__ void __cluster_dims__(APX_CL, 1, 1) __launch_bounds__(1024, 1) apx_me
         }
     }
     __syncthreads();
-    const int total = off_s[p.W], W = p.W;
+    const int total = off_s[NR], W = NR;   // (W = number of runs below)
     if (part == 0) XSTAMPC(c, 2);
     for (int r = 0; r < W; ++r) {
         const unsigned char *slot = half + p.sl.lists + (size_t)r * p.sl.list_stride;
@@ -1368,32 +1379,33 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
     OVDET_REQUIRE(nblocks == 0 || (blocks && block_n), "null block table");
     const bool exchange = world > 1 || (flags & OVDET_APX_FORCE_EXCHANGE);
     OVDET_REQUIRE(!exchange || peers, "the exchange needs the table of symmetric buffers");
+    const bool via_slots = peers != nullptr;   // lists travel as sorted runs through the (symmetric-layout) buffer, also on one rank
     ApxParams p;
     memset(&p, 0, sizeof(p));
     p.sl = apx_layout(C, cap_total, world);
     p.ll = apx_local(C, cap_total);
-    if (exchange) for (int r = 0; r < world; ++r) { OVDET_REQUIRE(peers[r], "null symmetric buffer"); p.peers.base[r] = static_cast<unsigned char *>(peers[r]); }
+    if (via_slots) for (int r = 0; r < world; ++r) { OVDET_REQUIRE(peers[r], "null symmetric buffer"); p.peers.base[r] = static_cast<unsigned char *>(peers[r]); }
     p.local = static_cast<unsigned char *>(local_ws);
     p.tp_key = tp_key; p.tp_bits = tp_bits; p.tp_cnt = tp_cnt; p.npos = reinterpret_cast<const long long *>(npos);
     p.C = C; p.cap_list = cap_list; p.cap = cap_total; p.nthr = nthr; p.use07 = (flags & OVDET_APX_USE_07_METRIC) ? 1 : 0;
-    p.rank = rank; p.W = world; p.exchange = exchange ? 1 : 0; p.result = result;
+    p.rank = rank; p.W = world; p.R = apx_runs_per_rank(world); p.exchange = exchange ? 1 : 0; p.result = result;
     { const char *e = getenv("OVDET_APX_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned stages = flags & (OVDET_APX_STAGE_PUSH | OVDET_APX_STAGE_MERGE_HIST | OVDET_APX_STAGE_FINAL);
     if (!stages) stages = OVDET_APX_STAGE_PUSH | OVDET_APX_STAGE_MERGE_HIST | OVDET_APX_STAGE_FINAL;
-    if (exchange && (stages & OVDET_APX_STAGE_PUSH)) {
+    if (via_slots && (stages & OVDET_APX_STAGE_PUSH)) {
         const size_t psmem = (size_t)cap_total * 12 + sizeof(uint16_t) * 32 * 256;
         OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_push_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-        OVDET_CUDA_TRY(launch_pdl(apx_push_lists_kernel, dim3(C), dim3(1024), psmem, st, p));
+        OVDET_CUDA_TRY(launch_pdl(apx_push_lists_kernel, dim3(p.R, C), dim3(1024), psmem, st, p));
         { const int rc = launch_ok("apx_push_lists_kernel"); if (rc) return rc; }
     }
-    if ((stages & OVDET_APX_STAGE_MERGE_HIST) && !exchange) {
+    if ((stages & OVDET_APX_STAGE_MERGE_HIST) && !via_slots) {
         const size_t smem = (size_t)cap_total * 12 + sizeof(uint16_t) * (32 * 256 + APX_BINS + 8);
         OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         OVDET_CUDA_TRY(launch_pdl(apx_merge_kernel, dim3(C), dim3(1024), smem, st, p));
         { const int rc = launch_ok("apx_merge_kernel"); if (rc) return rc; }
     }
-    if ((stages & OVDET_APX_STAGE_MERGE_HIST) && exchange) {   // the runs arrive sorted: a cluster of 8 CTAs per class merges them
+    if ((stages & OVDET_APX_STAGE_MERGE_HIST) && via_slots) {   // the runs arrive sorted: a cluster of 8 CTAs per class merges them
         const size_t smem = (size_t)cap_total * 8 + sizeof(uint16_t) * (APX_BINS / APX_CL + 8);
         OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_merge_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         OVDET_CUDA_TRY(launch_pdl(apx_merge_runs_kernel, dim3(APX_CL * C), dim3(1024), smem, st, p));   // cluster dims are compiled in

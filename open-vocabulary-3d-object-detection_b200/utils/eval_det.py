@@ -262,6 +262,7 @@ class ApxReducer(object):
             with torch.cuda.device(device):
                 self.symm = D.SymmetricBuffer(L.ovdet_apx_symm_bytes(self.C, self.cap_total, self.world), group=group, device=device)
             self._own_symm = True
+        self._peers = self.symm.peers_array if self.symm is not None else None
         self.nres = 2 * self.nthr * self.C + self.C + 3
         self.result = torch.empty((self.nres,), dtype=torch.float64, device=device)
         self.result_host = torch.empty((self.nres,), dtype=torch.float64).pin_memory()
@@ -286,7 +287,7 @@ class ApxReducer(object):
             C.check(C.lib().ovdet_apx_reduce(
                 ptrs, sizes, nb, self.C, lists.key_ptr, lists.bits_ptr, lists.tp_cnt_ptr, lists.npos_ptr,
                 lists.cap_list, self.cap_total, self.nthr, flags, self.rank, self.world,
-                self.symm.peers_array if self.exchange else None, self._local_ptr, self._result_ptr,
+                self._peers, self._local_ptr, self._result_ptr,
                 self._result_host_ptr, C.stream(self.device) if stream is None else stream))
 
     def read(self):

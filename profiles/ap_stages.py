@@ -56,6 +56,13 @@ if os.environ.get("APX_STAMPS"):
     os.environ["OVDET_APX_DBG_PTR"] = str(d.data_ptr())
     red.launch([rs], lists); torch.cuda.synchronize()
     a = d.cpu().numpy().astype(np.float64)
-    print("merge: gather issue %.2f, gather wait %.2f, rank+rest %.2f us; total entries %s" % (np.median(a[:, 6] - a[:, 2]) / 1e3, np.median(a[:, 7] - a[:, 6]) / 1e3, np.median(a[:, 3] - a[:, 7]) / 1e3, lists.tp_cnt.cpu().numpy()[:6]))
-    for i, nm in [(1, "pdl wait"), (2, "counts (thread 0)"), (3, "gather+sort"), (4, "bin search"), (5, "table+zero")]:
-        print("merge %-18s %6.2f us" % (nm, np.median(a[:, i] - a[:, i - 1]) / 1e3))
+    # stamp ids (ap_compact.cu XSTAMPC): push 8 start, 9 after the dependency wait, 10 sorted, 11 flags raised;
+    # cluster merge 0 start, 6 flags seen, 2 runs in shared memory, 3 ranked + stored, 5 bins done;
+    # hist ship 12/13; final 16 start, 17 after the dependency wait, 18 histograms summed, 19 done
+    t0 = a[:, 8].min()
+    for i, nm in [(8, "push start"), (9, "push dep wait"), (10, "push sorted"), (11, "push flags"), (0, "merge start"), (6, "merge flags seen"),
+                  (2, "merge runs in smem"), (3, "merge ranked"), (5, "merge bins"), (16, "final start"), (17, "final dep wait"),
+                  (18, "final summed"), (19, "final done")]:
+        col = a[:, i][a[:, i] > 0]
+        if len(col):
+            print("%-20s median %7.2f  max %7.2f us after the first push CTA" % (nm, (np.median(col) - t0) / 1e3, (col.max() - t0) / 1e3))
