@@ -2,13 +2,17 @@
 
 ``APCalculator`` keeps the reference interface (``step_meter/step/accumulate/
 compute_metrics/metrics_to_str/metrics_to_dict/reset``, :272-450) but its state
-is device-resident: every ``step`` runs the fused parse_predictions kernel (AABB,
-argmax, NMS, confidence gate) and the AP matching kernel on the batch and keeps
-only compact class-major (score, tp-bits) records; ``compute_metrics`` runs the
-segmented sort/scan once for all classes and thresholds.  With
-``torch.distributed`` initialised, ``compute_metrics(distributed=True)``
-all-gathers the per-class record lists (the one exchange step of SURVEY.md 8e)
-so that scenes can be sharded across ranks.
+is device-resident.  Every ``step`` is ONE launch of the fused front end
+(``ovdet_ap_front_f32``: AABB, argmax, NMS, confidence gate, AP matching) that
+leaves class-major score records and appends the true positives of the batch to
+small per-class lists.  ``compute_metrics`` is one ``ovdet_apx_reduce`` call
+(merge the lists, one histogram pass over the score records, VOC AP for every
+class and threshold) and a single 800-byte read-back.  With
+``torch.distributed`` initialised, ``compute_metrics(distributed=True)`` lets
+each rank evaluate its own scenes: the reduction kernels exchange the per-class
+lists and bucket histograms through CUDA-IPC symmetric buffers with plain stores
+over NVLink (the one exchange step of SURVEY.md 8e) -- no collective launch, no
+host round trip; every rank ends up with the same metrics.
 """
 from collections import OrderedDict
 

@@ -825,6 +825,45 @@ def test_lift_full_width_vs_oracle():
         assert int(r["keep"][s].sum()) == want.shape[0]
 
 
+def test_lift_sweep_chunks_equal_one_batch():
+    """The sweep entry of BASELINE config 5: any chunking gives the single-launch result, ragged counts included."""
+    bx, pool = synth.pseudo_label_scenes(11, P=256, pool=512, seed=9)
+    nb = torch.tensor([256, 0, 17, 256, 100, 256, 1, 256, 33, 256, 255], dtype=torch.int32)
+    npl = torch.tensor([512, 512, 0, 300, 512, 7, 512, 512, 512, 64, 512], dtype=torch.int32)
+    one = B3.lift_filter_batch(bx.to(DEV), pool.to(DEV), nboxes=nb, npool=npl)
+    for chunk in (1, 4, 8192):
+        res, kept = B3.lift_sweep(bx.to(DEV), pool.to(DEV), nboxes=nb, npool=npl, chunk=chunk)
+        assert kept == int(one["keep"].sum())
+        for s in range(11):   # rows beyond a scene's counts are unspecified
+            assert torch.equal(res["keep"][s, :npl[s]], one["keep"][s, :npl[s]])
+            assert torch.equal(res["label"][s, :npl[s]], one["label"][s, :npl[s]])
+            assert torch.equal(res["nms1_keep"][s, :nb[s]], one["nms1_keep"][s, :nb[s]])
+    want = oracle.lift_filter_scene(bx[4, :100].numpy(), pool[4].numpy())
+    assert int(one["keep"][4].sum()) == want.shape[0]
+
+
+def test_generate_pseudo_label_sweep(golden, tmp_path):
+    """generate_pseudo_label.py:209 without the network: step per batch, then process -> <scan>_bbox.npy + the count."""
+    from ovdet_b200.generate_pseudo_label import sweep
+    from ovdet_b200.utils.label_formatter import LabelFormatter
+    g = golden("labelfmt.npz")
+    (tmp_path / "labels").mkdir(); (tmp_path / "out").mkdir(); (tmp_path / "out2").mkdir()
+    scenes = ["sceneA", "sceneB"]
+    for si, name in enumerate(scenes):
+        np.save(tmp_path / "labels" / (name + ".npy"), g[f"raw_{si}"])
+    out, tgt = synth.detection_batch(B=2, Q=16, G=4, C=18, seed=1, room="scannet", heading=0.0, max_gt=4)
+    o = {k: v.to(DEV) for k, v in out.items()}
+    batches = [({"outputs": o}, {"scan_idx": torch.tensor([0, 1], device=DEV)})]
+    n = sweep(batches, scenes, str(tmp_path), str(tmp_path / "out"), str(tmp_path / "labels"), topk=50, conf_thresh=0.1, obj_thresh=0.5)
+    fmt = LabelFormatter(str(tmp_path), str(tmp_path / "out2"), str(tmp_path / "labels"), scenes)
+    fmt.step(o, {"scan_idx": torch.tensor([0, 1], device=DEV)})
+    fmt.compute(50, 0.1, 0.5)
+    want = sum(fmt.gen_pseudo(si) for si in range(2))
+    assert n == want
+    for name in scenes:
+        np.testing.assert_array_equal(np.load(tmp_path / "out" / (name + "_bbox.npy")), np.load(tmp_path / "out2" / (name + "_bbox.npy")))
+
+
 # ------------------------------------------------------------------ open-vocab logits (tcgen05)
 @pytest.mark.parametrize("M,K,N,l2,scale", [
     (8192, 640, 1203, False, 1.0),     # BASELINE config 4
