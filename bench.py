@@ -440,6 +440,7 @@ def bench_ap(args, rank, world, dev, peaks):
         return {"%s|%s" % (t, k): float(v) for t, d in m.items() for k, v in d.items()}
 
     steps = max(5, min(args.steps // 5, 40))
+    graph_ms = {}
 
     def strong(total, data):
         """`total` scenes cut across the ranks; every rank ends up with the metrics of all of them.  Wall clock per
@@ -450,6 +451,15 @@ def bench_ap(args, rank, world, dev, peaks):
         for _ in range(3):
             m = run(calc, dv, world > 1)
         dt = wall_loop(lambda i: run(calc, dv, world > 1), steps, world, dev)
+        # the same evaluation recorded once as a CUDA graph (APCalculator.capture) and replayed: one graph launch + the
+        # read of the metrics per evaluation; the ranks still meet only inside the kernels
+        calc.capture(dv["box_corners"], dv["sem_cls_prob"], dv["objectness_prob"], None, dv["gt_box_corners"],
+                     dv["gt_box_sem_cls_label"], dv["gt_box_present"], distributed=world > 1)
+        for _ in range(3):
+            mg = calc.replay()
+        assert flat(mg) == flat(m), "graph replay differs from the eager evaluation"
+        dtg = wall_loop(lambda i: calc.replay(), steps, world, dev)
+        graph_ms[total] = dtg / steps * 1e3
         return m, dt / steps, calc, dv
 
     # ---- strong scaling, 5050 scenes in total (BASELINE config 3)
@@ -457,7 +467,10 @@ def bench_ap(args, rank, world, dev, peaks):
     res = {"value": S / t_strong, "unit": "scenes/s", "ms_per_step": t_strong * 1e3, "steps": steps, "scaling": "strong",
            "mAP_0.25": float(m[0.25]["mAP"]), "mAP_0.5": float(m[0.5]["mAP"]), "timing": "wall clock around reset + step + compute_metrics "
            "(ends in the D2H read of the metrics), max over ranks",
-           "workload": "5050 scenes x 128 queries x 20 classes, NMS 0.25 + AP@0.25/0.5, %d scenes on this rank" % dv["box_corners"].shape[0]}
+           "workload": "5050 scenes x 128 queries x 20 classes, NMS 0.25 + AP@0.25/0.5, %d scenes on this rank" % dv["box_corners"].shape[0],
+           "graph_replay": {"value": S / (graph_ms[S] * 1e-3), "unit": "scenes/s", "ms_per_step": graph_ms[S], "identical_metrics": True,
+                            "timing": "wall clock around APCalculator.replay(): the evaluation recorded once by capture() (reset + step + "
+                                      "reduce + result copy) replayed as one CUDA graph, ends in the read of the metrics, max over ranks"}}
     # parity: the distributed result against a single-rank evaluation of ALL scenes (rank 0 holds them all anyway)
     if world > 1:
         if rank == 0:
@@ -515,8 +528,14 @@ def bench_ap(args, rank, world, dev, peaks):
         for _ in range(3):
             run(cw, dw, True)
         dtw = wall_loop(lambda i: run(cw, dw, True), steps, world, dev) / steps
+        cw.capture(dw["box_corners"], dw["sem_cls_prob"], dw["objectness_prob"], None, dw["gt_box_corners"],
+                   dw["gt_box_sem_cls_label"], dw["gt_box_present"], distributed=True)
+        for _ in range(3):
+            cw.replay()
+        dtwg = wall_loop(lambda i: cw.replay(), steps, world, dev) / steps
         res["weak"] = {"value": world * S / dtw, "unit": "scenes/s", "ms_per_step": dtw * 1e3, "scaling": "weak",
-                       "workload": "5050 scenes per rank", "efficiency_note": "value(N) / (N x value(1)) is computed by the driver"}
+                       "workload": "5050 scenes per rank", "efficiency_note": "value(N) / (N x value(1)) is computed by the driver",
+                       "graph_replay": {"value": world * S / dtwg, "unit": "scenes/s", "ms_per_step": dtwg * 1e3}}
         cw.close()
         del dw
     # ---- strong scaling on a problem large enough to shard: 40 400 scenes in total (8 x config 3)
@@ -526,7 +545,8 @@ def bench_ap(args, rank, world, dev, peaks):
     lo, hi = D.shard_range(8 * S, rank, world)
     m8, t8, c8, _ = strong(8 * S, big)
     res["strong_40k"] = {"value": 8 * S / t8, "unit": "scenes/s", "ms_per_step": t8 * 1e3, "scaling": "strong",
-                         "workload": "40 400 scenes in total (%d on this rank)" % (hi - lo), "mAP_0.25": float(m8[0.25]["mAP"])}
+                         "workload": "40 400 scenes in total (%d on this rank)" % (hi - lo), "mAP_0.25": float(m8[0.25]["mAP"]),
+                         "graph_replay_ms_per_step": graph_ms[8 * S]}
     c8.close()
     calc.close()
     return res
@@ -722,10 +742,13 @@ def main():
                "parallelism": "replicas x%d (path does not shard, SURVEY 8e); AP evaluation and the pseudo-label sweep are scene-sharded" % world,
                "l2": "48 rotating input/output sets = 250 MB > 126 MB L2"}
         if apres is not None:   # short keys the driver's record keeps: scenes/s and ms per evaluation
-            cfg["ap_strong"] = {"scenes_per_s": apres["value"], "ms": apres["ms_per_step"], "scenes_total": 5050, "ap_parity": apres.get("ap_parity")}
+            cfg["ap_strong"] = {"scenes_per_s": apres["value"], "ms": apres["ms_per_step"], "scenes_total": 5050, "ap_parity": apres.get("ap_parity"),
+                                "graph_replay_ms": apres["graph_replay"]["ms_per_step"]}
             if "weak" in apres:
-                cfg["ap_weak"] = {"scenes_per_s": apres["weak"]["value"], "ms": apres["weak"]["ms_per_step"], "scenes_per_rank": 5050}
-            cfg["ap_strong_40k"] = {"scenes_per_s": apres["strong_40k"]["value"], "ms": apres["strong_40k"]["ms_per_step"], "scenes_total": 40400}
+                cfg["ap_weak"] = {"scenes_per_s": apres["weak"]["value"], "ms": apres["weak"]["ms_per_step"], "scenes_per_rank": 5050,
+                                  "graph_replay_scenes_per_s": apres["weak"]["graph_replay"]["value"], "graph_replay_ms": apres["weak"]["graph_replay"]["ms_per_step"]}
+            cfg["ap_strong_40k"] = {"scenes_per_s": apres["strong_40k"]["value"], "ms": apres["strong_40k"]["ms_per_step"], "scenes_total": 40400,
+                                    "graph_replay_ms": apres["strong_40k"]["graph_replay_ms_per_step"]}
         if extras is not None:
             cfg["pseudo_label_strong"] = {"scenes_per_s": extras["pseudo_label"]["scenes_per_s"], "ms": extras["pseudo_label"]["ms_per_step"],
                                           "scenes_total": 100000, "kept_boxes": extras["pseudo_label"]["kept_boxes"]}

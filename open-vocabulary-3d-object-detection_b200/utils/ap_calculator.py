@@ -133,6 +133,7 @@ class APCalculator(object):
         self._cap_hint = {}
         self._iou_ws = None
         self._thr_np = None
+        self._graph = None              # (CUDAGraph, reducer, device, distributed, static inputs) of capture()
         self.reset()
 
     def make_gt_list(self, gt_box_corners, gt_box_sem_cls_labels, gt_box_present):
@@ -246,19 +247,93 @@ class APCalculator(object):
                 rs, rt, npos = gather_records(rs, rt, npos)
             ap, recall, ndet = E.ap_reduce(rs, rt, npos, nthr)
             ap, recall = ap.cpu().numpy(), recall.cpu().numpy()
-        for ti, thr in enumerate(self.ap_iou_thresh):
-            overall_ret[thr] = self._format_rows(np.asarray(ap[ti]), np.asarray(recall[ti]))
+        overall_ret.update(self._format_all(ap, recall))
         return overall_ret
 
-    def _format_rows(self, ap_row, rec_row):
-        """_format for dense per-class rows (class id = column): same keys, order and value types, without rebuilding
-        the key strings and per-class dicts on every call (the formatting was ~10 % of a 0.6 ms evaluation)."""
-        n = ap_row.shape[0]
+    def capture(self, predicted_box_corners, sem_cls_probs, objectness_probs, point_cloud, gt_box_corners,
+                gt_box_sem_cls_labels, gt_box_present, distributed=False):
+        """Record ONE whole evaluation -- ``reset``, ``step`` on these tensors, the reduction and the copy of the packed
+        result to the host -- as a CUDA graph, for evaluations that repeat on fixed shapes (every epoch's validation).
+        The tensors are the graph's static inputs: refill them in place (``copy_``) and call ``replay()``, which returns
+        what ``compute_metrics`` returns.  The call first runs the evaluation once eagerly (that sizes the workspaces and
+        the list capacity -- collective when ``distributed`` -- and is returned), then captures.  Every rank of a
+        distributed evaluation must capture and replay alike: the exchange between the ranks happens inside the captured
+        kernels (flag words tagged by a device-side epoch), so a replay needs no host-side coordination at all."""
+        args = (predicted_box_corners, sem_cls_probs, objectness_probs, point_cloud, gt_box_corners, gt_box_sem_cls_labels,
+                gt_box_present)
+        if self.reduce_mode != "compact":
+            raise C.OvdetError("capture() records the compact reducer (reduce_mode = 'compact')")
+        self.reset()
+        self.step(*args)
+        first = self.compute_metrics(distributed=distributed)
+        lists = self._lists
+        dev, Cn = lists.device, lists.C
+        world = 1
+        if distributed:
+            import torch.distributed as tdist
+            world = tdist.get_world_size(self.group)
+        cap = self._cap_hint.get(world)
+        if cap is None:
+            raise C.OvdetError("capture(): the evaluation did not go through the compact reducer (list overflow); nothing to record")
+        red = self._reducer(Cn, len(self.ap_iou_thresh), cap, world, dev)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.reset()
+            self.step(*args)
+            red.launch(self._blocks, lists)
+        self._graph = (graph, red, dev, distributed, args)    # args: keeps the static inputs alive
+        return first
+
+    def replay(self):
+        """Replay the evaluation recorded by ``capture`` on the current contents of its input tensors."""
+        if getattr(self, "_graph", None) is None:
+            raise C.OvdetError("replay() without capture()")
+        graph, red, dev, distributed, _ = self._graph
+        graph.replay()
+        C.stream_synchronize(dev)
+        ap, recall, _, ovf, _, _ = red.read()
+        if ovf < 0:
+            raise C.OvdetError("AP exchange timed out waiting for a peer rank (did every rank call replay?)")
+        if ovf > 0:     # lists outgrew the recorded capacity (every rank sees the same counts): the eager path re-sizes
+            return self.compute_metrics(distributed=distributed)
+        return self._format_all(ap, recall)
+
+    def _format_all(self, ap, recall):
+        """All thresholds at once ([nthr, C] arrays): the same keys, order and numbers as ``_format_rows`` per threshold,
+        with the NaN scrub and the two means vectorised over the thresholds and the per-class values converted in one
+        ``tolist`` (Python floats) -- the host-side formatting follows the last kernel of an evaluation un-overlapped."""
+        ap, recall = np.asarray(ap), np.asarray(recall)
+        n = ap.shape[1]
+        keys = self._keys(n)
+        ap32 = ap.astype(np.float32)
+        ap32[ap32 != ap32] = 0                               # NaN -> 0
+        m_ap = np.add.reduce(ap32, axis=1) / n               # float32 pairwise row sums / count == ap_vals.mean() per row
+        m_ar = np.add.reduce(recall, axis=1) / n
+        apl, rl = ap.tolist(), recall.tolist()
+        overall_ret = OrderedDict()
+        order = keys[2]                                      # AP keys, "mAP", recall keys, "AR": the reference's insertion order
+        for ti, thr in enumerate(self.ap_iou_thresh):
+            vals = apl[ti]
+            vals.append(m_ap[ti])
+            vals.extend(rl[ti])
+            vals.append(m_ar[ti])
+            overall_ret[thr] = OrderedDict(zip(order, vals))
+        return overall_ret
+
+    def _keys(self, n):
         keys = self._fmt_keys.get(n)
         if keys is None:
             names = [self.class2type_map[k] if self.class2type_map else str(k) for k in range(n)]
-            keys = (["%s Average Precision" % nm for nm in names], ["%s Recall" % nm for nm in names])
+            kap, krec = ["%s Average Precision" % nm for nm in names], ["%s Recall" % nm for nm in names]
+            keys = (kap, krec, kap + ["mAP"] + krec + ["AR"])
             self._fmt_keys[n] = keys
+        return keys
+
+    def _format_rows(self, ap_row, rec_row):
+        """_format for dense per-class rows (class id = column) of one threshold: same keys, order and value types."""
+        n = ap_row.shape[0]
+        keys = self._keys(n)
         ret_dict = OrderedDict(zip(keys[0], ap_row))
         ap_vals = ap_row.astype(np.float32)
         ap_vals[ap_vals != ap_vals] = 0                      # NaN -> 0
@@ -322,6 +397,7 @@ class APCalculator(object):
 
     def close(self):
         """Release the exchange workspaces (collective when distributed)."""
+        self._graph = None
         for r in self._reducers.values():
             r.close()
         self._reducers = {}

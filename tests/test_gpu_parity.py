@@ -662,6 +662,51 @@ def test_ap_exchange_overflow_and_force_exchange():
     calc.close()
 
 
+@pytest.mark.parametrize("force_exchange", [False, True])
+def test_ap_graph_replay_equals_eager(force_exchange):
+    """capture() records reset + step + reduce + read-back as one CUDA graph; replay() on refilled inputs must return
+    exactly what the eager calls return on the same data (also through the exchange code path)."""
+    S, Q, G, C = 96, 128, 24, 6
+    thrs = [0.25, 0.5]
+    keys = ("box_corners", "sem_cls_prob", "objectness_prob")
+    tkeys = ("gt_box_corners", "gt_box_sem_cls_label", "gt_box_present")
+    data = [synth.detection_batch(B=S, Q=Q, G=G, C=C, seed=sd, heading=np.pi, max_gt=12) for sd in (21, 22, 23)]
+    def eager(out, tgt):
+        c = APC.APCalculator(_Cfg(C), ap_iou_thresh=thrs, exact_eval=False)
+        c.force_exchange = force_exchange
+        c.step(*[out[k].to(DEV) for k in keys], None, *[tgt[k].to(DEV) for k in tkeys])
+        r = c.compute_metrics()
+        c.close()
+        return r
+    want = [eager(o, t) for o, t in data]
+    calc = APC.APCalculator(_Cfg(C), ap_iou_thresh=thrs, exact_eval=False)
+    calc.force_exchange = force_exchange
+    o0, t0 = data[0]
+    ins = [o0[k].to(DEV).clone() for k in keys]
+    gts = [t0[k].to(DEV).clone() for k in tkeys]
+    first = calc.capture(ins[0], ins[1], ins[2], None, gts[0], gts[1], gts[2])
+    def same(a, b):
+        for thr in thrs:
+            assert list(a[thr].keys()) == list(b[thr].keys())
+            for k in a[thr]:
+                x, y = float(a[thr][k]), float(b[thr][k])
+                assert x == y or (x != x and y != y), (thr, k, x, y)
+    same(first, want[0])
+    for rnd in (1, 2, 0, 0):       # refill in place, replay (twice on the same data at the end: epochs advance, result stays)
+        o, t = data[rnd]
+        for dst, k in zip(ins, keys):
+            dst.copy_(o[k])
+        for dst, k in zip(gts, tkeys):
+            dst.copy_(t[k])
+        same(calc.replay(), want[rnd])
+    # an eager evaluation on the same calculator in between does not disturb the recording
+    calc.reset()
+    calc.step(*[data[1][0][k].to(DEV) for k in keys], None, *[data[1][1][k].to(DEV) for k in tkeys])
+    same(calc.compute_metrics(), want[1])
+    same(calc.replay(), want[0])
+    calc.close()
+
+
 def test_tools_lhs_nms_golden(golden):
     """tools nms_3d_faster(lhs=True) (3DOVDet_tools/utils/box_3d_utils.py:113-116): reference fixture + random fuzz vs the oracle."""
     g = golden("holes.npz")
