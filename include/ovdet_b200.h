@@ -298,7 +298,8 @@ size_t ovdet_apx_symm_bytes(int C, int cap_total, int world);
  * count | largest merged list count; overflow > 0 means a merged list did not fit cap_total (the local lists are intact:
  * retry with a larger cap_total) or a local list overflowed cap_list; overflow < 0 = a peer's flag never arrived (timeout).
  * A symmetric buffer sized for a larger cap_total may be used with a smaller one.
- * result_host: optional pinned host copy target (async D2H on `stream`; the caller synchronises).
+ * result_host: optional host copy of `result`; pinned (mapped) memory is written by the final kernel itself, other memory
+ * by an async D2H copy on `stream`; either way the caller synchronises the stream before reading it.
  * Every rank must call this the same number of times (an epoch word in `local` tags the flags). */
 #define OVDET_APX_FORCE_EXCHANGE 0x1u
 #define OVDET_APX_USE_07_METRIC 0x2u

@@ -532,6 +532,7 @@ struct ApxParams {
     const uint32_t *tp_key; const uint8_t *tp_bits; const int *tp_cnt; const long long *npos;
     int C, cap_list, cap, nthr, use07, rank, W, R, exchange;   // R = sorted runs per rank (list slots = W * R)
     double *result;
+    double *result_m;   // the caller's pinned host result through its mapped device address (or null): no copy node needed
     unsigned long long *dbg;   // optional [C][8] globaltimer stamps of the merge stage (OVDET_APX_DBG_PTR; null in production)
 };
 #define XSTAMPC(cls, i) do { if (p.dbg && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[(size_t)(cls) * 32 + (i)] = t_; } } while (0)
@@ -1331,9 +1332,15 @@ __global__ void __launch_bounds__(1024) apx_final_kernel(ApxParams p)
     if (t == 0) XSTAMPC(c, 19);
     if (tid == 0) {
         const size_t kx = (size_t)p.nthr * p.C;
-        p.result[(size_t)t * p.C + c] = nvalid > 0 ? res : 0.0;
-        p.result[kx + (size_t)t * p.C + c] = (nvalid > 0 && npos > 0.0) ? __ddiv_rn((double)total_tp, npos) : 0.0;
+        const double v_ap = nvalid > 0 ? res : 0.0, v_rec = (nvalid > 0 && npos > 0.0) ? __ddiv_rn((double)total_tp, npos) : 0.0;
+        p.result[(size_t)t * p.C + c] = v_ap;
+        p.result[kx + (size_t)t * p.C + c] = v_rec;
         if (t == 0) p.result[2 * kx + c] = (double)nvalid;
+        if (p.result_m) {
+            p.result_m[(size_t)t * p.C + c] = v_ap;
+            p.result_m[kx + (size_t)t * p.C + c] = v_rec;
+            if (t == 0) p.result_m[2 * kx + c] = (double)nvalid;
+        }
         __threadfence();
         const unsigned tk = atomicAdd(&ctrl[1], 1u);
         last_s = (tk == gridDim.x * gridDim.y - 1);
@@ -1346,6 +1353,11 @@ __global__ void __launch_bounds__(1024) apx_final_kernel(ApxParams p)
             p.result[2 * kx + p.C] = to ? -1.0 : (double)ovf;
             p.result[2 * kx + p.C + 1] = (double)mx;
             p.result[2 * kx + p.C + 2] = (double)mt;
+            if (p.result_m) {
+                p.result_m[2 * kx + p.C] = to ? -1.0 : (double)ovf;
+                p.result_m[2 * kx + p.C + 1] = (double)mx;
+                p.result_m[2 * kx + p.C + 2] = (double)mt;
+            }
             ctrl[1] = 0u;
             __threadfence();
             ctrl[0] = tag;
@@ -1389,6 +1401,12 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
     p.tp_key = tp_key; p.tp_bits = tp_bits; p.tp_cnt = tp_cnt; p.npos = reinterpret_cast<const long long *>(npos);
     p.C = C; p.cap_list = cap_list; p.cap = cap_total; p.nthr = nthr; p.use07 = (flags & OVDET_APX_USE_07_METRIC) ? 1 : 0;
     p.rank = rank; p.W = world; p.R = apx_runs_per_rank(world); p.exchange = exchange ? 1 : 0; p.result = result;
+    p.result_m = nullptr;
+    if (result_host) {   // pinned host memory is written by the final kernel itself; anything else gets a copy node
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, result_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) p.result_m = static_cast<double *>(at.devicePointer);
+        else cudaGetLastError();
+    }
     { const char *e = getenv("OVDET_APX_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned stages = flags & (OVDET_APX_STAGE_PUSH | OVDET_APX_STAGE_MERGE_HIST | OVDET_APX_STAGE_FINAL);
@@ -1453,7 +1471,7 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
         OVDET_CUDA_TRY(launch_pdl(apx_final_kernel, dim3(C, nthr), dim3(1024), smem, st, p));
         { const int rc = launch_ok("apx_final_kernel"); if (rc) return rc; }
     }
-    if (result_host && (stages & OVDET_APX_STAGE_FINAL))
+    if (result_host && !p.result_m && (stages & OVDET_APX_STAGE_FINAL))
         OVDET_CUDA_TRY(cudaMemcpyAsync(result_host, result, sizeof(double) * (2 * (size_t)nthr * C + C + 3), cudaMemcpyDeviceToHost, st));
     return OVDET_OK;
 }
