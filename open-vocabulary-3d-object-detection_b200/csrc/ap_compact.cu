@@ -361,7 +361,7 @@ extern "C" int ovdet_apc_sort(uint32_t *tp_key, uint8_t *tp_bits, int C, int cap
     OVDET_REQUIRE(C > 0 && apc_cap_ok(cap), "bad size");
     OVDET_REQUIRE(tp_key && tp_bits, "null pointer");
     const size_t smem = (size_t)cap * 5;
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(apc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OVDET_CUDA_TRY(ensure_dyn_smem(apc_sort_kernel, smem));
     apc_sort_kernel<<<C, 1024, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tp_key, tp_bits, cap);
     return launch_ok("apc_sort_kernel");
 }
@@ -377,10 +377,10 @@ extern "C" int ovdet_apc_hist(const float *rec_score, int C, int64_t N, const ui
     // per-class bin edges of the sorted list, in the library's grow-only device scratch
     uint16_t *edge = nullptr;
     { void *ws = nullptr; int rc = device_scratch().acquire(sizeof(uint16_t) * (size_t)C * APC_ESTRIDE, st, &ws); if (rc) return rc; edge = static_cast<uint16_t *>(ws); }
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(apc_edges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * cap)));
+    OVDET_CUDA_TRY(ensure_dyn_smem(apc_edges_kernel, (sizeof(uint32_t) * cap)));
     apc_edges_kernel<<<C, 1024, sizeof(uint32_t) * cap, st>>>(tp_key, cap, edge);
     const size_t smem = sizeof(uint32_t) * (2 * (size_t)cap + 1) + sizeof(uint16_t) * (APC_BINS + 2);
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(apc_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OVDET_CUDA_TRY(ensure_dyn_smem(apc_hist_kernel, smem));
     // enough CTAs to fill the chip a few times over, few enough that the histogram flush stays small
     int per_sm = (int)(220 * 1024 / (smem + 1024));
     if (per_sm > 8) per_sm = 8;
@@ -407,7 +407,7 @@ extern "C" int ovdet_apc_final(const uint8_t *tp_bits, const int32_t *tp_cnt, co
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (overflow) OVDET_CUDA_TRY(cudaMemsetAsync(overflow, 0, sizeof(int32_t), st));
     const size_t smem = sizeof(unsigned int) * 2 * (size_t)cap;
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(apc_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OVDET_CUDA_TRY(ensure_dyn_smem(apc_final_kernel, smem));
     apc_final_kernel<<<dim3(C, nthr), 1024, smem, st>>>(p);
     return launch_ok("apc_final_kernel");
 }
@@ -1413,19 +1413,19 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
     if (!stages) stages = OVDET_APX_STAGE_PUSH | OVDET_APX_STAGE_MERGE_HIST | OVDET_APX_STAGE_FINAL;
     if (via_slots && (stages & OVDET_APX_STAGE_PUSH)) {
         const size_t psmem = (size_t)cap_total * 12 + sizeof(uint16_t) * 32 * 256;
-        OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_push_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        OVDET_CUDA_TRY(ensure_dyn_smem(apx_push_lists_kernel, psmem));
         OVDET_CUDA_TRY(launch_pdl(apx_push_lists_kernel, dim3(p.R, C), dim3(1024), psmem, st, p));
         { const int rc = launch_ok("apx_push_lists_kernel"); if (rc) return rc; }
     }
     if ((stages & OVDET_APX_STAGE_MERGE_HIST) && !via_slots) {
         const size_t smem = (size_t)cap_total * 12 + sizeof(uint16_t) * (32 * 256 + APX_BINS + 8);
-        OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OVDET_CUDA_TRY(ensure_dyn_smem(apx_merge_kernel, smem));
         OVDET_CUDA_TRY(launch_pdl(apx_merge_kernel, dim3(C), dim3(1024), smem, st, p));
         { const int rc = launch_ok("apx_merge_kernel"); if (rc) return rc; }
     }
     if ((stages & OVDET_APX_STAGE_MERGE_HIST) && via_slots) {   // the runs arrive sorted: a cluster of 8 CTAs per class merges them
         const size_t smem = (size_t)cap_total * 8 + sizeof(uint16_t) * (APX_BINS / APX_CL + 8);
-        OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_merge_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OVDET_CUDA_TRY(ensure_dyn_smem(apx_merge_runs_kernel, smem));
         OVDET_CUDA_TRY(launch_pdl(apx_merge_runs_kernel, dim3(APX_CL * C), dim3(1024), smem, st, p));   // cluster dims are compiled in
         { const int rc = launch_ok("apx_merge_runs_kernel"); if (rc) return rc; }
     }
@@ -1433,8 +1433,8 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
         const bool big = cap_total > 4096;
         const size_t smem = big ? sizeof(uint32_t) * ((size_t)cap_total + 1 + ((size_t)cap_total + 2) / 2) + sizeof(uint16_t) * APX_BINS
                                 : sizeof(uint32_t) * 2 * ((size_t)cap_total + 1) + sizeof(uint16_t) * APX_BINS;
-        if (big) OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_hist_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (big) OVDET_CUDA_TRY(ensure_dyn_smem(apx_hist_big_kernel, smem));
+        else OVDET_CUDA_TRY(ensure_dyn_smem(apx_hist_kernel, smem));
         int per_sm = (int)(220 * 1024 / (smem + 1024));
         if (per_sm > 8) per_sm = 8;
         if (per_sm < 1) per_sm = 1;
@@ -1467,7 +1467,7 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
     }
     if (stages & OVDET_APX_STAGE_FINAL) {
         const size_t smem = (sizeof(unsigned int) + 1) * (size_t)cap_total;
-        OVDET_CUDA_TRY(cudaFuncSetAttribute(apx_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OVDET_CUDA_TRY(ensure_dyn_smem(apx_final_kernel, smem));
         OVDET_CUDA_TRY(launch_pdl(apx_final_kernel, dim3(C, nthr), dim3(1024), smem, st, p));
         { const int rc = launch_ok("apx_final_kernel"); if (rc) return rc; }
     }

@@ -522,8 +522,14 @@ extern "C" int ovdet_ap_front_f32(const float *corners, const float *probs, cons
     OVDET_REQUIRE(tp_key == nullptr || tp_cap > 0, "tp_cap must be positive");
     OVDET_REQUIRE(rec_tp || tp_key, "need rec_tp and/or a TP list to report the true positives");
     if (flags & OVDET_FRONT_RESET) {   // start of an evaluation: the lists' counters and the GT counts, one memset each
-        if (tp_cnt) OVDET_CUDA_TRY(cudaMemsetAsync(tp_cnt, 0, sizeof(int32_t) * C, reinterpret_cast<cudaStream_t>(stream)));
-        OVDET_CUDA_TRY(cudaMemsetAsync(npos, 0, sizeof(int64_t) * C, reinterpret_cast<cudaStream_t>(stream)));
+        char *lo = reinterpret_cast<char *>(tp_cnt), *hi = reinterpret_cast<char *>(npos);
+        const size_t gap = sizeof(int32_t) * (size_t)((C + 1) / 2 * 2);
+        if (tp_cnt && hi == lo + gap)   // npos right behind tp_cnt (8-byte aligned), as the host shim lays them out: one memset
+            OVDET_CUDA_TRY(cudaMemsetAsync(lo, 0, gap + sizeof(int64_t) * C, reinterpret_cast<cudaStream_t>(stream)));
+        else {
+            if (tp_cnt) OVDET_CUDA_TRY(cudaMemsetAsync(tp_cnt, 0, sizeof(int32_t) * C, reinterpret_cast<cudaStream_t>(stream)));
+            OVDET_CUDA_TRY(cudaMemsetAsync(npos, 0, sizeof(int64_t) * C, reinterpret_cast<cudaStream_t>(stream)));
+        }
         flags &= ~OVDET_FRONT_RESET;
     }
     const int nt = K <= 128 ? 128 : 256;
@@ -545,10 +551,10 @@ extern "C" int ovdet_ap_front_f32(const float *corners, const float *probs, cons
     const size_t smem = f2_smem_bytes(K, G, C, nthr, nt, flags);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (nt == 128) {
-        OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_front2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OVDET_CUDA_TRY(ensure_dyn_smem(ap_front2_kernel<128>, smem));
         ap_front2_kernel<128><<<S, 128, smem, st>>>(p);
     } else {
-        OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_front2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OVDET_CUDA_TRY(ensure_dyn_smem(ap_front2_kernel<256>, smem));
         ap_front2_kernel<256><<<S, 256, smem, st>>>(p);
     }
     return launch_ok("ap_front2_kernel");

@@ -2,9 +2,34 @@
 // device probe and the host-staging scratch used by the *_host entry points.
 #include <stdarg.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace ovdet {
+
+cudaError_t ensure_dyn_smem_impl(const void *func, size_t bytes)
+{
+    struct Ent { const void *f; int dev; size_t bytes; };
+    static Ent tab[256];
+    static int n = 0;
+    static std::mutex mu;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> g(mu);
+    for (int i = 0; i < n; ++i)
+        if (tab[i].f == func && tab[i].dev == dev) {
+            if (bytes <= tab[i].bytes) return cudaSuccess;
+            e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (e == cudaSuccess) tab[i].bytes = bytes;
+            return e;
+        }
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && n < 256) tab[n++] = Ent{func, dev, bytes};
+    return e;
+}
+
 
 static thread_local char g_err[512] = "";
 

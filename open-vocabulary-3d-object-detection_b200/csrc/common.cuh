@@ -66,6 +66,11 @@ struct DeviceScratch {
 };
 DeviceScratch &device_scratch();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when a kernel needs MORE than what was already set for it on the
+// current device (capi.cu): the attribute call is ~1 us of host time, and the AP path launches five kernels per evaluation.
+cudaError_t ensure_dyn_smem_impl(const void *func, size_t bytes);
+template <typename F> inline cudaError_t ensure_dyn_smem(F func, size_t bytes) { return ensure_dyn_smem_impl(reinterpret_cast<const void *>(func), bytes); }
+
 // ------------------------------------------------ reference-faithful arithmetic
 // The reference evaluates every arithmetic op separately (Python floats, eager
 // torch, numpy), so the geometry kernels must not contract a*b+c into an FMA:

@@ -897,7 +897,7 @@ extern "C" int ovdet_box3d_iou_f64(const float *dets, const float *gts, const in
     OVDET_REQUIRE(dets && gts && out, "null pointer");
     IouParams p{dets, gts, nd, ng, S, D, G, out, out2d, (long long)S * D * G};
     const size_t smem = sizeof(V2<double>) * 2 * SH_MAXV * EV_NT;
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(box3d_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OVDET_CUDA_TRY(ensure_dyn_smem(box3d_iou_kernel, smem));
     long long blocks = (p.total + EV_NT - 1) / EV_NT;
     if (blocks > 148 * 12) blocks = 148 * 12;
     box3d_iou_kernel<<<(unsigned)blocks, EV_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
@@ -935,7 +935,7 @@ extern "C" int ovdet_ap_match(const float *corners, const float *probs, const fl
     { const int rc = fill_match_params(p, corners, probs, obj, keep, det_cls, gt_corners, gt_labels, gt_present, S, K, G, C, thr, nthr, iou_ws, rec_score, rec_tp, npos); if (rc) return rc; }
     const size_t smem = am_smem_bytes(K, G, nthr);
     OVDET_REQUIRE(smem <= 220 * 1024, "K + G too large for the shared-memory feature records");
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OVDET_CUDA_TRY(ensure_dyn_smem(ap_match_kernel, smem));
     ap_match_kernel<<<S, AM_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("ap_match_kernel");
 }
@@ -970,7 +970,7 @@ extern "C" int ovdet_ap_match_iou(const double *iou, const float *probs, const f
     p.iou_given = G > 0 ? iou : &dummy;   // G == 0: nothing is ever read
     const size_t smem = am_smem_bytes(K, G, nthr);
     OVDET_REQUIRE(smem <= 220 * 1024, "K + G too large for the shared-memory tables");
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OVDET_CUDA_TRY(ensure_dyn_smem(ap_match_kernel, smem));
     ap_match_kernel<<<S, AM_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("ap_match_kernel");
 }
@@ -1003,10 +1003,10 @@ int ovdet::front1_launch(const float *corners, const float *probs, const float *
     OVDET_REQUIRE(smem <= 220 * 1024, "K + G too large for the shared-memory tables");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (tile) {
-        OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OVDET_CUDA_TRY(ensure_dyn_smem(ap_front_kernel<true>, smem));
         ap_front_kernel<true><<<S, AM_NT, smem, st>>>(fp);
     } else {
-        OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OVDET_CUDA_TRY(ensure_dyn_smem(ap_front_kernel<false>, smem));
         ap_front_kernel<false><<<S, AM_NT, smem, st>>>(fp);
     }
     return launch_ok("ap_front_kernel");
@@ -1066,7 +1066,7 @@ extern "C" int ovdet_ap_reduce(const float *rec_score, const uint8_t *rec_tp, co
     sp.use07 = use_07_metric; sp.ap = ap; sp.recall = recall; sp.rec_out = rec_out; sp.prec_out = prec_out;
     sp.ndet_out = reinterpret_cast<long long *>(n_det);
     const size_t smem = sizeof(unsigned int) * ((size_t)(N + 1023) / 1024 + 2);
-    if (smem > 48 * 1024) OVDET_CUDA_TRY(cudaFuncSetAttribute(ap_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) OVDET_CUDA_TRY(ensure_dyn_smem(ap_scan_kernel, smem));
     OVDET_REQUIRE(smem <= 200 * 1024, "N too large for the chunk table");
     ap_scan_kernel<<<dim3(C, nthr), 1024, smem, st>>>(sp);
     return launch_ok("ap_reduce");

@@ -264,7 +264,7 @@ extern "C" int ovdet_lsap_f32(const float *cost, const int64_t *nactual_gt, int 
     const size_t slab = sizeof(float) * (size_t)(Q < G ? Q : G) * ((size_t)p.M + 1);
     p.stage_cost = (smem + slab <= 200 * 1024) ? 1 : 0;
     if (p.stage_cost) smem += slab;
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OVDET_CUDA_TRY(ensure_dyn_smem(lsap_kernel, smem));
     lsap_kernel<<<B, LS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("lsap_kernel");
 }

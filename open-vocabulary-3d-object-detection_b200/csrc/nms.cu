@@ -398,7 +398,7 @@ extern "C" int ovdet_nms_f64(const double *boxes, const int32_t *counts, int S, 
     OVDET_REQUIRE(ncols >= 2 * dims + 1 + ((flags & OVDET_NMS_SAMECLS) ? 1 : 0), "ncols too small");
     NmsParams p{boxes, counts, S, K, ncols, thr, vol_eps, flags, keep, pick_order, npick};
     const size_t smem = nms_smem_bytes(K);
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OVDET_CUDA_TRY(ensure_dyn_smem(nms_kernel, smem));
     nms_kernel<<<S, K <= 128 ? 128 : NMS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("nms_kernel");
 }
@@ -416,7 +416,7 @@ extern "C" int ovdet_parse_predictions_f32(const float *corners, const float *pr
     ParseParams p{corners, probs, obj, nonempty, S, K, C, nms_iou, conf_thresh, flags, pred_mask, keep, pred_cls, pred_cls_prob, nullptr};
     { const char *e = getenv("OVDET_PARSE_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
     const size_t smem = nms_smem_bytes(K) + sizeof(int) * (size_t)K;
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(parse_predictions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OVDET_CUDA_TRY(ensure_dyn_smem(parse_predictions_kernel, smem));
     parse_predictions_kernel<<<S, K <= 128 ? 128 : NMS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("parse_predictions_kernel");
 }
@@ -434,7 +434,7 @@ extern "C" int ovdet_pseudo_filter_f64(const double *boxes, const double *pool, 
                    nms1_keep, out_label, out_score, out_keep, nullptr};
     { const char *e = getenv("OVDET_PSEUDO_DBG_PTR"); p.dbg = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 0)) : nullptr; }
     const size_t smem = nms_smem_bytes(p.Kmax);
-    OVDET_CUDA_TRY(cudaFuncSetAttribute(pseudo_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OVDET_CUDA_TRY(ensure_dyn_smem(pseudo_filter_kernel, smem));
     pseudo_filter_kernel<<<S, NMS_NT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return launch_ok("pseudo_filter_kernel");
 }
