@@ -125,3 +125,39 @@ def test_fuzz_clip_logits_shapes(seed):
         N = min(max(N, 2), 2048)
         l2 = bool(rng.random() < 0.3)
         T._check_clip_logits(M, K, N, l2, (1.0 / 0.07) if l2 else float(rng.choice([0.5, 1.0])))
+
+
+@pytest.mark.parametrize("seed", [41])
+def test_fuzz_ap_configs_over_virtual_ranks(seed):
+    """Random parse_predictions configurations (NMS variant, record layout, thresholds) through the fused front end and
+    the exchange reducer for 1..8 virtual ranks (stage by stage on one GPU), against the oracle's parse_predictions +
+    eval_det of all scenes; every rank must report the oracle's numbers."""
+    from test_gpu_parity import _apx_virtual_ranks
+    rng = np.random.default_rng(seed)
+    for it in range(14):
+        S = int(rng.integers(1, 30)); Q = int(rng.choice([16, 64, 128, 160])); G = int(rng.choice([4, 24, 64])); C = int(rng.choice([2, 7, 20]))
+        nranks = int(rng.choice([1, 2, 3, 5, 8]))
+        thrs = tuple(sorted(rng.choice([0.1, 0.25, 0.5, 0.75], size=int(rng.integers(1, 4)), replace=False).tolist()))
+        kw = dict(nms_iou=float(rng.choice([0.1, 0.25, 0.5])), conf_thresh=float(rng.choice([0.0, 0.05, 0.3])),
+                  cls_nms=bool(rng.random() < 0.6), use_3d_nms=bool(rng.random() < 0.7), use_old_type_nms=bool(rng.random() < 0.3),
+                  no_nms=bool(rng.random() < 0.1))
+        if rng.random() < 0.4:
+            kw["per_class_proposal"] = False
+            kw["use_cls_confidence_only"] = bool(rng.random() < 0.5)
+        out, tgt = synth.detection_batch(B=S, Q=Q, G=G, C=C, seed=int(rng.integers(1 << 30)), heading=float(rng.choice([0.0, np.pi])),
+                                         max_gt=int(rng.integers(1, G + 1)))
+        cfg = APC.get_ap_config_dict(dataset_config=Cfg(C), remove_empty_box=False, **kw)
+        want, _ = oracle.ap_metrics(out["box_corners"], out["sem_cls_prob"], out["objectness_prob"], tgt["gt_box_corners"],
+                                    tgt["gt_box_sem_cls_label"], tgt["gt_box_present"], C, ap_iou_thresh=thrs,
+                                    config=oracle.default_ap_config(C, **kw))
+        res = _apx_virtual_ranks(out, tgt, C, thrs, nranks, cap_total=int(rng.choice([1024, 4096])), rounds=1, cfg=cfg)
+        for r, (ap, recall, ndet, ovf, _, _) in enumerate(res):
+            assert ovf == 0
+            for ti, thr in enumerate(thrs):
+                for c in range(C):
+                    k = "%d Average Precision" % c
+                    if k not in want[thr]:      # a class nobody predicted and no GT has: the reference has no entry for it
+                        continue
+                    a, b_ = float(ap[ti, c]), float(want[thr][k])
+                    if not (abs(a - b_) < 1e-9 or (np.isnan(a) and np.isnan(b_))):
+                        pytest.fail(str(("AP MISMATCH", dict(it=it, rank=r, S=S, Q=Q, G=G, C=C, nranks=nranks, thrs=thrs, kw=kw, cls=c, got=a, want=b_))))
