@@ -439,7 +439,7 @@ def bench_ap(args, rank, world, dev, peaks):
     def flat(m):
         return {"%s|%s" % (t, k): float(v) for t, d in m.items() for k, v in d.items()}
 
-    steps = max(5, min(args.steps // 5, 40))
+    steps = max(20, min(args.steps // 5, 40))   # AP evaluations per timed loop (0.2-2 ms each)
     graph_ms = {}
 
     def strong(total, data):
