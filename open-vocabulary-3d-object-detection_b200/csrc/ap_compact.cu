@@ -904,12 +904,16 @@ __global__ void __cluster_dims__(APX_CL, 1, 1) __launch_bounds__(1024, 1) apx_me
     __syncthreads();
     const int total = off_s[NR], W = NR;   // (W = number of runs below)
     if (part == 0) XSTAMPC(c, 2);
-    for (int r = 0; r < W; ++r) {
+    // one flat loop over the concatenated entries (not one loop per run: W dependent global round trips in a row)
+#pragma unroll 4
+    for (int i = tid; i < total; i += 1024) {
+        int r = 0;
+        while (r + 1 < W && i >= off_s[r + 1]) ++r;
         const unsigned char *slot = half + p.sl.lists + (size_t)r * p.sl.list_stride;
-        const uint32_t *ksrc = reinterpret_cast<const uint32_t *>(slot + p.sl.l_key) + (size_t)c * cap;
-        const uint8_t *bsrc = slot + p.sl.l_bits + (size_t)c * cap;
-        const int n = n_s[r], o = off_s[r];
-        for (int i = tid; i < n; i += 1024) v[o + i] = ((unsigned long long)ksrc[i] << 8) | bsrc[i];
+        const int j = i - off_s[r];
+        const uint32_t kk = __ldcg(reinterpret_cast<const uint32_t *>(slot + p.sl.l_key) + (size_t)c * cap + j);
+        const uint8_t bb = __ldcg(slot + p.sl.l_bits + (size_t)c * cap + j);
+        v[i] = ((unsigned long long)kk << 8) | bb;
     }
     __syncthreads();
     uint32_t *mk = reinterpret_cast<uint32_t *>(p.local + p.ll.mkey) + (size_t)c * cap;
@@ -1214,8 +1218,9 @@ __global__ void __launch_bounds__(1024) apx_final_kernel(ApxParams p)
     auto hist_at = [&](int i) -> unsigned int {
         if (!p.exchange) return hl[i];
         unsigned int v = 0;
-        for (int r = 0; r < p.W; ++r)
-            v += reinterpret_cast<const uint32_t *>(half + p.sl.hist + (size_t)r * p.sl.hist_stride)[(size_t)c * p.sl.hp + i];
+#pragma unroll 8
+        for (int r = 0; r < p.W; ++r)   // unrolled: the W slot reads of a bucket are independent loads, issued together
+            v += __ldcg(reinterpret_cast<const uint32_t *>(half + p.sl.hist + (size_t)r * p.sl.hist_stride) + (size_t)c * p.sl.hp + i);
         return v;
     };
     const int nch = max(1, (ntp + 1023) / 1024);
