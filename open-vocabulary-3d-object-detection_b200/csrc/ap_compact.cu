@@ -1142,22 +1142,48 @@ __global__ void __launch_bounds__(512) apx_hist_big_kernel(ApxParams p, const fl
         }
     };
     auto place = [&](float s) { const float sv[4] = {s, -INFINITY, -INFINITY, -INFINITY}; place4(sv); };
+    // The private counters are 16 bits wide: after at most 60 000 records of this CTA they are flushed to the class's
+    // global row and cleared, so a CTA may take any number of records and the grid stays one balanced wave.
+    auto flush = [&](bool clear) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < (ntp + 2) / 2; i += NT) {
+            const uint32_t w = hw[i];
+            if (w) {
+                if (w & 0xffffu) atomicAdd(&hist[2 * i], w & 0xffffu);
+                if (w >> 16) atomicAdd(&hist[2 * i + 1], w >> 16);
+                if (clear) hw[i] = 0;
+            }
+        }
+        if (clear) __syncthreads();
+    };
     if (((reinterpret_cast<uintptr_t>(sc) & 15) == 0) && N < 0x7fffffffLL) {
         const int n4 = (int)(N >> 2);
         const int step = (int)(gridDim.x * NT);
-        for (int i = (int)(blockIdx.x * NT + threadIdx.x); i < n4; i += step) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(sc) + i);
-            const float sv[4] = {v.x, v.y, v.z, v.w};
-            place4(sv);
+        const int iters = (n4 + step - 1) / step;               // the same trip count for every thread of the grid
+        const int per_flush = max(1, 60000 / (4 * NT));         // iterations of this CTA between two flushes
+        for (int it = 0; it < iters; ++it) {
+            if (it && it % per_flush == 0) flush(true);
+            const int i = it * step + (int)(blockIdx.x * NT + threadIdx.x);
+            if (i < n4) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(sc) + i);
+                const float sv[4] = {v.x, v.y, v.z, v.w};
+                place4(sv);
+            }
         }
-        for (long long i = ((long long)n4 << 2) + (long long)blockIdx.x * NT + threadIdx.x; i < N; i += (long long)gridDim.x * NT) place(sc[i]);
+        for (long long i = ((long long)n4 << 2) + (long long)blockIdx.x * NT + threadIdx.x; i < N; i += (long long)gridDim.x * NT) place(sc[i]);   // < 4 records
     } else {
-        for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < N; i += (long long)gridDim.x * NT) place(sc[i]);
+        const long long step = (long long)gridDim.x * NT;
+        const long long iters = (N + step - 1) / step;
+        const int per_flush = max(1, 60000 / NT);
+        for (long long it = 0; it < iters; ++it) {
+            if (it && it % per_flush == 0) flush(true);
+            const long long i = it * step + (long long)blockIdx.x * NT + threadIdx.x;
+            if (i < N) place(sc[i]);
+        }
     }
     for (int off = 16; off > 0; off >>= 1) tail += __shfl_xor_sync(0xffffffffu, tail, off);
     if ((threadIdx.x & 31) == 0 && tail) atomicAdd(&hist[ntp], tail);
-    __syncthreads();
-    for (int i = threadIdx.x; i <= ntp; i += NT) { const uint32_t v = (hw[i >> 1] >> ((i & 1) * 16)) & 0xffffu; if (v) atomicAdd(&hist[i], v); }
+    flush(false);
     (void)last_block; (void)last_s;   // shipping to the peers is a separate stage (apx_ship_hist_kernel): one CTA per (class, peer)
 }
 
@@ -1440,10 +1466,16 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
                                 : sizeof(uint32_t) * 2 * ((size_t)cap_total + 1) + sizeof(uint16_t) * APX_BINS;
         if (big) OVDET_CUDA_TRY(ensure_dyn_smem(apx_hist_big_kernel, smem));
         else OVDET_CUDA_TRY(ensure_dyn_smem(apx_hist_kernel, smem));
-        int per_sm = (int)(220 * 1024 / (smem + 1024));
+        // CTAs that fit one SM: 228 KB of shared memory, 1 KB reserved per CTA, 2048 threads.  The grid is ONE balanced wave:
+        // a few CTAs more than the slots would leave most SMs idle behind a second wave (measured on 8 GPUs: 220 CTAs of
+        // the long-list kernel on 148 SMs, two resident on half of them, 114 us against 51 us for the short-list kernel)
+        int per_sm = (int)(233472 / (smem + 1024 + 64));
+        const int by_threads = 2048 / (big ? 512 : APC_NT);
+        if (per_sm > by_threads) per_sm = by_threads;
         if (per_sm > 8) per_sm = 8;
         if (per_sm < 1) per_sm = 1;
-        const int gx_full = (148 * per_sm + C - 1) / C;
+        int gx_full = 148 * per_sm / C;
+        if (gx_full < 1) gx_full = 1;
         auto launch_hist = [&](const float *blk, long long N, int last) -> int {
             // a CTA pays the set-up of its tables (list keys, 16 KB of bins) and the flush of its histogram: with few records
             // per class use 1024-thread CTAs (the set-up is spread over 4x the threads) of >= 16 records per thread
@@ -1451,7 +1483,6 @@ extern "C" int ovdet_apx_reduce(const void *const *blocks, const int64_t *block_
             long long gx = (N + 8191) / 8192;
             if (!big && gx < gx_full / 2) { nt = 1024; gx = (N + 16383) / 16384; }
             if (gx > gx_full) gx = gx_full;
-            if (big && gx * 60000 < N) gx = (N + 59999) / 60000;   // 16-bit private counters: < 65 536 records per CTA
             if (gx < 1) gx = 1;
             if (big) OVDET_CUDA_TRY(launch_pdl(apx_hist_big_kernel, dim3((unsigned)gx, C), dim3(nt), smem, st, p, blk, N, last));
             else OVDET_CUDA_TRY(launch_pdl(apx_hist_kernel, dim3((unsigned)gx, C), dim3(nt), smem, st, p, blk, N, last));

@@ -498,6 +498,43 @@ def test_ap_compact_equals_sort_path():
 
 
 
+@pytest.mark.parametrize("C,N,rate,cap_total", [
+    (48, 500_000, 0.02, 16384),     # long lists, few CTAs per class: > 60 000 records per CTA -> the 16-bit counters are flushed mid-way
+    (20, 646_400, 0.0025, 2048),    # config-3 shape, short lists (one-rank sort + small histogram kernel)
+    (3, 1_000_001, 0.008, 8192),    # ragged N (scalar tail, unaligned rows), packed-counter kernel
+])
+def test_apx_reducer_equals_sort_path(C, N, rate, cap_total):
+    """ovdet_apx_reduce on one rank (merge, histogram, final) against the segmented radix sort + scan on synthetic
+    record streams with distinct scores; TP lists built from the records by ovdet_apc_collect (same key format)."""
+    from ovdet_b200 import _capi as CA
+    dev = torch.device(DEV, torch.cuda.current_device())
+    g = torch.Generator(device=DEV).manual_seed(7)
+    score = torch.stack([(torch.randperm(N, generator=g, device=DEV).float() + 0.5) / N for _ in range(C)])
+    score[torch.rand((C, N), generator=g, device=DEV) < 0.1] = float("-inf")
+    r = torch.rand((C, N), generator=g, device=DEV)
+    tp = (r < rate * 0.6).to(torch.uint8) * 3 + ((r >= rate * 0.6) & (r < rate * 0.8)).to(torch.uint8) * 1 + ((r >= rate * 0.8) & (r < rate)).to(torch.uint8) * 2
+    tp[score == float("-inf")] = 0
+    npos = (tp != 0).sum(1).to(torch.int64) + 5
+    assert int((tp != 0).sum(1).max()) <= cap_total
+    lists = ED.TpLists(C, dev, 16384)
+    nvalid = torch.zeros((C,), dtype=torch.int64, device=DEV)
+    CA.check(CA.lib().ovdet_apc_collect(score.data_ptr(), tp.data_ptr(), C, N, lists.cap_list, lists.key_ptr, lists.bits_ptr,
+                                        lists.tp_cnt_ptr, nvalid.data_ptr(), CA.stream(dev)))
+    lists.npos.copy_(npos)
+    for m07 in (False, True):
+        ap, recall, ndet = ED.ap_reduce(score, tp, npos, 2, use_07_metric=m07)
+        red = ED.ApxReducer(C, 2, cap_total, dev)
+        for _ in range(2):      # twice: epochs advance, the histogram rows are cleared by the merge stage
+            red.launch([score], lists, use_07_metric=m07)
+            torch.cuda.synchronize()
+            ap_, rec_, nd_, ovf, _, _ = red.read()
+            assert ovf == 0
+            np.testing.assert_allclose(ap_, ap.cpu().numpy(), rtol=0, atol=1e-13)
+            np.testing.assert_allclose(rec_, recall.cpu().numpy(), rtol=0, atol=0)
+            np.testing.assert_array_equal(nd_, ndet.cpu().numpy())
+        red.close()
+
+
 @pytest.mark.parametrize("case", [
     dict(K=128, C=20, thrs=(0.25, 0.5), max_gt=12),
     dict(K=128, C=20, thrs=(0.25, 0.5), max_gt=64, heading=0.3),                 # crowded: candidate queue overflows -> slabs
