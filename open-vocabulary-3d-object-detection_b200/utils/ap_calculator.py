@@ -301,8 +301,8 @@ class APCalculator(object):
 
     def _format_all(self, ap, recall):
         """All thresholds at once ([nthr, C] arrays): the same keys, order and numbers as ``_format_rows`` per threshold,
-        with the NaN scrub and the two means vectorised over the thresholds and the per-class values converted in one
-        ``tolist`` (Python floats) -- the host-side formatting follows the last kernel of an evaluation un-overlapped."""
+        with the NaN scrub and the two means vectorised over the thresholds and one dict build per threshold -- the
+        host-side formatting follows the last kernel of an evaluation un-overlapped."""
         ap, recall = np.asarray(ap), np.asarray(recall)
         n = ap.shape[1]
         keys = self._keys(n)
@@ -310,13 +310,12 @@ class APCalculator(object):
         ap32[ap32 != ap32] = 0                               # NaN -> 0
         m_ap = np.add.reduce(ap32, axis=1) / n               # float32 pairwise row sums / count == ap_vals.mean() per row
         m_ar = np.add.reduce(recall, axis=1) / n
-        apl, rl = ap.tolist(), recall.tolist()
         overall_ret = OrderedDict()
         order = keys[2]                                      # AP keys, "mAP", recall keys, "AR": the reference's insertion order
         for ti, thr in enumerate(self.ap_iou_thresh):
-            vals = apl[ti]
+            vals = list(ap[ti])                              # np.float64 scalars, the reference's value type
             vals.append(m_ap[ti])
-            vals.extend(rl[ti])
+            vals.extend(recall[ti])
             vals.append(m_ar[ti])
             overall_ret[thr] = OrderedDict(zip(order, vals))
         return overall_ret

@@ -57,6 +57,27 @@ def test_metric_formatting_matches_reference_layout():
     assert "mAP0.25, mAP0.50: 43.75, 43.75" in text and "bed Average Precision: 50.00" in text
 
 
+def test_metric_formatting_all_thresholds_equals_per_threshold():
+    """compute_metrics / replay format all thresholds at once (_format_all): keys, order, values and value types of the
+    reference's per-threshold _format (utils/ap_calculator.py:377-395)."""
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 7, 8, 9, 20, 37):
+        class Cfg:
+            num_semcls = n
+        calc = APC.APCalculator(Cfg(), ap_iou_thresh=[0.25, 0.5, 0.75], exact_eval=False)
+        for _ in range(40):
+            ap = rng.random((3, n)) * rng.choice([1.0, 1e-3]); rc = rng.random((3, n))
+            ap[rng.random((3, n)) < 0.15] = np.nan
+            got = calc._format_all(ap, rc)
+            assert isinstance(got, OrderedDict) and list(got.keys()) == [0.25, 0.5, 0.75]
+            for ti, thr in enumerate([0.25, 0.5, 0.75]):
+                want = calc._format({k: ap[ti, k] for k in range(n)}, {k: rc[ti, k] for k in range(n)})
+                assert isinstance(got[thr], OrderedDict) and list(got[thr].keys()) == list(want.keys())
+                for k in want:
+                    assert type(got[thr][k]) is type(want[k]), (k, type(got[thr][k]), type(want[k]))
+                    assert got[thr][k] == want[k] or (np.isnan(got[thr][k]) and np.isnan(want[k])), (n, thr, k)
+
+
 def test_giou_flag_words():
     assert BU.giou_flags(True, False, "cython", True, "aabb") == (C.GIOU_ROTATED | C.GIOU_PREFILTER | C.GIOU_CLIP_F64)
     assert BU.giou_flags(False, True, "tensor", False, "aabb") == C.GIOU_INTER_ONLY
