@@ -670,10 +670,12 @@ __global__ void __launch_bounds__(1024, 1) apx_push_lists_kernel(ApxParams p)
             reinterpret_cast<long long *>(slot + p.sl.l_npos)[c] = np;
         }
     }
-    __threadfence_system();
+    // CTA barrier, then ONE system-scope fence per flag writer: fences are cumulative, so the stores of all 1024 threads
+    // (ordered before the barrier) are visible to whoever acquires the flag.  A fence in every thread cost ~10 us here.
     __syncthreads();
     if (tid < p.W) {
         unsigned char *half = p.peers.base[tid] + (size_t)(tag & 1u) * p.sl.half;
+        __threadfence_system();
         st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_l) + (size_t)run * p.C + c, tag);
     }
     if (sub == 0) XSTAMPC(c, 11);
@@ -1203,9 +1205,11 @@ __global__ void __launch_bounds__(256) apx_ship_hist_kernel(ApxParams p)
     unsigned char *half = p.peers.base[dst] + (size_t)(tag & 1u) * p.sl.half;
     uint4 *out = reinterpret_cast<uint4 *>(half + p.sl.hist + (size_t)p.rank * p.sl.hist_stride + sizeof(uint32_t) * (size_t)c * p.sl.hp);
     for (int i = threadIdx.x; i < n4; i += 256) out[i] = __ldcg(src + i);
-    __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_h) + (size_t)p.rank * p.C + c, tag);
+    if (threadIdx.x == 0) {   // barrier + one cumulative system-scope fence (see apx_push_lists_kernel)
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned *>(half + p.sl.flags_h) + (size_t)p.rank * p.C + c, tag);
+    }
     if (dst == 0) XSTAMPC(c, 13);
 }
 

@@ -12,6 +12,7 @@ dev = torch.device("cuda", 0)
 out, tgt = bench.ap_inputs(S)
 dv = {k: v.to(dev).contiguous() for k, v in {**out, **tgt}.items()}
 calc = APC.APCalculator(bench._Cfg(), ap_iou_thresh=[0.25, 0.5], exact_eval=False)
+calc.force_exchange = bool(os.environ.get("APX_FORCE"))   # one rank through the push / cluster-merge / ship code path
 
 def run():
     calc.reset()
