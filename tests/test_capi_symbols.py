@@ -60,3 +60,18 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), os.path.join(dirpath, f)
                 assert "ovdet_oracle" not in txt
+
+
+def test_flag_words_match_header():
+    """Every `#define OVDET_<NAME> <int>` of the header has the same value as `_capi.<NAME>` (the host shims pass these)."""
+    import re
+    from ovdet_b200 import _capi as C
+    text = open(os.path.join(ROOT, "include", "ovdet_b200.h")).read()
+    seen = 0
+    for name, val in re.findall(r"#define OVDET_([A-Z0-9_]+) \(?(-?(?:0x[0-9a-fA-F]+|\d+))u?\)?", text):
+        if name in ("B200_H", "OK") or name.startswith("ERR_"):
+            continue
+        assert hasattr(C, name), "include/ovdet_b200.h defines OVDET_%s but _capi.py has no %s" % (name, name)
+        assert getattr(C, name) == int(val, 0), (name, getattr(C, name), val)
+        seen += 1
+    assert seen >= 20
